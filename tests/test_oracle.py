@@ -1,0 +1,115 @@
+"""CPU tests: pin the oracle restatement (oracle/reslim_oracle.py) to the reference.
+
+* against the committed golden fixtures (outputs + every parameter gradient of the LIVE reference,
+  float64, written by oracle/make_golden.py) -- runs everywhere;
+* against the live reference module itself when /root/reference is present (build container).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, reslim_oracle as O
+
+FIXTURES = [("tiny_mse.npz", "tiny", "mse", False), ("tiny_bayesian_tv_lat.npz", "tiny", "bayesian_tv", True),
+            ("tiny_prism_mae_lat.npz", "tiny_prism", "mae", True)]
+
+
+def _load(golden_dir, fn):
+    z = np.load(os.path.join(golden_dir, fn))
+    sd = {k[2:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("w/")}
+    gr = {k[2:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("g/")}
+    return z, sd, gr
+
+
+@pytest.mark.parametrize("fn,case,loss_name,use_lat", FIXTURES)
+def test_oracle_matches_golden(golden_dir, fn, case, loss_name, use_lat):
+    z, sd, gr = _load(golden_dir, fn)
+    cfg = cases.get_case(case)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x = torch.from_numpy(z["x"]).double()
+    y = torch.from_numpy(z["y"]).double()
+    lw = O.lat_weights(z["lat"]) if use_lat else None
+    taps = {}
+    loss = O.training_step(sd, cfg, x, y, cfg["in_vars"], cfg["out_vars"], loss_name, cfg["var_weights"], lw, taps)
+    loss.backward()
+    assert abs(loss.item() - z["loss_vec"][-1]) <= 1e-6 * abs(z["loss_vec"][-1])
+    np.testing.assert_allclose(taps["preds"].detach().numpy(), z["pred"], rtol=1e-5, atol=1e-6)
+    for k, g in gr.items():
+        got = sd[k].grad if sd[k].grad is not None else torch.zeros_like(sd[k])
+        scale = g.abs().max().item() + 1e-12
+        # fixtures store gradients as float32 of float64 results
+        assert (got - g).abs().max().item() <= 2e-6 * scale + 1e-12, k
+
+
+def test_oracle_loss_vectors(golden_dir):
+    z = np.load(os.path.join(golden_dir, "loss_vectors.npz"))
+    pred0 = torch.from_numpy(z["pred"]); tgt = torch.from_numpy(z["target"])
+    for use_lat in (False, True):
+        sfx = "_lat" if use_lat else ""
+        lw = O.lat_weights(z["lat"]) if use_lat else None
+        for nm, fn in (("mse", O.mse), ("bayesian_tv", O.bayesian_tv)):
+            p = pred0.clone().requires_grad_(True)
+            v = fn(p, tgt, cases.OUT_VARS_3, cases.VAR_WEIGHTS, False, lw)
+            v[-1].backward()
+            np.testing.assert_allclose(v.detach().numpy(), z[nm + sfx], rtol=1e-12)
+            np.testing.assert_allclose(p.grad.numpy(), z[nm + sfx + "_grad"], rtol=1e-10, atol=1e-15)
+        p = pred0.clone().requires_grad_(True)
+        v = O.mae(p, tgt, False, lw)
+        v[-1].backward()
+        np.testing.assert_allclose(v.detach().numpy(), z["mae" + sfx], rtol=1e-12)
+        np.testing.assert_allclose(p.grad.numpy(), z["mae" + sfx + "_grad"], rtol=1e-10, atol=1e-15)
+
+
+def test_unpatchify_index_map():
+    """the flat reinterpretation, checked with an index tensor."""
+    H, W, p, mag, C = 4, 8, 2, 4, 3
+    L = (H // p) * (W // p)
+    K = C * (mag * p) ** 2
+    x = torch.arange(L * K, dtype=torch.float64).reshape(1, L, K)
+    img = O.unpatchify(x, (H, W), p, mag, C)
+    w = W * mag // p
+    for l in range(L):
+        for k in range(K):
+            cell = l * (K // (p * p * C)) + k // (p * p * C)
+            hh, ww = divmod(cell, w)
+            r = k % (p * p * C)
+            pp, qq, cc = r // (p * C), (r // C) % p, r % C
+            assert img[0, cc, p * hh + pp, p * ww + qq].item() == x[0, l, k].item()
+
+
+def test_reference_error_paths():
+    cfg = cases.get_case("tiny")
+    with pytest.raises(ValueError):
+        O.find_var_index(["a", "b"], ["a"])                      # static field missing
+    with pytest.raises(ValueError):
+        O.clip_replace_constant(torch.zeros(1, 1, 2, 2), torch.zeros(1, 1, 2, 2), ["2m_temperature"])
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("case,B", [("tiny", 2), ("tiny_prism", 1)])
+def test_oracle_matches_live_reference(case, B):
+    from oracle import make_golden, ref_shim
+    ref = ref_shim.load_reference()
+    cfg = cases.get_case(case)
+    sd = {k: v.double() for k, v in O.init_state_dict(cfg, 3).items()}
+    x, y = O.synthetic_batch(cfg, B, cfg["in_vars"], cfg["out_vars"], 3)
+    m = make_golden.build_reference_model(ref, cfg, sd, torch.float64)
+    want = m.forward(x.double(), list(cfg["in_vars"]), list(cfg["out_vars"]))
+    got = O.forward(sd, cfg, x.double(), cfg["in_vars"], cfg["out_vars"])
+    assert (want - got).abs().max().item() < 1e-12
+
+
+@pytest.mark.reference
+def test_reference_bugs_documented():
+    """SURVEY.md headline 4: odd H raises in the reference (unpatchify), 180 rows works."""
+    from oracle import make_golden, ref_shim
+    ref = ref_shim.load_reference()
+    cfg = cases.get_case("tiny")
+    cfg["img_size"] = (9, 16); cfg["init_img_size"] = (9, 16)
+    sd = O.init_state_dict(cfg, 0)
+    m = make_golden.build_reference_model(ref, cfg, sd, torch.float32)
+    x, _ = O.synthetic_batch(cfg, 1, cfg["in_vars"], cfg["out_vars"], 0)
+    with pytest.raises(RuntimeError):
+        m.forward(x, list(cfg["in_vars"]), list(cfg["out_vars"]))
