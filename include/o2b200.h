@@ -1,0 +1,148 @@
+/* libo2b200 -- C ABI of the B200-native (sm_100a) kernels behind ORBIT-2's Reslim hot path.
+ *
+ * The reference (XiaoWang-Github/ORBIT-2) is 100% Python and has no FFI of its own: every device
+ * kernel on this path is a PyTorch library call.  Each entry point below therefore names the
+ * reference *call site* it replaces (paths relative to the reference root); INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers + sizes; no C++/torch types cross the boundary.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; buffers are owned by the
+ *     caller (torch allocator) and must outlive the launch; the library never allocates device memory.
+ *   - `stream` is a cudaStream_t (as void*); all work is enqueued there, no internal synchronisation.
+ *   - return 0 on success, a negative O2_ERR_* otherwise; o2_last_error() gives a thread-local message.
+ *   - "act dtype" (O2_F32 / O2_BF16) is the activation storage type; all accumulation is fp32 (fp64
+ *     for the loss sums).  Parameters that are reductions over tokens (d*-outputs marked "+=") are
+ *     ACCUMULATED into, so the caller zero-fills them once per step.
+ *   - no CPU fallback exists anywhere: without a CUDA device every compute call fails.
+ */
+#ifndef O2B200_H
+#define O2B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define O2_OK 0
+#define O2_ERR_ARG (-1)
+#define O2_ERR_CUDA (-2)
+#define O2_ERR_UNSUPPORTED (-3)
+
+enum { O2_F32 = 0, O2_BF16 = 1 };
+
+/* GEMM implementations: SIMT fp32 (exact-parity path, activations fp32) and tcgen05 bf16 (TMA + TMEM). */
+enum { O2_GEMM_SIMT_F32 = 0, O2_GEMM_TC_BF16 = 1 };
+
+/* GEMM epilogues (acc = op(A) op(B), fp32):                                                       */
+enum {
+  O2_EPI_NONE = 0,      /* C = acc                                                                */
+  O2_EPI_BIAS = 1,      /* C = acc + bias[n]                                                      */
+  O2_EPI_BIAS_GELU = 2, /* aux_out = acc + bias[n] (pre-activation, kept for backward); C = gelu   */
+  O2_EPI_BIAS_RES = 3,  /* C = acc + bias[n] + aux[m % aux_rows, n] (residual / broadcast pos-emb) */
+  O2_EPI_DGELU = 4,     /* C = acc * gelu'(aux[m, n])                                             */
+  O2_EPI_ACCUM = 5      /* C(f32) += acc (split-K atomics; weight gradients)                      */
+};
+
+enum { O2_LOSS_MSE = 0, O2_LOSS_MAE = 1, O2_LOSS_BAYESIAN_TV = 2 };
+
+int o2_version(void);
+const char* o2_last_error(void);
+/* 1 if a CUDA device of compute capability 10.x is visible, else 0 (never falls back). */
+int o2_device_ok(void);
+
+/* ---- dense contractions: every nn.Linear on the path -----------------------------------------
+ * replaces F.linear in components/attention.py:50,81,177 (qkv/proj), components/mlp.py:63,67
+ * (fc1/fc2), res_slimvit.py:115-120 (head) and their autograd backward.
+ * C[M,N] = op(A)[M,K] * op(B)[K,N];  trans_a=0: A stored [M,K] row-major, 1: stored [K,M];
+ * trans_b=0: B stored [N,K] row-major (nn.Linear weight layout), 1: stored [K,N].  ld* in elements.
+ * impl SIMT: A,B,aux,aux_out fp32.  impl TC: A,B bf16 (16-byte aligned rows), aux/aux_out bf16,
+ * C bf16 or fp32 (c_dtype).  bias is fp32 [N].  split_k>1 only with O2_EPI_ACCUM. */
+int o2_gemm(int impl, const void* A, int trans_a, int64_t lda, const void* B, int trans_b, int64_t ldb, void* C,
+            int c_dtype, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue, const float* bias,
+            const void* aux, int64_t ld_aux, int64_t aux_rows, void* aux_out, int64_t ld_aux_out, int split_k,
+            void* stream);
+
+/* ---- LayerNorm (vit_blocks.py:46,63 norm1/norm2; res_slimvit.py:104 norm), eps inside rsqrt ------- */
+int o2_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     int64_t T, int D, float eps, int dtype, void* stream);
+/* dx = LN'(dy) (+ dres if non-null: the residual-stream gradient); dgamma/dbeta "+=" (fp32 [D]). */
+int o2_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                     const void* dres, void* dx, float* dgamma, float* dbeta, int64_t T, int D, int dtype,
+                     void* stream);
+
+/* ---- multi-head self-attention, softmax(QK^T * scale) V, bidirectional, no mask -----------------
+ * replaces attention.py:50-78 (xformers CK FMHA / F.scaled_dot_product_attention / explicit softmax).
+ * qkv is the fused projection output [B, N, 3, heads, hd] (q rows, then k, then v: attention.py:50);
+ * out is [B, N, heads, hd] (= x.transpose(1,2).reshape(B,N,C), attention.py:71,80); lse is
+ * [B, heads, N] fp32 (natural log).  impl: O2_GEMM_SIMT_F32 (fp32 in/out) or O2_GEMM_TC_BF16. */
+int o2_attn_fwd(int impl, const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale,
+                void* stream);
+/* dqkv has qkv's layout and is fully overwritten; delta is a [B,heads,N] fp32 scratch. */
+int o2_attn_bwd(int impl, const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                float* delta, int B, int N, int heads, int hd, float scale, void* stream);
+
+/* ---- front end: per-variable patch embedding + variable embedding + variable aggregation ---------
+ * replaces res_slimvit.py:254-265 (23x PatchEmbed conv, var_embed add, aggregate_variables) and
+ * attention.py:132-176 (single-query cross attention over the V variable tokens) up to, not including,
+ * var_agg.proj.  Uses the exact per-token collapse: the host precomputes
+ *   tab_s [V, heads, PP+1]          score coefficients (last entry = constant term), pre-scaled
+ *   tab_v [heads, V*(PP+1), hd]     value operator
+ * (PP = patch_size^2) from the parameters; the kernel reads x [B, V, Hx, Wx] fp32 once and writes the
+ * concatenated head outputs o [B, gh*gw, heads*hd] in act dtype.  Rows >= gh*p of x are ignored. */
+int o2_frontend_fwd(const float* x, const float* tab_s, const float* tab_v, void* out, int out_dtype, int B, int V,
+                    int Hx, int Wx, int p, int gh, int gw, int heads, int hd, void* stream);
+/* dtab_s / dtab_v "+=" (fp32, same shapes as the tables). */
+int o2_frontend_bwd(const float* x, const float* tab_s, const float* tab_v, const void* dout, int dtype,
+                    float* dtab_s, float* dtab_v, int B, int V, int Hx, int Wx, int p, int gh, int gw, int heads,
+                    int hd, void* stream);
+
+/* ---- residual conv branch, first half (res_slimvit.py:107-109,233-242): gather the C+4 channels
+ * ch_idx_host[0..cin) of x, conv3x3(cin -> c1, pad 1) + bias.  Writes the PRE-activation h1
+ * [B, c1, Hx, Wx] in act dtype (GELU + PixelShuffle are applied on the fly by o2_headtail_*). */
+int o2_path2_conv1_fwd(const float* x, const int* ch_idx_host, const float* w1, const float* b1, void* h1,
+                       int dtype, int B, int V, int Hx, int Wx, int cin, int c1, void* stream);
+/* dw1 [c1,cin,3,3] / db1 [c1] "+=" from dh1 (gradient w.r.t. the pre-activation). */
+int o2_path2_conv1_bwd(const float* x, const int* ch_idx_host, const void* dh1, float* dw1, float* db1, int dtype,
+                       int B, int V, int Hx, int Wx, int cin, int c1, void* stream);
+
+/* ---- head tail (res_slimvit.py:329-338): unpatchify (the reference's flat re-interpretation, see
+ * SURVEY.md 8/a14) + conv_out 3x3 + [GELU -> PixelShuffle(mag) -> conv3x3(cr -> C)] of h1 + crop-add.
+ * head_out [B, gh*gw, C*(mag*p)^2] act dtype; preds [B, C, Ho, Wo] act dtype, Ho = gh*p*mag, Wo = gw*p*mag;
+ * h1 [B, cr*mag^2, Hx, Wx] with Hx*mag >= Ho, Wx*mag >= Wo (the branch is cropped to the ViT output). */
+int o2_headtail_fwd(const void* head_out, const void* h1, const float* w_out, const float* b_out, const float* w2,
+                    const float* b2, void* preds, int dtype, int B, int C, int gh, int gw, int p, int mag, int cr,
+                    int Hx, int Wx, void* stream);
+/* d_head_out / dh1 overwritten; dw_out [C,C,3,3], db_out [C], dw2 [C,cr,3,3], db2 [C] "+=". */
+int o2_headtail_bwd(const void* dpreds, const void* head_out, const void* h1, const float* w_out, const float* w2,
+                    void* d_head_out, void* dh1, float* dw_out, float* db_out, float* dw2, float* db2, int dtype,
+                    int B, int C, int gh, int gw, int p, int mag, int cr, int Hx, int Wx, void* stream);
+
+/* ---- loss: clip_replace_constant (examples/intermediate_downscaling.py:267-278) fused with
+ * mse / mae / bayesian_tv (metrics/functional.py:173-202, 218-232, 117-167) and their gradient.
+ * pred [B,C,H,W] act dtype (raw model output, NOT modified); target fp32 [B,C,tgt_H,tgt_W] with
+ * tgt_H>=H, tgt_W>=W (cropped like intermediate_downscaling.py:295-296).  clamp_ch: channel clamped
+ * at 0 (-1: none); const_mask: bit c set => channel c replaced by the target (zero gradient).
+ * lat_w fp32 [H] or NULL; ch_w fp32 [C] or NULL.  loss_vec [C+1] fp32: per-channel means then the
+ * aggregate.  dpred (nullable) = grad_scale * d(aggregate)/d(pred), act dtype.  accum_ws: [C] fp64. */
+int o2_loss_fwd_bwd(const void* pred, int dtype, const float* target, void* dpred, float* loss_vec,
+                    double* accum_ws, const float* lat_w, const float* ch_w, int kind, int clamp_ch,
+                    uint32_t const_mask, int B, int C, int H, int W, int tgt_H, int tgt_W, float grad_scale,
+                    void* stream);
+/* in-place clip_replace_constant for evaluation (intermediate_downscaling.py:333-334). */
+int o2_clip_replace(void* pred, int dtype, const float* target, int clamp_ch, uint32_t const_mask, int B, int C,
+                    int H, int W, int tgt_H, int tgt_W, void* stream);
+
+/* ---- small HBM-bound helpers ---------------------------------------------------------------- */
+int o2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* out[n] += sum_m X[m, n]  (bias gradients), X act dtype with row pitch ld. */
+int o2_colsum(const void* X, int dtype, float* out, int64_t M, int64_t N, int64_t ld, void* stream);
+/* fused AdamW (torch.optim.AdamW semantics, intermediate_downscaling.py:642-644) over a flat fp32
+ * buffer; g is multiplied by grad_scale first; optionally refreshes the bf16 compute copy. */
+int o2_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+             float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

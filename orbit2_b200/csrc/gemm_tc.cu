@@ -1,0 +1,323 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: C[M,N] = op(A)[M,K] op(B)[K,N] (+ fused epilogue), bf16 in,
+// fp32 accumulate in tensor memory.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
+// warps 2..5 = epilogue (one TMEM lane quarter each).  128 x BN output tile, BK = 64 (one
+// 128-byte swizzle atom of bf16), STAGES-deep smem ring, two TMEM accumulator stages so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Both operands may be K-major (row = M/N index, K contiguous) or MN-major (row = K index, M/N
+// contiguous); the latter is what weight-gradient (dY^T X) and data-gradient (dY W) GEMMs need, so
+// no transposed copies of activations or weights are ever materialised.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr uint32_t kStageA = BM * BK * 2;  // 16 KiB
+
+struct GemmArgs {
+  int M, N, K;
+  int epi, c_f32;
+  long long ldc, ld_aux, aux_rows, ld_aux_out;
+  const float* bias;
+  const __nv_bfloat16* aux;
+  __nv_bfloat16* aux_out;
+  void* C;
+  int a_mn, b_mn;
+  int num_m_blk, num_n_blk, split_k, kb_total, kb_per_split;
+  uint32_t mn_lbo, mn_sbo;  // descriptor strides for MN-major operands (bytes)
+};
+
+template <int BN> struct Cfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr uint32_t kStageB = BN * BK * 2;
+  static constexpr uint32_t kStageBytes = kStageA + kStageB;
+  static constexpr int kTmemCols = 2 * BN;  // 512 or 256
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI, bool C_F32>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&r)[32], long long row, int n0) {
+  // 32 consecutive columns [n0, n0+32) of one output row held by this thread
+  if (row >= g.M) return;
+#pragma unroll
+  for (int j0 = 0; j0 < 32; j0 += 8) {
+    const int n = n0 + j0;
+    if (n >= g.N) break;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j0 + j]);
+    if (EPI == O2_EPI_BIAS || EPI == O2_EPI_BIAS_GELU || EPI == O2_EPI_BIAS_RES) {
+      const float4 b0 = *reinterpret_cast<const float4*>(g.bias + n);
+      const float4 b1 = *reinterpret_cast<const float4*>(g.bias + n + 4);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (EPI == O2_EPI_BIAS_GELU) {
+      uint4 u;
+      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+      u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(g.aux_out + row * g.ld_aux_out + n) = u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gelu_f(v[j]);
+    }
+    if (EPI == O2_EPI_BIAS_RES || EPI == O2_EPI_DGELU) {
+      const long long ar = (EPI == O2_EPI_BIAS_RES) ? (row % g.aux_rows) : row;
+      const uint4 u = *reinterpret_cast<const uint4*>(g.aux + ar * g.ld_aux + n);
+      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+      const float a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (EPI == O2_EPI_BIAS_RES) ? (v[j] + a[j]) : (v[j] * dgelu_f(a[j]));
+    }
+    if (EPI == O2_EPI_ACCUM) {
+      float* c = reinterpret_cast<float*>(g.C) + row * g.ldc + n;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(c + j, v[j]);
+    } else if (C_F32) {
+      float* c = reinterpret_cast<float*>(g.C) + row * g.ldc + n;
+      *reinterpret_cast<float4*>(c) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint4 u;
+      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+      u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.C) + row * g.ldc + n) = u;
+    }
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, const uint32_t (&r)[32], long long row, int n0) {
+  switch (g.epi) {
+    case O2_EPI_NONE:
+      if (g.c_f32) epilogue_chunk<BN, O2_EPI_NONE, true>(g, r, row, n0);
+      else epilogue_chunk<BN, O2_EPI_NONE, false>(g, r, row, n0);
+      break;
+    case O2_EPI_BIAS:
+      if (g.c_f32) epilogue_chunk<BN, O2_EPI_BIAS, true>(g, r, row, n0);
+      else epilogue_chunk<BN, O2_EPI_BIAS, false>(g, r, row, n0);
+      break;
+    case O2_EPI_BIAS_GELU: epilogue_chunk<BN, O2_EPI_BIAS_GELU, false>(g, r, row, n0); break;
+    case O2_EPI_BIAS_RES: epilogue_chunk<BN, O2_EPI_BIAS_RES, false>(g, r, row, n0); break;
+    case O2_EPI_DGELU: epilogue_chunk<BN, O2_EPI_DGELU, false>(g, r, row, n0); break;
+    default: epilogue_chunk<BN, O2_EPI_ACCUM, true>(g, r, row, n0); break;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmArgs g) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < C::kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_work = g.num_m_blk * g.num_n_blk * g.split_k;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int n_blk = w % g.num_n_blk;
+        const int rest = w / g.num_n_blk;
+        const int m_blk = rest % g.num_m_blk;
+        const int split = rest / g.num_m_blk;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + kStageA;
+          ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          if (!g.a_mn) {
+            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              ptx::tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+          }
+          if (!g.b_mn) {
+            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              ptx::tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int rest = w / g.num_n_blk;
+        const int split = rest / g.num_m_blk;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + kStageA;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = g.a_mn ? ptx::umma_smem_desc(sa + k * 2048, g.mn_lbo, g.mn_sbo)
+                                       : ptx::umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = g.b_mn ? ptx::umma_smem_desc(sb + k * 2048, g.mn_lbo, g.mn_sbo)
+                                       : ptx::umma_smem_desc(sb + k * 32, 16, 1024);
+            ptx::umma_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue: TMEM -> registers -> global
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int n_blk = w % g.num_n_blk;
+      const int m_blk = (w / g.num_n_blk) % g.num_m_blk;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const long long row = (long long)m_blk * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        epilogue_dispatch<BN>(g, r, row, n_blk * BN + c * 32);
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+template <int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& g, cudaStream_t st) {
+  using C = Cfg<BN>;
+  g.num_m_blk = (g.M + BM - 1) / BM;
+  g.num_n_blk = (g.N + BN - 1) / BN;
+  static bool attr_done = false;
+  if (!attr_done) {
+    O2_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+    attr_done = true;
+  }
+  const int num_work = g.num_m_blk * g.num_n_blk * g.split_k;
+  const int grid = num_work < o2_num_sms() ? num_work : o2_num_sms();
+  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, g);
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
+
+}  // namespace
+
+int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans_b, int64_t ldb, void* Cp, int c_dtype,
+               int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue, const float* bias, const void* aux,
+               int64_t ld_aux, int64_t aux_rows, void* aux_out, int64_t ld_aux_out, int split_k, cudaStream_t st) {
+  O2_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_tc: empty problem %lld x %lld x %lld", (long long)M, (long long)N, (long long)K);
+  O2_REQUIRE(N % 8 == 0, "gemm_tc: N=%lld must be a multiple of 8", (long long)N);
+  O2_REQUIRE((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0, "gemm_tc: operand row pitch must be 16-byte aligned");
+  O2_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)Cp % 16) == 0,
+             "gemm_tc: operand base pointers must be 16-byte aligned");
+  O2_REQUIRE(ldc % 8 == 0, "gemm_tc: ldc must be a multiple of 8");
+  O2_REQUIRE(epilogue >= O2_EPI_NONE && epilogue <= O2_EPI_ACCUM, "gemm_tc: bad epilogue %d", epilogue);
+  if (epilogue == O2_EPI_BIAS || epilogue == O2_EPI_BIAS_GELU || epilogue == O2_EPI_BIAS_RES)
+    O2_REQUIRE(bias != nullptr, "gemm_tc: epilogue %d needs bias", epilogue);
+  if (epilogue == O2_EPI_BIAS_RES || epilogue == O2_EPI_DGELU)
+    O2_REQUIRE(aux != nullptr && ld_aux % 8 == 0, "gemm_tc: epilogue %d needs aux (ld multiple of 8)", epilogue);
+  if (epilogue == O2_EPI_BIAS_GELU)
+    O2_REQUIRE(aux_out != nullptr && ld_aux_out % 8 == 0, "gemm_tc: BIAS_GELU needs aux_out");
+  if (epilogue == O2_EPI_ACCUM) O2_REQUIRE(c_dtype == O2_F32, "gemm_tc: ACCUM needs fp32 C");
+  if (epilogue == O2_EPI_BIAS_GELU || epilogue == O2_EPI_BIAS_RES || epilogue == O2_EPI_DGELU)
+    O2_REQUIRE(c_dtype == O2_BF16, "gemm_tc: epilogue %d writes bf16", epilogue);
+  if (split_k < 1) split_k = 1;
+  O2_REQUIRE(split_k == 1 || epilogue == O2_EPI_ACCUM, "gemm_tc: split_k>1 only with O2_EPI_ACCUM");
+
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.epi = epilogue; g.c_f32 = (c_dtype == O2_F32);
+  g.ldc = ldc; g.ld_aux = ld_aux; g.aux_rows = aux_rows > 0 ? aux_rows : M; g.ld_aux_out = ld_aux_out;
+  g.bias = bias; g.aux = (const __nv_bfloat16*)aux; g.aux_out = (__nv_bfloat16*)aux_out; g.C = Cp;
+  g.a_mn = trans_a ? 1 : 0; g.b_mn = trans_b ? 1 : 0;
+  g.kb_total = (int)((K + BK - 1) / BK);
+  if (split_k > g.kb_total) split_k = g.kb_total;
+  g.kb_per_split = (g.kb_total + split_k - 1) / split_k;
+  g.split_k = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;
+  g.mn_lbo = BK * 128; g.mn_sbo = 1024;
+  if (const char* e = getenv("O2_DBG_MN_LBO")) g.mn_lbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("O2_DBG_MN_SBO")) g.mn_sbo = (uint32_t)atoi(e);
+
+  const int BN = (N > 128) ? 256 : 128;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2], str[1];
+    uint32_t box[2];
+    if (!trans_a) { dims[0] = K; dims[1] = M; box[0] = BK; box[1] = BM; }
+    else          { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = BK; }
+    str[0] = (uint64_t)lda * 2;
+    int rc = o2_make_tmap(&ta, A, 2, 2, dims, str, box, 1);
+    if (rc) return rc;
+    if (!trans_b) { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = (uint32_t)BN; }
+    else          { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
+    str[0] = (uint64_t)ldb * 2;
+    rc = o2_make_tmap(&tb, B, 2, 2, dims, str, box, 1);
+    if (rc) return rc;
+  }
+  return BN == 256 ? launch<256>(ta, tb, g, st) : launch<128>(ta, tb, g, st);
+}

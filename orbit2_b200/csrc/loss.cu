@@ -1,0 +1,183 @@
+// Fused clip_replace_constant + {mse, mae, bayesian_tv} forward and gradient (HBM-bound, one pass).
+//
+// reference: examples/intermediate_downscaling.py:267-278 (clamp precip >= 0, overwrite CONSTANT channels with the
+// target), metrics/functional.py:173-202 (mse), :218-232 (mae), :117-167 (bayesian_tv = mse + 0.02 * 4-direction total
+// variation of the prediction), latitude weights metrics/metrics.py:58-65, channel weights functional.py:188-196.
+//
+// One CTA stages a (TH+2) x (TW+2) halo tile of the *clipped* prediction in shared memory (coalesced reads along W),
+// then every thread produces 4 pixels: weighted error -> warp-shuffle/CTA reduction -> one fp64 atomic per CTA, and the
+// analytic gradient (gather form of the TV stencil, sign(0)=0 like torch.abs) written once.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TW = 128, TH = 8, NT = 256;
+
+struct LossArgs {
+  const void* pred; const float* target; void* dpred;
+  const float* lat_w; const float* ch_w; double* accum;
+  int kind, clamp_ch; uint32_t const_mask;
+  int B, C, H, W, tgt_H, tgt_W;
+  float gscale;  // grad_scale / (B*C*H*W)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NT) loss_kernel(const LossArgs a) {
+  __shared__ float sp[TH + 2][TW + 2];
+  __shared__ unsigned char spass[TH][TW];
+  __shared__ float swarp[NT / 32];
+  const int bc = blockIdx.z;
+  const int c = bc % a.C;
+  const int h0 = blockIdx.y * TH, w0 = blockIdx.x * TW;
+  const T* pred = reinterpret_cast<const T*>(a.pred) + (size_t)bc * a.H * a.W;
+  const float* tgt = a.target + (size_t)bc * a.tgt_H * a.tgt_W;
+  const bool is_const = (a.const_mask >> c) & 1u;
+  const bool is_clamp = (c == a.clamp_ch);
+  const bool tv = (a.kind == O2_LOSS_BAYESIAN_TV);
+
+  for (int i = threadIdx.x; i < (TH + 2) * (TW + 2); i += NT) {
+    const int r = i / (TW + 2), cc = i % (TW + 2);
+    const int h = h0 + r - 1, w = w0 + cc - 1;
+    float v = 0.f;
+    bool pass = false;
+    if (h >= 0 && h < a.H && w >= 0 && w < a.W) {
+      if (is_const) {
+        v = tgt[(size_t)h * a.tgt_W + w];
+      } else {
+        v = to_f(pred[(size_t)h * a.W + w]);
+        pass = true;
+        if (is_clamp && v < 0.f) { v = 0.f; pass = false; }   // clamp_(min=0): gradient only where raw >= 0
+      }
+    }
+    sp[r][cc] = v;
+    if (r >= 1 && r <= TH && cc >= 1 && cc <= TW) spass[r - 1][cc - 1] = pass ? 1 : 0;
+  }
+  __syncthreads();
+
+  const float chw = a.ch_w ? a.ch_w[c] : 1.0f;
+  float local = 0.f;
+#pragma unroll
+  for (int it = 0; it < (TH * TW) / NT; ++it) {
+    const int idx = it * NT + threadIdx.x;
+    const int r = idx / TW, cc = idx % TW;
+    const int h = h0 + r, w = w0 + cc;
+    if (h >= a.H || w >= a.W) continue;
+    const float p = sp[r + 1][cc + 1];
+    const float t = tgt[(size_t)h * a.tgt_W + w];
+    const float lw = a.lat_w ? a.lat_w[h] : 1.0f;
+    const float d = p - t;
+    float err, g;
+    if (a.kind == O2_LOSS_MAE) {
+      err = fabsf(d);
+      g = (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f);
+    } else {
+      err = d * d;
+      g = 2.f * d;
+    }
+    g *= lw;
+    if (tv) {
+      const bool hb = (h + 1 < a.H), ht = (h >= 1), wr = (w + 1 < a.W), wl = (w >= 1);
+      const float lwm = (a.lat_w && ht) ? a.lat_w[h - 1] : 1.0f;
+      auto sgn = [](float x) { return (x > 0.f) ? 1.f : (x < 0.f ? -1.f : 0.f); };
+      // own cell: |p(h+1,w)-p|, |p(h,w+1)-p|, 0.7|p(h+1,w+1)-p|, 0.7|p(h+1,w-1)-p|
+      float e = 0.f, gs = 0.f;
+      if (hb) { const float x = sp[r + 2][cc + 1] - p; e += fabsf(x); gs -= sgn(x); }
+      if (wr) { const float x = sp[r + 1][cc + 2] - p; e += fabsf(x); gs -= sgn(x); }
+      if (hb && wr) { const float x = sp[r + 2][cc + 2] - p; e += 0.7f * fabsf(x); gs -= 0.7f * sgn(x); }
+      if (hb && wl) { const float x = sp[r + 2][cc] - p; e += 0.7f * fabsf(x); gs -= 0.7f * sgn(x); }
+      err += 0.02f * e;
+      float gn = lw * gs;
+      // cells that reference p as their "+" neighbour: (h, w-1) same row; (h-1, w), (h-1, w-1), (h-1, w+1) row above
+      if (wl) gn += lw * sgn(p - sp[r + 1][cc]);
+      if (ht) {
+        float s = sgn(p - sp[r][cc + 1]);
+        if (wl) s += 0.7f * sgn(p - sp[r][cc]);
+        if (wr) s += 0.7f * sgn(p - sp[r][cc + 2]);
+        gn += lwm * s;
+      }
+      g += 0.02f * gn;
+    }
+    local += err * lw;
+    if (a.dpred) {
+      const float gv = spass[r][cc] ? g * chw * a.gscale : 0.f;
+      reinterpret_cast<T*>(a.dpred)[(size_t)bc * a.H * a.W + (size_t)h * a.W + w] = from_f<T>(gv);
+    }
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) swarp[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < NT / 32; ++i) s += swarp[i];
+    atomicAdd(&a.accum[c], (double)s);
+  }
+}
+
+__global__ void loss_finalize(const double* accum, const float* ch_w, float* loss_vec, int C, double inv_per_ch) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double tot = 0.0;
+    for (int c = 0; c < C; ++c) {
+      const double v = accum[c] * (ch_w ? (double)ch_w[c] : 1.0) * inv_per_ch;
+      loss_vec[c] = (float)v;
+      tot += v;
+    }
+    loss_vec[C] = (float)(tot / C);
+  }
+}
+
+template <typename T>
+__global__ void clip_replace_kernel(T* pred, const float* target, int clamp_ch, uint32_t const_mask, int C, int H, int W,
+                                    int tgt_H, int tgt_W, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const int h = (int)((i / W) % H);
+    const size_t bc = i / ((size_t)W * H);
+    const int c = (int)(bc % C);
+    if ((const_mask >> c) & 1u) pred[i] = from_f<T>(target[bc * tgt_H * tgt_W + (size_t)h * tgt_W + w]);
+    else if (c == clamp_ch) { const float v = to_f(pred[i]); if (v < 0.f) pred[i] = from_f<T>(0.f); }
+  }
+}
+
+}  // namespace
+
+extern "C" int o2_loss_fwd_bwd(const void* pred, int dtype, const float* target, void* dpred, float* loss_vec,
+                               double* accum_ws, const float* lat_w, const float* ch_w, int kind, int clamp_ch,
+                               uint32_t const_mask, int B, int C, int H, int W, int tgt_H, int tgt_W, float grad_scale,
+                               void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  O2_REQUIRE(pred && target && loss_vec && accum_ws, "loss: null pointer");
+  O2_REQUIRE(B > 0 && C > 0 && C <= 32 && H > 0 && W > 0, "loss: bad dims B=%d C=%d H=%d W=%d", B, C, H, W);
+  O2_REQUIRE(tgt_H >= H && tgt_W >= W, "loss: target %dx%d smaller than prediction %dx%d", tgt_H, tgt_W, H, W);
+  O2_REQUIRE(kind >= O2_LOSS_MSE && kind <= O2_LOSS_BAYESIAN_TV, "loss: unknown kind %d", kind);
+  O2_REQUIRE(dtype == O2_F32 || dtype == O2_BF16, "loss: bad dtype %d", dtype);
+  O2_REQUIRE((long long)B * C <= 65535, "loss: B*C too large");
+  LossArgs a;
+  a.pred = pred; a.target = target; a.dpred = dpred; a.lat_w = lat_w; a.ch_w = ch_w; a.accum = accum_ws;
+  a.kind = kind; a.clamp_ch = clamp_ch; a.const_mask = const_mask;
+  a.B = B; a.C = C; a.H = H; a.W = W; a.tgt_H = tgt_H; a.tgt_W = tgt_W;
+  a.gscale = (float)((double)grad_scale / ((double)B * C * H * W));
+  O2_CUDA(cudaMemsetAsync(accum_ws, 0, sizeof(double) * C, st));
+  dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * C);
+  if (dtype == O2_F32) loss_kernel<float><<<grid, NT, 0, st>>>(a);
+  else loss_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(a);
+  O2_LAUNCH_CHECK();
+  loss_finalize<<<1, 32, 0, st>>>(accum_ws, ch_w, loss_vec, C, 1.0 / ((double)B * H * W));
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
+
+extern "C" int o2_clip_replace(void* pred, int dtype, const float* target, int clamp_ch, uint32_t const_mask, int B, int C,
+                               int H, int W, int tgt_H, int tgt_W, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  O2_REQUIRE(pred && target, "clip_replace: null pointer");
+  O2_REQUIRE(tgt_H >= H && tgt_W >= W, "clip_replace: target smaller than prediction");
+  const size_t total = (size_t)B * C * H * W;
+  const int grid = (int)((total + 255) / 256 < (size_t)o2_num_sms() * 8 ? (total + 255) / 256 : (size_t)o2_num_sms() * 8);
+  if (dtype == O2_F32)
+    clip_replace_kernel<float><<<grid, 256, 0, st>>>((float*)pred, target, clamp_ch, const_mask, C, H, W, tgt_H, tgt_W, total);
+  else if (dtype == O2_BF16)
+    clip_replace_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)pred, target, clamp_ch, const_mask, C, H, W, tgt_H, tgt_W, total);
+  else O2_FAIL(O2_ERR_ARG, "clip_replace: bad dtype %d", dtype);
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
