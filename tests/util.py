@@ -1,0 +1,34 @@
+"""Shared helpers for the parity tests (oracle side = test infrastructure)."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = [str(s) for s in z["meta"]]
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.keys() if k.startswith("w/")}
+    grads = {k[2:]: torch.from_numpy(z[k]) for k in z.keys() if k.startswith("g/")}
+    return z, meta, sd, grads
+
+
+def build_model(cfg, sd=None, device="cpu", compute_dtype=None):
+    from orbit2_b200.reslim import Res_Slim_ViT
+    m = Res_Slim_ViT(cfg["default_vars"], cfg["init_img_size"], len(cfg["default_vars"]), cfg["out_channels"], 1,
+                     superres_mag=cfg["superres_mag"], cnn_ratio=cfg["cnn_ratio"], patch_size=cfg["patch_size"],
+                     drop_path=0.0, drop_rate=0.0, learn_pos_emb=True, embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                     decoder_depth=cfg["decoder_depth"], num_heads=cfg["num_heads"], mlp_ratio=cfg["mlp_ratio"],
+                     compute_dtype=compute_dtype)
+    if sd is not None:
+        m.load_state_dict(sd, strict=True)
+    m.spatial_resolution = cfg["spatial_resolution"]
+    m.img_size = tuple(cfg["img_size"])
+    return m.to(device)
