@@ -11,7 +11,8 @@ from . import _lib as L
 from ._lib import (EPI_ACCUM, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_NONE, GEMM_SIMT_F32, GEMM_TC_BF16,
                    O2_BF16, O2_F32)
 
-TC_ATTENTION = False  # flipped once the tcgen05 flash-attention kernels are in
+TC_ATTENTION_FWD = True
+TC_ATTENTION_BWD = False  # INTERIM: flipped once the tcgen05 backward kernel is in
 LAUNCHES = 0          # number of library kernels-launching calls (bench.py reports it)
 
 
@@ -94,7 +95,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None):
 def attn_fwd(qkv, B, N, heads, hd):
     """qkv [B*N, 3*heads*hd] -> (out [B*N, heads*hd], lse [B,heads,N])."""
     lib = L.load()
-    if qkv.dtype == torch.bfloat16 and not TC_ATTENTION:      # INTERIM until attn_tc.cu lands: fp32 SIMT kernel on up-cast operands
+    if qkv.dtype == torch.bfloat16 and not TC_ATTENTION_FWD:  # INTERIM: fp32 SIMT kernel on up-cast operands
         o32, lse = attn_fwd(qkv.float(), B, N, heads, hd)
         return o32.to(torch.bfloat16), lse
     out = torch.empty(B * N, heads * hd, device=qkv.device, dtype=qkv.dtype)
@@ -107,7 +108,7 @@ def attn_fwd(qkv, B, N, heads, hd):
 
 def attn_bwd(qkv, out, dout, lse, B, N, heads, hd):
     lib = L.load()
-    if qkv.dtype == torch.bfloat16 and not TC_ATTENTION:      # INTERIM (see attn_fwd)
+    if qkv.dtype == torch.bfloat16 and not TC_ATTENTION_BWD:  # INTERIM: fp32 SIMT kernel on up-cast operands
         return attn_bwd(qkv.float(), out.float(), dout.float(), lse, B, N, heads, hd).to(torch.bfloat16)
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, heads, N, device=qkv.device, dtype=torch.float32)

@@ -201,3 +201,32 @@ def test_conv1_headtail(dtype, B, C, gh, gw, extra):
     assert rel(dho, hod.grad) < gt
     for k, r in dict(wo=wod, bo=bod, w2=w2d, b2=b2d, w1=w1d, b1=b1d).items():
         assert rel(G[k], r.grad) < gt, k
+
+
+def _attn_ref(qkv, B, N, heads, hd):
+    t = qkv.double().reshape(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4).requires_grad_(True)
+    q, k, v = t.unbind(0)
+    s = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, heads * hd)
+    return t, o, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,N,heads,scale_in", [(1, 128, 1, 1.0), (2, 256, 2, 1.0), (1, 300, 2, 2.0), (2, 1000, 3, 1.0),
+                                                (1, 72, 1, 4.0), (1, 2049, 1, 1.0)])
+def test_attn_tc(B, N, heads, scale_in):
+    """tcgen05 flash attention (bf16) vs float64 softmax attention on the same bf16-rounded operands; N covers the
+    ragged tails (N % 128 = 72 like the 117M grid's 16200, < one tile, one past a tile) and large logits."""
+    from orbit2_b200 import ops
+    hd = 64
+    g = torch.Generator(device="cuda").manual_seed(N + heads)
+    D = heads * hd
+    qkv = (torch.randn(B * N, 3 * D, generator=g, device="cuda") * scale_in).to(torch.bfloat16)
+    dout = torch.randn(B * N, D, generator=g, device="cuda").to(torch.bfloat16)
+    out, lse = ops.attn_fwd(qkv, B, N, heads, hd)
+    t, o, lse_ref = _attn_ref(qkv, B, N, heads, hd)
+    assert rel(lse, lse_ref.detach()) < 1e-3
+    assert rel(out, o.detach()) < 1.5e-2
+    o.backward(dout.double())
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, B, N, heads, hd)
+    ref = t.grad.permute(1, 3, 0, 2, 4).reshape(B * N, 3 * D)
+    assert rel(dqkv, ref) < 2e-2
