@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- train samples/s of the ORBIT-2 Reslim hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 117m|8m] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One step = forward -> clip_replace_constant -> bayesian_tv loss (the shipped ``train_loss``, configs/interm_117m.yaml:10)
+-> backward -> data-parallel gradient all-reduce -> AdamW, on one batch of synthetic ERA5-shaped fields
+(interm_117m on the 180x360 -> 720x1440 grid, B = 8 per GPU: configs/interm_117m.yaml:6; weak scaling).
+Prints ONE JSON line (rank 0).  ``value`` is timed with the batch resident in HBM, ``e2e`` re-times the same steps
+through the public API (Res_Slim_ViT.forward + METRICS_REGISTRY loss + backward + AdamW) with pinned host inputs copied
+in and the loss read back every step.  ``--impl reference`` times the CPU restatement of the reference (oracle/, SDPA
+attention = the reference's FusedAttn.DEFAULT path) on the host cores -- the Python reference itself cannot travel to
+the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train samples/sec at 1/2/4/8 B200 (117M, ERA5 1.0°→0.25°); % bf16/HBM roofline"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx, self.rows, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def flops_per_sample(cfg):
+    """counted dense FLOPs, forward+backward (GEMMs x3, attention x3.5)."""
+    p = cfg["patch_size"]
+    L = (cfg["img_size"][0] // p) * (cfg["img_size"][1] // p)
+    D, depth, dec, C, mag = cfg["embed_dim"], cfg["depth"], cfg["decoder_depth"], cfg["out_channels"], cfg["superres_mag"]
+    lin = depth * 24 * L * D * D + dec * 2 * L * D * D + 2 * L * D * C * (mag * p) ** 2 + 2 * L * D * D
+    att = depth * 4 * L * L * D
+    return 3.0 * lin + 3.5 * att, att / depth, L
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_step_time(case_name, B, steps, warmup, threads):
+    """Seconds per step of the CPU restatement (fp32, SDPA attention) of forward+clip+loss+backward."""
+    import torch
+    from oracle import cases, reslim_oracle as O
+    torch.set_num_threads(threads)
+    O.USE_SDPA = True
+    cfg = cases.get_case(case_name)
+    sd = {k: v.requires_grad_(True) for k, v in O.init_state_dict(cfg, 0).items()}
+    x, y = O.synthetic_batch(cfg, B, cfg["in_vars"], cfg["out_vars"], 0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss = O.training_step(sd, cfg, x, y, cfg["in_vars"], cfg["out_vars"], "bayesian_tv", cfg["var_weights"])
+        loss.backward()
+        for v in sd.values():
+            v.grad = None
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), cfg
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    case, B = ("117m_90x180", 1) if args.workload == "117m" else ("8m", 8)
+    sec, cfg = cpu_reference_step_time(case, B, args.steps, args.warmup, threads)
+    val = B / sec
+    sample = (f"CPU restatement of the reference (oracle/, fp32, SDPA attention), forward+clip+bayesian_tv+backward, "
+              f"B={B} on the {cfg['img_size'][0]}x{cfg['img_size'][1]} grid "
+              + ("(a 1/4-area sub-grid of the 180x360 workload, L=4050: samples here are 1/4-size samples)" if case == "117m_90x180" else "")
+              + f", {args.steps} steps after {args.warmup} warm-up")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "interm_117m ERA5 1.0->0.25 (reference arm: CPU sample, see cpu_baseline.sample)"
+                       if args.workload == "117m" else "interm_8m"},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import cases, reslim_oracle as O            # synthetic inputs / weights only (bench baseline leg)
+    from orbit2_b200 import _lib, engine, losses, ops
+    from orbit2_b200.reslim import Res_Slim_ViT
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load(require_device=True)
+
+    cfg = cases.get_case(args.workload)
+    B = args.batch or (8 if args.workload == "117m" else 32)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    torch.manual_seed(0)
+    model = Res_Slim_ViT(cfg["default_vars"], cfg["img_size"], len(cfg["default_vars"]), cfg["out_channels"], 1,
+                         superres_mag=cfg["superres_mag"], cnn_ratio=cfg["cnn_ratio"], patch_size=cfg["patch_size"],
+                         drop_path=0.0, drop_rate=0.0, learn_pos_emb=True, embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                         decoder_depth=cfg["decoder_depth"], num_heads=cfg["num_heads"], mlp_ratio=cfg["mlp_ratio"],
+                         compute_dtype=dtype)
+    with torch.no_grad():                                   # zeros would hide the front end
+        model.var_embed.normal_(0, 0.02)
+        model.var_query.normal_(0, 0.02)
+    model.spatial_resolution = cfg["spatial_resolution"]
+    model = model.to(dev)
+    n_params = sum(p.numel() for p in model.parameters())
+    H_out = cfg["img_size"][0] * cfg["superres_mag"]
+    meta = losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None)
+    loss_fn = losses.METRICS_REGISTRY["bayesian_tv"](aggregate_only=True, metainfo=meta)
+    eng = engine.TrainEngine(model, loss_fn, cfg["in_vars"], cfg["out_vars"], cfg["var_weights"], lr=2e-4,
+                             betas=(0.9, 0.99), weight_decay=1e-5)
+
+    x_h, y_h = O.synthetic_batch(cfg, B, cfg["in_vars"], cfg["out_vars"], seed=rank)
+    x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
+    x_d, y_d = x_h.to(dev), y_h.to(dev)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / steps
+
+    # ---- device-resident arm, with per-kernel CUDA events (same stream) for the roofline
+    def dev_step():
+        return eng.step(x_d, y_d)
+
+    for _ in range(args.warmup):
+        dev_step()
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.TIMERS = {}
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        vec = dev_step()
+    e1.record()
+    sync_all()
+    clocks = sampler.summary()
+    ms_step = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_step], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = t.item()
+    timers, ops.TIMERS = ops.TIMERS, None
+    launches = (ops.LAUNCHES - launches0) // args.steps
+    loss_val = float(vec[-1].item())
+
+    kern = {}
+    for name, evs in timers.items():
+        if name == "gemm_flops":
+            continue
+        kern[name] = sum(a.elapsed_time(b) for a, b in evs) / args.steps          # ms per step
+    gemm_flops = sum(timers.get("gemm_flops", [])) / args.steps
+
+    # ---- end-to-end arm: public API, pinned host inputs in, loss out, every step
+    opt_state = {"loss": None}
+    loss_pub = losses.METRICS_REGISTRY["bayesian_tv"](aggregate_only=True, metainfo=meta)
+
+    def e2e_step():
+        x = x_h.to(dev, non_blocking=True)
+        y = y_h.to(dev, non_blocking=True)
+        eng.flat_g.zero_()
+        pred = model(x, cfg["in_vars"], cfg["out_vars"])
+        loss = loss_pub(pred, y, var_names=cfg["out_vars"], var_weights=cfg["var_weights"],
+                        clip_out_variables=cfg["out_vars"])
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(eng.flat_g, op=dist.ReduceOp.AVG)
+        eng.optimizer_step()
+        opt_state["loss"] = loss.item()                    # device -> host read of the step's result
+
+    model.external_wc = eng.Wc if dtype == torch.bfloat16 else None
+    model.train()
+    ms_e2e = timed(e2e_step, args.steps, max(1, args.warmup // 2))
+
+    peaks = load_peaks()
+    fl_sample, attn_fwd_flops_blk, L = flops_per_sample(cfg)
+    value = world * B / (ms_step * 1e-3)
+    e2e_val = world * B / (ms_e2e * 1e-3)
+    step_tflops = fl_sample * B / (ms_step * 1e-3) / 1e12
+
+    # dominant kernel = the attention launch group with the largest share of the step
+    att_names = [n for n in ("attn_fwd", "attn_bwd_dkv", "attn_bwd_dq") if n in kern]
+    roof = None
+    if att_names:
+        dom = max(att_names, key=lambda n: kern[n])
+        nlaunch = len(timers[dom]) / args.steps
+        mult = {"attn_fwd": 1.0, "attn_bwd_dkv": 2.0, "attn_bwd_dq": 1.5}[dom]    # 2 / 4 / 3 GEMMs of 2*L*L*D each
+        fl = attn_fwd_flops_blk * mult * B                                       # per launch
+        avg_ms = kern[dom] / nlaunch
+        ach = fl / (avg_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tf_sust"], "traffic": None, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
+                "avg_launch_ms": avg_ms, "flops_per_launch": fl,
+                "share_of_step": kern[dom] / ms_step}
+    kernels_ms = {k: round(v, 3) for k, v in sorted(kern.items(), key=lambda kv: -kv[1])}
+    if "gemm" in kern and kern["gemm"] > 0:
+        kernels_ms["gemm_tflops"] = round(gemm_flops / (kern["gemm"] * 1e-3) / 1e12, 1)
+    for n, mult in (("attn_fwd", 1.0), ("attn_bwd_dkv", 2.0), ("attn_bwd_dq", 1.5)):
+        if n in kern:
+            kernels_ms[n + "_tflops"] = round(attn_fwd_flops_blk * mult * B * cfg["depth"] / (kern[n] * 1e-3) / 1e12, 1)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        case, cb = ("117m_90x180", 1) if args.workload == "117m" else ("8m", 8)
+        sec, ccfg = cpu_reference_step_time(case, cb, 1, 0 if args.workload == "117m" else 1, threads)
+        cpu = {"value": cb / sec, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"CPU restatement of the reference (oracle/, fp32, SDPA), 1 fwd+loss+bwd step, B={cb} on the "
+                         f"{ccfg['img_size'][0]}x{ccfg['img_size'][1]} grid"
+                         + (" (1/4-area sub-grid of the 180x360 workload: 1/4-size samples, not extrapolated)"
+                            if case == "117m_90x180" else "")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"interm_{args.workload} Res_Slim_ViT ({n_params / 1e6:.1f}M params) ERA5 "
+                                   f"{cfg['img_size'][0]}x{cfg['img_size'][1]} -> {H_out}x{cfg['img_size'][1] * cfg['superres_mag']}"
+                                   ", V=23 in / 3 out vars, fwd+clip+bayesian_tv+bwd+allreduce+AdamW",
+                       "per_gpu_batch": B, "global_batch": B * world, "tokens_per_sample": L, "parallelism": f"dp{world}",
+                       "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB), no explicit flush"},
+            "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": (x_h.numel() + y_h.numel()) * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "step_tflops": step_tflops, "step_frac_of_bf16_peak": step_tflops / peaks["tf_sust"],
+            "kernels_ms_per_step": kernels_ms, "loss": loss_val,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="117m", choices=["117m", "8m", "117m_90x180"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "attn_tc" -x > gpurun_out/attn_test.log 2>&1
-echo "exit $?" >> gpurun_out/attn_test.log
-tail -40 gpurun_out/attn_test.log
+python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -5 gpurun_out/smoke.log
+timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench117.log 2>&1; echo "exit $?" >> gpurun_out/bench117.log
+tail -c 3000 gpurun_out/bench117.log

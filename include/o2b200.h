@@ -82,6 +82,12 @@ int o2_attn_fwd(int impl, const void* qkv, void* out, float* lse, int B, int N, 
 int o2_attn_bwd(int impl, const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                 float* delta, int B, int N, int heads, int hd, float scale, void* stream);
 
+/* The backward is three launches (delta = rowsum(dout*out); dK,dV; dQ).  o2_attn_bwd_parts runs the subset selected by
+ * `parts` (bit mask) so that a caller can time them separately; O2_ATTN_BWD_DELTA must have run before the other two. */
+enum { O2_ATTN_BWD_DELTA = 1, O2_ATTN_BWD_DKV = 2, O2_ATTN_BWD_DQ = 4, O2_ATTN_BWD_ALL = 7 };
+int o2_attn_bwd_parts(int impl, int parts, const void* qkv, const void* out, const void* dout, const float* lse,
+                      void* dqkv, float* delta, int B, int N, int heads, int hd, float scale, void* stream);
+
 /* ---- front end: per-variable patch embedding + variable embedding + variable aggregation ---------
  * replaces res_slimvit.py:254-265 (23x PatchEmbed conv, var_embed add, aggregate_variables) and
  * attention.py:132-176 (single-query cross attention over the V variable tokens) up to, not including,

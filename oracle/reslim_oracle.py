@@ -92,16 +92,25 @@ def var_agg_attention(sd, var_query, x, num_heads):
     return F.linear(o, sd["var_agg.proj.weight"], sd["var_agg.proj.bias"])
 
 
+# attention.py:54-78 offers three numerically equivalent back ends; parity tests use the explicit softmax
+# (FusedAttn.NONE), the CPU timing baseline uses F.scaled_dot_product_attention (FusedAttn.DEFAULT, :66-71) --
+# the only back end of the reference that is practical on host cores at L = 16200 (no [L, L] matrix).
+USE_SDPA = False
+
+
 def block(sd, pre: str, x, num_heads):
-    """components/vit_blocks.py:76-81, attention.py:43-87 (NONE path), mlp.py:57-73; dropout = 0."""
+    """components/vit_blocks.py:76-81, attention.py:43-87 (NONE / DEFAULT path), mlp.py:57-73; dropout = 0."""
     B, N, D = x.shape
     hd = D // num_heads
     h = F.layer_norm(x, (D,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-5)
     qkv = F.linear(h, sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"])
     qkv = qkv.reshape(B, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv.unbind(0)
-    attn = ((q * hd ** -0.5) @ k.transpose(-2, -1)).softmax(dim=-1)
-    o = (attn @ v).transpose(1, 2).reshape(B, N, D)
+    if USE_SDPA:
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, D)
+    else:
+        attn = ((q * hd ** -0.5) @ k.transpose(-2, -1)).softmax(dim=-1)
+        o = (attn @ v).transpose(1, 2).reshape(B, N, D)
     x = x + F.linear(o, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
     h = F.layer_norm(x, (D,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-5)
     h = F.gelu(F.linear(h, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"]))

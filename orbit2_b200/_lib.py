@@ -27,6 +27,7 @@ SIGNATURES = {
     "o2_layernorm_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p], _i),
     "o2_attn_fwd": ([_i, _p, _p, _p, _i, _i, _i, _i, _f, _p], _i),
     "o2_attn_bwd": ([_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p], _i),
+    "o2_attn_bwd_parts": ([_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p], _i),
     "o2_frontend_fwd": ([_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
     "o2_frontend_bwd": ([_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
     "o2_path2_conv1_fwd": ([_p, C.POINTER(C.c_int), _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p], _i),

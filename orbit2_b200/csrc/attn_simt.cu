@@ -360,7 +360,7 @@ int o2_attn_bwd_simt(const void* qkv, const void* out, const void* dout, const f
 
 int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, cudaStream_t st);
 int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B,
-                   int N, int heads, int hd, float scale, cudaStream_t st);
+                   int N, int heads, int hd, float scale, int parts, cudaStream_t st);
 
 extern "C" int o2_attn_fwd(int impl, const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale,
                            void* stream) {
@@ -371,13 +371,21 @@ extern "C" int o2_attn_fwd(int impl, const void* qkv, void* out, float* lse, int
   O2_FAIL(O2_ERR_ARG, "attn_fwd: unknown impl %d", impl);
 }
 
-extern "C" int o2_attn_bwd(int impl, const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                           float* delta, int B, int N, int heads, int hd, float scale, void* stream) {
+extern "C" int o2_attn_bwd_parts(int impl, int parts, const void* qkv, const void* out, const void* dout, const float* lse,
+                                 void* dqkv, float* delta, int B, int N, int heads, int hd, float scale, void* stream) {
   O2_REQUIRE(qkv && out && dout && lse && dqkv && delta, "attn_bwd: null pointer");
   O2_REQUIRE(B > 0 && N > 0 && heads > 0 && hd > 0, "attn_bwd: bad dims");
-  if (impl == O2_GEMM_SIMT_F32)
+  O2_REQUIRE(parts > 0 && parts <= O2_ATTN_BWD_ALL, "attn_bwd: bad parts mask %d", parts);
+  if (impl == O2_GEMM_SIMT_F32) {
+    O2_REQUIRE(parts == O2_ATTN_BWD_ALL, "attn_bwd: the fp32 SIMT path runs all parts in one call");
     return o2_attn_bwd_simt(qkv, out, dout, lse, dqkv, delta, B, N, heads, hd, scale, (cudaStream_t)stream);
+  }
   if (impl == O2_GEMM_TC_BF16)
-    return o2_attn_bwd_tc(qkv, out, dout, lse, dqkv, delta, B, N, heads, hd, scale, (cudaStream_t)stream);
+    return o2_attn_bwd_tc(qkv, out, dout, lse, dqkv, delta, B, N, heads, hd, scale, parts, (cudaStream_t)stream);
   O2_FAIL(O2_ERR_ARG, "attn_bwd: unknown impl %d", impl);
+}
+
+extern "C" int o2_attn_bwd(int impl, const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                           float* delta, int B, int N, int heads, int hd, float scale, void* stream) {
+  return o2_attn_bwd_parts(impl, O2_ATTN_BWD_ALL, qkv, out, dout, lse, dqkv, delta, B, N, heads, hd, scale, stream);
 }

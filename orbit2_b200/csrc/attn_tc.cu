@@ -264,6 +264,457 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
   if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
 }
 
+
+// =====================================================================================================
+// Backward.  Two kernels so that every gradient is accumulated in TMEM by exactly one CTA (no atomics,
+// deterministic): with hd = 64 a single-pass design would have to push 32 KiB of fp32 dQ partials per
+// 128x128 tile pair through L2 atomics (~7 TB/s at tensor-core speed), which is slower than recomputing S.
+//   preprocess : delta[b,h,n] = sum_d dO * O (fp32), lse and delta stored pre-scaled for exp2
+//   dq kernel  : CTA owns 256 query rows; per 64-key sub-tile  S = Q K^T, dP = dO V^T (TMEM) ->
+//                dS = P o (dP - delta) (bf16, over S in TMEM) -> dQ += dS K  (TS-MMA, K as MN-major B)
+//   dkv kernel : CTA owns 256 keys; per 64-query sub-tile  S^T = K Q^T, dP^T = V dO^T (TMEM) ->
+//                P^T over S^T, dS^T over dP^T (bf16) -> dV += P^T dO, dK += dS^T Q  (TS-MMA)
+// The softmax scale is applied once to dQ / dK in the epilogue.
+// =====================================================================================================
+constexpr int BS = 64;            // sub-tile width (keys in dq kernel, queries in dkv kernel)
+constexpr int kStagesB = 3;
+constexpr uint32_t kHalfBytes = BS * kHD * 2;   // 8 KiB: byte offset of rows 64.. inside a 128-row tile
+
+struct BwdArgs {
+  const float* lse;       // [B, heads, N] natural log
+  const float* delta;     // [B, heads, N]
+  __nv_bfloat16* dqkv;    // [B, N, 3, heads, hd]
+  int B, N, heads, n_sub; // n_sub = ceil(N / 64)
+  float scale, scale_log2;
+};
+
+__global__ void attn_delta_bf16_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                                       float* __restrict__ delta, int B, int N, int heads) {
+  // one 8-thread group per (b, n, h) row of 64 bf16 (8 x 16 B)
+  const long long gid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const long long total = (long long)B * N * heads;
+  float s = 0.f;
+  if (gid < total) {
+    const uint4 o = *reinterpret_cast<const uint4*>(out + gid * kHD + sub * 8);
+    const uint4 d = *reinterpret_cast<const uint4*>(dout + gid * kHD + sub * 8);
+    const float2 o0 = unpack_bf16x2(o.x), o1 = unpack_bf16x2(o.y), o2 = unpack_bf16x2(o.z), o3 = unpack_bf16x2(o.w);
+    const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
+    s = o0.x * d0.x + o0.y * d0.y + o1.x * d1.x + o1.y * d1.y + o2.x * d2.x + o2.y * d2.y + o3.x * d3.x + o3.y * d3.y;
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (gid < total && sub == 0) {
+    const int h = (int)(gid % heads);
+    const long long bn = gid / heads;
+    const int n = (int)(bn % N);
+    const int b = (int)(bn / N);
+    delta[((size_t)b * heads + h) * N + n] = s;
+  }
+}
+
+constexpr uint32_t kBwdSmemBytes = (4 + 2 * kStagesB) * kTileBytes + 1024 + 4 * 1024 + 256;
+
+// ---------------------------------------------------------------------------------------------- dQ
+__global__ void __launch_bounds__(kThreadsF, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                   const BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                               // 2 tiles
+  uint8_t* sdO = sQ + 2 * kTileBytes;               // 2 tiles
+  uint8_t* sK = sdO + 2 * kTileBytes;               // kStagesB tiles
+  uint8_t* sV = sK + kStagesB * kTileBytes;         // kStagesB tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStagesB * kTileBytes + 4 * 1024);
+  uint64_t* q_full = bars;                          // 1
+  uint64_t* kv_full = q_full + 1;                   // kStagesB
+  uint64_t* kv_empty = kv_full + kStagesB;
+  uint64_t* sd_full = kv_empty + kStagesB;          // 2: S_t and dP_t of a sub-tile are in TMEM
+  uint64_t* ds_full = sd_full + 2;                  // 2: dS_t written (128 arrivals)
+  uint64_t* dq_done = ds_full + 2;                  // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / a.heads, h = bh % a.heads;
+  const int q0 = blockIdx.x * 2 * BQ;
+  const int n_sub = a.n_sub;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_qkv);
+    ptx::prefetch_tmap(&tmap_do);
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < kStagesB; ++s) {
+      ptx::mbar_init(&kv_full[s], 1);
+      ptx::mbar_init(&kv_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      ptx::mbar_init(&sd_full[t], 1);
+      ptx::mbar_init(&ds_full[t], 128);
+      ptx::mbar_init(&dq_done[t], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns of query tile t: S_t [t*192, +64), dP_t [t*192+64, +64), dQ_t [t*192+128, +64)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(q_full, 4 * kTileBytes);
+      ptx::tma_load_4d(sQ, &tmap_qkv, q_full, 0, h, q0, b);
+      ptx::tma_load_4d(sQ + kTileBytes, &tmap_qkv, q_full, 0, h, q0 + BQ, b);
+      ptx::tma_load_4d(sdO, &tmap_do, q_full, 0, h, q0, b);
+      ptx::tma_load_4d(sdO + kTileBytes, &tmap_do, q_full, 0, h, q0 + BQ, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      const int n_kv = (n_sub + 1) / 2;
+      for (int j = 0; j < n_kv; ++j) {
+        ptx::mbar_wait(&kv_empty[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&kv_full[stage], 2 * kTileBytes);
+        ptx::tma_load_4d(sK + stage * kTileBytes, &tmap_qkv, &kv_full[stage], 0, a.heads + h, j * BKV, b);
+        ptx::tma_load_4d(sV + stage * kTileBytes, &tmap_qkv, &kv_full[stage], 0, 2 * a.heads + h, j * BKV, b);
+        if (++stage == kStagesB) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BS, 0, 0);    // S / dP: N = 64 keys
+      const uint32_t idesc_q = ptx::umma_idesc_bf16(BQ, kHD, 0, 1);   // dQ: A = dS (TMEM), B = K (MN-major)
+      const uint32_t sq = ptx::smem_u32(sQ), sdo = ptx::smem_u32(sdO), sk = ptx::smem_u32(sK), sv = ptx::smem_u32(sV);
+      auto issue_sd = [&](int t, int stage, int half) {
+        const uint32_t qa = sq + t * kTileBytes, da = sdo + t * kTileBytes;
+        const uint32_t ka = sk + stage * kTileBytes + half * kHalfBytes, va = sv + stage * kTileBytes + half * kHalfBytes;
+#pragma unroll
+        for (int k = 0; k < kHD / 16; ++k)
+          ptx::umma_ss(tmem_base + t * 192, ptx::umma_smem_desc(qa + k * 32, 16, 1024),
+                       ptx::umma_smem_desc(ka + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kHD / 16; ++k)
+          ptx::umma_ss(tmem_base + t * 192 + 64, ptx::umma_smem_desc(da + k * 32, 16, 1024),
+                       ptx::umma_smem_desc(va + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        ptx::umma_commit(&sd_full[t]);
+      };
+      ptx::mbar_wait(q_full, 0);
+      ptx::mbar_wait(&kv_full[0], 0);
+      ptx::tc_fence_after();
+      issue_sd(0, 0, 0);
+      issue_sd(1, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = 0; u < n_sub; ++u) {
+        const int half = u & 1;
+        const bool more = (u + 1 < n_sub);
+        int nstage = stage;
+        uint32_t nphase = phase;
+        if (half == 1) { if (++nstage == kStagesB) { nstage = 0; nphase ^= 1; } }
+        for (int t = 0; t < 2; ++t) {
+          ptx::mbar_wait(&ds_full[t], u & 1);
+          ptx::tc_fence_after();
+          const uint32_t ka = sk + stage * kTileBytes + half * kHalfBytes;
+#pragma unroll
+          for (int k = 0; k < BS / 16; ++k)
+            ptx::umma_ts(tmem_base + t * 192 + 128, tmem_base + t * 192 + k * 8,
+                         ptx::umma_smem_desc(ka + k * 2048, 8192, 1024), idesc_q, (u > 0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit(&dq_done[t]);
+          if (more) {
+            if (t == 0 && half == 1) {
+              ptx::mbar_wait(&kv_full[nstage], nphase);
+              ptx::tc_fence_after();
+            }
+            issue_sd(t, nstage, half ^ 1);
+          }
+        }
+        if (half == 1 || !more) ptx::umma_commit(&kv_empty[stage]);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    const int t = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t s_addr = lane_addr + t * 192;
+    const uint32_t dp_addr = s_addr + 64;
+    const uint32_t dq_addr = s_addr + 128;
+    const int row = q0 + t * BQ + r;
+    const size_t stat = ((size_t)b * a.heads + h) * a.N + row;
+    const float neg_lse2 = (row < a.N) ? -a.lse[stat] * kLog2e : 0.f;
+    const float delta = (row < a.N) ? a.delta[stat] : 0.f;
+    const float sc = a.scale_log2;
+    for (int u = 0; u < n_sub; ++u) {
+      ptx::mbar_wait(&sd_full[t], u & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BS / 32; ++c) {
+        uint32_t sv_[32], dv_[32];
+        ptx::tmem_ld_32x32(s_addr + c * 32, sv_);
+        ptx::tmem_ld_32x32(dp_addr + c * 32, dv_);
+        ptx::tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ptx::ex2(fmaf(__uint_as_float(sv_[i]), sc, neg_lse2));
+          const float p1 = ptx::ex2(fmaf(__uint_as_float(sv_[i + 1]), sc, neg_lse2));
+          pk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv_[i]) - delta), p1 * (__uint_as_float(dv_[i + 1]) - delta));
+        }
+        ptx::tmem_st_32x16(s_addr + c * 16, pk);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&ds_full[t]);
+    }
+    ptx::mbar_wait(&dq_done[t], (n_sub - 1) & 1);
+    ptx::tc_fence_after();
+    uint32_t o[2][32];
+    ptx::tmem_ld_32x32(dq_addr, o[0]);
+    ptx::tmem_ld_32x32(dq_addr + 32, o[1]);
+    ptx::tmem_ld_wait();
+    if (row < a.N) {
+      __nv_bfloat16* op = a.dqkv + ((((size_t)b * a.N + row) * 3 + 0) * a.heads + h) * kHD;
+      const float f = a.scale;
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[c][i]) * f, __uint_as_float(o[c][i + 1]) * f);
+          w.y = pack_bf16x2(__uint_as_float(o[c][i + 2]) * f, __uint_as_float(o[c][i + 3]) * f);
+          w.z = pack_bf16x2(__uint_as_float(o[c][i + 4]) * f, __uint_as_float(o[c][i + 5]) * f);
+          w.w = pack_bf16x2(__uint_as_float(o[c][i + 6]) * f, __uint_as_float(o[c][i + 7]) * f);
+          *reinterpret_cast<uint4*>(op + c * 32 + i) = w;
+        }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------- dK, dV
+__global__ void __launch_bounds__(kThreadsF, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                    const BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                               // 2 tiles
+  uint8_t* sV = sK + 2 * kTileBytes;                // 2 tiles
+  uint8_t* sQ = sV + 2 * kTileBytes;                // kStagesB tiles
+  uint8_t* sdO = sQ + kStagesB * kTileBytes;        // kStagesB tiles
+  float* sStat = reinterpret_cast<float*>(sdO + kStagesB * kTileBytes);   // [stage][2][128]: lse*log2e, delta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + 4 * 1024);
+  uint64_t* kv_full = bars;                         // 1
+  uint64_t* qdo_full = kv_full + 1;                 // kStagesB (2 arrivals: TMA expect_tx + statistics)
+  uint64_t* qdo_empty = qdo_full + kStagesB;
+  uint64_t* sd_full = qdo_empty + kStagesB;         // 2
+  uint64_t* pd_full = sd_full + 2;                  // 2 (128 arrivals)
+  uint64_t* dkv_done = pd_full + 2;                 // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dkv_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / a.heads, h = bh % a.heads;
+  const int k0 = blockIdx.x * 2 * BKV;
+  const int n_sub = a.n_sub;                        // 64-query sub-tiles
+  const int n_q = (n_sub + 1) / 2;                  // 128-query TMA tiles
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_qkv);
+    ptx::prefetch_tmap(&tmap_do);
+    ptx::mbar_init(kv_full, 1);
+    for (int s = 0; s < kStagesB; ++s) {
+      ptx::mbar_init(&qdo_full[s], 2);
+      ptx::mbar_init(&qdo_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      ptx::mbar_init(&sd_full[t], 1);
+      ptx::mbar_init(&pd_full[t], 128);
+      ptx::mbar_init(&dkv_done[t], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns of key tile t (base t*256): S^T [0,64) dP^T [64,128) dK [128,192) dV [192,256)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(kv_full, 4 * kTileBytes);
+      ptx::tma_load_4d(sK, &tmap_qkv, kv_full, 0, a.heads + h, k0, b);
+      ptx::tma_load_4d(sK + kTileBytes, &tmap_qkv, kv_full, 0, a.heads + h, k0 + BKV, b);
+      ptx::tma_load_4d(sV, &tmap_qkv, kv_full, 0, 2 * a.heads + h, k0, b);
+      ptx::tma_load_4d(sV + kTileBytes, &tmap_qkv, kv_full, 0, 2 * a.heads + h, k0 + BKV, b);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    const float* lse = a.lse + ((size_t)b * a.heads + h) * a.N;
+    const float* dlt = a.delta + ((size_t)b * a.heads + h) * a.N;
+    for (int i = 0; i < n_q; ++i) {
+      if (lane == 0) {
+        ptx::mbar_wait(&qdo_empty[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&qdo_full[stage], 2 * kTileBytes);
+        ptx::tma_load_4d(sQ + stage * kTileBytes, &tmap_qkv, &qdo_full[stage], 0, h, i * BQ, b);
+        ptx::tma_load_4d(sdO + stage * kTileBytes, &tmap_do, &qdo_full[stage], 0, h, i * BQ, b);
+      }
+      __syncwarp();
+      float* st = sStat + stage * 256;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int idx = e * 32 + lane;
+        const int row = i * BQ + idx;
+        st[idx] = (row < a.N) ? lse[row] * kLog2e : INFINITY;     // exp2(s - inf) = 0 for rows past N
+        st[128 + idx] = (row < a.N) ? dlt[row] : 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&qdo_full[stage]);
+      if (++stage == kStagesB) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = ptx::umma_idesc_bf16(BKV, BS, 0, 0);   // S^T / dP^T: N = 64 queries
+      const uint32_t idesc_g = ptx::umma_idesc_bf16(BKV, kHD, 0, 1);  // dV / dK: A (TMEM), B = dO / Q (MN-major)
+      const uint32_t sk = ptx::smem_u32(sK), sv = ptx::smem_u32(sV), sq = ptx::smem_u32(sQ), sdo = ptx::smem_u32(sdO);
+      auto issue_sd = [&](int t, int stage, int half) {
+        const uint32_t ka = sk + t * kTileBytes, va = sv + t * kTileBytes;
+        const uint32_t qa = sq + stage * kTileBytes + half * kHalfBytes, da = sdo + stage * kTileBytes + half * kHalfBytes;
+#pragma unroll
+        for (int k = 0; k < kHD / 16; ++k)
+          ptx::umma_ss(tmem_base + t * 256, ptx::umma_smem_desc(ka + k * 32, 16, 1024),
+                       ptx::umma_smem_desc(qa + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kHD / 16; ++k)
+          ptx::umma_ss(tmem_base + t * 256 + 64, ptx::umma_smem_desc(va + k * 32, 16, 1024),
+                       ptx::umma_smem_desc(da + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        ptx::umma_commit(&sd_full[t]);
+      };
+      ptx::mbar_wait(kv_full, 0);
+      ptx::mbar_wait(&qdo_full[0], 0);
+      ptx::tc_fence_after();
+      issue_sd(0, 0, 0);
+      issue_sd(1, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = 0; u < n_sub; ++u) {
+        const int half = u & 1;
+        const bool more = (u + 1 < n_sub);
+        int nstage = stage;
+        uint32_t nphase = phase;
+        if (half == 1) { if (++nstage == kStagesB) { nstage = 0; nphase ^= 1; } }
+        for (int t = 0; t < 2; ++t) {
+          ptx::mbar_wait(&pd_full[t], u & 1);
+          ptx::tc_fence_after();
+          const uint32_t da = sdo + stage * kTileBytes + half * kHalfBytes;
+          const uint32_t qa = sq + stage * kTileBytes + half * kHalfBytes;
+#pragma unroll
+          for (int k = 0; k < BS / 16; ++k)
+            ptx::umma_ts(tmem_base + t * 256 + 192, tmem_base + t * 256 + k * 8,
+                         ptx::umma_smem_desc(da + k * 2048, 8192, 1024), idesc_g, (u > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < BS / 16; ++k)
+            ptx::umma_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + 64 + k * 8,
+                         ptx::umma_smem_desc(qa + k * 2048, 8192, 1024), idesc_g, (u > 0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit(&dkv_done[t]);
+          if (more) {
+            if (t == 0 && half == 1) {
+              ptx::mbar_wait(&qdo_full[nstage], nphase);
+              ptx::tc_fence_after();
+            }
+            issue_sd(t, nstage, half ^ 1);
+          }
+        }
+        if (half == 1 || !more) ptx::umma_commit(&qdo_empty[stage]);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    const int t = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t st_addr = lane_addr + t * 256;
+    const uint32_t dp_addr = st_addr + 64;
+    const float sc = a.scale_log2;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = 0; u < n_sub; ++u) {
+      const int half = u & 1;
+      if (half == 0) ptx::mbar_wait(&qdo_full[stage], phase);     // statistics of this query tile are in smem
+      ptx::mbar_wait(&sd_full[t], u & 1);
+      ptx::tc_fence_after();
+      const float* st = sStat + stage * 256 + half * BS;
+#pragma unroll 1
+      for (int c = 0; c < BS / 32; ++c) {
+        uint32_t sv_[32], dv_[32];
+        ptx::tmem_ld_32x32(st_addr + c * 32, sv_);
+        ptx::tmem_ld_32x32(dp_addr + c * 32, dv_);
+        ptx::tmem_ld_wait();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(st + c * 32 + i);
+          const float4 d4 = *reinterpret_cast<const float4*>(st + 128 + c * 32 + i);
+          const float p0 = ptx::ex2(fmaf(__uint_as_float(sv_[i]), sc, -l4.x));
+          const float p1 = ptx::ex2(fmaf(__uint_as_float(sv_[i + 1]), sc, -l4.y));
+          const float p2 = ptx::ex2(fmaf(__uint_as_float(sv_[i + 2]), sc, -l4.z));
+          const float p3 = ptx::ex2(fmaf(__uint_as_float(sv_[i + 3]), sc, -l4.w));
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          dk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv_[i]) - d4.x), p1 * (__uint_as_float(dv_[i + 1]) - d4.y));
+          dk[(i >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dv_[i + 2]) - d4.z), p3 * (__uint_as_float(dv_[i + 3]) - d4.w));
+        }
+        ptx::tmem_st_32x16(st_addr + c * 16, pk);
+        ptx::tmem_st_32x16(dp_addr + c * 16, dk);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&pd_full[t]);
+      if (half == 1) { if (++stage == kStagesB) { stage = 0; phase ^= 1; } }
+    }
+    ptx::mbar_wait(&dkv_done[t], (n_sub - 1) & 1);
+    ptx::tc_fence_after();
+    const int key = k0 + t * BKV + r;
+#pragma unroll 1
+    for (int which = 1; which <= 2; ++which) {          // 1: dK (scaled), 2: dV
+      uint32_t o[2][32];
+      const uint32_t addr = st_addr + (which == 1 ? 128 : 192);
+      ptx::tmem_ld_32x32(addr, o[0]);
+      ptx::tmem_ld_32x32(addr + 32, o[1]);
+      ptx::tmem_ld_wait();
+      if (key < a.N) {
+        __nv_bfloat16* op = a.dqkv + ((((size_t)b * a.N + key) * 3 + which) * a.heads + h) * kHD;
+        const float f = (which == 1) ? a.scale : 1.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[c][i]) * f, __uint_as_float(o[c][i + 1]) * f);
+            w.y = pack_bf16x2(__uint_as_float(o[c][i + 2]) * f, __uint_as_float(o[c][i + 3]) * f);
+            w.z = pack_bf16x2(__uint_as_float(o[c][i + 4]) * f, __uint_as_float(o[c][i + 5]) * f);
+            w.w = pack_bf16x2(__uint_as_float(o[c][i + 6]) * f, __uint_as_float(o[c][i + 7]) * f);
+            *reinterpret_cast<uint4*>(op + c * 32 + i) = w;
+          }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
+}
+
 int make_qkv_tmap(CUtensorMap* tm, const void* qkv, int B, int N, int heads, int hd, int box_rows) {
   uint64_t dims[4] = {(uint64_t)hd, (uint64_t)(3 * heads), (uint64_t)N, (uint64_t)B};
   uint64_t str[3] = {(uint64_t)hd * 2, (uint64_t)3 * heads * hd * 2, (uint64_t)N * 3 * heads * hd * 2};
@@ -295,7 +746,47 @@ int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int hea
   return O2_OK;
 }
 
-int o2_attn_bwd_tc(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, float,
-                   cudaStream_t) {
-  O2_FAIL(O2_ERR_UNSUPPORTED, "attn_bwd_tc: not built yet");
+int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B,
+                   int N, int heads, int hd, float scale, int parts, cudaStream_t st) {
+  O2_REQUIRE(hd == kHD, "attn_bwd_tc: head dim %d not supported (64 only)", hd);
+  O2_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dout % 16) == 0 &&
+                 ((uintptr_t)dqkv % 16) == 0,
+             "attn_bwd_tc: pointers must be 16-byte aligned");
+  O2_REQUIRE((long long)B * heads <= 65535, "attn_bwd_tc: B*heads too large");
+  CUtensorMap tm_qkv, tm_do;
+  int rc = make_qkv_tmap(&tm_qkv, qkv, B, N, heads, hd, BQ);
+  if (rc) return rc;
+  {
+    uint64_t dims[4] = {(uint64_t)hd, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)hd * 2, (uint64_t)heads * hd * 2, (uint64_t)N * heads * hd * 2};
+    uint32_t box[4] = {(uint32_t)hd, 1, (uint32_t)BQ, 1};
+    rc = o2_make_tmap(&tm_do, dout, 2, 4, dims, str, box, 1);
+    if (rc) return rc;
+  }
+  const long long rows = (long long)B * N * heads;
+  if (parts & O2_ATTN_BWD_DELTA) {
+    attn_delta_bf16_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(
+        (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, N, heads);
+    O2_LAUNCH_CHECK();
+  }
+  BwdArgs a;
+  a.lse = lse; a.delta = delta; a.dqkv = (__nv_bfloat16*)dqkv; a.B = B; a.N = N; a.heads = heads;
+  a.n_sub = (N + BS - 1) / BS;
+  a.scale = scale; a.scale_log2 = scale * kLog2e;
+  static bool attr_done = false;
+  if (!attr_done) {
+    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
+    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
+    attr_done = true;
+  }
+  dim3 grid((N + 2 * BQ - 1) / (2 * BQ), B * heads);
+  if (parts & O2_ATTN_BWD_DKV) {
+    attn_bwd_dkv_kernel<<<grid, kThreadsF, kBwdSmemBytes, st>>>(tm_qkv, tm_do, a);
+    O2_LAUNCH_CHECK();
+  }
+  if (parts & O2_ATTN_BWD_DQ) {
+    attn_bwd_dq_kernel<<<grid, kThreadsF, kBwdSmemBytes, st>>>(tm_qkv, tm_do, a);
+    O2_LAUNCH_CHECK();
+  }
+  return O2_OK;
 }

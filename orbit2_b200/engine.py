@@ -1,0 +1,157 @@
+"""Training engine: the hot loop of examples/intermediate_downscaling.py:695-742 re-hosted for one process per GPU.
+
+    training_step (:281-306)  forward -> clip_replace_constant -> crop target -> loss         (+ backward, :723-742)
+    optimizer (:642-644)      AdamW(lr, betas=(beta_1, beta_2), weight_decay)
+    data parallel (:618-621)  FSDP NO_SHARD == gradient all-reduce over the data-parallel group
+
+Here the whole step is a fixed kernel schedule (``reslim_forward`` / ``o2_loss_fwd_bwd`` / ``reslim_backward``) with no
+autograd graph around the large tensors.  Parameters live in ONE flat fp32 master buffer (the module's parameters are
+views into it), gradients in one flat fp32 buffer, and the tcgen05 operands in one flat bf16 buffer that the fused AdamW
+kernel refreshes while it updates the master copy -- so a step contains no cast kernels.  With world_size > 1 each
+parameter group's gradient slice is all-reduced (NCCL, average) as soon as the backward schedule has finished it, on
+NCCL's own stream, overlapping the rest of the backward.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .losses import Metric, clip_spec
+from .reslim import Res_Slim_ViT, reslim_backward, reslim_forward
+
+
+class TrainEngine:
+    def __init__(self, model: Res_Slim_ViT, loss: Metric, in_variables: Sequence[str], out_variables: Sequence[str],
+                 var_weights: Optional[Dict[str, float]] = None, lr: float = 2e-4, betas=(0.9, 0.99),
+                 weight_decay: float = 1e-5, eps: float = 1e-8, process_group=None, clip_constants: bool = True):
+        self.model = model
+        self.loss = loss
+        self.in_variables, self.out_variables = list(in_variables), list(out_variables)
+        self.var_weights = dict(var_weights or {})
+        self.lr, self.betas, self.weight_decay, self.eps = lr, betas, weight_decay, eps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.clip = clip_spec(self.out_variables) if clip_constants else (-1, 0)
+        self.step_count = 0
+        self.act = model._act_dtype()
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("TrainEngine needs the model on a CUDA device (no CPU fallback)")
+        self.device = dev
+
+        # ---- flat buffers; parameters become views of the fp32 master
+        named = [(n, p) for n, p in model.named_parameters()]
+        self.names = [n for n, _ in named]
+        sizes = [p.numel() for _, p in named]
+        # 16-byte alignment of every slice in the bf16 buffer (TMA operand bases) => pad to multiples of 8 elements
+        offs, total = [], 0
+        for s in sizes:
+            offs.append(total)
+            total += (s + 7) // 8 * 8
+        self.total = total
+        self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_b = torch.zeros(total, device=dev, dtype=torch.bfloat16) if self.act == torch.bfloat16 else None
+        self.P: Dict[str, torch.Tensor] = {}
+        self.G: Dict[str, torch.Tensor] = {}
+        self.Wc: Dict[str, torch.Tensor] = {}
+        self.range: Dict[str, tuple] = {}
+        with torch.no_grad():
+            for (n, p), o, s in zip(named, offs, sizes):
+                view = self.flat_p[o:o + s].view(p.shape)
+                view.copy_(p.detach().float())
+                p.data = view
+                self.P[n] = view
+                self.G[n] = self.flat_g[o:o + s].view(p.shape)
+                p.grad = self.G[n] if p.requires_grad else None
+                self.range[n] = (o, o + (s + 7) // 8 * 8)
+                if self.flat_b is not None and n.endswith(".weight") and p.dim() == 2:
+                    self.Wc[n] = self.flat_b[o:o + s].view(p.shape)
+        self.frozen = [n for (n, p) in named if not p.requires_grad]
+        if self.flat_b is not None:
+            ops.cast_bf16(self.flat_p, self.flat_b)
+        self._pending: List = []
+        self._train_runs = None
+        self._lat = None
+        self._chw = None
+
+    # ------------------------------------------------------------------ pieces
+    def _on_ready(self, names: List[str]):
+        if self.world == 1:
+            return
+        for lo, hi in self._runs(names):
+            self._pending.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+
+    def _runs(self, names):
+        """Merge the flat-buffer ranges of ``names`` into maximal contiguous runs."""
+        rs = sorted(self.range[n] for n in names)
+        out = []
+        for lo, hi in rs:
+            if out and out[-1][1] == lo:
+                out[-1][1] = hi
+            else:
+                out.append([lo, hi])
+        return out
+
+    def forward_backward(self, x: torch.Tensor, y: torch.Tensor):
+        """x [B,V,H,W] fp32, y [B,C,H',W'] fp32 on the device.  Returns the [C+1] loss vector (device, fp32);
+        leaves the (all-reduced) gradients in the flat gradient buffer."""
+        m = self.model
+        self.flat_g.zero_()
+        if x.dim() == 5:
+            x = x.flatten(1, 2)
+        g = m.geometry(x, self.in_variables, self.out_variables, self.act)
+        # host prep on the small parameters (autograd-visible)
+        tab_s, tab_v = m.frontend_tables(m.get_var_ids(self.in_variables))
+        posres = m.pos_res_embed(g.gh, g.gw, self.act)
+        with torch.no_grad():
+            posres_act = posres if self.act == torch.float32 else ops.cast_bf16(posres)
+            Wc = self.P if self.act == torch.float32 else self.Wc
+            preds, S = reslim_forward(g, self.P, Wc, x, tab_s.detach(), tab_v.detach(), posres_act)
+            if self._lat is None:
+                self._lat = self.loss._lat(preds)
+                self._chw = self.loss._ch_w(preds, self.out_variables, self.var_weights)
+            vec, dpred = ops.loss_fwd_bwd(preds, y, self.loss.kind, lat_w=self._lat, ch_w=self._chw, clamp_ch=self.clip[0],
+                                          const_mask=self.clip[1])
+            self._pending = []
+            dts, dtv, dpos = reslim_backward(g, self.P, Wc, x, tab_s.detach(), tab_v.detach(), S, dpred, self.G,
+                                             on_ready=self._on_ready)
+        torch.autograd.backward([tab_s, tab_v, posres], [dts, dtv, dpos])
+        for n in self.frozen:                       # e.g. pos_embed when learn_pos_emb=False
+            self.G[n].zero_()
+        if self.world > 1:
+            small = [n for n in self.names if not self._is_kernel_param(n)]
+            self._on_ready(small)
+            for w in self._pending:
+                w.wait()
+            self._pending = []
+        return vec
+
+    def _is_kernel_param(self, n):
+        return n in self._kernel_set
+
+    @property
+    def _kernel_set(self):
+        s = getattr(self, "_ks", None)
+        if s is None:
+            s = self._ks = set(self.model._names)
+        return s
+
+    def optimizer_step(self, grad_scale: float = 1.0):
+        self.step_count += 1
+        if self._train_runs is None:                # frozen parameters get neither an update nor weight decay
+            self._train_runs = self._runs([n for n in self.names if n not in self.frozen])
+        for lo, hi in self._train_runs:
+            ops.adamw(self.flat_p[lo:hi], self.flat_g[lo:hi], self.flat_m[lo:hi], self.flat_v[lo:hi],
+                      self.flat_b[lo:hi] if self.flat_b is not None else None, self.lr, self.betas[0], self.betas[1],
+                      self.eps, self.weight_decay, self.step_count, grad_scale)
+
+    def step(self, x, y):
+        vec = self.forward_backward(x, y)
+        self.optimizer_step()
+        return vec

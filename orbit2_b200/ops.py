@@ -11,8 +11,7 @@ from . import _lib as L
 from ._lib import (EPI_ACCUM, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_NONE, GEMM_SIMT_F32, GEMM_TC_BF16,
                    O2_BF16, O2_F32)
 
-TC_ATTENTION_FWD = True
-TC_ATTENTION_BWD = False  # INTERIM: flipped once the tcgen05 backward kernel is in
+TIMERS = None         # bench.py sets this to {} to collect (name -> [(start_event, end_event), ...]) per kernel
 LAUNCHES = 0          # number of library kernels-launching calls (bench.py reports it)
 
 
@@ -60,9 +59,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, 
     assert out.shape[0] == M and out.shape[1] == N
     impl = impl_for(a.dtype)
     assert b.dtype == a.dtype
-    rc = lib.o2_gemm(impl, _ptr(a), int(trans_a), a.stride(0), _ptr(b), int(trans_b), b.stride(0), _ptr(out), dt(out),
-                     out.stride(0), M, N, K, epi, _ptr(bias), _ptr(aux), aux.stride(0) if aux is not None else 0,
-                     aux_rows, _ptr(aux_out), aux_out.stride(0) if aux_out is not None else 0, split_k, _stream())
+    with _timed("gemm"):
+        rc = lib.o2_gemm(impl, _ptr(a), int(trans_a), a.stride(0), _ptr(b), int(trans_b), b.stride(0), _ptr(out), dt(out),
+                         out.stride(0), M, N, K, epi, _ptr(bias), _ptr(aux), aux.stride(0) if aux is not None else 0,
+                         aux_rows, _ptr(aux_out), aux_out.stride(0) if aux_out is not None else 0, split_k, _stream())
+    if TIMERS is not None:
+        TIMERS.setdefault("gemm_flops", []).append(2.0 * M * N * K)
     L.check(rc, "o2_gemm")
     _count()
     return out
@@ -92,28 +94,49 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None):
     return dx
 
 
+class _timed:
+    """Records a CUDA-event pair around a launch on the current stream when TIMERS is enabled."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMERS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if TIMERS is not None:
+            self.e1.record()
+            TIMERS.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
+
 def attn_fwd(qkv, B, N, heads, hd):
     """qkv [B*N, 3*heads*hd] -> (out [B*N, heads*hd], lse [B,heads,N])."""
     lib = L.load()
-    if qkv.dtype == torch.bfloat16 and not TC_ATTENTION_FWD:  # INTERIM: fp32 SIMT kernel on up-cast operands
-        o32, lse = attn_fwd(qkv.float(), B, N, heads, hd)
-        return o32.to(torch.bfloat16), lse
     out = torch.empty(B * N, heads * hd, device=qkv.device, dtype=qkv.dtype)
     lse = torch.empty(B, heads, N, device=qkv.device, dtype=torch.float32)
-    L.check(lib.o2_attn_fwd(impl_for(qkv.dtype), _ptr(qkv), _ptr(out), _ptr(lse), B, N, heads, hd, hd ** -0.5, _stream()),
-            "o2_attn_fwd")
+    with _timed("attn_fwd"):
+        L.check(lib.o2_attn_fwd(impl_for(qkv.dtype), _ptr(qkv), _ptr(out), _ptr(lse), B, N, heads, hd, hd ** -0.5,
+                                _stream()), "o2_attn_fwd")
     _count()
     return out, lse
 
 
 def attn_bwd(qkv, out, dout, lse, B, N, heads, hd):
     lib = L.load()
-    if qkv.dtype == torch.bfloat16 and not TC_ATTENTION_BWD:  # INTERIM: fp32 SIMT kernel on up-cast operands
-        return attn_bwd(qkv.float(), out.float(), dout.float(), lse, B, N, heads, hd).to(torch.bfloat16)
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, heads, N, device=qkv.device, dtype=torch.float32)
-    L.check(lib.o2_attn_bwd(impl_for(qkv.dtype), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(delta),
-                            B, N, heads, hd, hd ** -0.5, _stream()), "o2_attn_bwd")
+    impl = impl_for(qkv.dtype)
+    args = (_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(delta), B, N, heads, hd, hd ** -0.5, _stream())
+    if TIMERS is not None and impl == GEMM_TC_BF16:
+        for name, part in (("attn_bwd_delta", 1), ("attn_bwd_dkv", 2), ("attn_bwd_dq", 4)):
+            with _timed(name):
+                L.check(lib.o2_attn_bwd_parts(impl, part, *args), "o2_attn_bwd_parts")
+    else:
+        L.check(lib.o2_attn_bwd(impl, *args), "o2_attn_bwd")
     _count(3)
     return dqkv
 
