@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -5 gpurun_out/smoke.log
-timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench117.log 2>&1; echo "exit $?" >> gpurun_out/bench117.log
-tail -c 3000 gpurun_out/bench117.log
+CMD="python tools/attn_bench.py --B 1 --iters 2"
+$CMD > gpurun_out/attn_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:attn_ -s 6 -c 3 -f -o gpurun_out/attn_prof $CMD > gpurun_out/attn_ncu.log 2>&1
+echo "exit $?"; cat gpurun_out/attn_plain.log; tail -3 gpurun_out/attn_ncu.log; ls -la gpurun_out/*.ncu-rep

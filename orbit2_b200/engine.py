@@ -19,6 +19,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
+from .dp import BucketReducer, FlatLayout
 from .losses import Metric, clip_spec
 from .reslim import Res_Slim_ViT, reslim_backward, reslim_forward
 
@@ -46,12 +47,9 @@ class TrainEngine:
         named = [(n, p) for n, p in model.named_parameters()]
         self.names = [n for n, _ in named]
         sizes = [p.numel() for _, p in named]
-        # 16-byte alignment of every slice in the bf16 buffer (TMA operand bases) => pad to multiples of 8 elements
-        offs, total = [], 0
-        for s in sizes:
-            offs.append(total)
-            total += (s + 7) // 8 * 8
-        self.total = total
+        self.layout = FlatLayout(self.names, sizes, align=8)
+        offs = [self.layout.range[n][0] for n in self.names]
+        total = self.total = self.layout.total
         self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -60,7 +58,6 @@ class TrainEngine:
         self.P: Dict[str, torch.Tensor] = {}
         self.G: Dict[str, torch.Tensor] = {}
         self.Wc: Dict[str, torch.Tensor] = {}
-        self.range: Dict[str, tuple] = {}
         with torch.no_grad():
             for (n, p), o, s in zip(named, offs, sizes):
                 view = self.flat_p[o:o + s].view(p.shape)
@@ -69,34 +66,19 @@ class TrainEngine:
                 self.P[n] = view
                 self.G[n] = self.flat_g[o:o + s].view(p.shape)
                 p.grad = self.G[n] if p.requires_grad else None
-                self.range[n] = (o, o + (s + 7) // 8 * 8)
                 if self.flat_b is not None and n.endswith(".weight") and p.dim() == 2:
                     self.Wc[n] = self.flat_b[o:o + s].view(p.shape)
         self.frozen = [n for (n, p) in named if not p.requires_grad]
         if self.flat_b is not None:
             ops.cast_bf16(self.flat_p, self.flat_b)
-        self._pending: List = []
+        self.reducer = BucketReducer(self.flat_g, self.layout, process_group)
         self._train_runs = None
         self._lat = None
         self._chw = None
 
     # ------------------------------------------------------------------ pieces
     def _on_ready(self, names: List[str]):
-        if self.world == 1:
-            return
-        for lo, hi in self._runs(names):
-            self._pending.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
-
-    def _runs(self, names):
-        """Merge the flat-buffer ranges of ``names`` into maximal contiguous runs."""
-        rs = sorted(self.range[n] for n in names)
-        out = []
-        for lo, hi in rs:
-            if out and out[-1][1] == lo:
-                out[-1][1] = hi
-            else:
-                out.append([lo, hi])
-        return out
+        self.reducer.ready(names)
 
     def forward_backward(self, x: torch.Tensor, y: torch.Tensor):
         """x [B,V,H,W] fp32, y [B,C,H',W'] fp32 on the device.  Returns the [C+1] loss vector (device, fp32);
@@ -118,18 +100,14 @@ class TrainEngine:
                 self._chw = self.loss._ch_w(preds, self.out_variables, self.var_weights)
             vec, dpred = ops.loss_fwd_bwd(preds, y, self.loss.kind, lat_w=self._lat, ch_w=self._chw, clamp_ch=self.clip[0],
                                           const_mask=self.clip[1])
-            self._pending = []
             dts, dtv, dpos = reslim_backward(g, self.P, Wc, x, tab_s.detach(), tab_v.detach(), S, dpred, self.G,
                                              on_ready=self._on_ready)
         torch.autograd.backward([tab_s, tab_v, posres], [dts, dtv, dpos])
         for n in self.frozen:                       # e.g. pos_embed when learn_pos_emb=False
             self.G[n].zero_()
         if self.world > 1:
-            small = [n for n in self.names if not self._is_kernel_param(n)]
-            self._on_ready(small)
-            for w in self._pending:
-                w.wait()
-            self._pending = []
+            self._on_ready([n for n in self.names if not self._is_kernel_param(n)])
+            self.reducer.finish()
         return vec
 
     def _is_kernel_param(self, n):
@@ -145,7 +123,7 @@ class TrainEngine:
     def optimizer_step(self, grad_scale: float = 1.0):
         self.step_count += 1
         if self._train_runs is None:                # frozen parameters get neither an update nor weight decay
-            self._train_runs = self._runs([n for n in self.names if n not in self.frozen])
+            self._train_runs = self.layout.runs([n for n in self.names if n not in self.frozen])
         for lo, hi in self._train_runs:
             ops.adamw(self.flat_p[lo:hi], self.flat_g[lo:hi], self.flat_m[lo:hi], self.flat_v[lo:hi],
                       self.flat_b[lo:hi] if self.flat_b is not None else None, self.lr, self.betas[0], self.betas[1],

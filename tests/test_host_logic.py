@@ -1,0 +1,115 @@
+"""CPU: host-side logic of the drop-in module against the oracle -- the exact front-end collapse tables, the
+position/resolution embedding, the state-dict ABI, clip specification, registry and flat-layout helpers."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import build_model, load_golden, rel
+
+
+def collapse_reference(m, x, var_ids):
+    """What o2_frontend_fwd + var_agg.proj compute, written in torch from the tables (float64)."""
+    tab_s, tab_v = m.frontend_tables(var_ids)
+    tab_s, tab_v = tab_s.double(), tab_v.double()
+    B, V, H, W = x.shape
+    p = m.patch_size
+    gh, gw = H // p, W // p
+    P = x.double().reshape(B, V, gh, p, gw, p).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, V, p * p)
+    P1 = torch.cat([P, torch.ones_like(P[..., :1])], -1)
+    a = torch.einsum("tvk,vhk->tvh", P1, tab_s).softmax(1)
+    heads = tab_s.shape[1]
+    coef = torch.einsum("tvh,tvk->thvk", a, P1).reshape(-1, heads, V * (p * p + 1))
+    o = torch.einsum("thk,hke->the", coef, tab_v).reshape(B, gh * gw, -1)
+    return torch.nn.functional.linear(o, m.var_agg.proj.weight.double(), m.var_agg.proj.bias.double())
+
+
+@pytest.mark.parametrize("fixture", ["tiny_mse", "tiny_prism_mae_lat"])
+def test_frontend_collapse_matches_oracle(fixture):
+    from oracle import cases, reslim_oracle as O
+    z, meta, sd, _ = load_golden(fixture)
+    cfg = cases.get_case(meta[0])
+    m = build_model(cfg, sd).double()
+    x = torch.from_numpy(z["x"]).double()
+    taps = {}
+    O.forward({k: v.double() for k, v in sd.items()}, cfg, x, cfg["in_vars"], cfg["out_vars"], taps)
+    ours = collapse_reference(m, x, m.get_var_ids(cfg["in_vars"]))
+    assert rel(ours, taps["agg"]) < 1e-6             # tables are built in fp32
+    gh, gw = cfg["img_size"][0] // 2, cfg["img_size"][1] // 2
+    tok0 = ours + m.pos_res_embed(gh, gw, torch.float64).double()[None]
+    assert rel(tok0, taps["tokens0"]) < 1e-6          # pos_res_embed is computed in fp32
+
+
+def test_pos_embed_resample_matches_oracle():
+    from oracle import cases, reslim_oracle as O
+    cfg = cases.get_case("tiny")
+    m = build_model(cfg)
+    m.img_size = (12, 24)                              # grid differs from the 8x16 init grid -> bicubic resample
+    with torch.no_grad():
+        m.pos_embed.normal_()
+    m.spatial_resolution = 0.0
+    with torch.no_grad():
+        m.spatial_embed.bias.zero_()
+    ref = O.interp_pos_embed(m.pos_embed.detach(), 2, (12, 24))[0]
+    assert rel(m.pos_res_embed(6, 12, torch.float32), ref) < 1e-6
+
+
+def test_state_dict_abi():
+    from oracle import cases, reslim_oracle as O
+    for name in ("tiny", "8m"):
+        cfg = cases.get_case(name)
+        m = build_model(cfg)
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert shapes == O.param_shapes(cfg)
+        assert list(shapes) == list(O.param_shapes(cfg))      # registration order too
+
+
+def test_init_like_reference():
+    from oracle import cases, reslim_oracle as O
+    cfg = cases.get_case("tiny")
+    m = build_model(cfg)
+    assert torch.count_nonzero(m.var_embed) == 0 and torch.count_nonzero(m.var_query) == 0     # res_slimvit.py:70,74
+    pe = torch.from_numpy(O.sincos_2d(cfg["embed_dim"], 4, 8)).float()
+    assert torch.allclose(m.pos_embed[0], pe)
+    assert float(m.blocks[0].attn.qkv.weight.std()) == pytest.approx(0.02, rel=0.15)
+    assert torch.count_nonzero(m.blocks[0].attn.qkv.bias) == 0
+    assert torch.all(m.norm.weight == 1)
+
+
+def test_clip_spec_and_registry():
+    from orbit2_b200 import losses
+    assert losses.clip_spec(["total_precipitation_24hr", "orography", "2m_temperature_max"]) == (0, 0b010)
+    assert losses.clip_spec(["2m_temperature", "total_precipitation_24hr"]) == (1, 0)
+    with pytest.raises(ValueError):
+        losses.clip_spec(["2m_temperature"])                    # reference: list.index raises
+    for k in ("mse", "mae", "lat_mse", "bayesian_tv"):
+        assert k in losses.METRICS_REGISTRY and losses.METRICS_REGISTRY[k].name == k
+    meta = losses.MetricsMetaInfo([], [], np.array([60.0, 0.0, -60.0]), None)
+    lw = losses.LatWeightedMSE(True, meta).lat_weights
+    w = np.cos(np.deg2rad([60.0, 0.0, -60.0]))
+    assert lw.shape == (1, 1, 3, 1) and lw.dtype == torch.float64
+    assert np.allclose(lw.reshape(-1).numpy(), w / w.mean())
+
+
+def test_geometry_errors():
+    from oracle import cases
+    cfg = cases.get_case("tiny")
+    m = build_model(cfg)
+    x = torch.zeros(1, 8, 8, 16)
+    g = m.geometry(x, cfg["in_vars"], cfg["out_vars"], torch.float32)
+    assert (g.gh, g.gw, g.L, g.T, g.hd) == (4, 8, 32, 32, 64)
+    assert g.idx7 == [cfg["in_vars"].index(v) for v in cfg["out_vars"] + ["land_sea_mask", "orography", "lattitude", "landcover"]]
+    m.img_size = (9, 16)                                   # odd rows: the reference's unpatchify raises (181-row case)
+    with pytest.raises(RuntimeError):
+        m.geometry(torch.zeros(1, 8, 9, 16), cfg["in_vars"], cfg["out_vars"], torch.float32)
+    m.img_size = (8, 16)
+    with pytest.raises(ValueError):
+        m.geometry(torch.zeros(1, 8, 10, 16), cfg["in_vars"], cfg["out_vars"], torch.float32)
+
+
+def test_flat_layout_runs():
+    from orbit2_b200.dp import FlatLayout
+    lay = FlatLayout(["a", "b", "c", "d"], [5, 16, 3, 8])
+    assert lay.range["b"] == (8, 24) and lay.padded["a"] == (0, 8) and lay.total == 40
+    assert lay.runs(["a", "b"]) == [[0, 24]]
+    assert lay.runs(["d", "a", "b"]) == [[0, 24], [32, 40]]
+    assert lay.runs(["c"]) == [[24, 32]]
