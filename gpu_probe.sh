@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-CMD="python tools/attn_bench.py --B 1 --iters 2"
-$CMD > gpurun_out/attn_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:attn_ -s 6 -c 3 -f -o gpurun_out/attn_prof $CMD > gpurun_out/attn_ncu.log 2>&1
-echo "exit $?"; cat gpurun_out/attn_plain.log; tail -3 gpurun_out/attn_ncu.log; ls -la gpurun_out/*.ncu-rep
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "attn_tc" -x > gpurun_out/attn_test.log 2>&1
+echo "exit $?" >> gpurun_out/attn_test.log
+tail -3 gpurun_out/attn_test.log
+timeout 300 python tools/attn_bench.py --B 2 --iters 5 2>&1 | tail -6

@@ -30,15 +30,17 @@ constexpr float kRescaleThreshold = 8.0f;
 struct FwdArgs {
   __nv_bfloat16* out;
   float* lse;
-  int B, N, heads, n_kv;
-  float scale_log2;   // softmax scale * log2(e)
+  int B, N, heads, n_sub;   // n_sub = ceil(N / 64) key sub-tiles
+  float scale_log2;         // softmax scale * log2(e)
 };
 
-struct FwdSmem {
-  // barriers live after the tiles; layout computed by hand below
-};
-
+constexpr int BS = 64;            // key sub-tile (forward, dq) / query sub-tile (dkv) processed per MMA group
+constexpr uint32_t kHalfBytes = BS * kHD * 2;   // 8 KiB: byte offset of rows 64.. inside a 128-row tile
 constexpr uint32_t kFwdSmemBytes = (2 + 2 * kStagesF) * kTileBytes + 1024 + 256;
+
+// descriptor arithmetic: the start-address field counts 16-byte units and smem addresses stay below 2^18, so a
+// descriptor can be advanced by adding (bytes >> 4) to its low word.
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
 __global__ void __launch_bounds__(kThreadsF, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a) {
@@ -53,17 +55,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
   uint64_t* k_empty = k_full + kStagesF;
   uint64_t* v_full = k_empty + kStagesF;
   uint64_t* v_empty = v_full + kStagesF;
-  uint64_t* s_full = v_empty + kStagesF;            // 2
-  uint64_t* p_full = s_full + 2;                    // 2
-  uint64_t* o_done = p_full + 2;                    // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_full = v_empty + kStagesF;            // [tile][buffer] = 4
+  uint64_t* p_full = s_full + 4;                    // [tile][buffer] = 4 (128 arrivals)
+  uint64_t* o_done = p_full + 4;                    // 2: one phase per sub-tile (gates the lazy rescale)
+  uint64_t* o_final = o_done + 2;                   // 2: completes once, after the last P V of the tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int b = bh / a.heads, h = bh % a.heads;
   const int q0 = blockIdx.x * 2 * BQ;
-  const int n_kv = a.n_kv;
+  const int n_sub = a.n_sub;
+  const int n_kv = (n_sub + 1) >> 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_qkv);
@@ -74,10 +78,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
       ptx::mbar_init(&v_full[s], 1);
       ptx::mbar_init(&v_empty[s], 1);
     }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], 128);
+    }
     for (int t = 0; t < 2; ++t) {
-      ptx::mbar_init(&s_full[t], 1);
-      ptx::mbar_init(&p_full[t], 128);
       ptx::mbar_init(&o_done[t], 1);
+      ptx::mbar_init(&o_final[t], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -86,6 +93,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S buffer (t, bb) at (2t + bb) * 64 (64 fp32 columns; bf16 P overwrites its first 32), O_t at 256 + 64t
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -107,54 +115,82 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ tcgen05 issuer
-    if (lane == 0) {
-      const uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
+    // The whole warp runs this loop (warp-uniform control flow, so descriptors live in uniform registers and an MMA
+    // costs a couple of issue slots); one elected lane executes the tcgen05 instructions.
+    {
+      const uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BS, 0, 0);
       const uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, kHD, 0, 1);   // A = P (TMEM, K-major), B = V (MN-major)
-      const uint32_t sq = ptx::smem_u32(sQ), sk = ptx::smem_u32(sK), sv = ptx::smem_u32(sV);
-      auto issue_s = [&](int t, int kstage) {
-        const uint32_t qa = sq + t * kTileBytes, ka = sk + kstage * kTileBytes;
+      const uint64_t dq0 = ptx::umma_smem_desc(ptx::smem_u32(sQ), 16, 1024);
+      const uint64_t dk0 = ptx::umma_smem_desc(ptx::smem_u32(sK), 16, 1024);
+      const uint64_t dv0 = ptx::umma_smem_desc(ptx::smem_u32(sV), 8192, 1024);
+      // S_t(u) = Q_t K_u^T into buffer (t, u & 1); K sub-tile u = rows [64 (u&1), +64) of K tile u >> 1
+      auto issue_s = [&](int t, int u, int kstage) {
+        if (ptx::elect_one()) {
+          const uint64_t qd = desc_add(dq0, t * kTileBytes);
+          const uint64_t kd = desc_add(dk0, kstage * kTileBytes + (u & 1) * kHalfBytes);
+          const uint32_t d = tmem_base + (2 * t + (u & 1)) * BS;
+          ptx::umma_ss_first(d, qd, kd, idesc_s);
 #pragma unroll
-        for (int k = 0; k < kHD / 16; ++k)
-          ptx::umma_ss(tmem_base + t * 128, ptx::umma_smem_desc(qa + k * 32, 16, 1024),
-                       ptx::umma_smem_desc(ka + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        ptx::umma_commit(&s_full[t]);
+          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(d, desc_add(qd, k * 32), desc_add(kd, k * 32), idesc_s);
+          ptx::umma_commit(&s_full[2 * t + (u & 1)]);
+        }
+        __syncwarp();
       };
       ptx::mbar_wait(q_full, 0);
       ptx::mbar_wait(&k_full[0], 0);
       ptx::tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      ptx::umma_commit(&k_empty[0]);
-      int kstage = 1 % kStagesF;
+      issue_s(0, 0, 0);
+      issue_s(1, 0, 0);
+      if (n_sub > 1) {
+        issue_s(0, 1, 0);
+        issue_s(1, 1, 0);
+      }
+      if (ptx::elect_one()) ptx::umma_commit(&k_empty[0]);
+      __syncwarp();
+      int kstage = 1 % kStagesF;               // stage / phase of K tile (u + 2) >> 1 while u runs over tile j
       uint32_t kphase = (kStagesF == 1) ? 1 : 0;
       int vstage = 0;
       uint32_t vphase = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        ptx::mbar_wait(&v_full[vstage], vphase);
-        const bool more = (j + 1 < n_kv);
-        for (int t = 0; t < 2; ++t) {
-          ptx::mbar_wait(&p_full[t], j & 1);
+      for (int u = 0; u < n_sub; ++u) {
+        const int half = u & 1;
+        const bool more = (u + 2 < n_sub);
+        if (half == 0) {
+          ptx::mbar_wait(&v_full[vstage], vphase);
           ptx::tc_fence_after();
-          const uint32_t va = sv + vstage * kTileBytes;
+        }
+        const uint64_t vd = desc_add(dv0, vstage * kTileBytes + half * kHalfBytes);
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k)
-            ptx::umma_ts(tmem_base + 256 + t * 64, tmem_base + t * 128 + k * 8,
-                         ptx::umma_smem_desc(va + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-          ptx::umma_commit(&o_done[t]);
+        for (int t = 0; t < 2; ++t) {
+          ptx::mbar_wait(&p_full[2 * t + half], (u >> 1) & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t pa = tmem_base + (2 * t + half) * BS;
+            const uint32_t od = tmem_base + 256 + t * 64;
+            ptx::umma_ts(od, pa, vd, idesc_o, u > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 1; k < BS / 16; ++k) ptx::umma_ts_acc(od, pa + k * 8, desc_add(vd, k * 2048), idesc_o);
+            ptx::umma_commit(&o_done[t]);
+            if (u + 1 == n_sub) ptx::umma_commit(&o_final[t]);
+          }
+          __syncwarp();
           if (more) {
-            if (t == 0) {
+            if (t == 0 && half == 0) {
               ptx::mbar_wait(&k_full[kstage], kphase);
               ptx::tc_fence_after();
             }
-            issue_s(t, kstage);
-            if (t == 1) {
-              ptx::umma_commit(&k_empty[kstage]);
+            issue_s(t, u + 2, kstage);
+            if (t == 1 && (half == 1 || u + 3 >= n_sub)) {   // last S that reads this K tile has been issued
+              if (ptx::elect_one()) ptx::umma_commit(&k_empty[kstage]);
+              __syncwarp();
               if (++kstage == kStagesF) { kstage = 0; kphase ^= 1; }
             }
           }
         }
-        ptx::umma_commit(&v_empty[vstage]);
-        if (++vstage == kStagesF) { vstage = 0; vphase ^= 1; }
+        if (half == 1 || u + 1 == n_sub) {
+          if (ptx::elect_one()) ptx::umma_commit(&v_empty[vstage]);
+          __syncwarp();
+          if (++vstage == kStagesF) { vstage = 0; vphase ^= 1; }
+        }
       }
     }
   } else {
@@ -163,80 +199,88 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
     const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
     const int r = quarter * 32 + lane;      // row inside the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t s_addr = lane_addr + t * 128;
     const uint32_t o_addr = lane_addr + 256 + t * 64;
     const float sc = a.scale_log2;
-    float m_ref = -INFINITY, l = 0.f;
-    const int kv_tail = a.N - (n_kv - 1) * BKV;   // valid keys in the last tile (1..128)
-    for (int j = 0; j < n_kv; ++j) {
-      ptx::mbar_wait(&s_full[t], j & 1);
+    float m_ref = -INFINITY;
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+    const int tail = a.N - (n_sub - 1) * BS;    // valid keys in the last sub-tile (1..64)
+    for (int u = 0; u < n_sub; ++u) {
+      const int bb = u & 1;
+      const uint32_t s_addr = lane_addr + (2 * t + bb) * BS;
+      ptx::mbar_wait(&s_full[2 * t + bb], (u >> 1) & 1);
       ptx::tc_fence_after();
-      const int valid = (j == n_kv - 1) ? kv_tail : BKV;
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(s_addr + c * 32, v);
-        ptx::tmem_ld_wait();
-        if (valid == BKV) {
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld_32x32(s_addr, v0);
+      ptx::tmem_ld_32x32(s_addr + 32, v1);
+      ptx::tmem_ld_wait();
+      const bool ragged = (u == n_sub - 1) && (tail != BS);
+      if (ragged) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) {
+          if (i >= tail) v0[i] = 0xff800000u;          // -inf
+          if (32 + i >= tail) v1[i] = 0xff800000u;
         }
       }
-      const float m_new = fmaxf(m_ref, mx * sc);
+      float mxa = __uint_as_float(v0[0]), mxb = __uint_as_float(v1[0]);
+#pragma unroll
+      for (int i = 1; i < 32; ++i) {
+        mxa = fmaxf(mxa, __uint_as_float(v0[i]));
+        mxb = fmaxf(mxb, __uint_as_float(v1[i]));
+      }
+      const float m_new = fmaxf(m_ref, fmaxf(mxa, mxb) * sc);
       const bool need = __any_sync(0xffffffffu, m_new - m_ref > kRescaleThreshold);
       if (need) {
-        const float f = ptx::ex2(m_ref - m_new);     // 0 on the first tile (m_ref = -inf)
-        l *= f;
+        const float f = ptx::ex2(m_ref - m_new);     // 0 on the first sub-tile (m_ref = -inf)
+        l0 *= f; l1 *= f; l2 *= f; l3 *= f;
         m_ref = m_new;
-        if (j > 0) {
-          ptx::mbar_wait(&o_done[t], (j - 1) & 1);
+        if (u > 0) {
+          ptx::mbar_wait(&o_done[t], (u - 1) & 1);
           ptx::tc_fence_after();
 #pragma unroll
           for (int c = 0; c < kHD / 32; ++c) {
-            uint32_t v[32];
-            ptx::tmem_ld_32x32(o_addr + c * 32, v);
+            uint32_t w[32];
+            ptx::tmem_ld_32x32(o_addr + c * 32, w);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-            ptx::tmem_st_32x32(o_addr + c * 32, v);
+            for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) * f);
+            ptx::tmem_st_32x32(o_addr + c * 32, w);
           }
         }
       }
-      // pass 2: p = exp2(s * sc - m_ref), row sum, bf16 P written over the head of S
       const float neg_m = -m_ref;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(s_addr + c * 32, v);
-        ptx::tmem_ld_wait();
-        uint32_t pk[16];
+      uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ptx::ex2(fmaf(__uint_as_float(v[i]), sc, neg_m));
-          float p1 = ptx::ex2(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
-          if (valid != BKV) {
-            if (c * 32 + i >= valid) p0 = 0.f;
-            if (c * 32 + i + 1 >= valid) p1 = 0.f;
-          }
-          l += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        ptx::tmem_st_32x16(s_addr + c * 16, pk);
+      for (int i = 0; i < 32; i += 4) {
+        const float p0 = ptx::ex2(fmaf(__uint_as_float(v0[i]), sc, neg_m));
+        const float p1 = ptx::ex2(fmaf(__uint_as_float(v0[i + 1]), sc, neg_m));
+        const float p2 = ptx::ex2(fmaf(__uint_as_float(v0[i + 2]), sc, neg_m));
+        const float p3 = ptx::ex2(fmaf(__uint_as_float(v0[i + 3]), sc, neg_m));
+        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+        pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
       }
+      ptx::tmem_st_32x16(s_addr, pk);
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float p0 = ptx::ex2(fmaf(__uint_as_float(v1[i]), sc, neg_m));
+        const float p1 = ptx::ex2(fmaf(__uint_as_float(v1[i + 1]), sc, neg_m));
+        const float p2 = ptx::ex2(fmaf(__uint_as_float(v1[i + 2]), sc, neg_m));
+        const float p3 = ptx::ex2(fmaf(__uint_as_float(v1[i + 3]), sc, neg_m));
+        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+        pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+      }
+      ptx::tmem_st_32x16(s_addr + 16, pk);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&p_full[t]);
+      ptx::mbar_arrive(&p_full[2 * t + bb]);
     }
     // epilogue: O / l -> bf16, lse
-    ptx::mbar_wait(&o_done[t], (n_kv - 1) & 1);
+    // (o_done may be up to two phases behind here, which a parity wait cannot tell apart: separate barrier)
+    ptx::mbar_wait(&o_final[t], 0);
     ptx::tc_fence_after();
     const int row = q0 + t * BQ + r;
+    const float l = (l0 + l1) + (l2 + l3);
     const float inv = 1.f / l;
     uint32_t o[2][32];
     ptx::tmem_ld_32x32(o_addr, o[0]);
@@ -248,12 +292,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[c][i]) * inv, __uint_as_float(o[c][i + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[c][i + 2]) * inv, __uint_as_float(o[c][i + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[c][i + 4]) * inv, __uint_as_float(o[c][i + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[c][i + 6]) * inv, __uint_as_float(o[c][i + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + c * 32 + i) = u;
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[c][i]) * inv, __uint_as_float(o[c][i + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[c][i + 2]) * inv, __uint_as_float(o[c][i + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[c][i + 4]) * inv, __uint_as_float(o[c][i + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[c][i + 6]) * inv, __uint_as_float(o[c][i + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + c * 32 + i) = w;
         }
       a.lse[((size_t)b * a.heads + h) * a.N + row] = (m_ref + log2f(l)) * kLn2;
     }
@@ -263,7 +307,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
 }
-
 
 // =====================================================================================================
 // Backward.  Two kernels so that every gradient is accumulated in TMEM by exactly one CTA (no atomics,
@@ -276,9 +319,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
 //                P^T over S^T, dS^T over dP^T (bf16) -> dV += P^T dO, dK += dS^T Q  (TS-MMA)
 // The softmax scale is applied once to dQ / dK in the epilogue.
 // =====================================================================================================
-constexpr int BS = 64;            // sub-tile width (keys in dq kernel, queries in dkv kernel)
 constexpr int kStagesB = 3;
-constexpr uint32_t kHalfBytes = BS * kHD * 2;   // 8 KiB: byte offset of rows 64.. inside a 128-row tile
 
 struct BwdArgs {
   const float* lse;       // [B, heads, N] natural log
@@ -733,7 +774,7 @@ int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int hea
   if (rc) return rc;
   FwdArgs a;
   a.out = (__nv_bfloat16*)out; a.lse = lse; a.B = B; a.N = N; a.heads = heads;
-  a.n_kv = (N + BKV - 1) / BKV;
+  a.n_sub = (N + BS - 1) / BS;
   a.scale_log2 = scale * kLog2e;
   static bool attr_done = false;
   if (!attr_done) {

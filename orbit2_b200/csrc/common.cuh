@@ -166,6 +166,28 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum)
       : "memory");
 }
+// variants with the accumulate flag fixed at compile time (no predicate set-up in the issue path)
+__device__ __forceinline__ void umma_ss_first(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_acc(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
