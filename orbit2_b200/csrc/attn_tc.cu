@@ -424,22 +424,29 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // warp-uniform issue loop (see the forward kernel)
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BS, 0, 0);    // S / dP: N = 64 keys
       const uint32_t idesc_q = ptx::umma_idesc_bf16(BQ, kHD, 0, 1);   // dQ: A = dS (TMEM), B = K (MN-major)
-      const uint32_t sq = ptx::smem_u32(sQ), sdo = ptx::smem_u32(sdO), sk = ptx::smem_u32(sK), sv = ptx::smem_u32(sV);
+      const uint64_t dq0 = ptx::umma_smem_desc(ptx::smem_u32(sQ), 16, 1024);
+      const uint64_t ddo0 = ptx::umma_smem_desc(ptx::smem_u32(sdO), 16, 1024);
+      const uint64_t dk0 = ptx::umma_smem_desc(ptx::smem_u32(sK), 16, 1024);
+      const uint64_t dv0 = ptx::umma_smem_desc(ptx::smem_u32(sV), 16, 1024);
+      const uint64_t dkm0 = ptx::umma_smem_desc(ptx::smem_u32(sK), 8192, 1024);   // K as MN-major B
       auto issue_sd = [&](int t, int stage, int half) {
-        const uint32_t qa = sq + t * kTileBytes, da = sdo + t * kTileBytes;
-        const uint32_t ka = sk + stage * kTileBytes + half * kHalfBytes, va = sv + stage * kTileBytes + half * kHalfBytes;
+        if (ptx::elect_one()) {
+          const uint64_t qa = desc_add(dq0, t * kTileBytes), da = desc_add(ddo0, t * kTileBytes);
+          const uint64_t ka = desc_add(dk0, stage * kTileBytes + half * kHalfBytes);
+          const uint64_t va = desc_add(dv0, stage * kTileBytes + half * kHalfBytes);
+          const uint32_t ds_ = tmem_base + t * 192;
+          ptx::umma_ss_first(ds_, qa, ka, idesc_s);
 #pragma unroll
-        for (int k = 0; k < kHD / 16; ++k)
-          ptx::umma_ss(tmem_base + t * 192, ptx::umma_smem_desc(qa + k * 32, 16, 1024),
-                       ptx::umma_smem_desc(ka + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(ds_, desc_add(qa, k * 32), desc_add(ka, k * 32), idesc_s);
+          ptx::umma_ss_first(ds_ + 64, da, va, idesc_s);
 #pragma unroll
-        for (int k = 0; k < kHD / 16; ++k)
-          ptx::umma_ss(tmem_base + t * 192 + 64, ptx::umma_smem_desc(da + k * 32, 16, 1024),
-                       ptx::umma_smem_desc(va + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        ptx::umma_commit(&sd_full[t]);
+          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(ds_ + 64, desc_add(da, k * 32), desc_add(va, k * 32), idesc_s);
+          ptx::umma_commit(&sd_full[t]);
+        }
+        __syncwarp();
       };
       ptx::mbar_wait(q_full, 0);
       ptx::mbar_wait(&kv_full[0], 0);
@@ -454,15 +461,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         int nstage = stage;
         uint32_t nphase = phase;
         if (half == 1) { if (++nstage == kStagesB) { nstage = 0; nphase ^= 1; } }
+        const uint64_t ka = desc_add(dkm0, stage * kTileBytes + half * kHalfBytes);
+#pragma unroll
         for (int t = 0; t < 2; ++t) {
           ptx::mbar_wait(&ds_full[t], u & 1);
           ptx::tc_fence_after();
-          const uint32_t ka = sk + stage * kTileBytes + half * kHalfBytes;
+          if (ptx::elect_one()) {
+            const uint32_t dd = tmem_base + t * 192 + 128, aa = tmem_base + t * 192;
+            ptx::umma_ts(dd, aa, ka, idesc_q, u > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BS / 16; ++k)
-            ptx::umma_ts(tmem_base + t * 192 + 128, tmem_base + t * 192 + k * 8,
-                         ptx::umma_smem_desc(ka + k * 2048, 8192, 1024), idesc_q, (u > 0 || k > 0) ? 1u : 0u);
-          ptx::umma_commit(&dq_done[t]);
+            for (int k = 1; k < BS / 16; ++k) ptx::umma_ts_acc(dd, aa + k * 8, desc_add(ka, k * 2048), idesc_q);
+            ptx::umma_commit(&dq_done[t]);
+          }
+          __syncwarp();
           if (more) {
             if (t == 0 && half == 1) {
               ptx::mbar_wait(&kv_full[nstage], nphase);
@@ -471,7 +482,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
             issue_sd(t, nstage, half ^ 1);
           }
         }
-        if (half == 1 || !more) ptx::umma_commit(&kv_empty[stage]);
+        if (half == 1 || !more) {
+          if (ptx::elect_one()) ptx::umma_commit(&kv_empty[stage]);
+          __syncwarp();
+        }
         stage = nstage;
         phase = nphase;
       }
@@ -622,22 +636,30 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       if (++stage == kStagesB) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // warp-uniform issue loop (see the forward kernel)
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BKV, BS, 0, 0);   // S^T / dP^T: N = 64 queries
       const uint32_t idesc_g = ptx::umma_idesc_bf16(BKV, kHD, 0, 1);  // dV / dK: A (TMEM), B = dO / Q (MN-major)
-      const uint32_t sk = ptx::smem_u32(sK), sv = ptx::smem_u32(sV), sq = ptx::smem_u32(sQ), sdo = ptx::smem_u32(sdO);
+      const uint64_t dk0 = ptx::umma_smem_desc(ptx::smem_u32(sK), 16, 1024);
+      const uint64_t dv0 = ptx::umma_smem_desc(ptx::smem_u32(sV), 16, 1024);
+      const uint64_t dq0 = ptx::umma_smem_desc(ptx::smem_u32(sQ), 16, 1024);
+      const uint64_t ddo0 = ptx::umma_smem_desc(ptx::smem_u32(sdO), 16, 1024);
+      const uint64_t dqm0 = ptx::umma_smem_desc(ptx::smem_u32(sQ), 8192, 1024);    // Q as MN-major B
+      const uint64_t ddom0 = ptx::umma_smem_desc(ptx::smem_u32(sdO), 8192, 1024);  // dO as MN-major B
       auto issue_sd = [&](int t, int stage, int half) {
-        const uint32_t ka = sk + t * kTileBytes, va = sv + t * kTileBytes;
-        const uint32_t qa = sq + stage * kTileBytes + half * kHalfBytes, da = sdo + stage * kTileBytes + half * kHalfBytes;
+        if (ptx::elect_one()) {
+          const uint64_t ka = desc_add(dk0, t * kTileBytes), va = desc_add(dv0, t * kTileBytes);
+          const uint64_t qa = desc_add(dq0, stage * kTileBytes + half * kHalfBytes);
+          const uint64_t da = desc_add(ddo0, stage * kTileBytes + half * kHalfBytes);
+          const uint32_t ds_ = tmem_base + t * 256;
+          ptx::umma_ss_first(ds_, ka, qa, idesc_s);
 #pragma unroll
-        for (int k = 0; k < kHD / 16; ++k)
-          ptx::umma_ss(tmem_base + t * 256, ptx::umma_smem_desc(ka + k * 32, 16, 1024),
-                       ptx::umma_smem_desc(qa + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(ds_, desc_add(ka, k * 32), desc_add(qa, k * 32), idesc_s);
+          ptx::umma_ss_first(ds_ + 64, va, da, idesc_s);
 #pragma unroll
-        for (int k = 0; k < kHD / 16; ++k)
-          ptx::umma_ss(tmem_base + t * 256 + 64, ptx::umma_smem_desc(va + k * 32, 16, 1024),
-                       ptx::umma_smem_desc(da + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        ptx::umma_commit(&sd_full[t]);
+          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(ds_ + 64, desc_add(va, k * 32), desc_add(da, k * 32), idesc_s);
+          ptx::umma_commit(&sd_full[t]);
+        }
+        __syncwarp();
       };
       ptx::mbar_wait(kv_full, 0);
       ptx::mbar_wait(&qdo_full[0], 0);
@@ -652,20 +674,23 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         int nstage = stage;
         uint32_t nphase = phase;
         if (half == 1) { if (++nstage == kStagesB) { nstage = 0; nphase ^= 1; } }
+        const uint64_t dam = desc_add(ddom0, stage * kTileBytes + half * kHalfBytes);
+        const uint64_t qam = desc_add(dqm0, stage * kTileBytes + half * kHalfBytes);
+#pragma unroll
         for (int t = 0; t < 2; ++t) {
           ptx::mbar_wait(&pd_full[t], u & 1);
           ptx::tc_fence_after();
-          const uint32_t da = sdo + stage * kTileBytes + half * kHalfBytes;
-          const uint32_t qa = sq + stage * kTileBytes + half * kHalfBytes;
+          if (ptx::elect_one()) {
+            const uint32_t base = tmem_base + t * 256;
+            ptx::umma_ts(base + 192, base, dam, idesc_g, u > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BS / 16; ++k)
-            ptx::umma_ts(tmem_base + t * 256 + 192, tmem_base + t * 256 + k * 8,
-                         ptx::umma_smem_desc(da + k * 2048, 8192, 1024), idesc_g, (u > 0 || k > 0) ? 1u : 0u);
+            for (int k = 1; k < BS / 16; ++k) ptx::umma_ts_acc(base + 192, base + k * 8, desc_add(dam, k * 2048), idesc_g);
+            ptx::umma_ts(base + 128, base + 64, qam, idesc_g, u > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BS / 16; ++k)
-            ptx::umma_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + 64 + k * 8,
-                         ptx::umma_smem_desc(qa + k * 2048, 8192, 1024), idesc_g, (u > 0 || k > 0) ? 1u : 0u);
-          ptx::umma_commit(&dkv_done[t]);
+            for (int k = 1; k < BS / 16; ++k) ptx::umma_ts_acc(base + 128, base + 64 + k * 8, desc_add(qam, k * 2048), idesc_g);
+            ptx::umma_commit(&dkv_done[t]);
+          }
+          __syncwarp();
           if (more) {
             if (t == 0 && half == 1) {
               ptx::mbar_wait(&qdo_full[nstage], nphase);
@@ -674,7 +699,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             issue_sd(t, nstage, half ^ 1);
           }
         }
-        if (half == 1 || !more) ptx::umma_commit(&qdo_empty[stage]);
+        if (half == 1 || !more) {
+          if (ptx::elect_one()) ptx::umma_commit(&qdo_empty[stage]);
+          __syncwarp();
+        }
         stage = nstage;
         phase = nphase;
       }
