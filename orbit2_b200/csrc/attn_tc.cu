@@ -356,6 +356,7 @@ __global__ void attn_delta_bf16_kernel(const __nv_bfloat16* __restrict__ out, co
 }
 
 constexpr uint32_t kBwdSmemBytes = (4 + 2 * kStagesB) * kTileBytes + 1024 + 4 * 1024 + 256;
+constexpr uint32_t kDkvSmemBytes = (4 + 2 * kStagesB + 2) * kTileBytes + 1024 + 256;
 
 // ---------------------------------------------------------------------------------------------- dQ
 __global__ void __launch_bounds__(kThreadsF, 1)
@@ -553,6 +554,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
 }
 
+// -(x) as three bf16 terms (hi, mid, lo) in K positions 0..2 of a 16-byte chunk; relative error ~2^-24
+__device__ __forceinline__ uint4 neg_split3(float x) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+  return make_uint4(pack_bf16x2(-__bfloat162float(hi), -__bfloat162float(mid)), pack_bf16x2(-__bfloat162float(lo), 0.f), 0u, 0u);
+}
+
 // ---------------------------------------------------------------------------------------------- dK, dV
 __global__ void __launch_bounds__(kThreadsF, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
@@ -563,8 +573,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   uint8_t* sV = sK + 2 * kTileBytes;                // 2 tiles
   uint8_t* sQ = sV + 2 * kTileBytes;                // kStagesB tiles
   uint8_t* sdO = sQ + kStagesB * kTileBytes;        // kStagesB tiles
-  float* sStat = reinterpret_cast<float*>(sdO + kStagesB * kTileBytes);   // [stage][2][128]: lse*log2e, delta
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + 4 * 1024);
+  // Per-query statistics enter through the tensor core as rank-1 updates (one extra K=16 MMA each):
+  //   S^T  <- K Q^T  - 1 (lse/scale)^T      dP^T <- V dO^T - 1 delta^T
+  // sOnes: [128 x 64] bf16 K-major tile; k-slice 0 has ones in K positions 0..2, k-slice 1 has ones in positions 8..10.
+  // sStat: [128 q x 64] tile; k-slice `stage` of row q holds -(3-term bf16 split of lse/scale) in positions 0..2 and
+  //        -(split of delta) in positions 8..10, so the same slice serves both updates.
+  uint8_t* sOnes = sdO + kStagesB * kTileBytes;
+  uint8_t* sStat = sOnes + kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + kTileBytes);
   uint64_t* kv_full = bars;                         // 1
   uint64_t* qdo_full = kv_full + 1;                 // kStagesB (2 arrivals: TMA expect_tx + statistics)
   uint64_t* qdo_empty = qdo_full + kStagesB;
@@ -597,6 +613,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BKV) {
+    const int r = threadIdx.x - 64;
+    const uint4 ones = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
+    uint4* row = reinterpret_cast<uint4*>(sOnes + r * 128);
+    row[0 ^ (r & 7)] = ones;  row[1 ^ (r & 7)] = zero;     // k-slice 0: positions 0..2
+    row[2 ^ (r & 7)] = zero;  row[3 ^ (r & 7)] = ones;     // k-slice 1: positions 8..10
+    ptx::fence_proxy_async_smem();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -615,6 +639,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     uint32_t phase = 0;
     const float* lse = a.lse + ((size_t)b * a.heads + h) * a.N;
     const float* dlt = a.delta + ((size_t)b * a.heads + h) * a.N;
+    const float inv_scale = 1.f / a.scale;
     for (int i = 0; i < n_q; ++i) {
       if (lane == 0) {
         ptx::mbar_wait(&qdo_empty[stage], phase ^ 1);
@@ -623,14 +648,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         ptx::tma_load_4d(sdO + stage * kTileBytes, &tmap_do, &qdo_full[stage], 0, h, i * BQ, b);
       }
       __syncwarp();
-      float* st = sStat + stage * 256;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int idx = e * 32 + lane;
         const int row = i * BQ + idx;
-        st[idx] = (row < a.N) ? lse[row] * kLog2e : INFINITY;     // exp2(s - inf) = 0 for rows past N
-        st[128 + idx] = (row < a.N) ? dlt[row] : 0.f;
+        const float x = (row < a.N) ? lse[row] * inv_scale : 1e30f;    // exp2((s - 1e30) * c) = 0 for rows past N
+        const float y = (row < a.N) ? dlt[row] : 0.f;
+        uint4* dst = reinterpret_cast<uint4*>(sStat + idx * 128);
+        dst[(2 * stage) ^ (idx & 7)] = neg_split3(x);
+        dst[(2 * stage + 1) ^ (idx & 7)] = neg_split3(y);
       }
+      ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&qdo_full[stage]);
       if (++stage == kStagesB) { stage = 0; phase ^= 1; }
@@ -645,6 +673,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       const uint64_t ddo0 = ptx::umma_smem_desc(ptx::smem_u32(sdO), 16, 1024);
       const uint64_t dqm0 = ptx::umma_smem_desc(ptx::smem_u32(sQ), 8192, 1024);    // Q as MN-major B
       const uint64_t ddom0 = ptx::umma_smem_desc(ptx::smem_u32(sdO), 8192, 1024);  // dO as MN-major B
+      const uint64_t dones = ptx::umma_smem_desc(ptx::smem_u32(sOnes), 16, 1024);
+      const uint64_t dstat0 = ptx::umma_smem_desc(ptx::smem_u32(sStat), 16, 1024);
       auto issue_sd = [&](int t, int stage, int half) {
         if (ptx::elect_one()) {
           const uint64_t ka = desc_add(dk0, t * kTileBytes), va = desc_add(dv0, t * kTileBytes);
@@ -654,9 +684,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
           ptx::umma_ss_first(ds_, ka, qa, idesc_s);
 #pragma unroll
           for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(ds_, desc_add(ka, k * 32), desc_add(qa, k * 32), idesc_s);
+          const uint64_t st = desc_add(dstat0, half * kHalfBytes + stage * 32);
+          ptx::umma_ss_acc(ds_, dones, st, idesc_s);                          // - lse / scale
           ptx::umma_ss_first(ds_ + 64, va, da, idesc_s);
 #pragma unroll
           for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(ds_ + 64, desc_add(va, k * 32), desc_add(da, k * 32), idesc_s);
+          ptx::umma_ss_acc(ds_ + 64, desc_add(dones, 32), st, idesc_s);       // - delta
           ptx::umma_commit(&sd_full[t]);
         }
         __syncwarp();
@@ -715,14 +748,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     const uint32_t st_addr = lane_addr + t * 256;
     const uint32_t dp_addr = st_addr + 64;
     const float sc = a.scale_log2;
-    int stage = 0;
-    uint32_t phase = 0;
     for (int u = 0; u < n_sub; ++u) {
-      const int half = u & 1;
-      if (half == 0) ptx::mbar_wait(&qdo_full[stage], phase);     // statistics of this query tile are in smem
       ptx::mbar_wait(&sd_full[t], u & 1);
       ptx::tc_fence_after();
-      const float* st = sStat + stage * 256 + half * BS;
 #pragma unroll 1
       for (int c = 0; c < BS / 32; ++c) {
         uint32_t sv_[32], dv_[32];
@@ -731,17 +759,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         ptx::tmem_ld_wait();
         uint32_t pk[16], dk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(st + c * 32 + i);
-          const float4 d4 = *reinterpret_cast<const float4*>(st + 128 + c * 32 + i);
-          const float p0 = ptx::ex2(fmaf(__uint_as_float(sv_[i]), sc, -l4.x));
-          const float p1 = ptx::ex2(fmaf(__uint_as_float(sv_[i + 1]), sc, -l4.y));
-          const float p2 = ptx::ex2(fmaf(__uint_as_float(sv_[i + 2]), sc, -l4.z));
-          const float p3 = ptx::ex2(fmaf(__uint_as_float(sv_[i + 3]), sc, -l4.w));
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ptx::ex2(__uint_as_float(sv_[i]) * sc);
+          const float p1 = ptx::ex2(__uint_as_float(sv_[i + 1]) * sc);
           pk[i >> 1] = pack_bf16x2(p0, p1);
-          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-          dk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv_[i]) - d4.x), p1 * (__uint_as_float(dv_[i + 1]) - d4.y));
-          dk[(i >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dv_[i + 2]) - d4.z), p3 * (__uint_as_float(dv_[i + 3]) - d4.w));
+          dk[i >> 1] = pack_bf16x2(p0 * __uint_as_float(dv_[i]), p1 * __uint_as_float(dv_[i + 1]));
         }
         ptx::tmem_st_32x16(st_addr + c * 16, pk);
         ptx::tmem_st_32x16(dp_addr + c * 16, dk);
@@ -749,7 +771,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&pd_full[t]);
-      if (half == 1) { if (++stage == kStagesB) { stage = 0; phase ^= 1; } }
     }
     ptx::mbar_wait(&dkv_done[t], (n_sub - 1) & 1);
     ptx::tc_fence_after();
@@ -845,12 +866,12 @@ int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const flo
   static bool attr_done = false;
   if (!attr_done) {
     O2_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
-    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
+    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDkvSmemBytes));
     attr_done = true;
   }
   dim3 grid((N + 2 * BQ - 1) / (2 * BQ), B * heads);
   if (parts & O2_ATTN_BWD_DKV) {
-    attn_bwd_dkv_kernel<<<grid, kThreadsF, kBwdSmemBytes, st>>>(tm_qkv, tm_do, a);
+    attn_bwd_dkv_kernel<<<grid, kThreadsF, kDkvSmemBytes, st>>>(tm_qkv, tm_do, a);
     O2_LAUNCH_CHECK();
   }
   if (parts & O2_ATTN_BWD_DQ) {
