@@ -105,60 +105,111 @@ __global__ void __launch_bounds__(NT) frontend_fwd_kernel(const FeArgs a) {
   }
 }
 
+// Backward of one head over persistent token tiles.  Per tile (TT tokens) two register-tiled fp32 contractions
+//   d(tab_v)[kk][e] += sum_t C[t][kk] dO[t][e]      C[t][kk] = a[t][v] P'[t][v][k']   (kk = v*(PP+1)+k')
+//   dC[t][kk]        = sum_e dO[t][e] tab_v[kk][e]
+// then da = <dC, P'>, ds = a (da - <a, da>) and d(tab_s)[v][k'] += sum_t ds[t][v] P'[t][v][k'].
+constexpr int KKP = 128;     // padded table rows (KK <= 128)
+constexpr int DOP = 4;       // padding of the dO rows (bank spread for the dC contraction)
+
 template <typename T, int HD>
 __global__ void __launch_bounds__(NT) frontend_bwd_kernel(const FeArgs a) {
   extern __shared__ float smem[];
   const int V = a.V, PP = a.PP, P1 = PP + 1, KK = a.KK;
-  float* sM = smem;                      // [KK][HD]
-  float* sP = sM + KK * HD;              // [TT][V][PP]
+  float* sM = smem;                      // [KKP][HD]   (rows >= KK zero)
+  float* sP = sM + KKP * HD;             // [TT][V][PP]
   float* sa = sP + TT * V * PP;          // [TT][V]
-  float* ssc = sa + TT * V;              // [TT][V]  (scores, then ds)
-  float* sdO = ssc + TT * V;             // [TT][HD]
-  float* sdC = sdO + TT * HD;            // [TT][KK]
+  float* ssc = sa + TT * V;              // [TT][V]  (scores, then da, then ds)
+  float* sdO = ssc + TT * V;             // [TT][HD + DOP]
+  float* sC = sdO + TT * (HD + DOP);     // [TT][KKP]  C, then dC
   const int h = blockIdx.y;
-  for (int i = threadIdx.x; i < KK * HD; i += NT) sM[i] = a.tab_v[(size_t)h * KK * HD + i];
+  for (int i = threadIdx.x; i < KKP * HD; i += NT) sM[i] = (i < KK * HD) ? a.tab_v[(size_t)h * KK * HD + i] : 0.f;
 
-  // d(tab_v) slice owned by this thread: rows kk = kt*KPT + r, columns e = et*4 .. +3 (for HD=64: 16 x 16 threads)
-  constexpr int ETH = HD / 4;            // threads along e
-  constexpr int KTH = NT / ETH;          // threads along kk
+  // d(tab_v) slice of this thread: rows kt*KROWS .. +KROWS, columns et*4 .. +3
+  constexpr int ETH = HD / 4;
+  constexpr int KTH = NT / ETH;
+  constexpr int KROWS = KKP / KTH;
   const int et = threadIdx.x % ETH, kt = threadIdx.x / ETH;
-  constexpr int KROWS = (128 + KTH - 1) / KTH;   // rows per thread to cover KK <= 128
   float dM[KROWS][4];
 #pragma unroll
   for (int r = 0; r < KROWS; ++r) { dM[r][0] = dM[r][1] = dM[r][2] = dM[r][3] = 0.f; }
   float dS = 0.f;                         // d(tab_s)[v,h,k'] for kk = threadIdx.x (< KK)
+  // dC tile of this thread: tokens tg*4 .. +3, rows kg*8 .. +7
+  const int tg = threadIdx.x % (TT / 4), kg = threadIdx.x / (TT / 4);
 
   const long long ntiles = (a.T + TT - 1) / TT;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long t0 = tile * TT;
     __syncthreads();
     stage_tile(a, h, t0, sP, sa, ssc);
-    for (int i = threadIdx.x; i < TT * HD; i += NT) {
-      const int tl = i / HD, e = i % HD;
+    for (int i = threadIdx.x; i < TT * (HD / 4); i += NT) {
+      const int tl = i / (HD / 4), e4 = i % (HD / 4);
       const long long t = t0 + tl;
-      sdO[i] = (t < a.T) ? to_f(reinterpret_cast<const T*>(a.dout)[(size_t)t * a.heads * HD + (size_t)h * HD + e]) : 0.f;
-    }
-    __syncthreads();
-    // dC[t][kk] = dO[t][:] . tab_v[kk][:]
-    for (int i = threadIdx.x; i < TT * KK; i += NT) {
-      const int tl = i / KK, kk = i % KK;
-      const float* d = sdO + tl * HD;
-      const float* m = sM + kk * HD;
-      float s = 0.f;
-#pragma unroll 4
-      for (int e = 0; e < HD; e += 4) {
-        const float4 d4 = *reinterpret_cast<const float4*>(d + e);
-        const float4 m4 = *reinterpret_cast<const float4*>(m + e);
-        s += d4.x * m4.x + d4.y * m4.y + d4.z * m4.z + d4.w * m4.w;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < a.T) {
+        const T* src = reinterpret_cast<const T*>(a.dout) + (size_t)t * a.heads * HD + (size_t)h * HD + e4 * 4;
+        v = make_float4(to_f(src[0]), to_f(src[1]), to_f(src[2]), to_f(src[3]));
       }
-      sdC[tl * KK + kk] = s;
+      *reinterpret_cast<float4*>(sdO + tl * (HD + DOP) + e4 * 4) = v;
+    }
+    for (int i = threadIdx.x; i < TT * KKP; i += NT) {
+      const int tl = i / KKP, kk = i % KKP;
+      float c = 0.f;
+      if (kk < KK) {
+        const int v = kk / P1, k = kk % P1;
+        const float w = sa[tl * V + v];
+        c = (k < PP) ? w * sP[(tl * V + v) * PP + k] : w;
+      }
+      sC[i] = c;
     }
     __syncthreads();
-    // da[t][v] = sum_k' dC[t][v,k'] P'[t][v][k'];  ds = a (da - sum_u a_u da_u)
+    // d(tab_v) += C^T dO
+#pragma unroll 2
+    for (int tl = 0; tl < TT; ++tl) {
+      const float4 d4 = *reinterpret_cast<const float4*>(sdO + tl * (HD + DOP) + et * 4);
+      float c[KROWS];
+#pragma unroll
+      for (int r = 0; r < KROWS; r += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(sC + tl * KKP + kt * KROWS + r);
+        c[r] = c4.x; c[r + 1] = c4.y; c[r + 2] = c4.z; c[r + 3] = c4.w;
+      }
+#pragma unroll
+      for (int r = 0; r < KROWS; ++r) {
+        dM[r][0] = fmaf(c[r], d4.x, dM[r][0]); dM[r][1] = fmaf(c[r], d4.y, dM[r][1]);
+        dM[r][2] = fmaf(c[r], d4.z, dM[r][2]); dM[r][3] = fmaf(c[r], d4.w, dM[r][3]);
+      }
+    }
+    // dC = dO tab_v^T (4 tokens x 8 rows per thread)
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+    for (int e = 0; e < HD; e += 4) {
+      float4 d[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[i] = *reinterpret_cast<const float4*>(sdO + (tg * 4 + i) * (HD + DOP) + e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 m4 = *reinterpret_cast<const float4*>(sM + (kg * 8 + j) * HD + e);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          acc[i][j] += d[i].x * m4.x + d[i].y * m4.y + d[i].z * m4.z + d[i].w * m4.w;
+      }
+    }
+    __syncthreads();                       // everyone is done reading C
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<float4*>(sC + (tg * 4 + i) * KKP + kg * 8) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(sC + (tg * 4 + i) * KKP + kg * 8 + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+    __syncthreads();
+    // da[t][v] = sum_k' dC[t][v,k'] P'[t][v][k']
     for (int i = threadIdx.x; i < TT * V; i += NT) {
       const int tl = i % TT, v = i / TT;
-      float da = sdC[tl * KK + v * P1 + PP];
-      for (int k = 0; k < PP; ++k) da = fmaf(sdC[tl * KK + v * P1 + k], sP[(tl * V + v) * PP + k], da);
+      float da = sC[tl * KKP + v * P1 + PP];
+      for (int k = 0; k < PP; ++k) da = fmaf(sC[tl * KKP + v * P1 + k], sP[(tl * V + v) * PP + k], da);
       ssc[tl * V + v] = da;
     }
     __syncthreads();
@@ -178,30 +229,14 @@ __global__ void __launch_bounds__(NT) frontend_bwd_kernel(const FeArgs a) {
       for (int i = threadIdx.x; i < TT * V; i += NT, ++n) ssc[i % TT * V + i / TT] = myds[n];
     }
     __syncthreads();
-    // d(tab_s): one (v,k') per thread
     if (threadIdx.x < KK) {
       const int v = threadIdx.x / P1, k = threadIdx.x % P1;
-      float s = 0.f;
+      float sum = 0.f;
       for (int tl = 0; tl < TT; ++tl) {
         const float pk = (k < PP) ? sP[(tl * V + v) * PP + k] : 1.f;
-        s = fmaf(ssc[tl * V + v], pk, s);
+        sum = fmaf(ssc[tl * V + v], pk, sum);
       }
-      dS += s;
-    }
-    // d(tab_v)[kk][e] += sum_t a[t][v] P'[t][v][k'] dO[t][e]
-    for (int tl = 0; tl < TT; ++tl) {
-      const float4 d4 = *reinterpret_cast<const float4*>(sdO + tl * HD + et * 4);
-#pragma unroll
-      for (int r = 0; r < KROWS; ++r) {
-        const int kk = kt * KROWS + r;
-        if (kk < KK) {
-          const int v = kk / P1, k = kk % P1;
-          const float w = sa[tl * V + v];
-          const float c = (k < PP) ? w * sP[(tl * V + v) * PP + k] : w;
-          dM[r][0] = fmaf(c, d4.x, dM[r][0]); dM[r][1] = fmaf(c, d4.y, dM[r][1]);
-          dM[r][2] = fmaf(c, d4.z, dM[r][2]); dM[r][3] = fmaf(c, d4.w, dM[r][3]);
-        }
-      }
+      dS += sum;
     }
   }
   if (threadIdx.x < KK) {
@@ -244,10 +279,12 @@ template <typename T, int HD> int launch_fwd(const FeArgs& a, cudaStream_t st) {
   return O2_OK;
 }
 template <typename T, int HD> int launch_bwd(const FeArgs& a, cudaStream_t st) {
-  const size_t smem = sizeof(float) * ((size_t)a.KK * HD + (size_t)TT * a.V * a.PP + 2 * (size_t)TT * a.V +
-                                       (size_t)TT * HD + (size_t)TT * a.KK);
+  const size_t smem = sizeof(float) * ((size_t)KKP * HD + (size_t)TT * a.V * a.PP + 2 * (size_t)TT * a.V +
+                                       (size_t)TT * (HD + DOP) + (size_t)TT * KKP);
+  O2_REQUIRE(smem <= 227 * 1024, "frontend_bwd: %zu bytes of shared memory needed", smem);
   O2_CUDA(cudaFuncSetAttribute(frontend_bwd_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  long long gx = ((long long)o2_num_sms() * 2 + a.heads - 1) / a.heads;
+  long long gx = (long long)o2_num_sms() / a.heads;     // one CTA per SM (shared memory), a single wave
+  if (gx < 1) gx = 1;
   const long long ntiles = (a.T + TT - 1) / TT;
   if (gx > ntiles) gx = ntiles;
   frontend_bwd_kernel<T, HD><<<dim3((unsigned)gx, a.heads), NT, smem, st>>>(a);
