@@ -22,6 +22,7 @@ constexpr int BQ = 128;          // rows per query tile
 constexpr int BKV = 128;         // keys per tile
 constexpr int kStagesF = 3;
 constexpr int kThreadsF = 320;
+constexpr int kThreadsB = 352;   // + one more issuing warp (one per tile)
 constexpr uint32_t kTileBytes = BQ * kHD * 2;   // 16 KiB (Q, K and V tiles alike)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -359,7 +360,10 @@ constexpr uint32_t kBwdSmemBytes = (4 + 2 * kStagesB) * kTileBytes + 1024 + 4 * 
 constexpr uint32_t kDkvSmemBytes = (4 + 2 * kStagesB + 2) * kTileBytes + 1024 + 256;
 
 // ---------------------------------------------------------------------------------------------- dQ
-__global__ void __launch_bounds__(kThreadsF, 1)
+// TMEM columns of query tile t (base t*256): S buffers [0,64) / [64,128), dP [128,192), dQ [192,256).
+// S is double-buffered (S(u+2) is issued as soon as dQ(u) has consumed the dS written over S(u)); dP has one buffer
+// that the softmax warps release as soon as they have it in registers, so dP(u+1) is computed while they work on u.
+__global__ void __launch_bounds__(kThreadsB, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                    const BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -372,10 +376,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   uint64_t* q_full = bars;                          // 1
   uint64_t* kv_full = q_full + 1;                   // kStagesB
   uint64_t* kv_empty = kv_full + kStagesB;
-  uint64_t* sd_full = kv_empty + kStagesB;          // 2: S_t and dP_t of a sub-tile are in TMEM
-  uint64_t* ds_full = sd_full + 2;                  // 2: dS_t written (128 arrivals)
-  uint64_t* dq_done = ds_full + 2;                  // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_done + 2);
+  uint64_t* s_full = kv_empty + kStagesB;           // [tile][buffer] = 4
+  uint64_t* ds_full = s_full + 4;                   // [tile][buffer] = 4 (128 arrivals): dS written over S
+  uint64_t* dp_full = ds_full + 4;                  // 2
+  uint64_t* dp_free = dp_full + 2;                  // 2 (128 arrivals): dP is in registers
+  uint64_t* dq_final = dp_free + 2;                 // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_final + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -390,12 +396,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < kStagesB; ++s) {
       ptx::mbar_init(&kv_full[s], 1);
-      ptx::mbar_init(&kv_empty[s], 1);
+      ptx::mbar_init(&kv_empty[s], 2);            // one commit per issuing warp
+    }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&ds_full[i], 128);
     }
     for (int t = 0; t < 2; ++t) {
-      ptx::mbar_init(&sd_full[t], 1);
-      ptx::mbar_init(&ds_full[t], 128);
-      ptx::mbar_init(&dq_done[t], 1);
+      ptx::mbar_init(&dp_full[t], 1);
+      ptx::mbar_init(&dp_free[t], 128);
+      ptx::mbar_init(&dq_final[t], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -404,7 +414,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns of query tile t: S_t [t*192, +64), dP_t [t*192+64, +64), dQ_t [t*192+128, +64)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -424,8 +433,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         if (++stage == kStagesB) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    {   // warp-uniform issue loop (see the forward kernel)
+  } else if (warp == 1 || warp == 10) {
+    {   // one issuing warp per query tile (warp-uniform loop, see the forward kernel): the two tiles' dependency
+        // chains never block each other; the tensor pipe interleaves their MMAs
+      const int t = (warp == 1) ? 0 : 1;
       const uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BS, 0, 0);    // S / dP: N = 64 keys
       const uint32_t idesc_q = ptx::umma_idesc_bf16(BQ, kHD, 0, 1);   // dQ: A = dS (TMEM), B = K (MN-major)
       const uint64_t dq0 = ptx::umma_smem_desc(ptx::smem_u32(sQ), 16, 1024);
@@ -433,100 +444,122 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       const uint64_t dk0 = ptx::umma_smem_desc(ptx::smem_u32(sK), 16, 1024);
       const uint64_t dv0 = ptx::umma_smem_desc(ptx::smem_u32(sV), 16, 1024);
       const uint64_t dkm0 = ptx::umma_smem_desc(ptx::smem_u32(sK), 8192, 1024);   // K as MN-major B
-      auto issue_sd = [&](int t, int stage, int half) {
+      auto issue_s = [&](int t, int u, int stage) {
         if (ptx::elect_one()) {
-          const uint64_t qa = desc_add(dq0, t * kTileBytes), da = desc_add(ddo0, t * kTileBytes);
-          const uint64_t ka = desc_add(dk0, stage * kTileBytes + half * kHalfBytes);
-          const uint64_t va = desc_add(dv0, stage * kTileBytes + half * kHalfBytes);
-          const uint32_t ds_ = tmem_base + t * 192;
-          ptx::umma_ss_first(ds_, qa, ka, idesc_s);
+          const uint64_t qa = desc_add(dq0, t * kTileBytes);
+          const uint64_t ka = desc_add(dk0, stage * kTileBytes + (u & 1) * kHalfBytes);
+          const uint32_t d = tmem_base + t * 256 + (u & 1) * BS;
+          ptx::umma_ss_first(d, qa, ka, idesc_s);
 #pragma unroll
-          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(ds_, desc_add(qa, k * 32), desc_add(ka, k * 32), idesc_s);
-          ptx::umma_ss_first(ds_ + 64, da, va, idesc_s);
+          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(d, desc_add(qa, k * 32), desc_add(ka, k * 32), idesc_s);
+          ptx::umma_commit(&s_full[2 * t + (u & 1)]);
+        }
+        __syncwarp();
+      };
+      auto issue_dp = [&](int t, int u, int stage) {
+        if (ptx::elect_one()) {
+          const uint64_t da = desc_add(ddo0, t * kTileBytes);
+          const uint64_t va = desc_add(dv0, stage * kTileBytes + (u & 1) * kHalfBytes);
+          const uint32_t d = tmem_base + t * 256 + 128;
+          ptx::umma_ss_first(d, da, va, idesc_s);
 #pragma unroll
-          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(ds_ + 64, desc_add(da, k * 32), desc_add(va, k * 32), idesc_s);
-          ptx::umma_commit(&sd_full[t]);
+          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(d, desc_add(da, k * 32), desc_add(va, k * 32), idesc_s);
+          ptx::umma_commit(&dp_full[t]);
         }
         __syncwarp();
       };
       ptx::mbar_wait(q_full, 0);
       ptx::mbar_wait(&kv_full[0], 0);
       ptx::tc_fence_after();
-      issue_sd(0, 0, 0);
-      issue_sd(1, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
+      issue_s(t, 0, 0);
+      issue_dp(t, 0, 0);
+      if (n_sub > 1) issue_s(t, 1, 0);
+      int stage = 0;                                   // K/V tile u >> 1
+      int nstage = 1 % kStagesB;                       // K/V tile (u >> 1) + 1
+      uint32_t nphase = (kStagesB == 1) ? 1 : 0;
       for (int u = 0; u < n_sub; ++u) {
         const int half = u & 1;
-        const bool more = (u + 1 < n_sub);
-        int nstage = stage;
-        uint32_t nphase = phase;
-        if (half == 1) { if (++nstage == kStagesB) { nstage = 0; nphase ^= 1; } }
+        // dP(u+1) as soon as the softmax warps hold dP(u) in registers
+        if (u + 1 < n_sub) {
+          ptx::mbar_wait(&dp_free[t], u & 1);
+          ptx::tc_fence_after();
+          issue_dp(t, u + 1, half ? nstage : stage);
+        }
         const uint64_t ka = desc_add(dkm0, stage * kTileBytes + half * kHalfBytes);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          ptx::mbar_wait(&ds_full[t], u & 1);
+        {
+          ptx::mbar_wait(&ds_full[2 * t + half], (u >> 1) & 1);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
-            const uint32_t dd = tmem_base + t * 192 + 128, aa = tmem_base + t * 192;
+            const uint32_t dd = tmem_base + t * 256 + 192, aa = tmem_base + t * 256 + half * BS;
             ptx::umma_ts(dd, aa, ka, idesc_q, u > 0 ? 1u : 0u);
 #pragma unroll
             for (int k = 1; k < BS / 16; ++k) ptx::umma_ts_acc(dd, aa + k * 8, desc_add(ka, k * 2048), idesc_q);
-            ptx::umma_commit(&dq_done[t]);
+            if (u + 1 == n_sub) ptx::umma_commit(&dq_final[t]);
           }
           __syncwarp();
-          if (more) {
-            if (t == 0 && half == 1) {
+          if (u + 2 < n_sub) {
+            if (half == 0) {                           // first touch of K/V tile (u >> 1) + 1
               ptx::mbar_wait(&kv_full[nstage], nphase);
               ptx::tc_fence_after();
             }
-            issue_sd(t, nstage, half ^ 1);
+            issue_s(t, u + 2, nstage);
           }
         }
-        if (half == 1 || !more) {
+        if (half == 1 || u + 1 == n_sub) {             // dQ of the K/V tile's last sub-tile has been issued
           if (ptx::elect_one()) ptx::umma_commit(&kv_empty[stage]);
           __syncwarp();
+          stage = nstage;
+          if (++nstage == kStagesB) { nstage = 0; nphase ^= 1; }
         }
-        stage = nstage;
-        phase = nphase;
       }
     }
   } else {
     const int t = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t s_addr = lane_addr + t * 192;
-    const uint32_t dp_addr = s_addr + 64;
-    const uint32_t dq_addr = s_addr + 128;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 256;
+    static_assert(kThreadsB == 352, "warps 2-9 are the softmax warps, warp 10 the second issuer");
+    const uint32_t dp_addr = lane_addr + 128;
+    const uint32_t dq_addr = lane_addr + 192;
     const int row = q0 + t * BQ + r;
     const size_t stat = ((size_t)b * a.heads + h) * a.N + row;
     const float neg_lse2 = (row < a.N) ? -a.lse[stat] * kLog2e : 0.f;
     const float delta = (row < a.N) ? a.delta[stat] : 0.f;
     const float sc = a.scale_log2;
     for (int u = 0; u < n_sub; ++u) {
-      ptx::mbar_wait(&sd_full[t], u & 1);
+      const int bb = u & 1;
+      const uint32_t s_addr = lane_addr + bb * BS;
+      ptx::mbar_wait(&s_full[2 * t + bb], (u >> 1) & 1);
+      ptx::mbar_wait(&dp_full[t], u & 1);
       ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BS / 32; ++c) {
-        uint32_t sv_[32], dv_[32];
-        ptx::tmem_ld_32x32(s_addr + c * 32, sv_);
-        ptx::tmem_ld_32x32(dp_addr + c * 32, dv_);
-        ptx::tmem_ld_wait();
-        uint32_t pk[16];
+      uint32_t s0[32], s1[32], d0[32], d1[32];
+      ptx::tmem_ld_32x32(dp_addr, d0);
+      ptx::tmem_ld_32x32(dp_addr + 32, d1);
+      ptx::tmem_ld_32x32(s_addr, s0);
+      ptx::tmem_ld_32x32(s_addr + 32, s1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&dp_free[t]);
+      uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = ptx::ex2(fmaf(__uint_as_float(sv_[i]), sc, neg_lse2));
-          const float p1 = ptx::ex2(fmaf(__uint_as_float(sv_[i + 1]), sc, neg_lse2));
-          pk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv_[i]) - delta), p1 * (__uint_as_float(dv_[i + 1]) - delta));
-        }
-        ptx::tmem_st_32x16(s_addr + c * 16, pk);
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = ptx::ex2(fmaf(__uint_as_float(s0[i]), sc, neg_lse2));
+        const float p1 = ptx::ex2(fmaf(__uint_as_float(s0[i + 1]), sc, neg_lse2));
+        pk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(d0[i]) - delta), p1 * (__uint_as_float(d0[i + 1]) - delta));
       }
+      ptx::tmem_st_32x16(s_addr, pk);
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = ptx::ex2(fmaf(__uint_as_float(s1[i]), sc, neg_lse2));
+        const float p1 = ptx::ex2(fmaf(__uint_as_float(s1[i + 1]), sc, neg_lse2));
+        pk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(d1[i]) - delta), p1 * (__uint_as_float(d1[i + 1]) - delta));
+      }
+      ptx::tmem_st_32x16(s_addr + 16, pk);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&ds_full[t]);
+      ptx::mbar_arrive(&ds_full[2 * t + bb]);
     }
-    ptx::mbar_wait(&dq_done[t], (n_sub - 1) & 1);
+    ptx::mbar_wait(&dq_final[t], 0);
     ptx::tc_fence_after();
     uint32_t o[2][32];
     ptx::tmem_ld_32x32(dq_addr, o[0]);
@@ -875,7 +908,7 @@ int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const flo
     O2_LAUNCH_CHECK();
   }
   if (parts & O2_ATTN_BWD_DQ) {
-    attn_bwd_dq_kernel<<<grid, kThreadsF, kBwdSmemBytes, st>>>(tm_qkv, tm_do, a);
+    attn_bwd_dq_kernel<<<grid, kThreadsB, kBwdSmemBytes, st>>>(tm_qkv, tm_do, a);
     O2_LAUNCH_CHECK();
   }
   return O2_OK;
