@@ -107,18 +107,37 @@ def cpu_reference_step_time(case_name, B, steps, warmup, threads):
     return sum(times) / len(times), cfg
 
 
+def pick_cpu_sample(workload, n_steps_total, threads, budget_s=260.0, force=None):
+    """Bounded CPU sample of the workload: B=1 on the full 180x360 grid when (steps+warmup) of them fit the time budget
+    (calibrated with one step on the quarter-area 90x180 sub-grid, full grid measured 5.9x, budgeted 6.5x), else the sub-grid itself."""
+    if workload != "117m":
+        return "8m", 8, None
+    if force in ("full", "sub"):
+        return ("117m" if force == "full" else "117m_90x180"), 1, None
+    sec, _ = cpu_reference_step_time("117m_90x180", 1, 1, 0, threads)
+    if 6.5 * sec * n_steps_total <= budget_s:
+        return "117m", 1, sec
+    return "117m_90x180", 1, sec
+
+
+def sample_note(case, cfg, B):
+    g = f"{cfg['img_size'][0]}x{cfg['img_size'][1]}"
+    if case == "117m_90x180":
+        return (f"B={B} on a {g} sub-grid (1/4 of the 180x360 field, L=4050): samples here are quarter-area samples, "
+                "not extrapolated")
+    return f"B={B} on the full {g} grid"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    case, B = ("117m_90x180", 1) if args.workload == "117m" else ("8m", 8)
+    case, B, _ = pick_cpu_sample(args.workload, args.steps + args.warmup, threads, force=args.ref_grid)
     sec, cfg = cpu_reference_step_time(case, B, args.steps, args.warmup, threads)
     val = B / sec
     sample = (f"CPU restatement of the reference (oracle/, fp32, SDPA attention), forward+clip+bayesian_tv+backward, "
-              f"B={B} on the {cfg['img_size'][0]}x{cfg['img_size'][1]} grid "
-              + ("(a 1/4-area sub-grid of the 180x360 workload, L=4050: samples here are 1/4-size samples)" if case == "117m_90x180" else "")
-              + f", {args.steps} steps after {args.warmup} warm-up")
+              + sample_note(case, cfg, B) + f", {args.steps} steps after {args.warmup} warm-up")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -278,13 +297,11 @@ def run_ours(args):
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        case, cb = ("117m_90x180", 1) if args.workload == "117m" else ("8m", 8)
+        case, cb, _ = pick_cpu_sample(args.workload, 1, threads, budget_s=60.0, force=args.ref_grid)
         sec, ccfg = cpu_reference_step_time(case, cb, 1, 0 if args.workload == "117m" else 1, threads)
         cpu = {"value": cb / sec, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"CPU restatement of the reference (oracle/, fp32, SDPA), 1 fwd+loss+bwd step, B={cb} on the "
-                         f"{ccfg['img_size'][0]}x{ccfg['img_size'][1]} grid"
-                         + (" (1/4-area sub-grid of the 180x360 workload: 1/4-size samples, not extrapolated)"
-                            if case == "117m_90x180" else "")}
+               "sample": "CPU restatement of the reference (oracle/, fp32, SDPA attention), 1 fwd+clip+bayesian_tv+bwd step, "
+                         + sample_note(case, ccfg, cb)}
 
     if rank == 0:
         line = {
@@ -318,6 +335,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-grid", default=None, choices=["full", "sub"], help="force the CPU sample (default: by time budget)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":

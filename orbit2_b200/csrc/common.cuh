@@ -64,6 +64,32 @@ __device__ __forceinline__ float dgelu_f(float x) {
   return cdf + x * pdf;
 }
 
+// Branch-free erf for the bf16 (tcgen05) epilogues: Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 -- two MUFU ops
+// (rcp, ex2) and ~10 FMA-pipe ops instead of libdevice's erff.  The fp32 parity arm keeps erff (gelu_f / dgelu_f).
+__device__ __forceinline__ float erf_fast_abs(float ax, float& e_x2) {   // ax = |x|; returns erf(|x|), e_x2 = exp(-x^2)
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
+  e_x2 = e;
+  return fmaf(-p, e, 1.0f);
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float e;
+  const float er = copysignf(erf_fast_abs(fabsf(x) * 0.70710678118654752f, e), x);
+  return 0.5f * x * (1.0f + er);
+}
+__device__ __forceinline__ float dgelu_fast(float x) {
+  float e;   // e = exp(-x^2 / 2)
+  const float er = copysignf(erf_fast_abs(fabsf(x) * 0.70710678118654752f, e), x);
+  return fmaf(x * 0.39894228040143268f, e, 0.5f * (1.0f + er));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -17,7 +17,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;    // epilogue warps: kEpiWarps / 4 per TMEM lane quarter, each draining a column slice
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // + TMA warp + MMA warp
 constexpr uint32_t kStageA = BM * BK * 2;  // 16 KiB
 
 struct GemmArgs {
@@ -64,7 +65,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
       u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
       *reinterpret_cast<uint4*>(g.aux_out + row * g.ld_aux_out + n) = u;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = gelu_f(v[j]);
+      for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
     }
     if (EPI == O2_EPI_BIAS_RES || EPI == O2_EPI_DGELU) {
       const long long ar = (EPI == O2_EPI_BIAS_RES) ? (row % g.aux_rows) : row;
@@ -72,7 +73,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
       const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
       const float a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (EPI == O2_EPI_BIAS_RES) ? (v[j] + a[j]) : (v[j] * dgelu_f(a[j]));
+      for (int j = 0; j < 8; ++j) v[j] = (EPI == O2_EPI_BIAS_RES) ? (v[j] + a[j]) : (v[j] * dgelu_fast(a[j]));
     }
     if (EPI == O2_EPI_ACCUM) {
       float* c = reinterpret_cast<float*>(g.C) + row * g.ldc + n;
@@ -134,7 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 128);
+      ptx::mbar_init(&tempty_bar[a], 32 * kEpiWarps);
     }
     ptx::fence_barrier_init();
   }
@@ -219,7 +220,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else {
     // ------------------------------------------------ epilogue: TMEM -> registers -> global
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int cpart = (warp - 2) >> 2;  // which slice of the tile's columns this warp drains
+    constexpr int kChunks = (BN / 32) / (kEpiWarps / 4);   // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -230,7 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const long long row = (long long)m_blk * BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = cpart * kChunks; c < (cpart + 1) * kChunks; ++c) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr + c * 32, r);
         ptx::tmem_ld_wait();

@@ -31,7 +31,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from ._lib import EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_NONE
+from ._lib import EPI_ACCUM, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_DGELU, EPI_NONE
 
 STATIC_VARS = ["land_sea_mask", "orography", "lattitude", "landcover"]      # res_slimvit.py:305-308
 
@@ -168,8 +168,8 @@ def reslim_forward(g: Geometry, P: Dict[str, torch.Tensor], Wc: Dict[str, torch.
 
 
 def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str, torch.Tensor], on_ready=None):
-    """Writes parameter gradients into the fp32 tensors of ``G`` (weights overwritten, bias / LN / conv gradients
-    accumulated into -- the caller zero-fills those) and returns (dtab_s, dtab_v, dposres).  ``on_ready(names)`` is
+    """ACCUMULATES parameter gradients into the fp32 tensors of ``G`` (the caller zero-fills them once per step) and
+    returns (dtab_s, dtab_v, dposres).  ``on_ready(names)`` is
     called as soon as a group of gradients is final (the data-parallel engine starts its all-reduce there)."""
     T, D, act = g.T, g.D, g.act
     dev = x.device
@@ -180,8 +180,10 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
         return ops.gemm(dy, w, out, trans_b=True, **kw)
 
     def wgrad(dy, a, name):
-        """dW[n_out, n_in] = dY^T A  (fp32, overwritten); db += colsum(dY)"""
-        ops.gemm(dy, a, G[name + ".weight"], trans_a=True, trans_b=True)
+        """dW[n_out, n_in] += dY^T A  (fp32, split-K over the token dimension so that small weight matrices still
+        fill the machine; partial tiles are accumulated with atomics); db += colsum(dY)"""
+        w = G[name + ".weight"]
+        ops.gemm(dy, a, w, trans_a=True, trans_b=True, epi=EPI_ACCUM, split_k=_wgrad_split(w.shape[0], w.shape[1]))
         ops.colsum(dy, G[name + ".bias"])
 
     def ready(names):
@@ -242,12 +244,18 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
     return dtab_s, dtab_v, dposres.view(g.L, D)
 
 
-_BIAS_LIKE = (".bias", "norm1.weight", "norm2.weight", "norm.weight", "path2.0.weight", "path2.3.weight", "conv_out.weight")
-
-
-def accumulated_grad(name: str) -> bool:
-    """True for gradients the kernels accumulate into (must be zero-filled), False for overwritten ones."""
-    return name.endswith(_BIAS_LIKE)
+def _wgrad_split(m: int, n: int, sms: int = 148, max_split: int = 8) -> int:
+    """Smallest split-K factor whose work items (128 x 256 output tiles x splits) fill >= 85 % of the last wave."""
+    tiles = ((m + 127) // 128) * ((n + 255) // 256)
+    best, best_eff = 1, 0.0
+    for sp in range(1, max_split + 1):
+        items = tiles * sp
+        eff = items / (((items + sms - 1) // sms) * sms)
+        if eff >= 0.85:
+            return sp
+        if eff > best_eff:
+            best, best_eff = sp, eff
+    return best
 
 
 class ReslimFunction(torch.autograd.Function):
@@ -282,7 +290,7 @@ class ReslimFunction(torch.autograd.Function):
         x, tab_s, tab_v = ctx.saved_tensors
         G = {}
         for n in names:
-            G[n] = (torch.zeros if accumulated_grad(n) else torch.empty)(P[n].shape, device=x.device, dtype=torch.float32)
+            G[n] = torch.zeros(P[n].shape, device=x.device, dtype=torch.float32)
         dpreds = dpreds.contiguous()
         if dpreds.dtype != g.act:
             dpreds = dpreds.to(g.act)
