@@ -637,7 +637,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     }
     for (int t = 0; t < 2; ++t) {
       ptx::mbar_init(&sd_full[t], 1);
-      ptx::mbar_init(&pd_full[t], 128);
+      ptx::mbar_init(&pd_full[t], 256);
       ptx::mbar_init(&dkv_done[t], 1);
     }
     ptx::fence_barrier_init();
@@ -748,10 +748,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             const uint32_t base = tmem_base + t * 256;
             ptx::umma_ts(base + 192, base, dam, idesc_g, u > 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 1; k < BS / 16; ++k) ptx::umma_ts_acc(base + 192, base + k * 8, desc_add(dam, k * 2048), idesc_g);
+            for (int k = 1; k < BS / 16; ++k)
+              ptx::umma_ts_acc(base + 192, base + (k >> 1) * 32 + (k & 1) * 8, desc_add(dam, k * 2048), idesc_g);
             ptx::umma_ts(base + 128, base + 64, qam, idesc_g, u > 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 1; k < BS / 16; ++k) ptx::umma_ts_acc(base + 128, base + 64 + k * 8, desc_add(qam, k * 2048), idesc_g);
+            for (int k = 1; k < BS / 16; ++k)
+              ptx::umma_ts_acc(base + 128, base + 64 + (k >> 1) * 32 + (k & 1) * 8, desc_add(qam, k * 2048), idesc_g);
             ptx::umma_commit(&dkv_done[t]);
           }
           __syncwarp();
@@ -772,21 +774,23 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       }
     }
   } else {
-    const int t = (warp - 2) >> 2;
+    // All eight softmax warps work on ONE key tile at a time (each thread: one key row, 32 of the 64 query columns), then
+    // on the other: the tiles are forced into anti-phase, so the MMA burst of one always overlaps the softmax of the other.
     const int quarter = warp & 3;
+    const int chalf = (warp - 2) >> 2;            // query columns [32 chalf, +32) of the sub-tile
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t st_addr = lane_addr + t * 256;
-    const uint32_t dp_addr = st_addr + 64;
     const float sc = a.scale_log2;
     for (int u = 0; u < n_sub; ++u) {
-      ptx::mbar_wait(&sd_full[t], u & 1);
-      ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BS / 32; ++c) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t st_addr = lane_addr + t * 256 + chalf * 32;       // this thread's S^T columns; P^T goes over their head
+        const uint32_t dp_addr = st_addr + 64;
+        ptx::mbar_wait(&sd_full[t], u & 1);
+        ptx::tc_fence_after();
         uint32_t sv_[32], dv_[32];
-        ptx::tmem_ld_32x32(st_addr + c * 32, sv_);
-        ptx::tmem_ld_32x32(dp_addr + c * 32, dv_);
+        ptx::tmem_ld_32x32(st_addr, sv_);
+        ptx::tmem_ld_32x32(dp_addr, dv_);
         ptx::tmem_ld_wait();
         uint32_t pk[16], dk[16];
 #pragma unroll
@@ -796,13 +800,16 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
           pk[i >> 1] = pack_bf16x2(p0, p1);
           dk[i >> 1] = pack_bf16x2(p0 * __uint_as_float(dv_[i]), p1 * __uint_as_float(dv_[i + 1]));
         }
-        ptx::tmem_st_32x16(st_addr + c * 16, pk);
-        ptx::tmem_st_32x16(dp_addr + c * 16, dk);
+        ptx::tmem_st_32x16(st_addr, pk);
+        ptx::tmem_st_32x16(dp_addr, dk);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&pd_full[t]);
       }
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&pd_full[t]);
     }
+    // epilogue: warps 2-5 drain key tile 0, warps 6-9 key tile 1
+    const int t = chalf;
+    const uint32_t st_addr = lane_addr + t * 256;
     ptx::mbar_wait(&dkv_done[t], (n_sub - 1) & 1);
     ptx::tc_fence_after();
     const int key = k0 + t * BKV + r;
