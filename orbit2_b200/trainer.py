@@ -1,0 +1,201 @@
+"""torchrun-compatible re-host of the reference training driver (examples/intermediate_downscaling.py) for the hot path.
+
+Consumes the reference YAMLs unchanged (configs/interm_*.yaml: sections trainer / parallelism / tiling / model / data, keys
+read at intermediate_downscaling.py:393-448), builds the drop-in model + registry loss + TrainEngine, runs the epoch loop
+with the per-epoch warmup-cosine schedule (models/lr_scheduler.py:9-115, stepped once per epoch at :756) and writes
+checkpoints in the reference's format (:775-791: epoch, model_state_dict, optimizer_state_dict, scheduler_state_dict;
+the optimizer state is emitted in torch.optim.AdamW's own layout so either side can resume the other's run).
+
+Out of scope here: the npz/Lustre data pipeline -- batches come from any iterable yielding
+``(x, y, in_variables, out_variables)`` like the reference's collate (itermodule.py:451-469); ``--synthetic`` uses seeded
+random fields of the configured grid.  Environment comes from torchrun (RANK / LOCAL_RANK / WORLD_SIZE), not SLURM.
+
+    torchrun --nproc-per-node 8 -m orbit2_b200.trainer /path/to/configs/interm_117m.yaml --data-key ERA5_2 \
+             --synthetic 180 360 --steps-per-epoch 20 --epochs 2
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import time
+from typing import Dict, Iterable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import losses
+from .engine import TrainEngine
+from .reslim import Res_Slim_ViT
+
+
+def load_config(path: str) -> dict:
+    import yaml
+    with open(path) as f:
+        return yaml.load(f, Loader=yaml.FullLoader)
+
+
+def model_kwargs(conf: dict) -> dict:
+    m = conf["model"]
+    return dict(superres_mag=m["superres_mag"], cnn_ratio=m["cnn_ratio"], patch_size=m["patch_size"],
+                embed_dim=m["embed_dim"], depth=m["depth"], decoder_depth=m["decoder_depth"], num_heads=m["num_heads"],
+                mlp_ratio=m["mlp_ratio"], drop_path=m["drop_path"], drop_rate=m["drop_rate"])
+
+
+def warmup_cosine_lr(epoch: int, base_lr: float, warmup_epochs: int, max_epochs: int, warmup_start_lr: float = 0.0,
+                     eta_min: float = 0.0) -> float:
+    """Closed form of LinearWarmupCosineAnnealingLR (lr_scheduler.py:97-115) = value after `epoch` scheduler steps."""
+    if epoch < warmup_epochs:
+        return warmup_start_lr + epoch * (base_lr - warmup_start_lr) / max(1, warmup_epochs - 1)
+    return eta_min + 0.5 * (base_lr - eta_min) * (1 + math.cos(math.pi * (epoch - warmup_epochs) / (max_epochs - warmup_epochs)))
+
+
+def build(conf: dict, data_key: str, img_size: Tuple[int, int], device, pos_grid: Optional[Tuple[int, int]] = None):
+    """-> (model, loss, engine).  img_size = the low-resolution grid of this dataset (load_architecture reads it from
+    data_module.get_data_dims(), loaders.py:261); spatial_resolution / variable lists come from the YAML's data section."""
+    d, t = conf["data"], conf["trainer"]
+    default_vars = list(d["default_vars"])
+    in_vars = list(d["dict_in_variables"][data_key])
+    out_vars = list(d["dict_out_variables"][data_key])
+    dtype = torch.bfloat16 if t["data_type"] == "bfloat16" else torch.float32
+    if conf["parallelism"]["tensor_par"] != 1 and int(os.environ.get("O2_IGNORE_TP", "1")):
+        pass        # the reference's 1b/10b YAMLs ask for TP=4 on Frontier; one 8-GPU B200 box runs them data-parallel
+    model = Res_Slim_ViT(default_vars, pos_grid or img_size, len(default_vars), len(out_vars), 1, learn_pos_emb=True,
+                         compute_dtype=dtype, **model_kwargs(conf))
+    model.spatial_resolution = d["spatial_resolution"][data_key]
+    model.img_size = tuple(img_size)
+    model = model.to(device)
+    meta = losses.MetricsMetaInfo(in_vars, out_vars, None, None)
+    loss = losses.METRICS_REGISTRY[t["train_loss"]](aggregate_only=True, metainfo=meta)
+    m = conf["model"]
+    eng = TrainEngine(model, loss, in_vars, out_vars, d["var_weights"], lr=float(m["lr"]),
+                      betas=(float(m["beta_1"]), float(m["beta_2"])), weight_decay=float(m["weight_decay"]))
+    return model, loss, eng
+
+
+# ------------------------------------------------------------------------------------------------ checkpoints
+def optimizer_state_dict(eng: TrainEngine) -> dict:
+    """torch.optim.AdamW.state_dict() layout for the engine's flat Adam state."""
+    state, ids = {}, []
+    for i, n in enumerate(eng.names):
+        ids.append(i)
+        if n in eng.frozen or eng.step_count == 0:
+            continue
+        lo, hi = eng.layout.range[n]
+        shape = eng.P[n].shape
+        state[i] = {"step": torch.tensor(float(eng.step_count)), "exp_avg": eng.flat_m[lo:hi].view(shape).clone(),
+                    "exp_avg_sq": eng.flat_v[lo:hi].view(shape).clone()}
+    group = {"lr": eng.lr, "betas": tuple(eng.betas), "eps": eng.eps, "weight_decay": eng.weight_decay, "amsgrad": False,
+             "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+             "params": ids}
+    return {"state": state, "param_groups": [group]}
+
+
+def load_optimizer_state_dict(eng: TrainEngine, sd: dict):
+    g = sd["param_groups"][0]
+    eng.lr, eng.betas, eng.eps, eng.weight_decay = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+    steps = [int(float(s["step"])) for s in sd["state"].values()]
+    eng.step_count = max(steps) if steps else 0
+    for i, st in sd["state"].items():
+        n = eng.names[int(i)]
+        lo, hi = eng.layout.range[n]
+        eng.flat_m[lo:hi].copy_(st["exp_avg"].reshape(-1))
+        eng.flat_v[lo:hi].copy_(st["exp_avg_sq"].reshape(-1))
+
+
+def save_checkpoint(path: str, epoch: int, eng: TrainEngine, sched: dict):
+    torch.save({"epoch": epoch, "model_state_dict": {k: v.detach().cpu().clone() for k, v in eng.model.state_dict().items()},
+                "optimizer_state_dict": optimizer_state_dict(eng), "scheduler_state_dict": dict(sched)}, path)
+
+
+def load_checkpoint(path: str, eng: TrainEngine) -> int:
+    """Returns the epoch to start from (reference: epoch_start = ckpt['epoch'] + 1, intermediate_downscaling.py:659-672)."""
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    with torch.no_grad():
+        sd = ck["model_state_dict"]
+        for n, p in eng.model.named_parameters():
+            p.copy_(sd[n].to(p.device))                    # parameters are views of the flat master buffer
+        if eng.flat_b is not None:
+            from . import ops
+            ops.cast_bf16(eng.flat_p, eng.flat_b)
+    if "optimizer_state_dict" in ck:
+        load_optimizer_state_dict(eng, ck["optimizer_state_dict"])
+    return int(ck["epoch"]) + 1
+
+
+# ------------------------------------------------------------------------------------------------ loop
+def synthetic_loader(conf, data_key, grid, batch, steps, device, seed):
+    d = conf["data"]
+    in_vars, out_vars = list(d["dict_in_variables"][data_key]), list(d["dict_out_variables"][data_key])
+    mag = conf["model"]["superres_mag"]
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    for _ in range(steps):
+        x = torch.randn(batch, len(in_vars), grid[0], grid[1], generator=g)
+        y = torch.randn(batch, len(out_vars), grid[0] * mag, grid[1] * mag, generator=g)
+        if losses.PRECIP in in_vars:
+            i = in_vars.index(losses.PRECIP)
+            x[:, i] = torch.log1p(torch.relu(x[:, i]) * 2.0)
+        if losses.PRECIP in out_vars:
+            i = out_vars.index(losses.PRECIP)
+            y[:, i] = torch.log1p(torch.relu(y[:, i]) * 2.0)
+        yield x.pin_memory().to(device, non_blocking=True), y.pin_memory().to(device, non_blocking=True), in_vars, out_vars
+
+
+def train(conf: dict, data_key: str, grid, epochs: int, steps_per_epoch: int, ckpt_dir: Optional[str] = None,
+          resume: Optional[str] = None, loader_factory=None, log=print):
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    device = torch.device("cuda", torch.cuda.current_device())
+    model, loss, eng = build(conf, data_key, grid, device)
+    m = conf["model"]
+    sched = dict(warmup_epochs=m["warmup_epochs"], max_epochs=conf["trainer"]["max_epochs"],
+                 warmup_start_lr=float(m["warmup_start_lr"]), eta_min=float(m["eta_min"]), base_lr=float(m["lr"]))
+    epoch0 = load_checkpoint(resume, eng) if resume else 0
+    B = conf["trainer"]["batch_size"]
+    hist = []
+    for epoch in range(epoch0, epoch0 + epochs):
+        eng.lr = warmup_cosine_lr(epoch, sched["base_lr"], sched["warmup_epochs"], sched["max_epochs"],
+                                  sched["warmup_start_lr"], sched["eta_min"])
+        loader = (loader_factory or synthetic_loader)(conf, data_key, grid, B, steps_per_epoch, device, 1000 * epoch + rank)
+        t0 = time.perf_counter()
+        tot, n = torch.zeros((), device=device), 0
+        for x, y, in_vars, out_vars in loader:
+            vec = eng.step(x, y)
+            tot += vec[-1]
+            n += 1
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        mean = (tot / max(n, 1)).item()
+        hist.append(mean)
+        if rank == 0:
+            log(f"epoch {epoch} lr {eng.lr:.3e} loss {mean:.5f} {n * B * world / dt:.2f} samples/s", flush=True)
+            if ckpt_dir:
+                os.makedirs(ckpt_dir, exist_ok=True)
+                save_checkpoint(os.path.join(ckpt_dir, f"interm_epoch_{epoch}.ckpt"), epoch, eng, dict(sched, last_epoch=epoch + 1))
+        if dist.is_initialized():
+            dist.barrier()
+    return hist, eng
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config")
+    ap.add_argument("--data-key", default="ERA5_2")
+    ap.add_argument("--synthetic", type=int, nargs=2, metavar=("H", "W"), required=True)
+    ap.add_argument("--epochs", type=int, default=1)
+    ap.add_argument("--steps-per-epoch", type=int, default=10)
+    ap.add_argument("--checkpoint-dir", default=None)
+    ap.add_argument("--resume", default=None)
+    a = ap.parse_args()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    conf = load_config(a.config)
+    train(conf, a.data_key, tuple(a.synthetic), a.epochs, a.steps_per_epoch, a.checkpoint_dir, a.resume)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,91 @@
+"""Trainer re-host: YAML schema, LR schedule (CPU); short run + checkpoint round trip (GPU)."""
+import importlib.util
+import math
+import os
+
+import pytest
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+REF_SCHED = "/root/reference/src/climate_learn/models/lr_scheduler.py"
+
+
+def test_own_yaml_has_reference_schema():
+    from orbit2_b200 import trainer
+    for name, dim in (("interm_8m", 256), ("interm_117m", 1024)):
+        c = trainer.load_config(os.path.join(ROOT, "configs", name + ".yaml"))
+        for sec, keys in (("trainer", ["max_epochs", "checkpoint", "pretrain", "batch_size", "num_workers", "buffer_size",
+                                       "data_type", "train_loss"]),
+                          ("parallelism", ["fsdp", "simple_ddp", "tensor_par", "seq_par"]),
+                          ("tiling", ["do_tiling", "div", "overlap"]),
+                          ("model", ["preset", "lr", "beta_1", "beta_2", "weight_decay", "warmup_epochs", "warmup_start_lr",
+                                     "eta_min", "superres_mag", "cnn_ratio", "patch_size", "embed_dim", "depth",
+                                     "decoder_depth", "num_heads", "mlp_ratio", "drop_path", "drop_rate"]),
+                          ("data", ["low_res_dir", "high_res_dir", "spatial_resolution", "default_vars", "dict_in_variables",
+                                    "dict_out_variables", "var_weights"])):
+            for k in keys:
+                assert k in c[sec], (name, sec, k)
+        assert trainer.model_kwargs(c)["embed_dim"] == dim
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("cfg", ["interm_8m", "interm_117m", "interm_1b", "interm_10b"])
+def test_reference_yaml_is_consumed_unchanged(cfg):
+    from orbit2_b200 import trainer
+    c = trainer.load_config(f"/root/reference/configs/{cfg}.yaml")
+    kw = trainer.model_kwargs(c)
+    assert kw["patch_size"] == 2 and kw["superres_mag"] == 4
+    assert set(c["data"]["dict_out_variables"]["ERA5_2"]) <= set(c["data"]["dict_in_variables"]["ERA5_2"])
+
+
+def test_lr_schedule_closed_form():
+    from orbit2_b200.trainer import warmup_cosine_lr as f
+    kw = dict(base_lr=5e-4, warmup_epochs=2, max_epochs=100, warmup_start_lr=1e-7, eta_min=1e-8)
+    assert f(0, **kw) == 1e-7 and f(1, **kw) == pytest.approx(5e-4) and f(2, **kw) == pytest.approx(5e-4)
+    assert f(51, **kw) == pytest.approx(1e-8 + 0.5 * (5e-4 - 1e-8) * (1 + math.cos(math.pi * 49 / 98)))
+    assert f(100, **kw) == pytest.approx(1e-8)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SCHED), reason="/root/reference not present on this box")
+def test_lr_schedule_matches_reference_class():
+    """the reference steps its chainable scheduler once per epoch (intermediate_downscaling.py:756)."""
+    from orbit2_b200.trainer import warmup_cosine_lr as f
+    spec = importlib.util.spec_from_file_location("ref_lr_scheduler", REF_SCHED)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=5e-4)
+    kw = dict(warmup_epochs=5, max_epochs=40, warmup_start_lr=1e-7, eta_min=1e-8)
+    sch = mod.LinearWarmupCosineAnnealingLR(opt, **kw)
+    for epoch in range(40):
+        assert opt.param_groups[0]["lr"] == pytest.approx(f(epoch, 5e-4, **kw), rel=1e-9, abs=1e-15), epoch
+        opt.step()
+        sch.step()
+
+
+@pytest.mark.gpu
+def test_short_run_and_checkpoint_roundtrip(tmp_path):
+    from orbit2_b200 import trainer
+    conf = trainer.load_config(os.path.join(ROOT, "configs", "interm_8m.yaml"))
+    conf["trainer"]["batch_size"] = 2
+    conf["model"].update(embed_dim=128, depth=2, num_heads=2, decoder_depth=2)
+    logs = []
+    hist, eng = trainer.train(conf, "ERA5_1", (8, 16), epochs=2, steps_per_epoch=3, ckpt_dir=str(tmp_path),
+                              log=lambda *a, **k: logs.append(a))
+    assert len(hist) == 2 and all(math.isfinite(h) for h in hist) and len(logs) == 2
+    ck = torch.load(tmp_path / "interm_epoch_1.ckpt", weights_only=False)
+    assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict"} and ck["epoch"] == 1
+    # torch.optim.AdamW accepts the optimizer state as is
+    params = [torch.nn.Parameter(v.clone()) for v in ck["model_state_dict"].values()]
+    opt = torch.optim.AdamW(params, lr=1.0)
+    opt.load_state_dict(ck["optimizer_state_dict"])
+    assert opt.param_groups[0]["betas"] == (0.9, 0.99)
+    # resume: a fresh engine restored from the checkpoint continues exactly like the original one
+    model2, _, eng2 = trainer.build(conf, "ERA5_1", (8, 16), torch.device("cuda"))
+    assert trainer.load_checkpoint(str(tmp_path / "interm_epoch_1.ckpt"), eng2) == 2
+    assert eng2.step_count == eng.step_count == 6
+    assert torch.equal(eng2.flat_p, eng.flat_p) and torch.equal(eng2.flat_m, eng.flat_m) and torch.equal(eng2.flat_v, eng.flat_v)
+    x, y, iv, ov = next(trainer.synthetic_loader(conf, "ERA5_1", (8, 16), 2, 1, torch.device("cuda"), 77))
+    eng.lr = eng2.lr = 1e-4
+    a, b = eng.step(x, y), eng2.step(x, y)
+    assert torch.allclose(a, b, rtol=1e-4) and torch.allclose(eng.flat_p, eng2.flat_p, rtol=1e-4, atol=1e-6)
