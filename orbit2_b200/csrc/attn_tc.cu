@@ -319,6 +319,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
 // =====================================================================================================
 constexpr int kStagesB = 3;
 
+#ifdef O2_TIMELINE
+// Debug build only: CTA (0,0) records clock64() at the hand-off points of sub-tiles [kTlFirst, kTlFirst + kTlCount).
+constexpr int kTlFirst = 100, kTlCount = 8, kTlSlots = 16;
+__device__ long long g_timeline[kTlCount * 2 * kTlSlots];
+#define O2_TL(u, t, slot)                                                                              \
+  do {                                                                                                 \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (u) >= kTlFirst && (u) < kTlFirst + kTlCount) \
+      g_timeline[(((u)-kTlFirst) * 2 + (t)) * kTlSlots + (slot)] = clock64();                            \
+  } while (0)
+#else
+#define O2_TL(u, t, slot) do { } while (0)
+#endif
+
 struct BwdArgs {
   const float* lse;       // [B, heads, N] natural log
   const float* delta;     // [B, heads, N]
@@ -670,7 +683,26 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     const float* lse = a.lse + ((size_t)b * a.heads + h) * a.N;
     const float* dlt = a.delta + ((size_t)b * a.heads + h) * a.N;
     const float inv_scale = 1.f / a.scale;
+    float xs[4], ys[4];
+    auto fetch_stats = [&](int i) {
+      float lv[4], dv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = i * BQ + e * 32 + lane;
+        const bool ok = row < a.N;
+        lv[e] = ok ? __ldg(lse + row) : 0.f;
+        dv[e] = ok ? __ldg(dlt + row) : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = i * BQ + e * 32 + lane;
+        xs[e] = (row < a.N) ? lv[e] * inv_scale : 1e30f;    // exp2((s - 1e30) * c) = 0 for rows past N
+        ys[e] = (row < a.N) ? dv[e] : 0.f;
+      }
+    };
+    fetch_stats(0);
     for (int i = 0; i < n_q; ++i) {
+      O2_TL(2 * i, 0, 10);                      // producer: wants the stage of query tile i
       if (lane == 0) {
         ptx::mbar_wait(&qdo_empty[stage], phase ^ 1);
         ptx::mbar_expect_tx(&qdo_full[stage], 2 * kTileBytes);
@@ -678,19 +710,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         ptx::tma_load_4d(sdO + stage * kTileBytes, &tmap_do, &qdo_full[stage], 0, h, i * BQ, b);
       }
       __syncwarp();
+      // the statistics of this tile were fetched one tile ahead (all eight loads in flight together: issued one by one
+      // behind the shared-memory stores they cost ~6700 cycles per tile and paced the whole kernel)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int idx = e * 32 + lane;
-        const int row = i * BQ + idx;
-        const float x = (row < a.N) ? lse[row] * inv_scale : 1e30f;    // exp2((s - 1e30) * c) = 0 for rows past N
-        const float y = (row < a.N) ? dlt[row] : 0.f;
         uint4* dst = reinterpret_cast<uint4*>(sStat + idx * 128);
-        dst[(2 * stage) ^ (idx & 7)] = neg_split3(x);
-        dst[(2 * stage + 1) ^ (idx & 7)] = neg_split3(y);
+        dst[(2 * stage) ^ (idx & 7)] = neg_split3(xs[e]);
+        dst[(2 * stage + 1) ^ (idx & 7)] = neg_split3(ys[e]);
       }
+      fetch_stats(i + 1);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&qdo_full[stage]);
+      O2_TL(2 * i, 0, 11);                      // producer: TMA issued + statistics written for query tile i
       if (++stage == kStagesB) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
@@ -742,8 +775,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         const uint64_t qam = desc_add(dqm0, stage * kTileBytes + half * kHalfBytes);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
+          O2_TL(u, t, 0);                       // issuer starts waiting for P^T / dS^T of (u, t)
           ptx::mbar_wait(&pd_full[t], u & 1);
           ptx::tc_fence_after();
+          O2_TL(u, t, 1);                       // issuer saw pd_full
           if (ptx::elect_one()) {
             const uint32_t base = tmem_base + t * 256;
             ptx::umma_ts(base + 192, base, dam, idesc_g, u > 0 ? 1u : 0u);
@@ -758,12 +793,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
           }
           __syncwarp();
           if (more) {
+            O2_TL(u, t, 3);                     // dV / dK issued
             if (t == 0 && half == 1) {
               ptx::mbar_wait(&qdo_full[nstage], nphase);
               ptx::tc_fence_after();
             }
+            O2_TL(u, t, 9);                     // next Q / dO tile present
             issue_sd(t, nstage, half ^ 1);
           }
+          O2_TL(u, t, 2);                       // all 18 MMAs of (u, t) issued
         }
         if (half == 1 || !more) {
           if (ptx::elect_one()) ptx::umma_commit(&qdo_empty[stage]);
@@ -786,12 +824,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       for (int t = 0; t < 2; ++t) {
         const uint32_t st_addr = lane_addr + t * 256 + chalf * 32;       // this thread's S^T columns; P^T goes over their head
         const uint32_t dp_addr = st_addr + 64;
+        if (warp == 2) O2_TL(u, t, 4);          // softmax starts waiting for S^T / dP^T of (u, t)
         ptx::mbar_wait(&sd_full[t], u & 1);
         ptx::tc_fence_after();
+        if (warp == 2) O2_TL(u, t, 5);          // saw sd_full
         uint32_t sv_[32], dv_[32];
         ptx::tmem_ld_32x32(st_addr, sv_);
         ptx::tmem_ld_32x32(dp_addr, dv_);
         ptx::tmem_ld_wait();
+        if (warp == 2) O2_TL(u, t, 6);          // TMEM loads landed
         uint32_t pk[16], dk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -802,9 +843,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         }
         ptx::tmem_st_32x16(st_addr, pk);
         ptx::tmem_st_32x16(dp_addr, dk);
+        if (warp == 2) O2_TL(u, t, 7);          // math done, stores issued
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&pd_full[t]);
+        if (warp == 2) O2_TL(u, t, 8);          // arrived on pd_full
       }
     }
     // epilogue: warps 2-5 drain key tile 0, warps 6-9 key tile 1
@@ -851,6 +894,12 @@ int make_qkv_tmap(CUtensorMap* tm, const void* qkv, int B, int N, int heads, int
 }
 
 }  // namespace
+
+#ifdef O2_TIMELINE
+extern "C" int o2_debug_timeline(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, g_timeline, sizeof(long long) * n);
+}
+#endif
 
 int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, cudaStream_t st) {
   O2_REQUIRE(hd == kHD, "attn_fwd_tc: head dim %d not supported (64 only)", hd);
