@@ -28,6 +28,19 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;
 
+#ifdef O2_TIMELINE
+// Debug build only: CTA (0,0) records clock64() at the hand-off points of sub-tiles [kTlFirst, kTlFirst + kTlCount).
+constexpr int kTlFirst = 100, kTlCount = 8, kTlSlots = 16;
+__device__ long long g_timeline[kTlCount * 2 * kTlSlots];
+#define O2_TL(u, t, slot)                                                                              \
+  do {                                                                                                 \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (u) >= kTlFirst && (u) < kTlFirst + kTlCount) \
+      g_timeline[(((u)-kTlFirst) * 2 + (t)) * kTlSlots + (slot)] = clock64();                            \
+  } while (0)
+#else
+#define O2_TL(u, t, slot) do { } while (0)
+#endif
+
 struct FwdArgs {
   __nv_bfloat16* out;
   float* lse;
@@ -159,8 +172,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
         }
         const uint64_t vd = desc_add(dv0, vstage * kTileBytes + half * kHalfBytes);
         {
+          O2_TL(u, t, 0);
           ptx::mbar_wait(&p_full[2 * t + half], (u >> 1) & 1);
           ptx::tc_fence_after();
+          O2_TL(u, t, 1);
           if (ptx::elect_one()) {
             const uint32_t pa = tmem_base + (2 * t + half) * BS;
             const uint32_t od = tmem_base + 256 + t * 64;
@@ -171,12 +186,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
             if (u + 1 == n_sub) ptx::umma_commit(&o_final[t]);
           }
           __syncwarp();
+          O2_TL(u, t, 3);
           if (more) {
             if (half == 0) {
               ptx::mbar_wait(&k_full[kstage], kphase);
               ptx::tc_fence_after();
             }
+            O2_TL(u, t, 9);
             issue_s(t, u + 2, kstage);
+            O2_TL(u, t, 2);
             if (half == 1 || u + 3 >= n_sub) {            // this warp's last S that reads the K tile has been issued
               if (ptx::elect_one()) ptx::umma_commit(&k_empty[kstage]);
               __syncwarp();
@@ -205,12 +223,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
     for (int u = 0; u < n_sub; ++u) {
       const int bb = u & 1;
       const uint32_t s_addr = lane_addr + (2 * t + bb) * BS;
+      if (quarter == 2) O2_TL(u, t, 4);
       ptx::mbar_wait(&s_full[2 * t + bb], (u >> 1) & 1);
       ptx::tc_fence_after();
+      if (quarter == 2) O2_TL(u, t, 5);
       uint32_t v0[32], v1[32];
       ptx::tmem_ld_32x32(s_addr, v0);
       ptx::tmem_ld_32x32(s_addr + 32, v1);
       ptx::tmem_ld_wait();
+      if (quarter == 2) O2_TL(u, t, 6);
       const bool ragged = (u == n_sub - 1) && (tail != BS);
       if (ragged) {
 #pragma unroll
@@ -269,9 +290,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
         pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
       }
       ptx::tmem_st_32x16(s_addr + 16, pk);
+      if (quarter == 2) O2_TL(u, t, 7);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&p_full[2 * t + bb]);
+      if (quarter == 2) O2_TL(u, t, 8);
     }
     // epilogue: O / l -> bf16, lse
     // (o_done may be up to two phases behind here, which a parity wait cannot tell apart: separate barrier)
@@ -318,19 +341,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
 // The softmax scale is applied once to dQ / dK in the epilogue.
 // =====================================================================================================
 constexpr int kStagesB = 3;
-
-#ifdef O2_TIMELINE
-// Debug build only: CTA (0,0) records clock64() at the hand-off points of sub-tiles [kTlFirst, kTlFirst + kTlCount).
-constexpr int kTlFirst = 100, kTlCount = 8, kTlSlots = 16;
-__device__ long long g_timeline[kTlCount * 2 * kTlSlots];
-#define O2_TL(u, t, slot)                                                                              \
-  do {                                                                                                 \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (u) >= kTlFirst && (u) < kTlFirst + kTlCount) \
-      g_timeline[(((u)-kTlFirst) * 2 + (t)) * kTlSlots + (slot)] = clock64();                            \
-  } while (0)
-#else
-#define O2_TL(u, t, slot) do { } while (0)
-#endif
 
 struct BwdArgs {
   const float* lse;       // [B, heads, N] natural log

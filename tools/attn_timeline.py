@@ -23,8 +23,10 @@ D = heads * hd
 g = torch.Generator(device="cuda").manual_seed(0)
 qkv = torch.randn(B * N, 3 * D, generator=g, device="cuda").to(torch.bfloat16)
 dout = torch.randn(B * N, D, generator=g, device="cuda").to(torch.bfloat16)
+which = sys.argv[1] if len(sys.argv) > 1 else "dkv"
 for _ in range(2):
     o, lse = ops.attn_fwd(qkv, B, N, heads, hd)
+if which != "fwd":
     ops.attn_bwd(qkv, o, dout, lse, B, N, heads, hd)
 torch.cuda.synchronize()
 lib = _lib.load()
@@ -34,6 +36,7 @@ lib.o2_debug_timeline.argtypes = [C.c_void_p, C.c_int]
 print("rc", lib.o2_debug_timeline(buf, n))
 v = list(buf)
 t0 = min(x for x in v if x > 0)
+which = sys.argv[1] if len(sys.argv) > 1 else "dkv"
 names = {0: "mma:wait_pd", 1: "mma:got_pd", 2: "mma:issued", 3: "mma:dvdk_issued", 9: "mma:qdo_present", 10: "prod:want_stage(tile u/2)", 11: "prod:done(tile u/2)", 4: "sm:wait_sd", 5: "sm:got_sd", 6: "sm:ld_done", 7: "sm:math_done", 8: "sm:arrived"}
 ev = []
 for u in range(8):
