@@ -270,6 +270,66 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2: two fp32 lanes per issue slot) and exp2 on the FMA pipe
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// 2^x for a pair, entirely on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + r with the 1.5*2^23 magic
+// constant, degree-3 minimax polynomial for 2^r on [-0.5, 0.5] (max relative error 1.3e-4, below bf16 resolution), exponent
+// insertion with one LEA.  Inputs are clamped at -125 (result ~2^-125 instead of 0); valid for x < 128.
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t X) {
+  float x0, x1;
+  unpack2(X, x0, x1);
+  X = pack2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const uint64_t T = add2(X, 0x4B4000004B400000ull);                 // x + 12582912
+  uint64_t R = add2(T, 0xCB400000CB400000ull);                       // n (as float)
+  R = fma2(R, 0xBF800000BF800000ull, X);                             // r = x - n
+  uint64_t P = fma2(R, pack2(0.0553272026f, 0.0553272026f), pack2(0.242996181f, 0.242996181f));
+  P = fma2(P, R, pack2(0.693246777f, 0.693246777f));
+  P = fma2(P, R, pack2(0.999868923f, 0.999868923f));
+  uint32_t p0, p1, t0, t1;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(P));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(T));
+  return pack2u(p0 + (t0 << 23), p1 + (t1 << 23));
+}
+// exp2 of a pair: MUFU for both lanes, or the polynomial when kPoly
+template <bool kPoly> __device__ __forceinline__ uint64_t exp2_pair(uint64_t X) {
+  if (kPoly) return exp2_poly2(X);
+  float x0, x1;
+  unpack2(X, x0, x1);
+  return pack2(ex2(x0), ex2(x1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_pair(uint64_t v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+
 __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t cnt) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(cnt) : "memory");
 }
