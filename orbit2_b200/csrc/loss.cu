@@ -113,6 +113,126 @@ __global__ void __launch_bounds__(NT) loss_kernel(const LossArgs a) {
   }
 }
 
+
+// Streaming variant (no shared memory, no barriers): one thread owns 8 consecutive pixels of one row, reads the three
+// prediction rows it needs with 16-byte loads (the two neighbour rows come out of L1/L2: DRAM sees every byte once),
+// the target with two 16-byte loads, and writes its 8 gradients with one 16/32-byte store.  Used when W % 8 == 0 and
+// the rows are 16-byte aligned; loss_kernel (tiled through shared memory) handles every other shape.
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 t;
+  t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]); t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+
+template <typename T, bool TV>
+__global__ void __launch_bounds__(NT) loss_stream_kernel(const LossArgs a) {
+  __shared__ float swarp[NT / 32];
+  const int bc = blockIdx.y;
+  const int c = bc % a.C;
+  const int W8 = a.W >> 3;
+  const long long item = (long long)blockIdx.x * NT + threadIdx.x;
+  const bool active = item < (long long)a.H * W8;
+  const int h = active ? (int)(item / W8) : 0;
+  const int w0 = active ? (int)(item % W8) * 8 : 0;
+  const T* pred = reinterpret_cast<const T*>(a.pred) + (size_t)bc * a.H * a.W;
+  const float* tgt = a.target + (size_t)bc * a.tgt_H * a.tgt_W;
+  const bool is_const = (a.const_mask >> c) & 1u;
+  const bool is_clamp = (c == a.clamp_ch);
+  float local = 0.f;
+  if (active) {
+    // clipped prediction rows h-1, h, h+1 at columns w0-1 .. w0+8
+    float pv[TV ? 3 : 1][10];
+    bool pass[8];
+    auto load_row = [&](int hh, float (&dst)[10], bool centre) {
+      float v[8];
+      if (is_const) load8<float>(tgt + (size_t)hh * a.tgt_W + w0, v);
+      else load8<T>(pred + (size_t)hh * a.W + w0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        bool ok = !is_const;
+        if (is_clamp && v[i] < 0.f) { v[i] = 0.f; ok = false; }
+        dst[i + 1] = v[i];
+        if (centre) pass[i] = ok;
+      }
+      if (TV) {
+        float l = 0.f, r = 0.f;
+        if (w0 > 0) l = is_const ? tgt[(size_t)hh * a.tgt_W + w0 - 1] : to_f(pred[(size_t)hh * a.W + w0 - 1]);
+        if (w0 + 8 < a.W) r = is_const ? tgt[(size_t)hh * a.tgt_W + w0 + 8] : to_f(pred[(size_t)hh * a.W + w0 + 8]);
+        if (is_clamp) { l = fmaxf(l, 0.f); r = fmaxf(r, 0.f); }
+        dst[0] = l; dst[9] = r;
+      }
+    };
+    constexpr int CR = TV ? 1 : 0;        // index of the centre row in pv
+    load_row(h, pv[CR], true);
+    if (TV) {
+      if (h >= 1) load_row(h - 1, pv[0], false);
+      if (h + 1 < a.H) load_row(h + 1, pv[TV ? 2 : 0], false);
+    }
+    float t[8];
+    load8<float>(tgt + (size_t)h * a.tgt_W + w0, t);
+    const float lw = a.lat_w ? a.lat_w[h] : 1.0f;
+    const float lwm = (a.lat_w && h >= 1) ? a.lat_w[h - 1] : 1.0f;
+    const float chw = a.ch_w ? a.ch_w[c] : 1.0f;
+    const bool hb = (h + 1 < a.H), ht = (h >= 1);
+    auto sgn = [](float x) { return (x > 0.f) ? 1.f : (x < 0.f ? -1.f : 0.f); };
+    float gout[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int w = w0 + i;
+      const float p = pv[CR][i + 1];
+      const float d = p - t[i];
+      float err, g;
+      if (a.kind == O2_LOSS_MAE) { err = fabsf(d); g = sgn(d); }
+      else { err = d * d; g = 2.f * d; }
+      g *= lw;
+      if (TV) {
+        const bool wr = (w + 1 < a.W), wl = (w >= 1);
+        float e = 0.f, gs = 0.f;
+        if (hb) { const float x = pv[2][i + 1] - p; e += fabsf(x); gs -= sgn(x); }
+        if (wr) { const float x = pv[1][i + 2] - p; e += fabsf(x); gs -= sgn(x); }
+        if (hb && wr) { const float x = pv[2][i + 2] - p; e += 0.7f * fabsf(x); gs -= 0.7f * sgn(x); }
+        if (hb && wl) { const float x = pv[2][i] - p; e += 0.7f * fabsf(x); gs -= 0.7f * sgn(x); }
+        err += 0.02f * e;
+        float gn = lw * gs;
+        if (wl) gn += lw * sgn(p - pv[1][i]);
+        if (ht) {
+          float s_ = sgn(p - pv[0][i + 1]);
+          if (wl) s_ += 0.7f * sgn(p - pv[0][i]);
+          if (wr) s_ += 0.7f * sgn(p - pv[0][i + 2]);
+          gn += lwm * s_;
+        }
+        g += 0.02f * gn;
+      }
+      local += err * lw;
+      gout[i] = pass[i] ? g * chw * a.gscale : 0.f;
+    }
+    if (a.dpred) store8<T>(reinterpret_cast<T*>(a.dpred) + (size_t)bc * a.H * a.W + (size_t)h * a.W + w0, gout);
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) swarp[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s_ = 0.f;
+    for (int i = 0; i < NT / 32; ++i) s_ += swarp[i];
+    atomicAdd(&a.accum[c], (double)s_);
+  }
+}
+
 __global__ void loss_finalize(const double* accum, const float* ch_w, float* loss_vec, int C, double inv_per_ch) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double tot = 0.0;
@@ -179,9 +299,21 @@ extern "C" int o2_loss_fwd_bwd(const void* pred, int dtype, const float* target,
   a.B = B; a.C = C; a.H = H; a.W = W; a.tgt_H = tgt_H; a.tgt_W = tgt_W;
   a.gscale = (float)((double)grad_scale / ((double)B * C * H * W));
   O2_CUDA(cudaMemsetAsync(accum_ws, 0, sizeof(double) * C, st));
-  dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * C);
-  if (dtype == O2_F32) loss_kernel<float><<<grid, NT, 0, st>>>(a);
-  else loss_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(a);
+  const size_t esz = dtype == O2_F32 ? 4 : 2;
+  const bool stream_ok = (W % 8 == 0) && (tgt_W % 4 == 0) && ((uintptr_t)pred % 16 == 0) && ((uintptr_t)target % 16 == 0) &&
+                         (dpred == nullptr || (uintptr_t)dpred % 16 == 0) && (((size_t)H * W * esz) % 16 == 0) &&
+                         (((size_t)tgt_H * tgt_W * 4) % 16 == 0);
+  if (stream_ok) {
+    const long long items = (long long)H * (W / 8);
+    dim3 grid((unsigned)((items + NT - 1) / NT), B * C);
+    const bool tv = (kind == O2_LOSS_BAYESIAN_TV);
+    if (dtype == O2_F32) { if (tv) loss_stream_kernel<float, true><<<grid, NT, 0, st>>>(a); else loss_stream_kernel<float, false><<<grid, NT, 0, st>>>(a); }
+    else { if (tv) loss_stream_kernel<__nv_bfloat16, true><<<grid, NT, 0, st>>>(a); else loss_stream_kernel<__nv_bfloat16, false><<<grid, NT, 0, st>>>(a); }
+  } else {
+    dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * C);
+    if (dtype == O2_F32) loss_kernel<float><<<grid, NT, 0, st>>>(a);
+    else loss_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(a);
+  }
   O2_LAUNCH_CHECK();
   loss_finalize<<<1, 32, 0, st>>>(accum_ws, ch_w, loss_vec, C, 1.0 / ((double)B * H * W));
   O2_LAUNCH_CHECK();

@@ -78,7 +78,8 @@ report("front end bwd (table grads)", lambda: ops.frontend_bwd(x, ts, tv, do, p,
 cs = torch.zeros(D, device=dev)
 report("colsum [T,1024] bf16 (bias grad)", lambda: ops.colsum(xt, cs), T * D * 2)
 n = 126_100_000
-P, Gd, M, Vv, Pb = (torch.zeros(n, device=dev) for _ in range(4)) + (torch.zeros(n, device=dev, dtype=bf),)
+P, Gd, M, Vv = (torch.zeros(n, device=dev) for _ in range(4))
+Pb = torch.zeros(n, device=dev, dtype=bf)
 report("fused AdamW 126.1M params", lambda: ops.adamw(P, Gd, M, Vv, Pb, 1e-3, 0.9, 0.99, 1e-8, 1e-5, 1), n * (4 * 4 + 3 * 4 + 2))
 a, b_ = torch.empty(1 << 29, device=dev, dtype=bf), torch.empty(1 << 29, device=dev, dtype=bf)
 report("torch copy 1 GiB bf16 (yardstick)", lambda: b_.copy_(a), 2 * a.numel() * 2)
