@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py -q -m gpu -k "loss or golden or 8m" 2>&1 | tail -3
-python tools/hbm_bench.py gpurun_out/hbm_table.md 2>&1 | tail -14
+timeout 300 python -m pytest tests/test_gemm_gpu.py -q -m gpu -x > gpurun_out/gemm_test.log 2>&1; echo "exit $?" >> gpurun_out/gemm_test.log; tail -5 gpurun_out/gemm_test.log
+timeout 200 python tools/gemm_bench.py 2>&1 | tail -13

@@ -39,12 +39,16 @@ template <int BN> struct Cfg {
   static constexpr uint32_t kStageB = BN * BK * 2;
   static constexpr uint32_t kStageBytes = kStageA + kStageB;
   static constexpr int kTmemCols = 2 * BN;  // 512 or 256
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 128 * 4 /*bias*/;
 };
 
+// One 32-column chunk of one output row.  `sbias` = this warp's bias slice staged in shared memory (broadcast reads), `ax` =
+// the chunk's aux values (residual / pre-activation), fetched by the caller BEFORE it waited for the TMEM load so that
+// their L2 latency overlaps it (the first version loaded bias and aux here, per 8 columns: the epilogue warps then sat
+// in long-scoreboard stalls for 2/3 of the time and the tensor pipe idled at 58 %).
 template <int BN, int EPI, bool C_F32>
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&r)[32], long long row, int n0) {
-  // 32 consecutive columns [n0, n0+32) of one output row held by this thread
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&r)[32], long long row, int n0,
+                                               const float* sbias, const uint4 (&ax)[4]) {
   if (row >= g.M) return;
 #pragma unroll
   for (int j0 = 0; j0 < 32; j0 += 8) {
@@ -54,8 +58,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j0 + j]);
     if (EPI == O2_EPI_BIAS || EPI == O2_EPI_BIAS_GELU || EPI == O2_EPI_BIAS_RES) {
-      const float4 b0 = *reinterpret_cast<const float4*>(g.bias + n);
-      const float4 b1 = *reinterpret_cast<const float4*>(g.bias + n + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(sbias + j0);
+      const float4 b1 = *reinterpret_cast<const float4*>(sbias + j0 + 4);
       v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
       v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
     }
@@ -68,8 +72,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
       for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
     }
     if (EPI == O2_EPI_BIAS_RES || EPI == O2_EPI_DGELU) {
-      const long long ar = (EPI == O2_EPI_BIAS_RES) ? (row % g.aux_rows) : row;
-      const uint4 u = *reinterpret_cast<const uint4*>(g.aux + ar * g.ld_aux + n);
+      const uint4 u = ax[j0 >> 3];
       const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
       const float a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
 #pragma unroll
@@ -93,24 +96,29 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
 }
 
 template <int BN>
-__device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, const uint32_t (&r)[32], long long row, int n0) {
+__device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, const uint32_t (&r)[32], long long row, int n0,
+                                                  const float* sbias, const uint4 (&ax)[4]) {
   switch (g.epi) {
     case O2_EPI_NONE:
-      if (g.c_f32) epilogue_chunk<BN, O2_EPI_NONE, true>(g, r, row, n0);
-      else epilogue_chunk<BN, O2_EPI_NONE, false>(g, r, row, n0);
+      if (g.c_f32) epilogue_chunk<BN, O2_EPI_NONE, true>(g, r, row, n0, sbias, ax);
+      else epilogue_chunk<BN, O2_EPI_NONE, false>(g, r, row, n0, sbias, ax);
       break;
     case O2_EPI_BIAS:
-      if (g.c_f32) epilogue_chunk<BN, O2_EPI_BIAS, true>(g, r, row, n0);
-      else epilogue_chunk<BN, O2_EPI_BIAS, false>(g, r, row, n0);
+      if (g.c_f32) epilogue_chunk<BN, O2_EPI_BIAS, true>(g, r, row, n0, sbias, ax);
+      else epilogue_chunk<BN, O2_EPI_BIAS, false>(g, r, row, n0, sbias, ax);
       break;
-    case O2_EPI_BIAS_GELU: epilogue_chunk<BN, O2_EPI_BIAS_GELU, false>(g, r, row, n0); break;
-    case O2_EPI_BIAS_RES: epilogue_chunk<BN, O2_EPI_BIAS_RES, false>(g, r, row, n0); break;
-    case O2_EPI_DGELU: epilogue_chunk<BN, O2_EPI_DGELU, false>(g, r, row, n0); break;
-    default: epilogue_chunk<BN, O2_EPI_ACCUM, true>(g, r, row, n0); break;
+    case O2_EPI_BIAS_GELU: epilogue_chunk<BN, O2_EPI_BIAS_GELU, false>(g, r, row, n0, sbias, ax); break;
+    case O2_EPI_BIAS_RES: epilogue_chunk<BN, O2_EPI_BIAS_RES, false>(g, r, row, n0, sbias, ax); break;
+    case O2_EPI_DGELU: epilogue_chunk<BN, O2_EPI_DGELU, false>(g, r, row, n0, sbias, ax); break;
+    default: epilogue_chunk<BN, O2_EPI_ACCUM, true>(g, r, row, n0, sbias, ax); break;
   }
 }
 
-template <int BN>
+// MC = 2: CTA pairs (cluster of 2 along M) share the B tile -- each CTA fetches half of it and multicasts it into both
+// shared memories, so the L2 -> SM operand traffic per 128 x BN x 64 block drops from 16 + 32 KiB to 16 + 16 KiB (the
+// kernel is bound by that traffic: 87 -> 131 FLOP per operand byte at BN = 256).  A stage is refilled only after BOTH
+// CTAs' MMAs have drained it (multicast tcgen05.commit onto both "empty" barriers).
+template <int BN, int MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmArgs g) {
@@ -122,16 +130,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tfull_bar = empty_bar + C::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sbias_all = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 256);   // [kEpiWarps][BN / 2] fp32
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  const uint32_t rank = (MC > 1) ? ptx::cluster_ctarank() : 0u;
+  const int first_work = (MC > 1) ? (int)(blockIdx.x / MC) : (int)blockIdx.x;
+  const int work_stride = (MC > 1) ? (int)(gridDim.x / MC) : (int)gridDim.x;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
     for (int s = 0; s < C::kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], MC);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
@@ -142,21 +154,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
+  if (MC > 1) ptx::cluster_sync();       // the peer's barriers are initialised before any multicast can reach them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_work = g.num_m_blk * g.num_n_blk * g.split_k;
+  // work items: (split, m block [pair], n block); with MC = 2 the pair (2 mp, 2 mp + 1) shares one item
+  const int num_m_items = (g.num_m_blk + MC - 1) / MC;
+  const int num_work = num_m_items * g.num_n_blk * g.split_k;
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = first_work; w < num_work; w += work_stride) {
         const int n_blk = w % g.num_n_blk;
         const int rest = w / g.num_n_blk;
-        const int m_blk = rest % g.num_m_blk;
-        const int split = rest / g.num_m_blk;
+        const int m_blk = (rest % num_m_items) * MC + (int)rank;      // may be >= num_m_blk for the odd tail: zero rows
+        const int split = rest / num_m_items;
         const int kb0 = split * g.kb_per_split;
         const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -171,12 +186,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int i = 0; i < BM / 64; ++i)
               ptx::tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
           }
-          if (!g.b_mn) {
-            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
-          } else {
+          if (MC == 1) {
+            if (!g.b_mn) {
+              ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              ptx::tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
+              for (int i = 0; i < BN / 64; ++i)
+                ptx::tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
+            }
+          } else {
+            constexpr uint16_t kMask = (1u << MC) - 1;
+            if (!g.b_mn) {           // rows [rank * BN/MC, +BN/MC) of the B tile, to both CTAs
+              ptx::tma_load_2d_mc(sb + rank * (BN / MC) * 128, &tmap_b, &full_bar[stage], kb * BK,
+                                  n_blk * BN + (int)rank * (BN / MC), kMask);
+            } else {                 // this CTA's share of the 64-column chunks
+#pragma unroll
+              for (int i = 0; i < BN / 64 / MC; ++i) {
+                const int ci = (int)rank * (BN / 64 / MC) + i;
+                ptx::tma_load_2d_mc(sb + ci * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + ci * 64, kb * BK, kMask);
+              }
+            }
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -190,9 +219,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = first_work; w < num_work; w += work_stride) {
         const int rest = w / g.num_n_blk;
-        const int split = rest / g.num_m_blk;
+        const int split = rest / num_m_items;
         const int kb0 = split * g.kb_per_split;
         const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -211,7 +240,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                        : ptx::umma_smem_desc(sb + k * 32, 16, 1024);
             ptx::umma_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (MC == 1) ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          else ptx::umma_commit_mc(&empty_bar[stage], (1u << MC) - 1);   // ... in both CTAs of the pair
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
@@ -225,19 +255,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     constexpr int kChunks = (BN / 32) / (kEpiWarps / 4);   // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    for (int w = first_work; w < num_work; w += work_stride) {
       const int n_blk = w % g.num_n_blk;
-      const int m_blk = (w / g.num_n_blk) % g.num_m_blk;
+      const int m_blk = ((w / g.num_n_blk) % num_m_items) * MC + (int)rank;
+      // stage this warp's bias slice (kChunks * 32 columns) in shared memory while the accumulator is still in flight
+      const bool has_bias = (g.epi == O2_EPI_BIAS || g.epi == O2_EPI_BIAS_GELU || g.epi == O2_EPI_BIAS_RES);
+      const bool has_aux = (g.epi == O2_EPI_BIAS_RES || g.epi == O2_EPI_DGELU);
+      const int ncol0 = n_blk * BN + cpart * kChunks * 32;
+      float* sb = sbias_all + (warp - 2) * (kChunks * 32);
+      __syncwarp();
+      if (has_bias) {
+        for (int i = lane * 4; i < kChunks * 32; i += 128) {
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ncol0 + i < g.N) bv = *reinterpret_cast<const float4*>(g.bias + ncol0 + i);
+          *reinterpret_cast<float4*>(sb + i) = bv;
+        }
+      }
+      __syncwarp();
+      const long long row = (long long)m_blk * BM + q * 32 + lane;
+      const long long arow = (g.epi == O2_EPI_BIAS_RES) ? (row % g.aux_rows) : row;
+      auto load_aux = [&](int c, uint4 (&ax)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n_blk * BN + c * 32 + j * 8;
+          ax[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (has_aux && row < g.M && n < g.N) ax[j] = *reinterpret_cast<const uint4*>(g.aux + arow * g.ld_aux + n);
+        }
+      };
+      uint4 ax[4];
+      load_aux(cpart * kChunks, ax);                 // first chunk's aux before waiting for the accumulator
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const long long row = (long long)m_blk * BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = cpart * kChunks; c < (cpart + 1) * kChunks; ++c) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr + c * 32, r);
+        uint4 axn[4];
+        if (c + 1 < (cpart + 1) * kChunks) load_aux(c + 1, axn);      // next chunk's aux rides under this chunk's math
         ptx::tmem_ld_wait();
-        epilogue_dispatch<BN>(g, r, row, n_blk * BN + c * 32);
+        epilogue_dispatch<BN>(g, r, row, n_blk * BN + c * 32, sb + (c - cpart * kChunks) * 32, ax);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ax[j] = axn[j];
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty_bar[acc]);
@@ -247,23 +306,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (MC > 1) ptx::cluster_sync();       // no multicast / remote arrive may still target a CTA that has exited
   if (warp == 1) ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
-template <int BN>
+template <int BN, int MC>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& g, cudaStream_t st) {
   using C = Cfg<BN>;
-  g.num_m_blk = (g.M + BM - 1) / BM;
-  g.num_n_blk = (g.N + BN - 1) / BN;
   static bool attr_done = false;
   if (!attr_done) {
-    O2_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+    O2_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
     attr_done = true;
   }
-  const int num_work = g.num_m_blk * g.num_n_blk * g.split_k;
-  const int grid = num_work < o2_num_sms() ? num_work : o2_num_sms();
-  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, g);
-  O2_LAUNCH_CHECK();
+  const int num_work = ((g.num_m_blk + MC - 1) / MC) * g.num_n_blk * g.split_k;
+  int ctas = num_work * MC < o2_num_sms() ? num_work * MC : o2_num_sms() / MC * MC;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = MC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  O2_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MC>, ta, tb, g));
   return O2_OK;
 }
 
@@ -307,6 +377,9 @@ int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans
   if (const char* e = getenv("O2_DBG_MN_SBO")) g.mn_sbo = (uint32_t)atoi(e);
 
   const int BN = (N > 128) ? 256 : 128;
+  g.num_m_blk = (int)((M + BM - 1) / BM);
+  g.num_n_blk = (int)((N + BN - 1) / BN);
+  const int MC = (g.num_m_blk >= 2 && !getenv("O2_GEMM_NO_MULTICAST")) ? 2 : 1;
   CUtensorMap ta, tb;
   {
     uint64_t dims[2], str[1];
@@ -316,11 +389,12 @@ int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans
     str[0] = (uint64_t)lda * 2;
     int rc = o2_make_tmap(&ta, A, 2, 2, dims, str, box, 1);
     if (rc) return rc;
-    if (!trans_b) { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = (uint32_t)BN; }
+    if (!trans_b) { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = (uint32_t)(BN / MC); }
     else          { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
     str[0] = (uint64_t)ldb * 2;
     rc = o2_make_tmap(&tb, B, 2, 2, dims, str, box, 1);
     if (rc) return rc;
   }
-  return BN == 256 ? launch<256>(ta, tb, g, st) : launch<128>(ta, tb, g, st);
+  if (MC == 2) return BN == 256 ? launch<256, 2>(ta, tb, g, st) : launch<128, 2>(ta, tb, g, st);
+  return BN == 256 ? launch<256, 1>(ta, tb, g, st) : launch<128, 1>(ta, tb, g, st);
 }
