@@ -1,4 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gemm_gpu.py -q -m gpu -x > gpurun_out/gemm_test.log 2>&1; echo "exit $?" >> gpurun_out/gemm_test.log; tail -5 gpurun_out/gemm_test.log
-timeout 200 python tools/gemm_bench.py 2>&1 | tail -13
+timeout 900 python -m pytest tests -q -m gpu > gpurun_out/gpu_tests.log 2>&1; echo "exit $?" >> gpurun_out/gpu_tests.log; tail -3 gpurun_out/gpu_tests.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench117.log 2>&1; echo "exit $?" >> gpurun_out/bench117.log
+python - <<'PY'
+import json
+l=[x for x in open('gpurun_out/bench117.log') if x.startswith('{')]
+d=json.loads(l[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['kernel'], d['roofline']['frac'], d['kernels_ms_per_step'], d['clocks'])
+PY
