@@ -1,9 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu > gpurun_out/gpu_tests.log 2>&1; echo "exit $?" >> gpurun_out/gpu_tests.log; tail -3 gpurun_out/gpu_tests.log
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench117.log 2>&1; echo "exit $?" >> gpurun_out/bench117.log
-python - <<'PY'
-import json
-l=[x for x in open('gpurun_out/bench117.log') if x.startswith('{')]
-d=json.loads(l[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['kernel'], d['roofline']['frac'], d['kernels_ms_per_step'], d['clocks'])
-PY
+timeout 600 python -m pytest tests/test_dp_gpu.py -q -m gpu > gpurun_out/dp_test.log 2>&1; echo "exit $?" >> gpurun_out/dp_test.log; tail -6 gpurun_out/dp_test.log
+timeout 300 python bench.py --workload 8m --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.readline()); print('8m:', d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'])"

@@ -1,0 +1,60 @@
+"""GPU, 2 ranks (NCCL): the data-parallel engine averages gradients correctly -- two ranks fed DIFFERENT halves of a batch
+end up with the same parameters as one rank fed the whole batch (mean-reduced loss => gradient of the full batch is the
+average of the half-batch gradients).  Needs >= 2 GPUs (gpurun --gpus 2); skipped otherwise."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.util import build_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _make(cfg, sd, dev):
+    from orbit2_b200 import engine, losses
+    m = build_model(cfg, sd, dev, torch.float32)
+    loss = losses.METRICS_REGISTRY["mse"](aggregate_only=True, metainfo=losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None))
+    return engine.TrainEngine(m, loss, cfg["in_vars"], cfg["out_vars"], cfg["var_weights"], lr=1e-3, betas=(0.9, 0.99), weight_decay=1e-5)
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle import cases, reslim_oracle as O
+    cfg = cases.get_case("tiny")
+    sd = O.init_state_dict(cfg, seed=9)
+    x, y = O.synthetic_batch(cfg, 4, cfg["in_vars"], cfg["out_vars"], seed=9)
+    eng = _make(cfg, sd, f"cuda:{rank}")
+    assert eng.world == 2
+    for _ in range(3):
+        eng.step(x[2 * rank:2 * rank + 2].cuda(), y[2 * rank:2 * rank + 2].cuda())
+    torch.cuda.synchronize()
+    ret[rank] = eng.flat_p.detach().cpu()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_ranks_equal_one_rank_full_batch():
+    from oracle import cases, reslim_oracle as O
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    cfg = cases.get_case("tiny")
+    sd = O.init_state_dict(cfg, seed=9)
+    x, y = O.synthetic_batch(cfg, 4, cfg["in_vars"], cfg["out_vars"], seed=9)
+    eng = _make(cfg, sd, "cuda:0")
+    for _ in range(3):
+        eng.step(x.cuda(), y.cuda())
+    ref = eng.flat_p.detach().cpu()
+    assert torch.equal(ret[0], ret[1])                                  # replicas stay bit-identical
+    assert (ret[0] - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 1e-7
