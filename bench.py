@@ -287,8 +287,15 @@ def run_ours(args):
         fl = attn_fwd_flops_blk * mult * B                                       # per launch
         avg_ms = kern[dom] / nlaunch
         ach = fl / (avg_ms * 1e-3) / 1e12
+        traffic = None                       # DRAM bytes per launch from the committed ncu --set full capture (same shape only)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom)
+            if tr and tr["B"] == B and tr["N"] == L and tr["heads"] == cfg["num_heads"]:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tf_sust"], "traffic": None, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
+                "frac": ach / peaks["tf_sust"], "traffic": traffic, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
                 "avg_launch_ms": avg_ms, "flops_per_launch": fl,
                 "share_of_step": kern[dom] / ms_step}
     kernels_ms = {k: round(v, 3) for k, v in sorted(kern.items(), key=lambda kv: -kv[1])}

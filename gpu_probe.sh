@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_dp_gpu.py -q -m gpu > gpurun_out/dp_test.log 2>&1; echo "exit $?" >> gpurun_out/dp_test.log; tail -6 gpurun_out/dp_test.log
-timeout 300 python bench.py --workload 8m --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
-import json,sys; d=json.loads(sys.stdin.readline()); print('8m:', d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'])"
+CMD="python tools/attn_bench.py --B 8 --iters 1"
+$CMD > gpurun_out/attn_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:attn_ -s 9 -c 3 -f -o gpurun_out/attn_prof_final $CMD > gpurun_out/attn_ncu.log 2>&1
+echo "exit $?"; cat gpurun_out/attn_plain.log; tail -2 gpurun_out/attn_ncu.log
