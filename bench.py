@@ -188,7 +188,7 @@ def run_ours(args):
     meta = losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None)
     loss_fn = losses.METRICS_REGISTRY["bayesian_tv"](aggregate_only=True, metainfo=meta)
     eng = engine.TrainEngine(model, loss_fn, cfg["in_vars"], cfg["out_vars"], cfg["var_weights"], lr=2e-4,
-                             betas=(0.9, 0.99), weight_decay=1e-5)
+                             betas=(0.9, 0.99), weight_decay=1e-5, shard_optimizer=args.shard)
 
     x_h, y_h = O.synthetic_batch(cfg, B, cfg["in_vars"], cfg["out_vars"], seed=rank)
     x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
@@ -263,7 +263,8 @@ def run_ours(args):
                         clip_out_variables=cfg["out_vars"])
         loss.backward()
         if world > 1:
-            dist.all_reduce(eng.flat_g, op=dist.ReduceOp.AVG)
+            eng.reducer.ready(eng.names)
+            eng.reducer.finish()
         eng.optimizer_step()
         opt_state["loss"] = loss.item()                    # device -> host read of the step's result
 
@@ -322,7 +323,7 @@ def run_ours(args):
             "config": {"workload": f"interm_{args.workload} Res_Slim_ViT ({n_params / 1e6:.1f}M params) ERA5 "
                                    f"{cfg['img_size'][0]}x{cfg['img_size'][1]} -> {H_out}x{cfg['img_size'][1] * cfg['superres_mag']}"
                                    ", V=23 in / 3 out vars, fwd+clip+bayesian_tv+bwd+allreduce+AdamW",
-                       "per_gpu_batch": B, "global_batch": B * world, "tokens_per_sample": L, "parallelism": f"dp{world}",
+                       "per_gpu_batch": B, "global_batch": B * world, "tokens_per_sample": L, "parallelism": (f"fsdp{world} (sharded Adam state + update, reduce-scatter / all-gather)" if (args.shard and world > 1) else f"dp{world}"),
                        "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB), no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": (x_h.numel() + y_h.numel()) * 4, "d2h_bytes_per_step": 4},
@@ -346,6 +347,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", action="store_true", help="FSDP-style sharded optimizer instead of plain data parallel")
     ap.add_argument("--ref-grid", default=None, choices=["full", "sub"], help="force the CPU sample (default: by time budget)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -66,3 +66,54 @@ class BucketReducer:
             if t is not None:
                 t.div_(self.world)
         self.pending = []
+
+
+class ShardedReducer:
+    """FSDP-style gradient reduction for a flat buffer whose optimizer state is sharded evenly over the ranks (rank r owns
+    elements [r*S, (r+1)*S)): every finished slice is reduced (averaged) onto the rank(s) that own it -- a reduce-scatter
+    issued bucket by bucket -- so that no rank ever holds, or updates, more than its own shard of the summed gradient
+    (reference: FSDP FULL_SHARD, examples/intermediate_downscaling.py:615-617)."""
+
+    def __init__(self, flat_grad: torch.Tensor, layout: FlatLayout, group=None):
+        self.flat, self.layout, self.group = flat_grad, layout, group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.shard = shard_size(layout.total, self.world)
+        self.own = (self.rank * self.shard, (self.rank + 1) * self.shard)
+        self.pending = []
+        self.reduced_elems = 0
+        self._nccl = self.world > 1 and dist.get_backend(group) == "nccl"
+
+    def segments(self, lo: int, hi: int):
+        """[(owner, seg_lo, seg_hi)] of a run split at shard boundaries."""
+        out = []
+        r = lo // self.shard
+        while lo < hi:
+            end = min(hi, (r + 1) * self.shard)
+            out.append((r, lo, end))
+            lo, r = end, r + 1
+        return out
+
+    def ready(self, names: Sequence[str]):
+        if self.world == 1:
+            return
+        for lo, hi in self.layout.runs(names):
+            for owner, a, b in self.segments(lo, hi):
+                t = self.flat[a:b]
+                dst = owner if self.group is None else dist.get_global_rank(self.group, owner)
+                op = dist.ReduceOp.AVG if self._nccl else dist.ReduceOp.SUM
+                self.pending.append((dist.reduce(t, dst=dst, op=op, group=self.group, async_op=True),
+                                     t if (not self._nccl and owner == self.rank) else None))
+                self.reduced_elems += b - a
+
+    def finish(self):
+        for work, t in self.pending:
+            work.wait()
+            if t is not None:
+                t.div_(self.world)
+        self.pending = []
+
+
+def shard_size(total: int, world: int, align: int = 8) -> int:
+    per = (total + world - 1) // world
+    return (per + align - 1) // align * align

@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .dp import BucketReducer, FlatLayout
+from .dp import BucketReducer, FlatLayout, ShardedReducer, shard_size
 from .losses import Metric, clip_spec
 from .reslim import Res_Slim_ViT, reslim_backward, reslim_forward
 
@@ -27,7 +27,8 @@ from .reslim import Res_Slim_ViT, reslim_backward, reslim_forward
 class TrainEngine:
     def __init__(self, model: Res_Slim_ViT, loss: Metric, in_variables: Sequence[str], out_variables: Sequence[str],
                  var_weights: Optional[Dict[str, float]] = None, lr: float = 2e-4, betas=(0.9, 0.99),
-                 weight_decay: float = 1e-5, eps: float = 1e-8, process_group=None, clip_constants: bool = True):
+                 weight_decay: float = 1e-5, eps: float = 1e-8, process_group=None, clip_constants: bool = True,
+                 shard_optimizer: bool = False):
         self.model = model
         self.loss = loss
         self.in_variables, self.out_variables = list(in_variables), list(out_variables)
@@ -50,10 +51,19 @@ class TrainEngine:
         self.layout = FlatLayout(self.names, sizes, align=8)
         offs = [self.layout.range[n][0] for n in self.names]
         total = self.total = self.layout.total
+        # FSDP-style mode: Adam state and the update are sharded (rank r owns [r*S, (r+1)*S) of the flat buffers), gradients
+        # are reduce-scattered bucket by bucket, updated fp32 / bf16 parameters are all-gathered (in place) after the step
+        self.sharded = bool(shard_optimizer) and self.world > 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self.shard = shard_size(total, self.world) if self.sharded else total
+        if self.sharded:
+            total = self.shard * self.world             # flat buffers padded so that every rank's shard has equal size
+        self.own = (self.rank * self.shard, (self.rank + 1) * self.shard) if self.sharded else (0, total)
         self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.flat_v = torch.zeros(total, device=dev, dtype=torch.float32)
+        n_state = self.shard if self.sharded else total
+        self.flat_m = torch.zeros(n_state, device=dev, dtype=torch.float32)      # sharded mode: this rank's shard only
+        self.flat_v = torch.zeros(n_state, device=dev, dtype=torch.float32)
         self.flat_b = torch.zeros(total, device=dev, dtype=torch.bfloat16) if self.act == torch.bfloat16 else None
         self.P: Dict[str, torch.Tensor] = {}
         self.G: Dict[str, torch.Tensor] = {}
@@ -71,7 +81,7 @@ class TrainEngine:
         self.frozen = [n for (n, p) in named if not p.requires_grad]
         if self.flat_b is not None:
             ops.cast_bf16(self.flat_p, self.flat_b)
-        self.reducer = BucketReducer(self.flat_g, self.layout, process_group)
+        self.reducer = (ShardedReducer if self.sharded else BucketReducer)(self.flat_g, self.layout, process_group)
         self._train_runs = None
         self._lat = None
         self._chw = None
@@ -124,10 +134,18 @@ class TrainEngine:
         self.step_count += 1
         if self._train_runs is None:                # frozen parameters get neither an update nor weight decay
             self._train_runs = self.layout.runs([n for n in self.names if n not in self.frozen])
+        o0, o1 = self.own
         for lo, hi in self._train_runs:
-            ops.adamw(self.flat_p[lo:hi], self.flat_g[lo:hi], self.flat_m[lo:hi], self.flat_v[lo:hi],
+            lo, hi = max(lo, o0), min(hi, o1)           # sharded mode: only this rank's part of every run
+            if lo >= hi:
+                continue
+            ops.adamw(self.flat_p[lo:hi], self.flat_g[lo:hi], self.flat_m[lo - o0:hi - o0], self.flat_v[lo - o0:hi - o0],
                       self.flat_b[lo:hi] if self.flat_b is not None else None, self.lr, self.betas[0], self.betas[1],
                       self.eps, self.weight_decay, self.step_count, grad_scale)
+        if self.sharded:                                # in-place all-gather of the updated shards
+            dist.all_gather_into_tensor(self.flat_p, self.flat_p[o0:o1], group=self.pg)
+            if self.flat_b is not None:
+                dist.all_gather_into_tensor(self.flat_b, self.flat_b[o0:o1], group=self.pg)
 
     def step(self, x, y):
         vec = self.forward_backward(x, y)

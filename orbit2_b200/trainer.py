@@ -69,13 +69,16 @@ def build(conf: dict, data_key: str, img_size: Tuple[int, int], device, pos_grid
     loss = losses.METRICS_REGISTRY[t["train_loss"]](aggregate_only=True, metainfo=meta)
     m = conf["model"]
     eng = TrainEngine(model, loss, in_vars, out_vars, d["var_weights"], lr=float(m["lr"]),
-                      betas=(float(m["beta_1"]), float(m["beta_2"])), weight_decay=float(m["weight_decay"]))
+                      betas=(float(m["beta_1"]), float(m["beta_2"])), weight_decay=float(m["weight_decay"]),
+                      shard_optimizer=int(conf["parallelism"].get("fsdp", 1)) > 1)     # fsdp > 1 in the YAML -> sharded mode
     return model, loss, eng
 
 
 # ------------------------------------------------------------------------------------------------ checkpoints
 def optimizer_state_dict(eng: TrainEngine) -> dict:
     """torch.optim.AdamW.state_dict() layout for the engine's flat Adam state."""
+    if eng.sharded:
+        raise NotImplementedError("checkpointing the sharded Adam state (gather to rank 0) is not implemented yet")
     state, ids = {}, []
     for i, n in enumerate(eng.names):
         ids.append(i)

@@ -38,6 +38,21 @@ def _worker(rank, world, port, ret):
     red.finish()
     expect = torch.arange(lay.total, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
     ok = torch.allclose(flat, expect) and red.reduced_elems == lay.total
+    # FSDP-style: every slice is reduced onto its owner only; each rank ends with the averaged gradient of ITS shard
+    from orbit2_b200.dp import ShardedReducer, shard_size
+    S = shard_size(lay.total, world)
+    flat2 = torch.zeros(S * world)
+    flat2[:lay.total] = torch.arange(lay.total, dtype=torch.float32) * (rank + 1)
+    sred = ShardedReducer(flat2, lay)
+    assert sred.shard == S and sred.own == (rank * S, (rank + 1) * S)
+    for grp in groups:
+        sred.ready(grp)
+    sred.finish()
+    o0, o1 = sred.own
+    o1 = min(o1, lay.total)
+    ok = ok and torch.allclose(flat2[o0:o1], expect[o0:o1]) and sred.reduced_elems == lay.total
+    segs = sred.segments(S - 3, S + 5)
+    ok = ok and segs == [(0, S - 3, S), (1, S, S + 5)]
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -19,11 +19,12 @@ def _free_port():
     return p
 
 
-def _make(cfg, sd, dev):
+def _make(cfg, sd, dev, shard=False, dtype=torch.float32):
     from orbit2_b200 import engine, losses
-    m = build_model(cfg, sd, dev, torch.float32)
+    m = build_model(cfg, sd, dev, dtype)
     loss = losses.METRICS_REGISTRY["mse"](aggregate_only=True, metainfo=losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None))
-    return engine.TrainEngine(m, loss, cfg["in_vars"], cfg["out_vars"], cfg["var_weights"], lr=1e-3, betas=(0.9, 0.99), weight_decay=1e-5)
+    return engine.TrainEngine(m, loss, cfg["in_vars"], cfg["out_vars"], cfg["var_weights"], lr=1e-3, betas=(0.9, 0.99), weight_decay=1e-5,
+                              shard_optimizer=shard)
 
 
 def _worker(rank, world, port, ret):
@@ -40,6 +41,20 @@ def _worker(rank, world, port, ret):
         eng.step(x[2 * rank:2 * rank + 2].cuda(), y[2 * rank:2 * rank + 2].cuda())
     torch.cuda.synchronize()
     ret[rank] = eng.flat_p.detach().cpu()
+    # FSDP-style sharded optimizer (reduce-scatter + sharded AdamW + all-gather) must give the same parameters
+    for dtype in (torch.float32, torch.bfloat16):
+        a = _make(cfg, sd, f"cuda:{rank}", shard=False, dtype=dtype)
+        b = _make(cfg, sd, f"cuda:{rank}", shard=True, dtype=dtype)
+        assert b.sharded and b.flat_m.numel() == b.shard and b.shard * 2 >= a.total
+        for _ in range(3):
+            xa, ya = x[2 * rank:2 * rank + 2].cuda(), y[2 * rank:2 * rank + 2].cuda()
+            a.step(xa, ya)
+            b.step(xa, ya)
+        torch.cuda.synchronize()
+        n = a.total
+        ret[f"shard{rank}{dtype}"] = bool(torch.allclose(a.flat_p[:n], b.flat_p[:n], rtol=1e-5, atol=1e-7)) and \
+            (a.flat_b is None or bool(torch.equal(a.flat_b[:n], b.flat_b[:n]) or
+                                      (a.flat_b[:n].float() - b.flat_b[:n].float()).abs().max().item() < 1e-2))
     dist.destroy_process_group()
 
 
@@ -56,5 +71,6 @@ def test_two_ranks_equal_one_rank_full_batch():
     for _ in range(3):
         eng.step(x.cuda(), y.cuda())
     ref = eng.flat_p.detach().cpu()
+    assert all(v for k, v in ret.items() if str(k).startswith("shard")), dict((k, v) for k, v in ret.items() if str(k).startswith("shard"))
     assert torch.equal(ret[0], ret[1])                                  # replicas stay bit-identical
     assert (ret[0] - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 1e-7
