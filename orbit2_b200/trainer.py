@@ -108,7 +108,8 @@ def load_optimizer_state_dict(eng: TrainEngine, sd: dict):
 
 def save_checkpoint(path: str, epoch: int, eng: TrainEngine, sched: dict):
     torch.save({"epoch": epoch, "model_state_dict": {k: v.detach().cpu().clone() for k, v in eng.model.state_dict().items()},
-                "optimizer_state_dict": optimizer_state_dict(eng), "scheduler_state_dict": dict(sched)}, path)
+                "optimizer_state_dict": None if eng.sharded else optimizer_state_dict(eng),   # sharded: model only for now
+                "scheduler_state_dict": dict(sched)}, path)
 
 
 def load_checkpoint(path: str, eng: TrainEngine) -> int:
