@@ -11,6 +11,8 @@
 // (x stays L2-resident) and writes o [B*L, heads*hd]; var_agg.proj follows as a tensor-core GEMM.
 // Backward reduces d(tab_s), d(tab_v) over all tokens: persistent CTAs keep their slice in registers, one atomic
 // per element per CTA at the end.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -254,6 +256,151 @@ __global__ void __launch_bounds__(NT) frontend_bwd_kernel(const FeArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ bf16 arm: HMMA
+// The two big contractions of the collapsed front end are small-K GEMMs against the per-head table (K = V*(PP+1) <= 128):
+//   forward   o[t, e]   = sum_kk C[t, kk] tab_v[kk, e]            backward  dC[t, kk] = sum_e dO[t, e] tab_v[kk, e]
+//                                                                            dM[kk, e] += sum_t C[t, kk] dO[t, e]
+// In the bf16 arm they run on the tensor cores with warp-level mma.sync (m16n8k16, bf16 in, fp32 accumulate): the work is
+// ~30 GFLOP per pass -- far too little to justify a tcgen05/TMEM pipeline, and at mma.sync speed the kernels are bound by
+// the x read and the o / dO traffic.  The fp32 arm keeps the exact SIMT kernels above.
+constexpr int LDS_ = 136;          // bf16 row pitch of the smem operand tiles (128 + 8: conflict-free fragment loads)
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a_)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a_[0]), "r"(a_[1]), "r"(a_[2]), "r"(a_[3]), "r"(b0), "r"(b1));
+}
+
+// pixels of one token tile for all variables (head independent)
+__device__ __forceinline__ void stage_pixels(const FeArgs& a, long long t0, float* sP) {
+  const int V = a.V, PP = a.PP, L = a.gh * a.gw;
+  for (int i = threadIdx.x; i < TT * V; i += NT) {
+    const int tl = i % TT, v = i / TT;
+    const long long t = t0 + tl;
+    if (t < a.T) {
+      const int b = (int)(t / L), l = (int)(t % L);
+      const int gy = l / a.gw, gx = l % a.gw;
+      const float* xp = a.x + (((size_t)b * V + v) * a.Hx + (size_t)gy * a.p) * a.Wx + (size_t)gx * a.p;
+      for (int pi = 0; pi < a.p; ++pi)
+        for (int pj = 0; pj < a.p; ++pj) sP[(tl * V + v) * PP + pi * a.p + pj] = xp[(size_t)pi * a.Wx + pj];
+    } else {
+      for (int k = 0; k < PP; ++k) sP[(tl * V + v) * PP + k] = 0.f;
+    }
+  }
+}
+
+constexpr int LDB_ = 72;           // bf16 row pitch of the [kk][e] table tile (64 + 8)
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(smem_row)));
+}
+
+// softmax weights a[t][v] of head h from the staged pixels (NT == 4 * TT: four threads per token), then the bf16 coefficient tile
+// sC[t][kk] = a[t][v] * [pixels, 1] (kk = v*(PP+1)+k'; columns >= KK stay zero from the caller's one-time clear)
+__device__ __forceinline__ void head_coefficients(const FeArgs& a, int h, long long t0, const float* sP, float* sa,
+                                                  __nv_bfloat16* sC) {
+  const int V = a.V, PP = a.PP, P1 = PP + 1;
+  {   // four threads per token: scores of every 4th variable, max / sum combined with two shuffles
+    const int tl = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    float mx = -INFINITY;
+    for (int v = sub; v < V; v += 4) {
+      const float* ts = a.tab_s + ((size_t)v * a.heads + h) * P1;
+      float sc = ts[PP];
+      for (int k = 0; k < PP; ++k) sc = fmaf(sP[(tl * V + v) * PP + k], ts[k], sc);
+      sa[tl * V + v] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
+    for (int v = sub; v < V; v += 4) {
+      const float e = __expf(sa[tl * V + v] - mx);
+      sa[tl * V + v] = e;
+      sum += e;
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = (t0 + tl < a.T) ? 1.f / sum : 0.f;
+    for (int v = sub; v < V; v += 4) sa[tl * V + v] *= inv;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TT * V; i += NT) {
+    const int tl = i % TT, v = i / TT;
+    const float w = sa[tl * V + v];
+    __nv_bfloat16* c = sC + tl * LDS_ + v * P1;
+    for (int k = 0; k < PP; ++k) c[k] = __float2bfloat16_rn(w * sP[(tl * V + v) * PP + k]);
+    c[PP] = __float2bfloat16_rn(w);
+  }
+}
+
+// o[t, h*64 + e] for a tile of 64 tokens and ALL heads (the pixels are staged once per tile)
+__global__ void __launch_bounds__(NT) frontend_fwd_mma_kernel(const FeArgs a) {
+  constexpr int HD = 64;
+  extern __shared__ float smem[];
+  const int V = a.V, PP = a.PP, KK = a.KK;
+  float* sP = smem;                                   // [TT][V][PP]
+  float* sa = sP + TT * V * PP;                       // [TT][V]
+  __nv_bfloat16* sC = reinterpret_cast<__nv_bfloat16*>(sa + TT * V);   // [TT][LDS_]  coefficients
+  __nv_bfloat16* sB = sC + TT * LDS_;                 // [KKP][LDB_] tab_v[h] (row kk, e contiguous; rows >= KK zero)
+  __nv_bfloat16* sO = sB + KKP * LDB_;                // [TT][LDB_]  output tile
+  const long long t0 = (long long)blockIdx.x * TT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  const int mt = warp & 3, nh = warp >> 2;            // 16-token row tile, 32-column half
+  stage_pixels(a, t0, sP);
+  for (int i = threadIdx.x; i < TT * LDS_ / 2; i += NT) reinterpret_cast<uint32_t*>(sC)[i] = 0u;
+  for (int i = threadIdx.x; i < KKP * LDB_ / 2; i += NT) reinterpret_cast<uint32_t*>(sB)[i] = 0u;
+  __syncthreads();
+  for (int h = 0; h < a.heads; ++h) {
+    head_coefficients(a, h, t0, sP, sa, sC);
+    for (int i = threadIdx.x; i < KK * (HD / 4); i += NT) {          // fp32 table -> bf16 tile, 16-byte reads
+      const int kk = i / (HD / 4), e4 = i % (HD / 4);
+      const float4 v4 = *reinterpret_cast<const float4*>(a.tab_v + ((size_t)h * KK + kk) * HD + e4 * 4);
+      uint2 pk;
+      pk.x = pack_bf16x2(v4.x, v4.y);
+      pk.y = pack_bf16x2(v4.z, v4.w);
+      *reinterpret_cast<uint2*>(sB + kk * LDB_ + e4 * 4) = pk;
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < KKP / 16; ++ks) {
+      const int k0 = ks * 16 + tig * 2;
+      uint32_t af[4];
+      af[0] = *reinterpret_cast<const uint32_t*>(sC + (mt * 16 + g) * LDS_ + k0);
+      af[1] = *reinterpret_cast<const uint32_t*>(sC + (mt * 16 + g + 8) * LDS_ + k0);
+      af[2] = *reinterpret_cast<const uint32_t*>(sC + (mt * 16 + g) * LDS_ + k0 + 8);
+      af[3] = *reinterpret_cast<const uint32_t*>(sC + (mt * 16 + g + 8) * LDS_ + k0 + 8);
+      // B fragments of two n-tiles per ldmatrix.x4.trans: matrices (k 0-7 | 8-15) x (n 0-7 | 8-15) of the row-major table
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t bf[4];
+        ldmatrix_x4_trans(bf, sB + (ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDB_ + nh * 32 + np * 16 + (lane >> 4) * 8);
+        mma_bf16_16816(acc[np * 2], af, bf[0], bf[1]);
+        mma_bf16_16816(acc[np * 2 + 1], af, bf[2], bf[3]);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int col = nh * 32 + nt * 8 + tig * 2;
+      *reinterpret_cast<uint32_t*>(sO + (mt * 16 + g) * LDB_ + col) = pack_bf16x2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<uint32_t*>(sO + (mt * 16 + g + 8) * LDB_ + col) = pack_bf16x2(acc[nt][2], acc[nt][3]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TT * (HD / 8); i += NT) {      // 128-byte rows, 16 bytes per thread
+      const int tl = i / (HD / 8), c8 = i % (HD / 8);
+      if (t0 + tl < a.T)
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + (size_t)(t0 + tl) * a.heads * HD + (size_t)h * HD + c8 * 8) =
+            *reinterpret_cast<const uint4*>(sO + tl * LDB_ + c8 * 8);
+    }
+    // (the next head's coefficient / table writes are ordered behind this head's reads by the barrier inside
+    //  head_coefficients and the one after the table copy; sO is rewritten only after the next MMA phase)
+  }
+}
+
 int fill(FeArgs& a, const float* x, const float* tab_s, const float* tab_v, int B, int V, int Hx, int Wx, int p, int gh,
          int gw, int heads, int hd) {
   O2_REQUIRE(x && tab_s && tab_v, "frontend: null pointer");
@@ -315,6 +462,13 @@ extern "C" int o2_frontend_fwd(const float* x, const float* tab_s, const float* 
   if (rc) return rc;
   O2_REQUIRE(out, "frontend_fwd: null out");
   a.out = out;
+  if (out_dtype == O2_BF16 && hd == 64 && ((uintptr_t)out % 16) == 0 && !getenv("O2_FRONTEND_SIMT")) {
+    const size_t smem = sizeof(float) * ((size_t)TT * a.V * a.PP + (size_t)TT * a.V) + 2 * ((size_t)TT * LDS_ + (size_t)(KKP + TT) * LDB_);
+    O2_CUDA(cudaFuncSetAttribute(frontend_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    frontend_fwd_mma_kernel<<<(unsigned)((a.T + TT - 1) / TT), NT, smem, (cudaStream_t)stream>>>(a);
+    O2_LAUNCH_CHECK();
+    return O2_OK;
+  }
   O2_FE_DISPATCH(launch_fwd, a, out_dtype, (cudaStream_t)stream);
 }
 
