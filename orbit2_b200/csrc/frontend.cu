@@ -401,6 +401,144 @@ __global__ void __launch_bounds__(NT) frontend_fwd_mma_kernel(const FeArgs a) {
   }
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(smem_row)));
+}
+
+// Backward of one head over persistent token tiles, bf16 arm.  Per tile two tensor-core contractions
+//   dM[kk][e] += sum_t C[t][kk] dO[t][e]   (warp w owns rows 16w..16w+15 of dM in registers for the whole kernel)
+//   dC[t][kk]  = sum_e dO[t][e] M[kk][e]
+// then the small SIMT tail (da, ds, d tab_s) of the fp32 kernel.
+__global__ void __launch_bounds__(NT) frontend_bwd_mma_kernel(const FeArgs a) {
+  constexpr int HD = 64;
+  constexpr int LDC_ = KKP + 4;                       // fp32 pitch of the dC tile
+  extern __shared__ float smem[];
+  const int V = a.V, PP = a.PP, P1 = PP + 1, KK = a.KK;
+  float* sP = smem;                                   // [TT][V][PP]
+  float* sa = sP + TT * V * PP;                       // [TT][V]
+  float* ssc = sa + TT * V;                           // [TT][V]
+  float* sdC = ssc + TT * V;                          // [TT][LDC_] fp32; its head doubles as the bf16 coefficient tile sC
+  __nv_bfloat16* sC = reinterpret_cast<__nv_bfloat16*>(sdC);
+  __nv_bfloat16* sdO = reinterpret_cast<__nv_bfloat16*>(sdC + TT * LDC_);   // [TT][LDB_]
+  __nv_bfloat16* sM = sdO + TT * LDB_;                // [KKP][LDB_]  tab_v[h] (rows >= KK zero)
+  const int h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  for (int i = threadIdx.x; i < KKP * LDB_ / 2; i += NT) reinterpret_cast<uint32_t*>(sM)[i] = 0u;
+  __syncthreads();
+  for (int i = threadIdx.x; i < KK * (HD / 4); i += NT) {
+    const int kk = i / (HD / 4), e4 = i % (HD / 4);
+    const float4 v4 = *reinterpret_cast<const float4*>(a.tab_v + ((size_t)h * KK + kk) * HD + e4 * 4);
+    uint2 pk;
+    pk.x = pack_bf16x2(v4.x, v4.y);
+    pk.y = pack_bf16x2(v4.z, v4.w);
+    *reinterpret_cast<uint2*>(sM + kk * LDB_ + e4 * 4) = pk;
+  }
+  float dM[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { dM[nt][0] = dM[nt][1] = dM[nt][2] = dM[nt][3] = 0.f; }
+  float dS = 0.f;
+  const int mt = warp & 3, nq = warp >> 2;            // dC: 16-token row tile, 64-column half of kk
+
+  const long long ntiles = (a.T + TT - 1) / TT;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long t0 = tile * TT;
+    __syncthreads();                                  // previous tile's tail is done with sP / sa / sdC
+    stage_pixels(a, t0, sP);
+    for (int i = threadIdx.x; i < TT * LDS_ / 2; i += NT) reinterpret_cast<uint32_t*>(sC)[i] = 0u;
+    for (int i = threadIdx.x; i < TT * (HD / 8); i += NT) {
+      const int tl = i / (HD / 8), c8 = i % (HD / 8);
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (t0 + tl < a.T)
+        v = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.dout) + (size_t)(t0 + tl) * a.heads * HD +
+                                            (size_t)h * HD + c8 * 8);
+      *reinterpret_cast<uint4*>(sdO + tl * LDB_ + c8 * 8) = v;
+    }
+    __syncthreads();
+    head_coefficients(a, h, t0, sP, sa, sC);
+    __syncthreads();
+    // ---- dM += C^T dO   (M = kk rows 16*warp.., N = e, K = t)
+#pragma unroll
+    for (int ks = 0; ks < TT / 16; ++ks) {
+      uint32_t af[4];   // A = C^T: matrices (kk 0-7 | 8-15) x (t 0-7 | 8-15), transposed out of the row-major [t][kk] tile
+      ldmatrix_x4_trans(af, sC + (ks * 16 + (lane >> 4) * 8 + (lane & 7)) * LDS_ + warp * 16 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t bf[4];
+        ldmatrix_x4_trans(bf, sdO + (ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDB_ + np * 16 + (lane >> 4) * 8);
+        mma_bf16_16816(dM[np * 2], af, bf[0], bf[1]);
+        mma_bf16_16816(dM[np * 2 + 1], af, bf[2], bf[3]);
+      }
+    }
+    // ---- dC = dO M^T   (M = t rows 16*mt.., N = kk in [64 nq, +64), K = e)
+    float dc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { dc[nt][0] = dc[nt][1] = dc[nt][2] = dc[nt][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      uint32_t af[4];   // A = dO row-major: matrices (t 0-7 | 8-15) x (e 0-7 | 8-15)
+      ldmatrix_x4(af, sdO + (mt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDB_ + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const __nv_bfloat16* bp = sM + (nq * 64 + nt * 8 + g) * LDB_ + ks * 16 + tig * 2;
+        mma_bf16_16816(dc[nt], af, *reinterpret_cast<const uint32_t*>(bp), *reinterpret_cast<const uint32_t*>(bp + 8));
+      }
+    }
+    __syncthreads();                                  // all reads of sC are done: overwrite it with the fp32 dC tile
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int col = nq * 64 + nt * 8 + tig * 2;
+      *reinterpret_cast<float2*>(sdC + (mt * 16 + g) * LDC_ + col) = make_float2(dc[nt][0], dc[nt][1]);
+      *reinterpret_cast<float2*>(sdC + (mt * 16 + g + 8) * LDC_ + col) = make_float2(dc[nt][2], dc[nt][3]);
+    }
+    __syncthreads();
+    // ---- SIMT tail: da[t][v] = <dC[t][v,:], P'[t][v,:]>,  ds = a (da - <a, da>),  d tab_s[v][k'] += sum_t ds P'
+    for (int i = threadIdx.x; i < TT * V; i += NT) {
+      const int tl = i % TT, v = i / TT;
+      float da = sdC[tl * LDC_ + v * P1 + PP];
+      for (int k = 0; k < PP; ++k) da = fmaf(sdC[tl * LDC_ + v * P1 + k], sP[(tl * V + v) * PP + k], da);
+      ssc[tl * V + v] = da;
+    }
+    __syncthreads();
+    {
+      const int tl = threadIdx.x >> 2, sub = threadIdx.x & 3;     // four threads per token
+      float dot = 0.f;
+      for (int v = sub; v < V; v += 4) dot = fmaf(sa[tl * V + v], ssc[tl * V + v], dot);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      for (int v = sub; v < V; v += 4) ssc[tl * V + v] = sa[tl * V + v] * (ssc[tl * V + v] - dot);
+    }
+    __syncthreads();
+    if (threadIdx.x < KK) {
+      const int v = threadIdx.x / P1, k = threadIdx.x % P1;
+      float sum = 0.f;
+      for (int tl = 0; tl < TT; ++tl) {
+        const float pk = (k < PP) ? sP[(tl * V + v) * PP + k] : 1.f;
+        sum = fmaf(ssc[tl * V + v], pk, sum);
+      }
+      dS += sum;
+    }
+  }
+  if (threadIdx.x < KK) {
+    const int v = threadIdx.x / P1, k = threadIdx.x % P1;
+    atomicAdd(&a.dtab_s[((size_t)v * a.heads + h) * P1 + k], dS);
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = nt * 8 + tig * 2;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int kk = warp * 16 + g + half * 8;
+      if (kk < KK) {
+        float* dst = a.dtab_v + ((size_t)h * KK + kk) * HD + col;
+        atomicAdd(dst, dM[nt][half * 2]);
+        atomicAdd(dst + 1, dM[nt][half * 2 + 1]);
+      }
+    }
+  }
+}
+
 int fill(FeArgs& a, const float* x, const float* tab_s, const float* tab_v, int B, int V, int Hx, int Wx, int p, int gh,
          int gw, int heads, int hd) {
   O2_REQUIRE(x && tab_s && tab_v, "frontend: null pointer");
@@ -480,5 +618,17 @@ extern "C" int o2_frontend_bwd(const float* x, const float* tab_s, const float* 
   if (rc) return rc;
   O2_REQUIRE(dout && dtab_s && dtab_v, "frontend_bwd: null pointer");
   a.dout = dout; a.dtab_s = dtab_s; a.dtab_v = dtab_v;
+  if (dtype == O2_BF16 && hd == 64 && ((uintptr_t)dout % 16) == 0 && !getenv("O2_FRONTEND_SIMT")) {
+    const size_t smem = sizeof(float) * ((size_t)TT * a.V * a.PP + 2 * (size_t)TT * a.V + (size_t)TT * (KKP + 4)) +
+                        2 * ((size_t)TT + KKP) * LDB_;
+    O2_CUDA(cudaFuncSetAttribute(frontend_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ntiles = (a.T + TT - 1) / TT;
+    long long gx = (long long)o2_num_sms() * 2 / a.heads;
+    if (gx < 1) gx = 1;
+    if (gx > ntiles) gx = ntiles;
+    frontend_bwd_mma_kernel<<<dim3((unsigned)gx, a.heads), NT, smem, (cudaStream_t)stream>>>(a);
+    O2_LAUNCH_CHECK();
+    return O2_OK;
+  }
   O2_FE_DISPATCH(launch_bwd, a, dtype, (cudaStream_t)stream);
 }

@@ -160,8 +160,9 @@ def test_frontend(dtype, B, V, gh, gw, heads, hd, extra):
     assert rel(o, ref.detach()) < tol
     ref.backward(dout.double())
     dts, dtv = ops.frontend_bwd(x, tab_s, tab_v, dout, p, gh, gw, hd)
-    assert rel(dts, ts.grad) < 2e-5
-    assert rel(dtv, tv.grad) < 2e-5
+    gt = 2e-5 if dtype == torch.float32 else 1e-2      # bf16 arm: tensor-core contractions on bf16-rounded operands
+    assert rel(dts, ts.grad) < gt
+    assert rel(dtv, tv.grad) < gt
 
 
 @pytest.mark.parametrize("dtype", DT)
