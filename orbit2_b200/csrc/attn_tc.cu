@@ -20,7 +20,6 @@ namespace {
 constexpr int kHD = 64;
 constexpr int BQ = 128;          // rows per query tile
 constexpr int BKV = 128;         // keys per tile
-constexpr int kStagesF = 3;
 constexpr int kThreadsF = 320;
 constexpr int kThreadsB = 352;   // + one more issuing warp (one per tile)
 constexpr uint32_t kTileBytes = BQ * kHD * 2;   // 16 KiB (Q, K and V tiles alike)
@@ -54,20 +53,28 @@ struct FwdArgs {
 
 constexpr int BS = 64;            // key sub-tile (forward, dq) / query sub-tile (dkv) processed per MMA group
 constexpr uint32_t kHalfBytes = BS * kHD * 2;   // 8 KiB: byte offset of rows 64.. inside a 128-row tile
-constexpr uint32_t kFwdSmemBytes = (2 + 2 * kStagesF) * kTileBytes + 1024 + 256;
+template <int NH> struct FwdCfg {
+  static constexpr int kStages = (NH == 1) ? 3 : 2;
+  static constexpr uint32_t kSmemBytes = (2 + 2 * kStages) * NH * kTileBytes + 1024 + 256;
+};
 
 // descriptor arithmetic: the start-address field counts 16-byte units and smem addresses stay below 2^18, so a
 // descriptor can be advanced by adding (bytes >> 4) to its low word.
 __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
+// NH = head dim / 64: Q, K and V tiles are kept as NH separate 64-column (128-byte, one swizzle atom) half-tiles; S sums
+// over them (NH x 4 MMAs), O has NH 64-column accumulators per query tile.  NH = 2 fills TMEM exactly (4 x 64 + 4 x 64).
+template <int NH>
 __global__ void __launch_bounds__(kThreadsB, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kStagesF = FwdCfg<NH>::kStages;
+  constexpr uint32_t kQKV = NH * kTileBytes;        // bytes of one Q / K / V tile (NH half-tiles)
   uint8_t* sQ = smem;                               // 2 tiles
-  uint8_t* sK = sQ + 2 * kTileBytes;                // kStagesF tiles
-  uint8_t* sV = sK + kStagesF * kTileBytes;         // kStagesF tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStagesF * kTileBytes);
+  uint8_t* sK = sQ + 2 * kQKV;                      // kStagesF tiles
+  uint8_t* sV = sK + kStagesF * kQKV;               // kStagesF tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStagesF * kQKV);
   uint64_t* q_full = bars;                          // 1
   uint64_t* k_full = q_full + 1;                    // kStagesF
   uint64_t* k_empty = k_full + kStagesF;
@@ -116,18 +123,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      ptx::mbar_expect_tx(q_full, 2 * kTileBytes);
-      ptx::tma_load_4d(sQ, &tmap_qkv, q_full, 0, h, q0, b);
-      ptx::tma_load_4d(sQ + kTileBytes, &tmap_qkv, q_full, 0, h, q0 + BQ, b);
+      ptx::mbar_expect_tx(q_full, 2 * kQKV);
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh) {
+        ptx::tma_load_4d(sQ + hh * kTileBytes, &tmap_qkv, q_full, hh * 64, h, q0, b);
+        ptx::tma_load_4d(sQ + kQKV + hh * kTileBytes, &tmap_qkv, q_full, hh * 64, h, q0 + BQ, b);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
         ptx::mbar_wait(&k_empty[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&k_full[stage], kTileBytes);
-        ptx::tma_load_4d(sK + stage * kTileBytes, &tmap_qkv, &k_full[stage], 0, a.heads + h, j * BKV, b);
+        ptx::mbar_expect_tx(&k_full[stage], kQKV);
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh)
+          ptx::tma_load_4d(sK + stage * kQKV + hh * kTileBytes, &tmap_qkv, &k_full[stage], hh * 64, a.heads + h, j * BKV, b);
         ptx::mbar_wait(&v_empty[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&v_full[stage], kTileBytes);
-        ptx::tma_load_4d(sV + stage * kTileBytes, &tmap_qkv, &v_full[stage], 0, 2 * a.heads + h, j * BKV, b);
+        ptx::mbar_expect_tx(&v_full[stage], kQKV);
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh)
+          ptx::tma_load_4d(sV + stage * kQKV + hh * kTileBytes, &tmap_qkv, &v_full[stage], hh * 64, 2 * a.heads + h, j * BKV, b);
         if (++stage == kStagesF) { stage = 0; phase ^= 1; }
       }
     }
@@ -146,12 +160,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
       // S_t(u) = Q_t K_u^T into buffer (t, u & 1); K sub-tile u = rows [64 (u&1), +64) of K tile u >> 1
       auto issue_s = [&](int t, int u, int kstage) {
         if (ptx::elect_one()) {
-          const uint64_t qd = desc_add(dq0, t * kTileBytes);
-          const uint64_t kd = desc_add(dk0, kstage * kTileBytes + (u & 1) * kHalfBytes);
+          const uint64_t qd = desc_add(dq0, t * kQKV);
+          const uint64_t kd = desc_add(dk0, kstage * kQKV + (u & 1) * kHalfBytes);
           const uint32_t d = tmem_base + (2 * t + (u & 1)) * BS;
           ptx::umma_ss_first(d, qd, kd, idesc_s);
 #pragma unroll
-          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(d, desc_add(qd, k * 32), desc_add(kd, k * 32), idesc_s);
+          for (int k = 1; k < NH * 4; ++k)          // 16-wide K slices: 4 per 64-column half-tile
+            ptx::umma_ss_acc(d, desc_add(qd, (k >> 2) * kTileBytes + (k & 3) * 32), desc_add(kd, (k >> 2) * kTileBytes + (k & 3) * 32),
+                             idesc_s);
           ptx::umma_commit(&s_full[2 * t + (u & 1)]);
         }
         __syncwarp();
@@ -174,7 +190,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
           ptx::mbar_wait(&v_full[vstage], vphase);
           ptx::tc_fence_after();
         }
-        const uint64_t vd = desc_add(dv0, vstage * kTileBytes + half * kHalfBytes);
+        const uint64_t vd = desc_add(dv0, vstage * kQKV + half * kHalfBytes);
         {
           O2_TL(u, t, 0);
           ptx::mbar_wait(&p_full[2 * t + half], (u >> 1) & 1);
@@ -182,10 +198,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
           O2_TL(u, t, 1);
           if (ptx::elect_one()) {
             const uint32_t pa = tmem_base + (2 * t + half) * BS;
-            const uint32_t od = tmem_base + 256 + t * 64;
-            ptx::umma_ts(od, pa, vd, idesc_o, u > 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 1; k < BS / 16; ++k) ptx::umma_ts_acc(od, pa + k * 8, desc_add(vd, k * 2048), idesc_o);
+            for (int hh = 0; hh < NH; ++hh) {          // O_t[:, 64 hh .. +64) += P V[:, 64 hh .. +64)
+              const uint32_t od = tmem_base + 256 + (t * NH + hh) * 64;
+              const uint64_t vh = desc_add(vd, hh * kTileBytes);
+              ptx::umma_ts(od, pa, vh, idesc_o, u > 0 ? 1u : 0u);
+#pragma unroll
+              for (int k = 1; k < BS / 16; ++k) ptx::umma_ts_acc(od, pa + k * 8, desc_add(vh, k * 2048), idesc_o);
+            }
             ptx::umma_commit(&o_done[t]);
             if (u + 1 == n_sub) ptx::umma_commit(&o_final[t]);
           }
@@ -219,7 +239,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
     const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
     const int r = quarter * 32 + lane;      // row inside the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t o_addr = lane_addr + 256 + t * 64;
+    const uint32_t o_addr = lane_addr + 256 + t * NH * 64;
     const float sc = a.scale_log2;
     float m_ref = -INFINITY;
     uint64_t lA = 0ull, lB = 0ull;          // packed partial row sums
@@ -261,7 +281,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
           ptx::mbar_wait(&o_done[t], (u - 1) & 1);
           ptx::tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < kHD / 32; ++c) {
+          for (int c = 0; c < NH * 2; ++c) {
             uint32_t w[32];
             ptx::tmem_ld_32x32(o_addr + c * 32, w);
             ptx::tmem_ld_wait();
@@ -307,23 +327,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
     ptx::unpack2(lB, l2, l3);
     const float l = (l0 + l1) + (l2 + l3);
     const float inv = 1.f / l;
-    uint32_t o[2][32];
-    ptx::tmem_ld_32x32(o_addr, o[0]);
-    ptx::tmem_ld_32x32(o_addr + 32, o[1]);
-    ptx::tmem_ld_wait();
-    if (row < a.N) {
-      __nv_bfloat16* op = a.out + (((size_t)b * a.N + row) * a.heads + h) * kHD;
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
+    __nv_bfloat16* op = a.out + (((size_t)b * a.N + row) * a.heads + h) * (NH * 64);
+#pragma unroll 1
+    for (int c = 0; c < NH * 2; ++c) {
+      uint32_t o[32];
+      ptx::tmem_ld_32x32(o_addr + c * 32, o);
+      ptx::tmem_ld_wait();
+      if (row < a.N) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[c][i]) * inv, __uint_as_float(o[c][i + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(o[c][i + 2]) * inv, __uint_as_float(o[c][i + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(o[c][i + 4]) * inv, __uint_as_float(o[c][i + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(o[c][i + 6]) * inv, __uint_as_float(o[c][i + 7]) * inv);
+          w.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
           *reinterpret_cast<uint4*>(op + c * 32 + i) = w;
         }
+      }
+    }
+    if (row < a.N) {
       a.lse[((size_t)b * a.heads + h) * a.N + row] = (m_ref + log2f(l)) * kLn2;
     }
   }
@@ -905,11 +927,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 int make_qkv_tmap(CUtensorMap* tm, const void* qkv, int B, int N, int heads, int hd, int box_rows) {
   uint64_t dims[4] = {(uint64_t)hd, (uint64_t)(3 * heads), (uint64_t)N, (uint64_t)B};
   uint64_t str[3] = {(uint64_t)hd * 2, (uint64_t)3 * heads * hd * 2, (uint64_t)N * 3 * heads * hd * 2};
-  uint32_t box[4] = {(uint32_t)hd, 1, (uint32_t)box_rows, 1};
+  uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};       // 64-column half-tiles (one 128-byte swizzle atom per row)
   return o2_make_tmap(tm, qkv, 2, 4, dims, str, box, 1);
 }
 
-}  // namespace
+
 
 #ifdef O2_TIMELINE
 extern "C" int o2_debug_timeline(long long* host, int n) {
@@ -917,8 +939,23 @@ extern "C" int o2_debug_timeline(long long* host, int n) {
 }
 #endif
 
+template <int NH>
+int launch_fwd(const CUtensorMap& tm, const FwdArgs& a, dim3 grid, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    O2_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)FwdCfg<NH>::kSmemBytes));
+    attr_done = true;
+  }
+  attn_fwd_tc_kernel<NH><<<grid, kThreadsB, FwdCfg<NH>::kSmemBytes, st>>>(tm, a);
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
+
+}  // namespace
+
 int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, cudaStream_t st) {
-  O2_REQUIRE(hd == kHD, "attn_fwd_tc: head dim %d not supported (64 only)", hd);
+  O2_REQUIRE(hd == 64 || hd == 128, "attn_fwd_tc: head dim %d not supported (64 or 128)", hd);
   O2_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0, "attn_fwd_tc: pointers must be 16-byte aligned");
   O2_REQUIRE((long long)B * heads <= 65535, "attn_fwd_tc: B*heads too large");
   CUtensorMap tm;
@@ -928,15 +965,8 @@ int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int hea
   a.out = (__nv_bfloat16*)out; a.lse = lse; a.B = B; a.N = N; a.heads = heads;
   a.n_sub = (N + BS - 1) / BS;
   a.scale_log2 = scale * kLog2e;
-  static bool attr_done = false;
-  if (!attr_done) {
-    O2_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes));
-    attr_done = true;
-  }
   dim3 grid((N + 2 * BQ - 1) / (2 * BQ), B * heads);
-  attn_fwd_tc_kernel<<<grid, kThreadsB, kFwdSmemBytes, st>>>(tm, a);
-  O2_LAUNCH_CHECK();
-  return O2_OK;
+  return hd == 64 ? launch_fwd<1>(tm, a, grid, st) : launch_fwd<2>(tm, a, grid, st);
 }
 
 int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B,
