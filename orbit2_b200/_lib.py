@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libo2b200.so")
+LIB_PATH = os.environ.get("O2B200_LIB") or os.path.join(HERE, "libo2b200.so")   # override: A/B kernel experiments
 
 O2_F32, O2_BF16 = 0, 1
 GEMM_SIMT_F32, GEMM_TC_BF16 = 0, 1

@@ -264,12 +264,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
           if (32 + i >= tail) v1[i] = 0xff800000u;
         }
       }
-      float mxa = __uint_as_float(v0[0]), mxb = __uint_as_float(v1[0]);
+      // 3-input max (FMNMX3): half the issue slots of a 2-input chain
+      float mxa = ptx::max3(__uint_as_float(v0[0]), __uint_as_float(v0[1]), __uint_as_float(v0[2]));
+      float mxb = ptx::max3(__uint_as_float(v1[0]), __uint_as_float(v1[1]), __uint_as_float(v1[2]));
 #pragma unroll
-      for (int i = 1; i < 32; ++i) {
-        mxa = fmaxf(mxa, __uint_as_float(v0[i]));
-        mxb = fmaxf(mxb, __uint_as_float(v1[i]));
+      for (int i = 3; i < 31; i += 2) {
+        mxa = ptx::max3(mxa, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
+        mxb = ptx::max3(mxb, __uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
       }
+      mxa = fmaxf(mxa, __uint_as_float(v0[31]));
+      mxb = fmaxf(mxb, __uint_as_float(v1[31]));
       const float m_new = fmaxf(m_ref, fmaxf(mxa, mxb) * sc);
       const bool need = __any_sync(0xffffffffu, m_new - m_ref > kRescaleThreshold);
       if (need) {
@@ -366,7 +370,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
 //                P^T over S^T, dS^T over dP^T (bf16) -> dV += P^T dO, dK += dS^T Q  (TS-MMA)
 // The softmax scale is applied once to dQ / dK in the epilogue.
 // =====================================================================================================
-constexpr int kStagesB = 3;
+// NH = head dim / 64 (as in the forward kernel).  Head dim 64: two 128-row tiles per CTA in ping-pong, 3-stage rings.
+// Head dim 128 (interm_1b): dK / dV (dQ) need 2 x 128 TMEM columns per tile and every operand tile is 32 KiB, so a CTA
+// owns ONE tile and the rings have 2 stages.
+template <int NH> struct BwdCfg {
+  static constexpr int kTiles = (NH == 1) ? 2 : 1;
+  static constexpr int kStages = (NH == 1) ? 3 : 2;
+  static constexpr uint32_t kT = NH * kTileBytes;                     // bytes of one 128-row operand tile
+  static constexpr uint32_t kDqSmem = (2 * kTiles + 2 * kStages) * kT + 1024 + 4 * 1024 + 256;
+  static constexpr uint32_t kDkvSmem = (2 * kTiles + 2 * kStages) * kT + 2 * kTileBytes + 1024 + 256;
+  static constexpr int kDqThreads = (kTiles == 2) ? kThreadsB : 192;  // producer + issuer + 4 softmax warps per tile (+ issuer)
+  static constexpr int kTmemTile = 256;                               // TMEM column stride between the two tiles (NH = 1)
+};
 
 struct BwdArgs {
   const float* lse;       // [B, heads, N] natural log
@@ -376,16 +391,18 @@ struct BwdArgs {
   float scale, scale_log2;
 };
 
+template <int NH>
 __global__ void attn_delta_bf16_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                                        float* __restrict__ delta, int B, int N, int heads) {
-  // one 8-thread group per (b, n, h) row of 64 bf16 (8 x 16 B)
-  const long long gid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
-  const int sub = threadIdx.x & 7;
+  // one (8 NH)-thread group per (b, n, h) row of 64 NH bf16 (16 B per thread)
+  constexpr int G = 8 * NH;
+  const long long gid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
+  const int sub = threadIdx.x & (G - 1);
   const long long total = (long long)B * N * heads;
   float s = 0.f;
   if (gid < total) {
-    const uint4 o = *reinterpret_cast<const uint4*>(out + gid * kHD + sub * 8);
-    const uint4 d = *reinterpret_cast<const uint4*>(dout + gid * kHD + sub * 8);
+    const uint4 o = *reinterpret_cast<const uint4*>(out + gid * (NH * 64) + sub * 8);
+    const uint4 d = *reinterpret_cast<const uint4*>(dout + gid * (NH * 64) + sub * 8);
     const float2 o0 = unpack_bf16x2(o.x), o1 = unpack_bf16x2(o.y), o2 = unpack_bf16x2(o.z), o3 = unpack_bf16x2(o.w);
     const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
     s = o0.x * d0.x + o0.y * d0.y + o1.x * d1.x + o1.y * d1.y + o2.x * d2.x + o2.y * d2.y + o3.x * d3.x + o3.y * d3.y;
@@ -393,6 +410,7 @@ __global__ void attn_delta_bf16_kernel(const __nv_bfloat16* __restrict__ out, co
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (NH == 2) s += __shfl_xor_sync(0xffffffffu, s, 8);
   if (gid < total && sub == 0) {
     const int h = (int)(gid % heads);
     const long long bn = gid / heads;
@@ -402,23 +420,25 @@ __global__ void attn_delta_bf16_kernel(const __nv_bfloat16* __restrict__ out, co
   }
 }
 
-constexpr uint32_t kBwdSmemBytes = (4 + 2 * kStagesB) * kTileBytes + 1024 + 4 * 1024 + 256;
-constexpr uint32_t kDkvSmemBytes = (4 + 2 * kStagesB + 2) * kTileBytes + 1024 + 256;
 
 // ---------------------------------------------------------------------------------------------- dQ
-// TMEM columns of query tile t (base t*256): S buffers [0,64) / [64,128), dP [128,192), dQ [192,256).
+// TMEM columns of query tile t (base t*256): S buffers [0,64) / [64,128), dP [128,192), dQ [192, 192 + 64 NH).
 // S is double-buffered (S(u+2) is issued as soon as dQ(u) has consumed the dS written over S(u)); dP has one buffer
 // that the softmax warps release as soon as they have it in registers, so dP(u+1) is computed while they work on u.
-__global__ void __launch_bounds__(kThreadsB, 1)
+template <int NH>
+__global__ void __launch_bounds__(BwdCfg<NH>::kDqThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                    const BwdArgs a) {
+  constexpr int kStagesB = BwdCfg<NH>::kStages;
+  constexpr int kTiles = BwdCfg<NH>::kTiles;
+  constexpr uint32_t kT = BwdCfg<NH>::kT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                               // 2 tiles
-  uint8_t* sdO = sQ + 2 * kTileBytes;               // 2 tiles
-  uint8_t* sK = sdO + 2 * kTileBytes;               // kStagesB tiles
-  uint8_t* sV = sK + kStagesB * kTileBytes;         // kStagesB tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStagesB * kTileBytes + 4 * 1024);
+  uint8_t* sQ = smem;                               // kTiles tiles
+  uint8_t* sdO = sQ + kTiles * kT;                  // kTiles tiles
+  uint8_t* sK = sdO + kTiles * kT;                  // kStagesB tiles
+  uint8_t* sV = sK + kStagesB * kT;                 // kStagesB tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStagesB * kT + 4 * 1024);
   uint64_t* q_full = bars;                          // 1
   uint64_t* kv_full = q_full + 1;                   // kStagesB
   uint64_t* kv_empty = kv_full + kStagesB;
@@ -433,7 +453,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   const int lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int b = bh / a.heads, h = bh % a.heads;
-  const int q0 = blockIdx.x * 2 * BQ;
+  const int q0 = blockIdx.x * kTiles * BQ;
   const int n_sub = a.n_sub;
 
   if (warp == 0 && lane == 0) {
@@ -442,7 +462,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < kStagesB; ++s) {
       ptx::mbar_init(&kv_full[s], 1);
-      ptx::mbar_init(&kv_empty[s], 2);            // one commit per issuing warp
+      ptx::mbar_init(&kv_empty[s], kTiles);       // one commit per issuing warp
     }
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&s_full[i], 1);
@@ -463,23 +483,29 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_expect_tx(q_full, 4 * kTileBytes);
-      ptx::tma_load_4d(sQ, &tmap_qkv, q_full, 0, h, q0, b);
-      ptx::tma_load_4d(sQ + kTileBytes, &tmap_qkv, q_full, 0, h, q0 + BQ, b);
-      ptx::tma_load_4d(sdO, &tmap_do, q_full, 0, h, q0, b);
-      ptx::tma_load_4d(sdO + kTileBytes, &tmap_do, q_full, 0, h, q0 + BQ, b);
+      ptx::mbar_expect_tx(q_full, 2 * kTiles * kT);
+#pragma unroll
+      for (int t = 0; t < kTiles; ++t)
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          ptx::tma_load_4d(sQ + t * kT + hh * kTileBytes, &tmap_qkv, q_full, hh * 64, h, q0 + t * BQ, b);
+          ptx::tma_load_4d(sdO + t * kT + hh * kTileBytes, &tmap_do, q_full, hh * 64, h, q0 + t * BQ, b);
+        }
       int stage = 0;
       uint32_t phase = 0;
       const int n_kv = (n_sub + 1) / 2;
       for (int j = 0; j < n_kv; ++j) {
         ptx::mbar_wait(&kv_empty[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&kv_full[stage], 2 * kTileBytes);
-        ptx::tma_load_4d(sK + stage * kTileBytes, &tmap_qkv, &kv_full[stage], 0, a.heads + h, j * BKV, b);
-        ptx::tma_load_4d(sV + stage * kTileBytes, &tmap_qkv, &kv_full[stage], 0, 2 * a.heads + h, j * BKV, b);
+        ptx::mbar_expect_tx(&kv_full[stage], 2 * kT);
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          ptx::tma_load_4d(sK + stage * kT + hh * kTileBytes, &tmap_qkv, &kv_full[stage], hh * 64, a.heads + h, j * BKV, b);
+          ptx::tma_load_4d(sV + stage * kT + hh * kTileBytes, &tmap_qkv, &kv_full[stage], hh * 64, 2 * a.heads + h, j * BKV, b);
+        }
         if (++stage == kStagesB) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 || warp == 10) {
+  } else if (warp == 1 || (kTiles == 2 && warp == 10)) {
     {   // one issuing warp per query tile (warp-uniform loop, see the forward kernel): the two tiles' dependency
         // chains never block each other; the tensor pipe interleaves their MMAs
       const int t = (warp == 1) ? 0 : 1;
@@ -492,24 +518,28 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       const uint64_t dkm0 = ptx::umma_smem_desc(ptx::smem_u32(sK), 8192, 1024);   // K as MN-major B
       auto issue_s = [&](int t, int u, int stage) {
         if (ptx::elect_one()) {
-          const uint64_t qa = desc_add(dq0, t * kTileBytes);
-          const uint64_t ka = desc_add(dk0, stage * kTileBytes + (u & 1) * kHalfBytes);
+          const uint64_t qa = desc_add(dq0, t * kT);
+          const uint64_t ka = desc_add(dk0, stage * kT + (u & 1) * kHalfBytes);
           const uint32_t d = tmem_base + t * 256 + (u & 1) * BS;
           ptx::umma_ss_first(d, qa, ka, idesc_s);
 #pragma unroll
-          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(d, desc_add(qa, k * 32), desc_add(ka, k * 32), idesc_s);
+          for (int k = 1; k < NH * 4; ++k)
+            ptx::umma_ss_acc(d, desc_add(qa, (k >> 2) * kTileBytes + (k & 3) * 32),
+                             desc_add(ka, (k >> 2) * kTileBytes + (k & 3) * 32), idesc_s);
           ptx::umma_commit(&s_full[2 * t + (u & 1)]);
         }
         __syncwarp();
       };
       auto issue_dp = [&](int t, int u, int stage) {
         if (ptx::elect_one()) {
-          const uint64_t da = desc_add(ddo0, t * kTileBytes);
-          const uint64_t va = desc_add(dv0, stage * kTileBytes + (u & 1) * kHalfBytes);
+          const uint64_t da = desc_add(ddo0, t * kT);
+          const uint64_t va = desc_add(dv0, stage * kT + (u & 1) * kHalfBytes);
           const uint32_t d = tmem_base + t * 256 + 128;
           ptx::umma_ss_first(d, da, va, idesc_s);
 #pragma unroll
-          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(d, desc_add(da, k * 32), desc_add(va, k * 32), idesc_s);
+          for (int k = 1; k < NH * 4; ++k)
+            ptx::umma_ss_acc(d, desc_add(da, (k >> 2) * kTileBytes + (k & 3) * 32),
+                             desc_add(va, (k >> 2) * kTileBytes + (k & 3) * 32), idesc_s);
           ptx::umma_commit(&dp_full[t]);
         }
         __syncwarp();
@@ -531,15 +561,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           ptx::tc_fence_after();
           issue_dp(t, u + 1, half ? nstage : stage);
         }
-        const uint64_t ka = desc_add(dkm0, stage * kTileBytes + half * kHalfBytes);
+        const uint64_t ka = desc_add(dkm0, stage * kT + half * kHalfBytes);
         {
           ptx::mbar_wait(&ds_full[2 * t + half], (u >> 1) & 1);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
-            const uint32_t dd = tmem_base + t * 256 + 192, aa = tmem_base + t * 256 + half * BS;
-            ptx::umma_ts(dd, aa, ka, idesc_q, u > 0 ? 1u : 0u);
+            const uint32_t aa = tmem_base + t * 256 + half * BS;
 #pragma unroll
-            for (int k = 1; k < BS / 16; ++k) ptx::umma_ts_acc(dd, aa + k * 8, desc_add(ka, k * 2048), idesc_q);
+            for (int hh = 0; hh < NH; ++hh) {            // dQ[:, 64 hh .. +64) += dS K[:, 64 hh .. +64)
+              const uint32_t dd = tmem_base + t * 256 + 192 + hh * 64;
+              const uint64_t kh = desc_add(ka, hh * kTileBytes);
+              ptx::umma_ts(dd, aa, kh, idesc_q, u > 0 ? 1u : 0u);
+#pragma unroll
+              for (int k = 1; k < BS / 16; ++k) ptx::umma_ts_acc(dd, aa + k * 8, desc_add(kh, k * 2048), idesc_q);
+            }
             if (u + 1 == n_sub) ptx::umma_commit(&dq_final[t]);
           }
           __syncwarp();
@@ -564,7 +599,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 256;
-    static_assert(kThreadsB == 352, "warps 2-9 are the softmax warps, warp 10 the second issuer");
+    static_assert(kThreadsB == 352, "warps 2-9 are the softmax warps, warp 10 the second issuer (NH = 1)");
     const uint32_t dp_addr = lane_addr + 128;
     const uint32_t dq_addr = lane_addr + 192;
     const int row = q0 + t * BQ + r;
@@ -608,24 +643,24 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     }
     ptx::mbar_wait(&dq_final[t], 0);
     ptx::tc_fence_after();
-    uint32_t o[2][32];
-    ptx::tmem_ld_32x32(dq_addr, o[0]);
-    ptx::tmem_ld_32x32(dq_addr + 32, o[1]);
-    ptx::tmem_ld_wait();
-    if (row < a.N) {
-      __nv_bfloat16* op = a.dqkv + ((((size_t)b * a.N + row) * 3 + 0) * a.heads + h) * kHD;
-      const float f = a.scale;
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
+    __nv_bfloat16* op = a.dqkv + ((((size_t)b * a.N + row) * 3 + 0) * a.heads + h) * (NH * 64);
+    const float f = a.scale;
+#pragma unroll 1
+    for (int c = 0; c < NH * 2; ++c) {
+      uint32_t o[32];
+      ptx::tmem_ld_32x32(dq_addr + c * 32, o);
+      ptx::tmem_ld_wait();
+      if (row < a.N) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[c][i]) * f, __uint_as_float(o[c][i + 1]) * f);
-          w.y = pack_bf16x2(__uint_as_float(o[c][i + 2]) * f, __uint_as_float(o[c][i + 3]) * f);
-          w.z = pack_bf16x2(__uint_as_float(o[c][i + 4]) * f, __uint_as_float(o[c][i + 5]) * f);
-          w.w = pack_bf16x2(__uint_as_float(o[c][i + 6]) * f, __uint_as_float(o[c][i + 7]) * f);
+          w.x = pack_bf16x2(__uint_as_float(o[i]) * f, __uint_as_float(o[i + 1]) * f);
+          w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * f, __uint_as_float(o[i + 3]) * f);
+          w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * f, __uint_as_float(o[i + 5]) * f);
+          w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * f, __uint_as_float(o[i + 7]) * f);
           *reinterpret_cast<uint4*>(op + c * 32 + i) = w;
         }
+      }
     }
   }
 
@@ -644,21 +679,26 @@ __device__ __forceinline__ uint4 neg_split3(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------- dK, dV
+template <int NH>
 __global__ void __launch_bounds__(kThreadsF, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                     const BwdArgs a) {
+  constexpr int kStagesB = BwdCfg<NH>::kStages;
+  constexpr int kTiles = BwdCfg<NH>::kTiles;
+  constexpr uint32_t kT = BwdCfg<NH>::kT;
+  constexpr uint32_t kColDK = 128, kColDV = 128 + 64 * NH;   // TMEM columns inside a key tile's block
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;                               // 2 tiles
-  uint8_t* sV = sK + 2 * kTileBytes;                // 2 tiles
-  uint8_t* sQ = sV + 2 * kTileBytes;                // kStagesB tiles
-  uint8_t* sdO = sQ + kStagesB * kTileBytes;        // kStagesB tiles
+  uint8_t* sK = smem;                               // kTiles tiles
+  uint8_t* sV = sK + kTiles * kT;                   // kTiles tiles
+  uint8_t* sQ = sV + kTiles * kT;                   // kStagesB tiles
+  uint8_t* sdO = sQ + kStagesB * kT;                // kStagesB tiles
   // Per-query statistics enter through the tensor core as rank-1 updates (one extra K=16 MMA each):
   //   S^T  <- K Q^T  - 1 (lse/scale)^T      dP^T <- V dO^T - 1 delta^T
   // sOnes: [128 x 64] bf16 K-major tile; k-slice 0 has ones in K positions 0..2, k-slice 1 has ones in positions 8..10.
   // sStat: [128 q x 64] tile; k-slice `stage` of row q holds -(3-term bf16 split of lse/scale) in positions 0..2 and
   //        -(split of delta) in positions 8..10, so the same slice serves both updates.
-  uint8_t* sOnes = sdO + kStagesB * kTileBytes;
+  uint8_t* sOnes = sdO + kStagesB * kT;
   uint8_t* sStat = sOnes + kTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + kTileBytes);
   uint64_t* kv_full = bars;                         // 1
@@ -673,7 +713,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   const int lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int b = bh / a.heads, h = bh % a.heads;
-  const int k0 = blockIdx.x * 2 * BKV;
+  const int k0 = blockIdx.x * kTiles * BKV;
   const int n_sub = a.n_sub;                        // 64-query sub-tiles
   const int n_q = (n_sub + 1) / 2;                  // 128-query TMA tiles
 
@@ -705,15 +745,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns of key tile t (base t*256): S^T [0,64) dP^T [64,128) dK [128,192) dV [192,256)
+  // TMEM columns of key tile t (base t*256): S^T [0,64) dP^T [64,128) dK [128, +64 NH) dV [128 + 64 NH, +64 NH)
 
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_expect_tx(kv_full, 4 * kTileBytes);
-      ptx::tma_load_4d(sK, &tmap_qkv, kv_full, 0, a.heads + h, k0, b);
-      ptx::tma_load_4d(sK + kTileBytes, &tmap_qkv, kv_full, 0, a.heads + h, k0 + BKV, b);
-      ptx::tma_load_4d(sV, &tmap_qkv, kv_full, 0, 2 * a.heads + h, k0, b);
-      ptx::tma_load_4d(sV + kTileBytes, &tmap_qkv, kv_full, 0, 2 * a.heads + h, k0 + BKV, b);
+      ptx::mbar_expect_tx(kv_full, 2 * kTiles * kT);
+#pragma unroll
+      for (int t = 0; t < kTiles; ++t)
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          ptx::tma_load_4d(sK + t * kT + hh * kTileBytes, &tmap_qkv, kv_full, hh * 64, a.heads + h, k0 + t * BKV, b);
+          ptx::tma_load_4d(sV + t * kT + hh * kTileBytes, &tmap_qkv, kv_full, hh * 64, 2 * a.heads + h, k0 + t * BKV, b);
+        }
     }
     int stage = 0;
     uint32_t phase = 0;
@@ -742,9 +785,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       O2_TL(2 * i, 0, 10);                      // producer: wants the stage of query tile i
       if (lane == 0) {
         ptx::mbar_wait(&qdo_empty[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&qdo_full[stage], 2 * kTileBytes);
-        ptx::tma_load_4d(sQ + stage * kTileBytes, &tmap_qkv, &qdo_full[stage], 0, h, i * BQ, b);
-        ptx::tma_load_4d(sdO + stage * kTileBytes, &tmap_do, &qdo_full[stage], 0, h, i * BQ, b);
+        ptx::mbar_expect_tx(&qdo_full[stage], 2 * kT);
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          ptx::tma_load_4d(sQ + stage * kT + hh * kTileBytes, &tmap_qkv, &qdo_full[stage], hh * 64, h, i * BQ, b);
+          ptx::tma_load_4d(sdO + stage * kT + hh * kTileBytes, &tmap_do, &qdo_full[stage], hh * 64, h, i * BQ, b);
+        }
       }
       __syncwarp();
       // the statistics of this tile were fetched one tile ahead (all eight loads in flight together: issued one by one
@@ -778,18 +824,22 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       const uint64_t dstat0 = ptx::umma_smem_desc(ptx::smem_u32(sStat), 16, 1024);
       auto issue_sd = [&](int t, int stage, int half) {
         if (ptx::elect_one()) {
-          const uint64_t ka = desc_add(dk0, t * kTileBytes), va = desc_add(dv0, t * kTileBytes);
-          const uint64_t qa = desc_add(dq0, stage * kTileBytes + half * kHalfBytes);
-          const uint64_t da = desc_add(ddo0, stage * kTileBytes + half * kHalfBytes);
+          const uint64_t ka = desc_add(dk0, t * kT), va = desc_add(dv0, t * kT);
+          const uint64_t qa = desc_add(dq0, stage * kT + half * kHalfBytes);
+          const uint64_t da = desc_add(ddo0, stage * kT + half * kHalfBytes);
           const uint32_t ds_ = tmem_base + t * 256;
           ptx::umma_ss_first(ds_, ka, qa, idesc_s);
 #pragma unroll
-          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(ds_, desc_add(ka, k * 32), desc_add(qa, k * 32), idesc_s);
+          for (int k = 1; k < NH * 4; ++k)
+            ptx::umma_ss_acc(ds_, desc_add(ka, (k >> 2) * kTileBytes + (k & 3) * 32),
+                             desc_add(qa, (k >> 2) * kTileBytes + (k & 3) * 32), idesc_s);
           const uint64_t st = desc_add(dstat0, half * kHalfBytes + stage * 32);
           ptx::umma_ss_acc(ds_, dones, st, idesc_s);                          // - lse / scale
           ptx::umma_ss_first(ds_ + 64, va, da, idesc_s);
 #pragma unroll
-          for (int k = 1; k < kHD / 16; ++k) ptx::umma_ss_acc(ds_ + 64, desc_add(va, k * 32), desc_add(da, k * 32), idesc_s);
+          for (int k = 1; k < NH * 4; ++k)
+            ptx::umma_ss_acc(ds_ + 64, desc_add(va, (k >> 2) * kTileBytes + (k & 3) * 32),
+                             desc_add(da, (k >> 2) * kTileBytes + (k & 3) * 32), idesc_s);
           ptx::umma_ss_acc(ds_ + 64, desc_add(dones, 32), st, idesc_s);       // - delta
           ptx::umma_commit(&sd_full[t]);
         }
@@ -798,8 +848,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       ptx::mbar_wait(kv_full, 0);
       ptx::mbar_wait(&qdo_full[0], 0);
       ptx::tc_fence_after();
-      issue_sd(0, 0, 0);
-      issue_sd(1, 0, 0);
+#pragma unroll
+      for (int t = 0; t < kTiles; ++t) issue_sd(t, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int u = 0; u < n_sub; ++u) {
@@ -808,30 +858,40 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         int nstage = stage;
         uint32_t nphase = phase;
         if (half == 1) { if (++nstage == kStagesB) { nstage = 0; nphase ^= 1; } }
-        const uint64_t dam = desc_add(ddom0, stage * kTileBytes + half * kHalfBytes);
-        const uint64_t qam = desc_add(dqm0, stage * kTileBytes + half * kHalfBytes);
+        const uint64_t dam = desc_add(ddom0, stage * kT + half * kHalfBytes);
+        const uint64_t qam = desc_add(dqm0, stage * kT + half * kHalfBytes);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
+        for (int t = 0; t < kTiles; ++t) {
           O2_TL(u, t, 0);                       // issuer starts waiting for P^T / dS^T of (u, t)
           ptx::mbar_wait(&pd_full[t], u & 1);
           ptx::tc_fence_after();
           O2_TL(u, t, 1);                       // issuer saw pd_full
           if (ptx::elect_one()) {
             const uint32_t base = tmem_base + t * 256;
-            ptx::umma_ts(base + 192, base, dam, idesc_g, u > 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 1; k < BS / 16; ++k)
-              ptx::umma_ts_acc(base + 192, base + (k >> 1) * 32 + (k & 1) * 8, desc_add(dam, k * 2048), idesc_g);
-            ptx::umma_ts(base + 128, base + 64, qam, idesc_g, u > 0 ? 1u : 0u);
+            for (int hh = 0; hh < NH; ++hh) {          // dV[:, 64 hh .. +64) += P^T dO[:, 64 hh .. +64)
+              const uint32_t dd = base + kColDV + hh * 64;
+              const uint64_t bh_ = desc_add(dam, hh * kTileBytes);
+              ptx::umma_ts(dd, base, bh_, idesc_g, u > 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 1; k < BS / 16; ++k)
-              ptx::umma_ts_acc(base + 128, base + 64 + (k >> 1) * 32 + (k & 1) * 8, desc_add(qam, k * 2048), idesc_g);
+              for (int k = 1; k < BS / 16; ++k)
+                ptx::umma_ts_acc(dd, base + (k >> 1) * 32 + (k & 1) * 8, desc_add(bh_, k * 2048), idesc_g);
+            }
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh) {          // dK[:, 64 hh .. +64) += dS^T Q[:, 64 hh .. +64)
+              const uint32_t dd = base + kColDK + hh * 64;
+              const uint64_t bh_ = desc_add(qam, hh * kTileBytes);
+              ptx::umma_ts(dd, base + 64, bh_, idesc_g, u > 0 ? 1u : 0u);
+#pragma unroll
+              for (int k = 1; k < BS / 16; ++k)
+                ptx::umma_ts_acc(dd, base + 64 + (k >> 1) * 32 + (k & 1) * 8, desc_add(bh_, k * 2048), idesc_g);
+            }
             ptx::umma_commit(&dkv_done[t]);
           }
           __syncwarp();
           if (more) {
             O2_TL(u, t, 3);                     // dV / dK issued
-            if (t == 0 && half == 1) {
+            if (t == 0 && half == 1) {                // first touch of the next Q / dO tile
               ptx::mbar_wait(&qdo_full[nstage], nphase);
               ptx::tc_fence_after();
             }
@@ -859,7 +919,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     const uint64_t sc2 = ptx::pack2(sc, sc);
     for (int u = 0; u < n_sub; ++u) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < kTiles; ++t) {
         const uint32_t st_addr = lane_addr + t * 256 + chalf * 32;       // this thread's S^T columns; P^T goes over their head
         const uint32_t dp_addr = st_addr + 64;
         if (warp == 2) O2_TL(u, t, 4);          // softmax starts waiting for S^T / dP^T of (u, t)
@@ -888,33 +948,34 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         if (warp == 2) O2_TL(u, t, 8);          // arrived on pd_full
       }
     }
-    // epilogue: warps 2-5 drain key tile 0, warps 6-9 key tile 1
-    const int t = chalf;
+    // epilogue.  Two key tiles: warps 2-5 drain tile 0, warps 6-9 tile 1 (dK then dV).  One key tile: warps 2-5 drain
+    // dK, warps 6-9 dV.
+    const int t = (kTiles == 2) ? chalf : 0;
     const uint32_t st_addr = lane_addr + t * 256;
     ptx::mbar_wait(&dkv_done[t], (n_sub - 1) & 1);
     ptx::tc_fence_after();
     const int key = k0 + t * BKV + r;
+    const int w_lo = (kTiles == 2) ? 1 : 1 + chalf, w_hi = (kTiles == 2) ? 2 : 1 + chalf;
 #pragma unroll 1
-    for (int which = 1; which <= 2; ++which) {          // 1: dK (scaled), 2: dV
-      uint32_t o[2][32];
-      const uint32_t addr = st_addr + (which == 1 ? 128 : 192);
-      ptx::tmem_ld_32x32(addr, o[0]);
-      ptx::tmem_ld_32x32(addr + 32, o[1]);
-      ptx::tmem_ld_wait();
-      if (key < a.N) {
-        __nv_bfloat16* op = a.dqkv + ((((size_t)b * a.N + key) * 3 + which) * a.heads + h) * kHD;
-        const float f = (which == 1) ? a.scale : 1.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
+    for (int which = w_lo; which <= w_hi; ++which) {    // 1: dK (scaled), 2: dV
+      __nv_bfloat16* op = a.dqkv + ((((size_t)b * a.N + key) * 3 + which) * a.heads + h) * (NH * 64);
+      const float f = (which == 1) ? a.scale : 1.f;
+#pragma unroll 1
+      for (int c = 0; c < NH * 2; ++c) {
+        uint32_t o[32];
+        ptx::tmem_ld_32x32(st_addr + (which == 1 ? kColDK : kColDV) + c * 32, o);
+        ptx::tmem_ld_wait();
+        if (key < a.N) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(o[c][i]) * f, __uint_as_float(o[c][i + 1]) * f);
-            w.y = pack_bf16x2(__uint_as_float(o[c][i + 2]) * f, __uint_as_float(o[c][i + 3]) * f);
-            w.z = pack_bf16x2(__uint_as_float(o[c][i + 4]) * f, __uint_as_float(o[c][i + 5]) * f);
-            w.w = pack_bf16x2(__uint_as_float(o[c][i + 6]) * f, __uint_as_float(o[c][i + 7]) * f);
+            w.x = pack_bf16x2(__uint_as_float(o[i]) * f, __uint_as_float(o[i + 1]) * f);
+            w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * f, __uint_as_float(o[i + 3]) * f);
+            w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * f, __uint_as_float(o[i + 5]) * f);
+            w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * f, __uint_as_float(o[i + 7]) * f);
             *reinterpret_cast<uint4*>(op + c * 32 + i) = w;
           }
+        }
       }
     }
   }
@@ -952,6 +1013,28 @@ int launch_fwd(const CUtensorMap& tm, const FwdArgs& a, dim3 grid, cudaStream_t 
   return O2_OK;
 }
 
+template <int NH>
+int launch_bwd(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const BwdArgs& a, int parts, cudaStream_t st) {
+  using Cfg = BwdCfg<NH>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kDqSmem));
+    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kDkvSmem));
+    attr_done = true;
+  }
+  const int rows_per_cta = Cfg::kTiles * BQ;
+  dim3 grid((a.N + rows_per_cta - 1) / rows_per_cta, a.B * a.heads);
+  if (parts & O2_ATTN_BWD_DKV) {
+    attn_bwd_dkv_kernel<NH><<<grid, kThreadsF, Cfg::kDkvSmem, st>>>(tm_qkv, tm_do, a);
+    O2_LAUNCH_CHECK();
+  }
+  if (parts & O2_ATTN_BWD_DQ) {
+    attn_bwd_dq_kernel<NH><<<grid, Cfg::kDqThreads, Cfg::kDqSmem, st>>>(tm_qkv, tm_do, a);
+    O2_LAUNCH_CHECK();
+  }
+  return O2_OK;
+}
+
 }  // namespace
 
 int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, cudaStream_t st) {
@@ -971,7 +1054,7 @@ int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int hea
 
 int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B,
                    int N, int heads, int hd, float scale, int parts, cudaStream_t st) {
-  O2_REQUIRE(hd == kHD, "attn_bwd_tc: head dim %d not supported (64 only)", hd);
+  O2_REQUIRE(hd == 64 || hd == 128, "attn_bwd_tc: head dim %d not supported (64 or 128)", hd);
   O2_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dout % 16) == 0 &&
                  ((uintptr_t)dqkv % 16) == 0,
              "attn_bwd_tc: pointers must be 16-byte aligned");
@@ -982,34 +1065,23 @@ int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const flo
   {
     uint64_t dims[4] = {(uint64_t)hd, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)hd * 2, (uint64_t)heads * hd * 2, (uint64_t)N * heads * hd * 2};
-    uint32_t box[4] = {(uint32_t)hd, 1, (uint32_t)BQ, 1};
+    uint32_t box[4] = {64, 1, (uint32_t)BQ, 1};            // 64-column half-tiles, like q / k / v
     rc = o2_make_tmap(&tm_do, dout, 2, 4, dims, str, box, 1);
     if (rc) return rc;
   }
   const long long rows = (long long)B * N * heads;
   if (parts & O2_ATTN_BWD_DELTA) {
-    attn_delta_bf16_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(
-        (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, N, heads);
+    if (hd == 64)
+      attn_delta_bf16_kernel<1><<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(
+          (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, N, heads);
+    else
+      attn_delta_bf16_kernel<2><<<(unsigned)((rows * 16 + 255) / 256), 256, 0, st>>>(
+          (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, N, heads);
     O2_LAUNCH_CHECK();
   }
   BwdArgs a;
   a.lse = lse; a.delta = delta; a.dqkv = (__nv_bfloat16*)dqkv; a.B = B; a.N = N; a.heads = heads;
   a.n_sub = (N + BS - 1) / BS;
   a.scale = scale; a.scale_log2 = scale * kLog2e;
-  static bool attr_done = false;
-  if (!attr_done) {
-    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
-    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDkvSmemBytes));
-    attr_done = true;
-  }
-  dim3 grid((N + 2 * BQ - 1) / (2 * BQ), B * heads);
-  if (parts & O2_ATTN_BWD_DKV) {
-    attn_bwd_dkv_kernel<<<grid, kThreadsF, kDkvSmemBytes, st>>>(tm_qkv, tm_do, a);
-    O2_LAUNCH_CHECK();
-  }
-  if (parts & O2_ATTN_BWD_DQ) {
-    attn_bwd_dq_kernel<<<grid, kThreadsB, kBwdSmemBytes, st>>>(tm_qkv, tm_do, a);
-    O2_LAUNCH_CHECK();
-  }
-  return O2_OK;
+  return hd == 64 ? launch_bwd<1>(tm_qkv, tm_do, a, parts, st) : launch_bwd<2>(tm_qkv, tm_do, a, parts, st);
 }

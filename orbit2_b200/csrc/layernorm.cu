@@ -1,8 +1,9 @@
 // LayerNorm forward / backward (HBM-bound).  reference: nn.LayerNorm(D, eps=1e-5) at vit_blocks.py:46,63 and
 // res_slimvit.py:104; backward fused with the residual-stream gradient add of Block.forward (vit_blocks.py:78-79).
 //
-// One warp per token row, 16-byte vector loads, the row lives in registers between the statistics and the normalise
-// pass (D <= kMaxVec*32*VEC); statistics reduced with warp shuffles.  Backward = the same row kernel for dx plus a
+// One warp per token row (a group of G = 2 / 4 / 8 warps for the wide rows of interm_1b / 10b: D = 3072 / 8192), 16-byte
+// vector loads, the row lives in registers between the statistics and the normalise pass (D <= kMaxVec*32*G*VEC);
+// statistics reduced with warp shuffles (+ one shared-memory exchange when G > 1).  Backward = the same row kernel for dx plus a
 // streaming column reduction for dgamma / dbeta (a fused register-accumulator version ran at 222 registers, one CTA
 // per SM and 29 % of HBM peak).
 #include "common.cuh"
@@ -34,44 +35,63 @@ template <> struct Vec<__nv_bfloat16> {
   }
 };
 
-template <typename T, int NV>
+// sum over the G warps that share a row (G = 1: plain warp reduction).  Every thread of the CTA must call it.
+template <int G>
+__device__ __forceinline__ float group_sum(float v, float* sbuf) {
+  v = warp_sum(v);
+  if (G == 1) return v;
+  const int warp = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sbuf[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < G; ++i) s += sbuf[(warp / G) * G + i];
+  return s;
+}
+
+template <typename T, int NV, int G>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, T* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd, long long rows,
                                                      int D, float eps) {
   constexpr int VN = Vec<T>::N;
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  __shared__ float sbuf[8];
+  const int lane = (threadIdx.x & (32 * G - 1));            // position inside the row's thread group
+  long long row = (long long)blockIdx.x * (8 / G) + threadIdx.x / (32 * G);
+  const bool valid = row < rows;
+  if (G == 1 && !valid) return;
+  if (!valid) row = rows - 1;                                // G > 1: keep every thread for the CTA barriers
   const int nvec = D / VN;
   const T* xr = x + row * D;
   float v[NV][VN];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = lane + i * 32;
+    const int vi = lane + i * 32 * G;
     if (vi < nvec) {
       Vec<T>::load(xr + vi * VN, v[i]);
 #pragma unroll
       for (int j = 0; j < VN; ++j) s += v[i][j];
     }
   }
-  const float mu = warp_sum(s) / D;
+  const float mu = group_sum<G>(s, sbuf) / D;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = lane + i * 32;
+    const int vi = lane + i * 32 * G;
     if (vi < nvec) {
 #pragma unroll
       for (int j = 0; j < VN; ++j) { const float d = v[i][j] - mu; q += d * d; }
     }
   }
-  const float rs = rsqrtf(warp_sum(q) / D + eps);
+  const float rs = rsqrtf(group_sum<G>(q, sbuf) / D + eps);
+  if (!valid) return;
   if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
   T* yr = y + row * D;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = lane + i * 32;
+    const int vi = lane + i * 32 * G;
     if (vi < nvec) {
       float o[VN], gm[VN], bt[VN];
 #pragma unroll
@@ -88,22 +108,25 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
 
 // dx = LN'(dy) (+ dres): one warp per row, same shape as the forward kernel (no column accumulators -> low register
 // count, full occupancy).  The column gradients are a separate streaming reduction (ln_colgrad_kernel).
-template <typename T, int NV>
+template <typename T, int NV, int G>
 __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                         const float* __restrict__ gamma, const float* __restrict__ mean,
                                                         const float* __restrict__ rstd, const T* __restrict__ dres,
                                                         T* __restrict__ dx, long long rows, int D) {
   constexpr int VN = Vec<T>::N;
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  __shared__ float sbuf[8];
+  const int lane = (threadIdx.x & (32 * G - 1));
+  long long row = (long long)blockIdx.x * (8 / G) + threadIdx.x / (32 * G);
+  const bool valid = row < rows;
+  if (G == 1 && !valid) return;
+  if (!valid) row = rows - 1;
   const int nvec = D / VN;
   const float mu = mean[row], rs = rstd[row];
   float xh[NV][VN], gy[NV][VN];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = lane + i * 32;
+    const int vi = lane + i * 32 * G;
     if (vi < nvec) {
       float xv[VN], dv[VN], gm[VN];
       Vec<T>::load(x + row * D + vi * VN, xv);
@@ -119,11 +142,12 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const T* __restrict__ dy
       }
     }
   }
-  s1 = warp_sum(s1) / D;
-  s2 = warp_sum(s2) / D;
+  s1 = group_sum<G>(s1, sbuf) / D;
+  s2 = group_sum<G>(s2, sbuf) / D;
+  if (!valid) return;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = lane + i * 32;
+    const int vi = lane + i * 32 * G;
     if (vi < nvec) {
       float o[VN];
       if (dres) Vec<T>::load(dres + row * D + vi * VN, o);
@@ -182,11 +206,13 @@ template <typename T>
 int ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, long long T_, int D,
            float eps, cudaStream_t st) {
   constexpr int VN = Vec<T>::N;
-  const int nv = (D / VN + 31) / 32;
-  const int wpb = 8;
-  const unsigned grid = (unsigned)((T_ + wpb - 1) / wpb);
-#define O2_LN_FWD(NV) ln_fwd_kernel<T, NV><<<grid, wpb * 32, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, T_, D, eps)
-  if (nv <= 1) O2_LN_FWD(1); else if (nv <= 2) O2_LN_FWD(2); else if (nv <= 4) O2_LN_FWD(4); else O2_LN_FWD(8);
+  const int nv = (D / VN + 31) / 32;                       // 16-byte vectors per lane if one warp held the row
+#define O2_LN_FWD(NV, G)                                                                                       \
+  ln_fwd_kernel<T, NV, G><<<(unsigned)((T_ + 8 / G - 1) / (8 / G)), 256, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, \
+                                                                                   rstd, T_, D, eps)
+  if (nv <= 1) O2_LN_FWD(1, 1); else if (nv <= 2) O2_LN_FWD(2, 1); else if (nv <= 4) O2_LN_FWD(4, 1);
+  else if (nv <= 8) O2_LN_FWD(8, 1); else if (nv <= 16) O2_LN_FWD(8, 2); else if (nv <= 32) O2_LN_FWD(8, 4);
+  else O2_LN_FWD(8, 8);
 #undef O2_LN_FWD
   O2_LAUNCH_CHECK();
   return O2_OK;
@@ -197,12 +223,12 @@ int ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
            void* dx, float* dgamma, float* dbeta, long long T_, int D, cudaStream_t st) {
   constexpr int VN = Vec<T>::N;
   const int nv = (D / VN + 31) / 32;
-  const int wpb = 8;
-  const unsigned grid = (unsigned)((T_ + wpb - 1) / wpb);
-#define O2_LN_BWD(NV)                                                                                                  \
-  ln_bwd_dx_kernel<T, NV><<<grid, wpb * 32, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, \
-                                                     T_, D)
-  if (nv <= 1) O2_LN_BWD(1); else if (nv <= 2) O2_LN_BWD(2); else if (nv <= 4) O2_LN_BWD(4); else O2_LN_BWD(8);
+#define O2_LN_BWD(NV, G)                                                                                        \
+  ln_bwd_dx_kernel<T, NV, G><<<(unsigned)((T_ + 8 / G - 1) / (8 / G)), 256, 0, st>>>(                            \
+      (const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, T_, D)
+  if (nv <= 1) O2_LN_BWD(1, 1); else if (nv <= 2) O2_LN_BWD(2, 1); else if (nv <= 4) O2_LN_BWD(4, 1);
+  else if (nv <= 8) O2_LN_BWD(8, 1); else if (nv <= 16) O2_LN_BWD(8, 2); else if (nv <= 32) O2_LN_BWD(8, 4);
+  else O2_LN_BWD(8, 8);
 #undef O2_LN_BWD
   O2_LAUNCH_CHECK();
   const unsigned gx = (unsigned)((D + 32 * VN - 1) / (32 * VN));
@@ -219,7 +245,7 @@ int check_dims(long long T_, int D, int dtype) {
   O2_REQUIRE(dtype == O2_F32 || dtype == O2_BF16, "layernorm: bad dtype %d", dtype);
   const int vn = dtype == O2_F32 ? 4 : 8;
   O2_REQUIRE(D % vn == 0, "layernorm: D=%d must be a multiple of %d", D, vn);
-  O2_REQUIRE(D / vn <= kMaxVec * 32, "layernorm: D=%d exceeds the register-resident limit %d", D, kMaxVec * 32 * vn);
+  O2_REQUIRE(D / vn <= kMaxVec * 32 * 8, "layernorm: D=%d exceeds the register-resident limit %d", D, kMaxVec * 32 * 8 * vn);
   return O2_OK;
 }
 

@@ -13,9 +13,10 @@ ap.add_argument("--B", type=int, default=2)
 ap.add_argument("--N", type=int, default=16200)
 ap.add_argument("--heads", type=int, default=16)
 ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--hd", type=int, default=64)
 ap.add_argument("--fwd-only", action="store_true")
 a = ap.parse_args()
-hd = 64
+hd = a.hd
 D = a.heads * hd
 g = torch.Generator(device="cuda").manual_seed(0)
 qkv = torch.randn(a.B * a.N, 3 * D, generator=g, device="cuda").to(torch.bfloat16)
