@@ -45,6 +45,11 @@ CASES = {
     "8m": lambda: _cfg(DEFAULT_VARS_23, (32, 64), 256, 6, 4, 4, 625.0),
     # BASELINE.json configs[1]: interm_117m, ERA5 1.0 -> 0.25 on the 180x360 -> 720x1440 grid
     "117m": lambda: _cfg(DEFAULT_VARS_23, (180, 360), 1024, 8, 4, 16, 111.0),
+    # BASELINE.json configs[2]: interm_1b widths (configs/interm_1b.yaml:39-42: D=3072, 24 heads x 128, depth 8, dec 4),
+    # PRISM 7-variable batches at 18 km (:80); "1b_small" keeps the widths on a 16x32 grid with depth 2 / dec 1 so the
+    # float64 oracle finishes in seconds, "1b" is the full model on a 64x128 PRISM-like grid
+    "1b_small": lambda: _cfg(DEFAULT_VARS_23, (16, 32), 3072, 2, 1, 24, 18.0, in_vars=PRISM_VARS_7),
+    "1b": lambda: _cfg(DEFAULT_VARS_23, (64, 128), 3072, 8, 4, 24, 18.0, in_vars=PRISM_VARS_7),
     # reduced-grid 117M (same widths, L=4050) for bounded CPU timing
     "117m_90x180": lambda: _cfg(DEFAULT_VARS_23, (90, 180), 1024, 8, 4, 16, 111.0),
 }

@@ -10,6 +10,9 @@
 namespace {
 
 constexpr int BQ = 64, BKV = 64, NT = 256;
+// row padding of the shared-memory tiles (bank-conflict-free transposing stores); head dim 128 only fits the 227 KiB of
+// shared memory unpadded (backward: 4 transposed + 2 row-major operand tiles), trading store conflicts for capacity
+template <int HD> constexpr int kPad = (HD <= 64) ? 4 : 0;
 
 struct AttnArgs {
   const float* qkv; float* out; float* lse;
@@ -25,7 +28,7 @@ __device__ __forceinline__ size_t qkv_rs(const AttnArgs& a) { return (size_t)3 *
 
 // load a [64 rows x HD] tile transposed into smem: dst[d][row] (row pitch 64+pad), rows >= n_valid zero
 template <int HD>
-__device__ __forceinline__ void load_tile_T(float (*dst)[BQ + 4], const float* src, size_t row_stride, int row0, int N) {
+__device__ __forceinline__ void load_tile_T(float (*dst)[BQ + kPad<HD>], const float* src, size_t row_stride, int row0, int N) {
   for (int i = threadIdx.x; i < 64 * HD; i += NT) {
     const int r = i / HD, d = i % HD;
     const int gr = row0 + r;
@@ -33,7 +36,7 @@ __device__ __forceinline__ void load_tile_T(float (*dst)[BQ + 4], const float* s
   }
 }
 template <int HD>
-__device__ __forceinline__ void load_tile(float (*dst)[HD + 4], const float* src, size_t row_stride, int row0, int N) {
+__device__ __forceinline__ void load_tile(float (*dst)[HD + kPad<HD>], const float* src, size_t row_stride, int row0, int N) {
   for (int i = threadIdx.x; i < 64 * HD; i += NT) {
     const int r = i / HD, d = i % HD;
     const int gr = row0 + r;
@@ -45,10 +48,10 @@ template <int HD>
 __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnArgs a) {
   constexpr int DC = HD / 16;
   extern __shared__ float smem[];
-  float (*qT)[BQ + 4] = reinterpret_cast<float (*)[BQ + 4]>(smem);                       // [HD][68]
-  float (*kT)[BKV + 4] = reinterpret_cast<float (*)[BKV + 4]>(smem + HD * (BQ + 4));     // [HD][68]
-  float (*vS)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(smem + 2 * HD * (BQ + 4));   // [64][HD+4]
-  float (*pT)[BQ + 4] = reinterpret_cast<float (*)[BQ + 4]>(smem + 2 * HD * (BQ + 4) + BKV * (HD + 4));  // [64 key][68]
+  float (*qT)[BQ + kPad<HD>] = reinterpret_cast<float (*)[BQ + kPad<HD>]>(smem);                       // [HD][68]
+  float (*kT)[BKV + kPad<HD>] = reinterpret_cast<float (*)[BKV + kPad<HD>]>(smem + HD * (BQ + kPad<HD>));     // [HD][68]
+  float (*vS)[HD + kPad<HD>] = reinterpret_cast<float (*)[HD + kPad<HD>]>(smem + 2 * HD * (BQ + kPad<HD>));   // [64][HD+4]
+  float (*pT)[BQ + kPad<HD>] = reinterpret_cast<float (*)[BQ + kPad<HD>]>(smem + 2 * HD * (BQ + kPad<HD>) + BKV * (HD + kPad<HD>));  // [64 key][68]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int b = blockIdx.y / a.heads, h = blockIdx.y % a.heads;
   const int q0 = blockIdx.x * BQ;
@@ -144,8 +147,8 @@ __global__ void attn_delta_kernel(const float* __restrict__ out, const float* __
 
 // Shared S / dS recomputation for the two backward kernels.  On return: p[i][j] and ds[i][j] for rows ty*4+i, keys tx*4+j.
 template <int HD>
-__device__ __forceinline__ void recompute_p_ds(const AttnArgs& a, float (*qT)[BQ + 4], float (*kT)[BKV + 4],
-                                               float (*doT)[BQ + 4], float (*vT)[BKV + 4], const float* lse_s,
+__device__ __forceinline__ void recompute_p_ds(const AttnArgs& a, float (*qT)[BQ + kPad<HD>], float (*kT)[BKV + kPad<HD>],
+                                               float (*doT)[BQ + kPad<HD>], float (*vT)[BKV + kPad<HD>], const float* lse_s,
                                                const float* delta_s, int q0, int k0, int tx, int ty, float (&p)[4][4],
                                                float (&ds)[4][4]) {
   float s[4][4] = {}, dp[4][4] = {};
@@ -180,15 +183,15 @@ template <int HD>
 __global__ void __launch_bounds__(NT) attn_bwd_kv_kernel(const AttnArgs a) {
   constexpr int DC = HD / 16;
   extern __shared__ float smem[];
-  float (*qT)[BQ + 4] = reinterpret_cast<float (*)[BQ + 4]>(smem);
-  float (*kT)[BKV + 4] = qT + HD;
-  float (*doT)[BQ + 4] = kT + HD;
-  float (*vT)[BKV + 4] = doT + HD;
-  float* after = smem + 4 * HD * (BQ + 4);
-  float (*qS)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(after);              // [64 row][HD+4]
-  float (*doS)[HD + 4] = qS + BQ;
-  float (*pS)[BKV + 4] = reinterpret_cast<float (*)[BKV + 4]>(after + 2 * BQ * (HD + 4));   // [row][key]
-  float (*dsS)[BKV + 4] = pS + BQ;
+  float (*qT)[BQ + kPad<HD>] = reinterpret_cast<float (*)[BQ + kPad<HD>]>(smem);
+  float (*kT)[BKV + kPad<HD>] = qT + HD;
+  float (*doT)[BQ + kPad<HD>] = kT + HD;
+  float (*vT)[BKV + kPad<HD>] = doT + HD;
+  float* after = smem + 4 * HD * (BQ + kPad<HD>);
+  float (*qS)[HD + kPad<HD>] = reinterpret_cast<float (*)[HD + kPad<HD>]>(after);              // [64 row][HD+4]
+  float (*doS)[HD + kPad<HD>] = qS + BQ;
+  float (*pS)[BKV + kPad<HD>] = reinterpret_cast<float (*)[BKV + kPad<HD>]>(after + 2 * BQ * (HD + kPad<HD>));   // [row][key]
+  float (*dsS)[BKV + kPad<HD>] = pS + BQ;
   float* lse_s = reinterpret_cast<float*>(dsS + BQ);
   float* delta_s = lse_s + BQ;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -248,13 +251,13 @@ template <int HD>
 __global__ void __launch_bounds__(NT) attn_bwd_q_kernel(const AttnArgs a) {
   constexpr int DC = HD / 16;
   extern __shared__ float smem[];
-  float (*qT)[BQ + 4] = reinterpret_cast<float (*)[BQ + 4]>(smem);
-  float (*kT)[BKV + 4] = qT + HD;
-  float (*doT)[BQ + 4] = kT + HD;
-  float (*vT)[BKV + 4] = doT + HD;
-  float* after = smem + 4 * HD * (BQ + 4);
-  float (*kS)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(after);                       // [64 key][HD+4]
-  float (*dsT)[BQ + 4] = reinterpret_cast<float (*)[BQ + 4]>(after + BKV * (HD + 4));     // [key][row]
+  float (*qT)[BQ + kPad<HD>] = reinterpret_cast<float (*)[BQ + kPad<HD>]>(smem);
+  float (*kT)[BKV + kPad<HD>] = qT + HD;
+  float (*doT)[BQ + kPad<HD>] = kT + HD;
+  float (*vT)[BKV + kPad<HD>] = doT + HD;
+  float* after = smem + 4 * HD * (BQ + kPad<HD>);
+  float (*kS)[HD + kPad<HD>] = reinterpret_cast<float (*)[HD + kPad<HD>]>(after);                       // [64 key][HD+4]
+  float (*dsT)[BQ + kPad<HD>] = reinterpret_cast<float (*)[BQ + kPad<HD>]>(after + BKV * (HD + kPad<HD>));     // [key][row]
   float* lse_s = reinterpret_cast<float*>(dsT + BKV);
   float* delta_s = lse_s + BQ;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -305,12 +308,12 @@ __global__ void __launch_bounds__(NT) attn_bwd_q_kernel(const AttnArgs a) {
   }
 }
 
-template <int HD> constexpr size_t fwd_smem() { return sizeof(float) * (2 * HD * (BQ + 4) + BKV * (HD + 4) + BKV * (BQ + 4)); }
+template <int HD> constexpr size_t fwd_smem() { return sizeof(float) * (2 * HD * (BQ + kPad<HD>) + BKV * (HD + kPad<HD>) + BKV * (BQ + kPad<HD>)); }
 template <int HD> constexpr size_t bwd_kv_smem() {
-  return sizeof(float) * (4 * HD * (BQ + 4) + 2 * BQ * (HD + 4) + 2 * BQ * (BKV + 4) + 2 * BQ);
+  return sizeof(float) * (4 * HD * (BQ + kPad<HD>) + 2 * BQ * (HD + kPad<HD>) + 2 * BQ * (BKV + kPad<HD>) + 2 * BQ);
 }
 template <int HD> constexpr size_t bwd_q_smem() {
-  return sizeof(float) * (4 * HD * (BQ + 4) + BKV * (HD + 4) + BKV * (BQ + 4) + 2 * BQ);
+  return sizeof(float) * (4 * HD * (BQ + kPad<HD>) + BKV * (HD + kPad<HD>) + BKV * (BQ + kPad<HD>) + 2 * BQ);
 }
 
 template <int HD> int run_fwd(const AttnArgs& a, cudaStream_t st) {
@@ -355,7 +358,8 @@ int o2_attn_bwd_simt(const void* qkv, const void* out, const void* dout, const f
   O2_REQUIRE((long long)B * heads <= 65535, "attn: B*heads too large");
   if (hd == 32) return run_bwd<32>(a, st);
   if (hd == 64) return run_bwd<64>(a, st);
-  O2_FAIL(O2_ERR_UNSUPPORTED, "attn_simt backward: head dim %d not in {32,64}", hd);
+  if (hd == 128) return run_bwd<128>(a, st);
+  O2_FAIL(O2_ERR_UNSUPPORTED, "attn_simt backward: head dim %d not in {32,64,128}", hd);
 }
 
 int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, cudaStream_t st);

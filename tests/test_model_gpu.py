@@ -76,6 +76,26 @@ def test_8m_vs_oracle(dtype):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_1b_widths_vs_oracle(dtype):
+    """BASELINE configs[2] widths (interm_1b: D=3072, 24 heads x 128 -> the head-dim-128 attention kernels, LayerNorm rows
+    shared by several warps), PRISM 7-variable batch, reduced depth/grid, against the float64 CPU oracle."""
+    from oracle import cases, reslim_oracle as O
+    cfg = cases.get_case("1b_small")
+    sd = O.init_state_dict(cfg, seed=2)
+    x, y = O.synthetic_batch(cfg, 2, cfg["in_vars"], cfg["out_vars"], seed=2)
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    loss = O.training_step(sd64, cfg, x.double(), y.double(), cfg["in_vars"], cfg["out_vars"], "bayesian_tv",
+                           cfg["var_weights"], None, {})
+    loss.backward()
+    pred, vec, grads = run_ours(cfg, sd, x, y, "bayesian_tv", False, dtype)
+    tol = TOL[dtype]
+    assert rel(vec[-1], loss) < tol
+    worst = {k: rel(grads[k], v.grad) for k, v in sd64.items() if v.grad is not None and v.grad.abs().max() > 0}
+    bad = {k: v for k, v in worst.items() if v > tol * (1 if dtype == torch.float32 else 2.5)}
+    assert not bad, bad
+
+
 def test_errors_like_reference():
     """ValueError when a static field is missing (res_slimvit.py:302-310), KeyError for unknown variables (:182-201),
     loud failure on CPU tensors (no fallback)."""
