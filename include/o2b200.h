@@ -143,6 +143,16 @@ int o2_clip_replace(void* pred, int dtype, const float* target, int clamp_ch, ui
  * (loss.backward() with a non-unit / per-channel grad_output; GradScaler-style loss scaling). */
 int o2_scale_channels(void* g, int dtype, const float* scale, int B, int C, int64_t hw, void* stream);
 
+/* ---- dropout / stochastic depth on the token stream ------------------------------------------
+ * replaces nn.Dropout at res_slimvit.py:284 (pos_drop), components/attention.py:81 (proj_drop),
+ * components/mlp.py:65,68 (drop1/drop2) and timm DropPath at components/vit_blocks.py:78-79, forward AND backward
+ * (the same call on the gradient).  out[r,c] = res[r,c] + y[r,c] * keep(e)/(1-p) * sample_scale[r / rows_per_sample],
+ * e = r*cols + c; res / sample_scale (fp32 [rows / rows_per_sample], per-sample drop-path factor) may be NULL;
+ * out may alias y or res.  keep(e) is a counter-based hash of (seed, site, e) -- no mask is stored; the exact
+ * function is documented in csrc/dropout.cu and restated in oracle/dropout_mask.py. */
+int o2_dropout(const void* y, const void* res, void* out, int dtype, int64_t rows, int64_t cols,
+               int64_t rows_per_sample, float p, const float* sample_scale, uint64_t seed, uint32_t site, void* stream);
+
 /* ---- small HBM-bound helpers ---------------------------------------------------------------- */
 int o2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* out[n] += sum_m X[m, n]  (bias gradients), X act dtype with row pitch ld. */

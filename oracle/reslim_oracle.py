@@ -98,23 +98,41 @@ def var_agg_attention(sd, var_query, x, num_heads):
 USE_SDPA = False
 
 
-def block(sd, pre: str, x, num_heads):
-    """components/vit_blocks.py:76-81, attention.py:43-87 (NONE / DEFAULT path), mlp.py:57-73; dropout = 0."""
+def block(sd, pre: str, x, num_heads, masks=None):
+    """components/vit_blocks.py:76-81, attention.py:43-87 (NONE / DEFAULT path), mlp.py:57-73.
+    ``masks`` (training mode with dropout): dict of PRE-SCALED keep masks (nn.Dropout: mask / (1 - p); timm DropPath:
+    per-sample bernoulli(keep) / keep), keys pre + {attn [B,h,N,N], proj [B,N,D], path1 [B,1,1], drop1 [B,N,4D],
+    drop2 [B,N,D], path2 [B,1,1]}; a missing key means the site is inactive."""
+    m = masks or {}
     B, N, D = x.shape
     hd = D // num_heads
     h = F.layer_norm(x, (D,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-5)
     qkv = F.linear(h, sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"])
     qkv = qkv.reshape(B, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv.unbind(0)
-    if USE_SDPA:
+    if USE_SDPA and (pre + "attn") not in m:
         o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, D)
     else:
         attn = ((q * hd ** -0.5) @ k.transpose(-2, -1)).softmax(dim=-1)
+        if (pre + "attn") in m:
+            attn = attn * m[pre + "attn"]                                   # attention.py:75 attn_drop
         o = (attn @ v).transpose(1, 2).reshape(B, N, D)
-    x = x + F.linear(o, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
+    br = F.linear(o, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
+    if (pre + "proj") in m:
+        br = br * m[pre + "proj"]                                           # attention.py:81 proj_drop
+    if (pre + "path1") in m:
+        br = br * m[pre + "path1"]                                          # vit_blocks.py:78 drop_path1
+    x = x + br
     h = F.layer_norm(x, (D,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-5)
     h = F.gelu(F.linear(h, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"]))
-    return x + F.linear(h, sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+    if (pre + "drop1") in m:
+        h = h * m[pre + "drop1"]                                            # mlp.py:65 drop1
+    br = F.linear(h, sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+    if (pre + "drop2") in m:
+        br = br * m[pre + "drop2"]                                          # mlp.py:68 drop2
+    if (pre + "path2") in m:
+        br = br * m[pre + "path2"]                                          # vit_blocks.py:79 drop_path2
+    return x + br
 
 
 def unpatchify(x: torch.Tensor, img_size, patch_size: int, scaling: int, c: int) -> torch.Tensor:
@@ -128,8 +146,9 @@ def unpatchify(x: torch.Tensor, img_size, patch_size: int, scaling: int, c: int)
 
 
 def forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, in_vars: Sequence[str],
-            out_vars: Sequence[str], taps: Optional[dict] = None) -> torch.Tensor:
-    """Res_Slim_ViT.forward, res_slimvit.py:312-338.
+            out_vars: Sequence[str], taps: Optional[dict] = None, masks: Optional[dict] = None) -> torch.Tensor:
+    """Res_Slim_ViT.forward, res_slimvit.py:312-338.  ``masks``: pre-scaled dropout / drop-path keep masks of a
+    training-mode forward (see ``block``; "pos" [B,L,D] is pos_drop, res_slimvit.py:284); None = eval / p = 0.
 
     cfg keys: default_vars, img_size (current input grid), patch_size, superres_mag, num_heads, depth,
     decoder_depth, spatial_resolution.
@@ -165,8 +184,10 @@ def forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, in_vars: Se
     t = t + F.linear(res, sd["spatial_embed.weight"], sd["spatial_embed.bias"])[None, None]  # :277-281
     if taps is not None:
         taps["tokens0"] = t
+    if masks is not None and "pos" in masks:
+        t = t * masks["pos"]                                             # :284 pos_drop
     for i in range(cfg["depth"]):                                        # :291-292
-        t = block(sd, f"blocks.{i}.", t, heads)
+        t = block(sd, f"blocks.{i}.", t, heads, masks)
         if taps is not None:
             taps[f"block{i}"] = t
     t = F.layer_norm(t, (D,), sd["norm.weight"], sd["norm.bias"], 1e-5)  # :294
@@ -248,9 +269,9 @@ LOSSES = {"mse": mse, "bayesian_tv": bayesian_tv}
 
 
 def training_step(sd, cfg, x, y, in_vars, out_vars, loss_name="mse", var_weights=None, lat_w=None,
-                  taps: Optional[dict] = None) -> torch.Tensor:
+                  taps: Optional[dict] = None, masks: Optional[dict] = None) -> torch.Tensor:
     """intermediate_downscaling.py:281-306: forward, clip/replace, crop target, loss (aggregate)."""
-    yhat = forward(sd, cfg, x, in_vars, out_vars, taps)
+    yhat = forward(sd, cfg, x, in_vars, out_vars, taps, masks)
     yhat = clip_replace_constant(y, yhat, out_vars)
     if taps is not None:
         taps["preds"] = yhat

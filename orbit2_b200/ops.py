@@ -282,3 +282,17 @@ def scale_channels_(g, scale):
     L.check(lib.o2_scale_channels(_ptr(g), dt(g), _ptr(scale), B, Cc, H * W, _stream()), "o2_scale_channels")
     _count()
     return g
+
+
+def dropout(y, p, seed, site, *, res=None, sample_scale=None, rows_per_sample=0, out=None):
+    """out = res + y * keep(seed, site, element) / (1 - p) * sample_scale[row // rows_per_sample]; y [rows, cols].
+    The same call on a gradient is the backward.  ``out`` may be ``y`` (in place)."""
+    lib = L.load()
+    rows, cols = y.shape
+    assert y.is_contiguous() and (res is None or (res.is_contiguous() and res.shape == y.shape and res.dtype == y.dtype))
+    if out is None:
+        out = torch.empty_like(y)
+    L.check(lib.o2_dropout(_ptr(y), _ptr(res), _ptr(out), dt(y), rows, cols, rows_per_sample, float(p), _ptr(sample_scale),
+                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF, _stream()), "o2_dropout")
+    _count()
+    return out

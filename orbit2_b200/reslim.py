@@ -97,10 +97,40 @@ def get_2d_sincos_pos_embed(embed_dim, gh, gw):
 # ------------------------------------------------------------------------------------------------
 class Geometry:
     __slots__ = ("B", "V", "Hx", "Wx", "p", "gh", "gw", "L", "T", "D", "heads", "hd", "depth", "dec", "mag", "C", "cr",
-                 "hidden", "idx7", "act")
+                 "hidden", "idx7", "act", "drop")
 
     def __repr__(self):
         return "Geometry(" + ", ".join(f"{k}={getattr(self, k)}" for k in self.__slots__ if hasattr(self, k)) + ")"
+
+
+# dropout site numbering (the keep mask is a hash of (seed, site, element), csrc/dropout.cu)
+SITE_POS, SITE_ATTN, SITE_PROJ, SITE_DROP1, SITE_DROP2 = 0, 1, 2, 3, 4
+
+
+def drop_site(block: int, which: int) -> int:
+    return 16 * block + which
+
+
+class DropPlan:
+    """One training-mode forward's dropout / stochastic-depth decisions: the reference's nn.Dropout(p=drop_rate) at
+    res_slimvit.py:284, attention.py:81, mlp.py:65,68 and DropPath(dpr[i]) at vit_blocks.py:78-79 with
+    dpr = linspace(0, drop_path, depth) (res_slimvit.py:84).  Masks are never stored: the element masks are regenerated
+    from ``seed``; the per-sample drop-path factors (bernoulli(keep) / keep, timm semantics) are tiny [B] tensors."""
+
+    def __init__(self, rate: float, dpr: Sequence[float], B: int, seed: int, device):
+        self.rate, self.seed = float(rate), int(seed)
+        self.path = []
+        for i, dp in enumerate(dpr):
+            if dp > 0.0:
+                gen = torch.Generator().manual_seed((self.seed + 7919 * (i + 1)) & 0x7FFFFFFFFFFFFFFF)
+                keep = 1.0 - float(dp)
+                sc = (torch.rand(2, B, generator=gen) < keep).to(torch.float32) / keep
+                self.path.append((sc[0].to(device), sc[1].to(device)))
+            else:
+                self.path.append((None, None))
+
+    def branch_active(self, i: int) -> bool:
+        return self.rate > 0.0 or self.path[i][0] is not None
 
 
 def kernel_param_names(depth: int, dec: int) -> List[str]:
@@ -136,6 +166,9 @@ def reslim_forward(g: Geometry, P: Dict[str, torch.Tensor], Wc: Dict[str, torch.
     S["h1"] = h1 = ops.path2_conv1_fwd(x, g.idx7, P["path2.0.weight"], P["path2.0.bias"], act)
     S["o"] = o = ops.frontend_fwd(x, tab_s, tab_v, g.p, g.gh, g.gw, g.hd, act)
     tok = gemm(o, Wc["var_agg.proj.weight"], D, epi=EPI_BIAS_RES, bias=P["var_agg.proj.bias"], aux=posres, aux_rows=g.L)
+    dp = getattr(g, "drop", None)
+    if dp is not None and dp.rate > 0:
+        ops.dropout(tok, dp.rate, dp.seed, SITE_POS, out=tok)                       # pos_drop, res_slimvit.py:284
     blocks = []
     for i in range(g.depth):
         b = f"blocks.{i}."
@@ -143,11 +176,24 @@ def reslim_forward(g: Geometry, P: Dict[str, torch.Tensor], Wc: Dict[str, torch.
         y1, s["mean1"], s["rstd1"] = ops.layernorm_fwd(tok, P[b + "norm1.weight"], P[b + "norm1.bias"])
         qkv = gemm(y1, Wc[b + "attn.qkv.weight"], 3 * D, epi=EPI_BIAS, bias=P[b + "attn.qkv.bias"])
         ao, s["lse"] = ops.attn_fwd(qkv, g.B, g.L, g.heads, g.hd)
-        xm = gemm(ao, Wc[b + "attn.proj.weight"], D, epi=EPI_BIAS_RES, bias=P[b + "attn.proj.bias"], aux=tok)
+        if dp is not None and dp.branch_active(i):
+            # x + drop_path1(proj_drop(proj(.))): attention.py:81, vit_blocks.py:78
+            br = gemm(ao, Wc[b + "attn.proj.weight"], D, epi=EPI_BIAS, bias=P[b + "attn.proj.bias"])
+            xm = ops.dropout(br, dp.rate, dp.seed, drop_site(i, SITE_PROJ), res=tok, sample_scale=dp.path[i][0],
+                             rows_per_sample=g.L, out=br)
+        else:
+            xm = gemm(ao, Wc[b + "attn.proj.weight"], D, epi=EPI_BIAS_RES, bias=P[b + "attn.proj.bias"], aux=tok)
         y2, s["mean2"], s["rstd2"] = ops.layernorm_fwd(xm, P[b + "norm2.weight"], P[b + "norm2.bias"])
         pre = torch.empty(T, g.hidden, device=dev, dtype=act)
         h = gemm(y2, Wc[b + "mlp.fc1.weight"], g.hidden, epi=EPI_BIAS_GELU, bias=P[b + "mlp.fc1.bias"], aux_out=pre)
-        tok = gemm(h, Wc[b + "mlp.fc2.weight"], D, epi=EPI_BIAS_RES, bias=P[b + "mlp.fc2.bias"], aux=xm)
+        if dp is not None and dp.rate > 0:
+            ops.dropout(h, dp.rate, dp.seed, drop_site(i, SITE_DROP1), out=h)       # mlp.py:65 drop1
+        if dp is not None and dp.branch_active(i):
+            br = gemm(h, Wc[b + "mlp.fc2.weight"], D, epi=EPI_BIAS, bias=P[b + "mlp.fc2.bias"])
+            tok = ops.dropout(br, dp.rate, dp.seed, drop_site(i, SITE_DROP2), res=xm, sample_scale=dp.path[i][1],
+                              rows_per_sample=g.L, out=br)                          # mlp.py:68 drop2, vit_blocks.py:79
+        else:
+            tok = gemm(h, Wc[b + "mlp.fc2.weight"], D, epi=EPI_BIAS_RES, bias=P[b + "mlp.fc2.bias"], aux=xm)
         s.update(y1=y1, qkv=qkv, ao=ao, xm=xm, y2=y2, pre=pre, h=h)
         blocks.append(s)
     S["blocks"] = blocks
@@ -212,18 +258,29 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
     ready([f"head.{2 * j}.{s}" for j in range(g.dec + 1) for s in ("weight", "bias")])
     dx = ops.layernorm_bwd(d, S["xf"], P["norm.weight"], S["meanf"], S["rstdf"], G["norm.weight"], G["norm.bias"])
     ready(["norm.weight", "norm.bias"])
+    dp = getattr(g, "drop", None)
     for i in range(g.depth - 1, -1, -1):
         b = f"blocks.{i}."
         s = S["blocks"][i]
-        wgrad(dx, s["h"], b + "mlp.fc2")
-        dpre = dgrad(dx, Wc[b + "mlp.fc2.weight"], g.hidden, epi=EPI_DGELU, aux=s["pre"])
+        branch_drop = dp is not None and dp.branch_active(i)
+        # gradient entering the MLP branch = the stream gradient through drop_path2 / drop2 (same mask, same scale)
+        dbr = ops.dropout(dx, dp.rate, dp.seed, drop_site(i, SITE_DROP2), sample_scale=dp.path[i][1],
+                          rows_per_sample=g.L) if branch_drop else dx
+        wgrad(dbr, s["h"], b + "mlp.fc2")
+        dpre = dgrad(dbr, Wc[b + "mlp.fc2.weight"], g.hidden, epi=EPI_DGELU, aux=s["pre"])
+        if dp is not None and dp.rate > 0:
+            ops.dropout(dpre, dp.rate, dp.seed, drop_site(i, SITE_DROP1), out=dpre)
+        del dbr
         wgrad(dpre, s["y2"], b + "mlp.fc1")
         dy2 = dgrad(dpre, Wc[b + "mlp.fc1.weight"], D)
         del dpre
         dxm = ops.layernorm_bwd(dy2, s["xm"], P[b + "norm2.weight"], s["mean2"], s["rstd2"], G[b + "norm2.weight"],
                                 G[b + "norm2.bias"], dres=dx)
-        wgrad(dxm, s["ao"], b + "attn.proj")
-        dao = dgrad(dxm, Wc[b + "attn.proj.weight"], D)
+        dbr = ops.dropout(dxm, dp.rate, dp.seed, drop_site(i, SITE_PROJ), sample_scale=dp.path[i][0],
+                          rows_per_sample=g.L) if branch_drop else dxm
+        wgrad(dbr, s["ao"], b + "attn.proj")
+        dao = dgrad(dbr, Wc[b + "attn.proj.weight"], D)
+        del dbr
         dqkv = ops.attn_bwd(s["qkv"], s["ao"], dao, s["lse"], g.B, g.L, g.heads, g.hd)
         wgrad(dqkv, s["y1"], b + "attn.qkv")
         dy1 = dgrad(dqkv, Wc[b + "attn.qkv.weight"], D)
@@ -234,7 +291,9 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
         ready([b + n for n in ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight",
                                "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias",
                                "mlp.fc2.weight", "mlp.fc2.bias")])
-    # tok = proj(o) + bias + posres
+    # tok = pos_drop(proj(o) + bias + posres)
+    if dp is not None and dp.rate > 0:
+        dx = ops.dropout(dx, dp.rate, dp.seed, SITE_POS, out=dx)
     dposres = torch.zeros(g.L * D, device=dev, dtype=torch.float32)
     ops.colsum(dx.view(g.B, g.L * D), dposres)
     wgrad(dx, S["o"], "var_agg.proj")
@@ -359,8 +418,7 @@ class Res_Slim_ViT(nn.Module):
         self._names = kernel_param_names(depth, decoder_depth)
         self._wc_cache = None           # (versions, dict) bf16 copies of the GEMM weights
         self.external_wc = None         # set by the training engine (flat bf16 buffer refreshed by fused AdamW)
-        if (self.drop_rate > 0 or self.drop_path > 0):
-            self._warned_drop = False
+        self._warned_drop = False
 
     # res_slimvit.py:125-145
     def initialize_weights(self):
@@ -474,6 +532,12 @@ class Res_Slim_ViT(nn.Module):
         g.hidden = self.blocks[0].mlp.fc1.weight.shape[0] if self.depth else 0
         g.idx7 = self.find_var_index(in_variables, out_variables)
         g.act = act
+        g.drop = None
+        if self.training and (self.drop_rate > 0 or self.drop_path > 0):
+            # seeds come from torch's CPU generator: reproducible under torch.manual_seed, no device sync
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            dpr = [float(v) for v in torch.linspace(0, self.drop_path, self.depth)] if self.depth else []
+            g.drop = DropPlan(self.drop_rate, dpr, B, seed, x.device)
         if g.C != self.conv_out.weight.shape[0]:
             raise ValueError(f"{g.C} output variables but the model was built for {self.conv_out.weight.shape[0]}")
         return g
@@ -484,8 +548,9 @@ class Res_Slim_ViT(nn.Module):
             x = x.flatten(1, 2)
         if not x.is_cuda:
             raise RuntimeError("orbit2_b200.Res_Slim_ViT runs on sm_100a CUDA kernels only (no CPU fallback)")
-        if self.training and (self.drop_rate > 0 or self.drop_path > 0) and not self._warned_drop:
-            warnings.warn("orbit2_b200: dropout / drop-path are not applied by this build (treated as 0)")
+        if self.training and self.drop_rate > 0 and not self._warned_drop:
+            warnings.warn("orbit2_b200: attention-probability dropout (attention.py:75, attn_drop) is not applied by "
+                          "this build; pos_drop, proj_drop, the MLP dropouts and DropPath are")
             self._warned_drop = True
         act = self._act_dtype()
         x = x.contiguous().float()

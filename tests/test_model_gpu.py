@@ -96,6 +96,78 @@ def test_1b_widths_vs_oracle(dtype):
     assert not bad, bad
 
 
+def oracle_masks_for(plan, cfg, B, attn=False):
+    """The masks a DropPlan implies, rebuilt on the CPU from the documented hash (oracle/dropout_mask.py)."""
+    from oracle import dropout_mask as DM
+    from orbit2_b200 import reslim as R
+    p_ = cfg["patch_size"]
+    L = (cfg["img_size"][0] // p_) * (cfg["img_size"][1] // p_)
+    D, hid = cfg["embed_dim"], int(cfg["embed_dim"] * cfg["mlp_ratio"])
+    masks = {}
+    if plan.rate > 0:
+        masks["pos"] = DM.scaled_mask(plan.seed, R.SITE_POS, (B, L, D), plan.rate)
+    for i in range(cfg["depth"]):
+        b = f"blocks.{i}."
+        if plan.rate > 0:
+            masks[b + "proj"] = DM.scaled_mask(plan.seed, R.drop_site(i, R.SITE_PROJ), (B, L, D), plan.rate)
+            masks[b + "drop1"] = DM.scaled_mask(plan.seed, R.drop_site(i, R.SITE_DROP1), (B, L, hid), plan.rate)
+            masks[b + "drop2"] = DM.scaled_mask(plan.seed, R.drop_site(i, R.SITE_DROP2), (B, L, D), plan.rate)
+        if plan.path[i][0] is not None:
+            masks[b + "path1"] = plan.path[i][0].double().cpu().view(B, 1, 1)
+            masks[b + "path2"] = plan.path[i][1].double().cpu().view(B, 1, 1)
+    return masks
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rate,path", [(0.1, 0.0), (0.0, 0.3), (0.1, 0.3)])
+def test_dropout_training_mode_vs_oracle(dtype, rate, path):
+    """Training-mode forward/backward with dropout + stochastic depth (the reference's shipped drop_rate / drop_path,
+    configs/interm_117m.yaml:44-45) against the float64 oracle fed the SAME masks (the oracle's mask placement is pinned
+    to the live reference in tests/test_oracle.py).  Attention-probability dropout is not part of this build yet."""
+    from oracle import cases, reslim_oracle as O
+    from orbit2_b200 import losses, reslim as R
+    cfg = cases.get_case("tiny")
+    B = 3
+    sd = O.init_state_dict(cfg, seed=4)
+    x, y = O.synthetic_batch(cfg, B, cfg["in_vars"], cfg["out_vars"], seed=4)
+    m = build_model(cfg, sd, "cuda", dtype, drop_rate=rate, drop_path=path)
+    m.train()
+    torch.manual_seed(123)
+    meta = losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], np.linspace(90, -90, 32), None)
+    loss_fn = losses.METRICS_REGISTRY["mse"](aggregate_only=False, metainfo=meta)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pred = m(x.cuda(), cfg["in_vars"], cfg["out_vars"])
+    vec = loss_fn(pred, y.cuda(), var_names=cfg["out_vars"], var_weights=cfg["var_weights"], clip_out_variables=cfg["out_vars"])
+    vec[-1].backward()
+    # the plan of that forward: same CPU generator state -> same seed -> same masks
+    torch.manual_seed(123)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    dpr = [float(v) for v in torch.linspace(0, path, cfg["depth"])]
+    plan = R.DropPlan(rate, dpr, B, seed, "cpu")
+    masks = oracle_masks_for(plan, cfg, B)
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    loss = O.training_step(sd64, cfg, x.double(), y.double(), cfg["in_vars"], cfg["out_vars"], "mse", cfg["var_weights"],
+                           None, None, masks)
+    loss.backward()
+    sd_plain = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    O.training_step(sd_plain, cfg, x.double(), y.double(), cfg["in_vars"], cfg["out_vars"], "mse", cfg["var_weights"]).backward()
+    key = "blocks.1.mlp.fc2.weight"
+    assert rel(sd64[key].grad, sd_plain[key].grad) > 5e-2                 # the masks matter (far above the tolerances)
+    tol = TOL[dtype]
+    assert rel(vec[-1], loss) < tol
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    worst = {k: rel(grads[k], v.grad) for k, v in sd64.items() if v.grad is not None and v.grad.abs().max() > 0}
+    bad = {k: v for k, v in worst.items() if v > tol * (1 if dtype == torch.float32 else 2.5)}
+    assert not bad, bad
+    # eval mode ignores dropout
+    m.eval()
+    with torch.no_grad():
+        pe = m(x.cuda(), cfg["in_vars"], cfg["out_vars"])
+    assert rel(pe, O.forward({k: v.double() for k, v in sd.items()}, cfg, x.double(), cfg["in_vars"], cfg["out_vars"])) < tol
+
+
 def test_errors_like_reference():
     """ValueError when a static field is missing (res_slimvit.py:302-310), KeyError for unknown variables (:182-201),
     loud failure on CPU tensors (no fallback)."""

@@ -102,6 +102,65 @@ def test_oracle_matches_live_reference(case, B):
 
 
 @pytest.mark.reference
+def test_oracle_dropout_sites_match_live_reference(monkeypatch):
+    """Training-mode forward of the LIVE reference (drop_rate 0.1, drop_path 0.2) with every nn.Dropout / DropPath draw
+    recorded, replayed through the oracle's ``masks``: pins the position and scaling of all seven dropout sites
+    (res_slimvit.py:284, attention.py:75,81, mlp.py:65,68, vit_blocks.py:78-79)."""
+    from oracle import make_golden, ref_shim
+    ref = ref_shim.load_reference()
+    cfg = cases.get_case("tiny")
+    sd = {k: v.double() for k, v in O.init_state_dict(cfg, 5).items()}
+    x, _ = O.synthetic_batch(cfg, 2, cfg["in_vars"], cfg["out_vars"], 5)
+    m = ref.Res_Slim_ViT(cfg["default_vars"], cfg["init_img_size"], len(cfg["default_vars"]), cfg["out_channels"],
+                         history=1, superres_mag=cfg["superres_mag"], cnn_ratio=cfg["cnn_ratio"],
+                         patch_size=cfg["patch_size"], drop_path=0.2, drop_rate=0.1, learn_pos_emb=True,
+                         embed_dim=cfg["embed_dim"], depth=cfg["depth"], decoder_depth=cfg["decoder_depth"],
+                         num_heads=cfg["num_heads"], mlp_ratio=cfg["mlp_ratio"], FusedAttn_option=ref.FusedAttn.NONE)
+    m.load_state_dict(sd, strict=True)
+    m = m.double().train()
+    m.spatial_resolution = cfg["spatial_resolution"]
+    rec = []
+
+    def fake_dropout(inp, p=0.5, training=True, inplace=False):
+        if not training or p == 0.0:
+            return inp
+        mask = (torch.rand(inp.shape, dtype=inp.dtype) >= p).to(inp.dtype) / (1.0 - p)
+        rec.append(("drop", mask))
+        return inp * mask
+
+    def fake_droppath(self, t):
+        if self.drop_prob == 0.0 or not self.training:
+            return t
+        keep = 1.0 - self.drop_prob
+        mask = t.new_empty((t.shape[0],) + (1,) * (t.ndim - 1)).bernoulli_(keep) / keep
+        rec.append(("path", mask))
+        return t * mask
+
+    monkeypatch.setattr(torch.nn.functional, "dropout", fake_dropout)
+    monkeypatch.setattr(ref_shim._DropPath, "forward", fake_droppath)
+    torch.manual_seed(11)
+    want = m.forward(x.double(), list(cfg["in_vars"]), list(cfg["out_vars"]))
+    monkeypatch.undo()
+    # call order: pos_drop; per block attn_drop, proj_drop, [drop_path1], drop1, drop2, [drop_path2]
+    # (dpr = linspace(0, 0.2, depth): block 0 has Identity instead of DropPath, res_slimvit.py:84, vit_blocks.py:61)
+    it = iter(rec)
+    masks = {"pos": next(it)[1]}
+    for i in range(cfg["depth"]):
+        b = f"blocks.{i}."
+        has_path = i > 0
+        order = ["attn", "proj"] + (["path1"] if has_path else []) + ["drop1", "drop2"] + (["path2"] if has_path else [])
+        for key in order:
+            kind, mk = next(it)
+            assert kind == ("path" if key.startswith("path") else "drop"), (b, key, kind)
+            masks[b + key] = mk
+    assert next(it, None) is None
+    got = O.forward(sd, cfg, x.double(), cfg["in_vars"], cfg["out_vars"], None, masks)
+    assert (want - got).abs().max().item() < 1e-12
+    plain = O.forward(sd, cfg, x.double(), cfg["in_vars"], cfg["out_vars"])
+    assert (want - plain).abs().max().item() > 1e-3          # the masks do something
+
+
+@pytest.mark.reference
 def test_reference_bugs_documented():
     """SURVEY.md headline 4: odd H raises in the reference (unpatchify), 180 rows works."""
     from oracle import make_golden, ref_shim

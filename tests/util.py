@@ -20,13 +20,13 @@ def load_golden(name):
     return z, meta, sd, grads
 
 
-def build_model(cfg, sd=None, device="cpu", compute_dtype=None):
+def build_model(cfg, sd=None, device="cpu", compute_dtype=None, drop_rate=0.0, drop_path=0.0):
     from orbit2_b200.reslim import Res_Slim_ViT
     m = Res_Slim_ViT(cfg["default_vars"], cfg["init_img_size"], len(cfg["default_vars"]), cfg["out_channels"], 1,
                      superres_mag=cfg["superres_mag"], cnn_ratio=cfg["cnn_ratio"], patch_size=cfg["patch_size"],
-                     drop_path=0.0, drop_rate=0.0, learn_pos_emb=True, embed_dim=cfg["embed_dim"], depth=cfg["depth"],
-                     decoder_depth=cfg["decoder_depth"], num_heads=cfg["num_heads"], mlp_ratio=cfg["mlp_ratio"],
-                     compute_dtype=compute_dtype)
+                     drop_path=drop_path, drop_rate=drop_rate, learn_pos_emb=True, embed_dim=cfg["embed_dim"],
+                     depth=cfg["depth"], decoder_depth=cfg["decoder_depth"], num_heads=cfg["num_heads"],
+                     mlp_ratio=cfg["mlp_ratio"], compute_dtype=compute_dtype)
     if sd is not None:
         m.load_state_dict(sd, strict=True)
     m.spatial_resolution = cfg["spatial_resolution"]
