@@ -114,6 +114,8 @@ def cpu_reference_step_time(case_name, B, steps, warmup, threads):
 def pick_cpu_sample(workload, n_steps_total, threads, budget_s=260.0, force=None):
     """Bounded CPU sample of the workload: B=1 on the full 180x360 grid when (steps+warmup) of them fit the time budget
     (calibrated with one step on the quarter-area 90x180 sub-grid, full grid measured 5.9x, budgeted 6.5x), else the sub-grid itself."""
+    if workload == "1b":
+        return "1b", 1, None
     if workload != "117m":
         return "8m", 8, None
     if force in ("full", "sub"):
@@ -170,7 +172,7 @@ def run_ours(args):
     _lib.load(require_device=True)
 
     cfg = cases.get_case(args.workload)
-    B = args.batch or (8 if args.workload == "117m" else 32)
+    B = args.batch or {"117m": 8, "1b": 8}.get(args.workload, 32)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     torch.manual_seed(0)
     model = Res_Slim_ViT(cfg["default_vars"], cfg["img_size"], len(cfg["default_vars"]), cfg["out_channels"], 1,
@@ -322,7 +324,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"interm_{args.workload} Res_Slim_ViT ({n_params / 1e6:.1f}M params) ERA5 "
                                    f"{cfg['img_size'][0]}x{cfg['img_size'][1]} -> {H_out}x{cfg['img_size'][1] * cfg['superres_mag']}"
-                                   ", V=23 in / 3 out vars, fwd+clip+bayesian_tv+bwd+allreduce+AdamW",
+                                   f", V={len(cfg['in_vars'])} in / {len(cfg['out_vars'])} out vars, fwd+clip+bayesian_tv+bwd+allreduce+AdamW",
                        "per_gpu_batch": B, "global_batch": B * world, "tokens_per_sample": L, "parallelism": (f"fsdp{world} (sharded Adam state + update, reduce-scatter / all-gather)" if (args.shard and world > 1) else f"dp{world}"),
                        "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB), no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e,
@@ -343,7 +345,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="117m", choices=["117m", "8m", "117m_90x180"])
+    ap.add_argument("--workload", default="117m", choices=["117m", "8m", "117m_90x180", "1b"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
