@@ -153,6 +153,18 @@ int o2_scale_channels(void* g, int dtype, const float* scale, int B, int C, int6
 int o2_dropout(const void* y, const void* res, void* out, int dtype, int64_t rows, int64_t cols,
                int64_t rows_per_sample, float p, const float* sample_scale, uint64_t seed, uint32_t site, void* stream);
 
+/* ---- either side of the hot path: input normalisation and evaluation statistics ---------------
+ * o2_normalize_fields replaces the per-sample host transforms of the data pipeline (data/itermodule.py:202-211,
+ * iterdataset.py:360-379): x [B,V,hw] fp32 RAW fields, in place; kind[v] = 0: (x - mean[v]) / std[v] (torchvision
+ * Normalize), 1: LogTransform (precipmodule.py:21-42: x*1000, values <= 0.25 -> 0, log1p).  mean/std/kind: device [V].
+ * o2_eval_stats feeds rmse / pearson / mean_bias (metrics/functional.py:236-257, 294-324): out [B,C,6] fp64 (zeroed by
+ * the call) = sums over H x W of { w e^2, p, t, p^2, t^2, p t } with p = scale[c]*pred + shift[c], t likewise (the
+ * denormalising TransformedMetric, metrics/metrics.py:100-115; NULL = identity), e = p - t, w = lat_w[y] or 1. */
+int o2_normalize_fields(float* x, const float* mean, const float* stdv, const int* kind, int B, int V, int64_t hw,
+                        void* stream);
+int o2_eval_stats(const void* pred, int dtype, const float* target, const float* lat_w, const float* scale,
+                  const float* shift, double* out, int B, int C, int H, int W, int tgt_H, int tgt_W, void* stream);
+
 /* ---- small HBM-bound helpers ---------------------------------------------------------------- */
 int o2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* out[n] += sum_m X[m, n]  (bias gradients), X act dtype with row pitch ld. */

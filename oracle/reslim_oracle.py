@@ -363,3 +363,51 @@ def synthetic_batch(cfg: dict, B: int, in_vars: Sequence[str], out_vars: Sequenc
         i = out_vars.index("total_precipitation_24hr")
         y[:, i] = torch.log1p(torch.relu(y[:, i]) * 2.0)
     return x, y
+
+
+# ----------------------------------------------------------------------------------------------
+# either side of the hot path: evaluation metrics and the data pipeline's per-variable transforms
+# ----------------------------------------------------------------------------------------------
+def rmse(pred, target, aggregate_only=False, lat_w=None):
+    """metrics/functional.py:236-257 (no mask)."""
+    error = (pred - target).square()
+    if lat_w is not None:
+        error = error * lat_w
+    per_ch = error.mean([2, 3]).sqrt().mean(0)
+    loss = per_ch.mean()
+    return loss if aggregate_only else torch.cat((per_ch, loss.unsqueeze(0)))
+
+
+def pearson(pred, target, aggregate_only=False):
+    """metrics/functional.py:294-309, :327-337."""
+    p = pred.transpose(0, 1).flatten(1)
+    t = target.transpose(0, 1).flatten(1)
+    p = p - p.mean(1, keepdim=True)
+    t = t - t.mean(1, keepdim=True)
+    per_ch = F.cosine_similarity(p, t)
+    c = per_ch.mean()
+    return c if aggregate_only else torch.cat((per_ch, c.unsqueeze(0)))
+
+
+def mean_bias(pred, target, aggregate_only=False):
+    """metrics/functional.py:312-324."""
+    per_ch = torch.stack([target[:, i].mean() - pred[:, i].mean() for i in range(pred.shape[1])])
+    r = per_ch.mean()
+    return r if aggregate_only else torch.cat((per_ch, r.unsqueeze(0)))
+
+
+def log_transform(x: torch.Tensor) -> torch.Tensor:
+    """data/precipmodule.py:21-42 with the pipeline's arguments (m2mm=True, LOG1P=True, thres 0.25 mm/day,
+    itermodule.py:208); out of place."""
+    t = x * 1000.0
+    t = torch.where(t <= 0.25, torch.zeros((), dtype=t.dtype), t)
+    return torch.log1p(t)
+
+
+def normalize_sample(x: torch.Tensor, variables, mean: dict, std: dict, precip=("total_precipitation_24hr", "total_precipitation")):
+    """itermodule.py:202-211 + iterdataset.py:360-379: per-variable Normalize(mean, std) or LogTransform; x [.., V, H, W]."""
+    out = []
+    for i, v in enumerate(variables):
+        c = x[..., i, :, :]
+        out.append(log_transform(c) if v in precip else (c - float(mean[v][0])) / float(std[v][0]))
+    return torch.stack(out, dim=-3)

@@ -187,3 +187,92 @@ class LatWeightedMAE(LatitudeWeightedMetric):
     """Not in the reference registry: functional mae(..., lat_weights=w) (functional.py:218-232) as a class."""
     kind = LOSS_MAE
     uses_var_weights = False
+
+
+# ------------------------------------------------------------------------------------------------ evaluation metrics
+class _EvalMetric:
+    """Validation / test metrics of the downscaling task (utils/loaders.py:251-252: rmse, pearson, mean_bias) on ONE pass
+    over prediction and target (``o2_eval_stats``).  ``denorm=(scale[C], shift[C])`` folds the reference's
+    ``TransformedMetric(denormalise, metric)`` (metrics/metrics.py:100-115) into the same pass.  Evaluation only: the
+    result carries no autograd history."""
+
+    def __init__(self, aggregate_only: bool = False, metainfo: Optional[MetricsMetaInfo] = None, denorm=None):
+        self.aggregate_only = aggregate_only
+        self.metainfo = metainfo
+        self.denorm = denorm
+        self._dev = {}
+
+    def _lat(self, pred):
+        return None
+
+    def _stats(self, pred, target):
+        if not pred.is_cuda:
+            raise RuntimeError("orbit2_b200 metrics run on sm_100a CUDA kernels only (no CPU fallback)")
+        if pred.dtype not in (torch.float32, torch.bfloat16):
+            pred = pred.float()
+        sc = sh = None
+        if self.denorm is not None:
+            key = pred.device
+            if key not in self._dev:
+                self._dev[key] = tuple(torch.as_tensor(np.asarray(v, dtype=np.float32)).to(pred.device) for v in self.denorm)
+            sc, sh = self._dev[key]
+        with torch.no_grad():
+            return ops.eval_stats(pred.detach().contiguous(), target.float().contiguous(), lat_w=self._lat(pred),
+                                  scale=sc, shift=sh), pred.shape[2] * pred.shape[3]
+
+    def _finish(self, per_channel):
+        agg = per_channel.mean()
+        out = agg if self.aggregate_only else torch.cat((per_channel, agg.unsqueeze(0)))
+        return out.float()
+
+    def _compose(self, s, n):
+        raise NotImplementedError
+
+    def __call__(self, pred, target, **_ignored):
+        s, n = self._stats(pred, target)
+        return self._finish(self._compose(s, n))
+
+
+@register("rmse")
+class RMSE(_EvalMetric):
+    """functional.py:236-257: sqrt of the spatial mean per (sample, channel), then the batch mean."""
+
+    def _compose(self, s, n):
+        return (s[:, :, 0] / n).sqrt().mean(0)
+
+
+@register("lat_rmse")
+class LatWeightedRMSE(RMSE):
+    def __init__(self, aggregate_only: bool = False, metainfo: Optional[MetricsMetaInfo] = None, denorm=None):
+        super().__init__(aggregate_only, metainfo, denorm)
+        w = np.cos(np.deg2rad(np.asarray(self.metainfo.lat, dtype=np.float64)))
+        self.lat_weights = torch.from_numpy(w / w.mean()).view(1, 1, -1, 1)
+        self._lat_dev = None
+
+    def _lat(self, pred):
+        if self._lat_dev is None or self._lat_dev.device != pred.device:
+            self._lat_dev = self.lat_weights.reshape(-1).to(device=pred.device, dtype=torch.float32).contiguous()
+        return self._lat_dev
+
+
+@register("pearson")
+class Pearson(_EvalMetric):
+    """functional.py:294-309: cosine similarity of the mean-removed channel over all of B x H x W."""
+
+    def _compose(self, s, n):
+        t = s.sum(0)                                       # [C, 6]
+        N = n * s.shape[0]
+        sp, st_, spp, stt, spt = t[:, 1], t[:, 2], t[:, 3], t[:, 4], t[:, 5]
+        cov = spt - sp * st_ / N
+        vp = (spp - sp * sp / N).clamp_min(0).sqrt().clamp_min(1e-8)     # F.cosine_similarity clamps each norm at eps = 1e-8
+        vt = (stt - st_ * st_ / N).clamp_min(0).sqrt().clamp_min(1e-8)
+        return cov / (vp * vt)
+
+
+@register("mean_bias")
+class MeanBias(_EvalMetric):
+    """functional.py:312-324: mean(target) - mean(pred) per channel."""
+
+    def _compose(self, s, n):
+        t = s.sum(0)
+        return (t[:, 2] - t[:, 1]) / (n * s.shape[0])

@@ -296,3 +296,26 @@ def dropout(y, p, seed, site, *, res=None, sample_scale=None, rows_per_sample=0,
                            int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF, _stream()), "o2_dropout")
     _count()
     return out
+
+
+def normalize_fields_(x, mean, std, kind):
+    """x [B,V,H,W] fp32 raw fields, normalised in place; mean/std fp32 [V], kind int32 [V] (0 Normalize, 1 LogTransform)."""
+    lib = L.load()
+    B, V = x.shape[0], x.shape[1]
+    assert x.dtype == torch.float32 and x.is_contiguous() and kind.dtype == torch.int32
+    L.check(lib.o2_normalize_fields(_ptr(x), _ptr(mean), _ptr(std), _ptr(kind), B, V, x[0, 0].numel(), _stream()),
+            "o2_normalize_fields")
+    _count()
+    return x
+
+
+def eval_stats(pred, target, *, lat_w=None, scale=None, shift=None):
+    """-> [B, C, 6] fp64 sums {w e^2, p, t, p^2, t^2, p t} (see o2b200.h)."""
+    lib = L.load()
+    B, Cc, H, W = pred.shape
+    assert pred.is_contiguous() and target.is_contiguous() and target.dtype == torch.float32
+    out = torch.empty(B, Cc, 6, device=pred.device, dtype=torch.float64)
+    L.check(lib.o2_eval_stats(_ptr(pred), dt(pred), _ptr(target), _ptr(lat_w), _ptr(scale), _ptr(shift), _ptr(out), B, Cc,
+                              H, W, target.shape[2], target.shape[3], _stream()), "o2_eval_stats")
+    _count(2)
+    return out

@@ -6,9 +6,12 @@ with the per-epoch warmup-cosine schedule (models/lr_scheduler.py:9-115, stepped
 checkpoints in the reference's format (:775-791: epoch, model_state_dict, optimizer_state_dict, scheduler_state_dict;
 the optimizer state is emitted in torch.optim.AdamW's own layout so either side can resume the other's run).
 
-Out of scope here: the npz/Lustre data pipeline -- batches come from any iterable yielding
-``(x, y, in_variables, out_variables)`` like the reference's collate (itermodule.py:451-469); ``--synthetic`` uses seeded
-random fields of the configured grid.  Environment comes from torchrun (RANK / LOCAL_RANK / WORLD_SIZE), not SLURM.
+Batches come from any iterable yielding ``(x, y, in_variables, out_variables)`` like the reference's collate
+(itermodule.py:451-469): ``--synthetic H W`` uses seeded random fields of that grid; ``--npz`` reads the reference's shard
+directories named by the YAML (``data.low_res_dir`` / ``high_res_dir``) through ``orbit2_b200.data`` (raw fields copied to
+the GPU, normalised there) and ends every epoch with the validation metrics of the downscaling task (rmse, pearson,
+mean_bias on denormalised fields, utils/loaders.py:251-252).  Environment comes from torchrun (RANK / LOCAL_RANK /
+WORLD_SIZE), not SLURM.
 
     torchrun --nproc-per-node 8 -m orbit2_b200.trainer /path/to/configs/interm_117m.yaml --data-key ERA5_2 \
              --synthetic 180 360 --steps-per-epoch 20 --epochs 2
@@ -145,8 +148,52 @@ def synthetic_loader(conf, data_key, grid, batch, steps, device, seed):
         yield x.pin_memory().to(device, non_blocking=True), y.pin_memory().to(device, non_blocking=True), in_vars, out_vars
 
 
+def npz_data(conf: dict, data_key: str, device, rank: int, world: int):
+    """DownscalingData over the YAML's shard directories (intermediate_downscaling.py:453-476 builds the same module)."""
+    from .data import DownscalingData
+    d, t = conf["data"], conf["trainer"]
+    til = conf.get("tiling", {}) or {}
+    div = int(til.get("div", 1)) if til.get("do_tiling", False) else 1
+    return DownscalingData(d["low_res_dir"][data_key], d["high_res_dir"][data_key], list(d["dict_in_variables"][data_key]),
+                           list(d["dict_out_variables"][data_key]), t["batch_size"], device, rank, world, div=div,
+                           overlap=int(til.get("overlap", 4)), subsample=1, buffer_size=int(t.get("buffer_size", 0)), seed=rank)
+
+
+def validate(eng: TrainEngine, dm, max_batches: Optional[int] = None) -> Dict[str, float]:
+    """One pass over the validation split: clip_replace_constant, then rmse / pearson / mean_bias on denormalised fields
+    (intermediate_downscaling.py:321-371), averaged over batches and ranks."""
+    from .data import denorm_affine
+    model = eng.model
+    was_training = model.training
+    model.eval()
+    lat, lon = dm.get_lat_lon()
+    meta = losses.MetricsMetaInfo(dm.in_vars, dm.out_vars, lat, lon)
+    mets = {n: losses.METRICS_REGISTRY[n](aggregate_only=True, metainfo=meta, denorm=denorm_affine(dm.out_stats))
+            for n in ("rmse", "pearson", "mean_bias")}
+    tot = {n: torch.zeros((), device="cuda") for n in mets}
+    k = 0
+    with torch.no_grad():
+        for x, y, in_vars, out_vars in dm.loader("val"):
+            pred = model(x, in_vars, out_vars)
+            yc = y[:, :, :pred.shape[2], :pred.shape[3]].contiguous()
+            pred = losses.clip_replace_constant(yc, pred, out_vars)
+            for n, fn in mets.items():
+                tot[n] += fn(pred, yc)
+            k += 1
+            if max_batches and k >= max_batches:
+                break
+    out = {}
+    for n in mets:
+        v = tot[n] / max(k, 1)
+        if dist.is_initialized():
+            dist.all_reduce(v, op=dist.ReduceOp.AVG)
+        out[n] = float(v)
+    model.train(was_training)
+    return out
+
+
 def train(conf: dict, data_key: str, grid, epochs: int, steps_per_epoch: int, ckpt_dir: Optional[str] = None,
-          resume: Optional[str] = None, loader_factory=None, log=print):
+          resume: Optional[str] = None, loader_factory=None, log=print, data_module=None):
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     device = torch.device("cuda", torch.cuda.current_device())
@@ -160,19 +207,26 @@ def train(conf: dict, data_key: str, grid, epochs: int, steps_per_epoch: int, ck
     for epoch in range(epoch0, epoch0 + epochs):
         eng.lr = warmup_cosine_lr(epoch, sched["base_lr"], sched["warmup_epochs"], sched["max_epochs"],
                                   sched["warmup_start_lr"], sched["eta_min"])
-        loader = (loader_factory or synthetic_loader)(conf, data_key, grid, B, steps_per_epoch, device, 1000 * epoch + rank)
+        if data_module is not None:
+            loader = data_module.loader("train")
+        else:
+            loader = (loader_factory or synthetic_loader)(conf, data_key, grid, B, steps_per_epoch, device, 1000 * epoch + rank)
         t0 = time.perf_counter()
         tot, n = torch.zeros((), device=device), 0
         for x, y, in_vars, out_vars in loader:
             vec = eng.step(x, y)
             tot += vec[-1]
             n += 1
+            if data_module is not None and steps_per_epoch and n >= steps_per_epoch:
+                break
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         mean = (tot / max(n, 1)).item()
         hist.append(mean)
+        val = validate(eng, data_module) if data_module is not None else None
         if rank == 0:
-            log(f"epoch {epoch} lr {eng.lr:.3e} loss {mean:.5f} {n * B * world / dt:.2f} samples/s", flush=True)
+            log(f"epoch {epoch} lr {eng.lr:.3e} loss {mean:.5f} {n * B * world / dt:.2f} samples/s"
+                + ("" if val is None else " val " + " ".join(f"{k} {v:.5f}" for k, v in val.items())), flush=True)
             if ckpt_dir:
                 os.makedirs(ckpt_dir, exist_ok=True)
                 save_checkpoint(os.path.join(ckpt_dir, f"interm_epoch_{epoch}.ckpt"), epoch, eng, dict(sched, last_epoch=epoch + 1))
@@ -185,7 +239,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("config")
     ap.add_argument("--data-key", default="ERA5_2")
-    ap.add_argument("--synthetic", type=int, nargs=2, metavar=("H", "W"), required=True)
+    ap.add_argument("--synthetic", type=int, nargs=2, metavar=("H", "W"), default=None)
+    ap.add_argument("--npz", action="store_true", help="read data.low_res_dir / high_res_dir[data-key] (reference shard layout)")
     ap.add_argument("--epochs", type=int, default=1)
     ap.add_argument("--steps-per-epoch", type=int, default=10)
     ap.add_argument("--checkpoint-dir", default=None)
@@ -196,7 +251,15 @@ def main():
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     conf = load_config(a.config)
-    train(conf, a.data_key, tuple(a.synthetic), a.epochs, a.steps_per_epoch, a.checkpoint_dir, a.resume)
+    if a.npz:
+        dm = npz_data(conf, a.data_key, torch.device("cuda", local), int(os.environ.get("RANK", "0")),
+                      int(os.environ.get("WORLD_SIZE", "1")))
+        grid = dm.get_data_dims()[0][2:]
+        train(conf, a.data_key, tuple(grid), a.epochs, a.steps_per_epoch, a.checkpoint_dir, a.resume, data_module=dm)
+    else:
+        if a.synthetic is None:
+            ap.error("give --synthetic H W or --npz")
+        train(conf, a.data_key, tuple(a.synthetic), a.epochs, a.steps_per_epoch, a.checkpoint_dir, a.resume)
     if dist.is_initialized():
         dist.destroy_process_group()
 
