@@ -177,7 +177,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = Res_Slim_ViT(cfg["default_vars"], cfg["img_size"], len(cfg["default_vars"]), cfg["out_channels"], 1,
                          superres_mag=cfg["superres_mag"], cnn_ratio=cfg["cnn_ratio"], patch_size=cfg["patch_size"],
-                         drop_path=0.0, drop_rate=0.0, learn_pos_emb=True, embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                         drop_path=args.drop, drop_rate=args.drop, learn_pos_emb=True, embed_dim=cfg["embed_dim"], depth=cfg["depth"],
                          decoder_depth=cfg["decoder_depth"], num_heads=cfg["num_heads"], mlp_ratio=cfg["mlp_ratio"],
                          compute_dtype=dtype)
     with torch.no_grad():                                   # zeros would hide the front end
@@ -326,7 +326,8 @@ def run_ours(args):
                                    f"{cfg['img_size'][0]}x{cfg['img_size'][1]} -> {H_out}x{cfg['img_size'][1] * cfg['superres_mag']}"
                                    f", V={len(cfg['in_vars'])} in / {len(cfg['out_vars'])} out vars, fwd+clip+bayesian_tv+bwd+allreduce+AdamW",
                        "per_gpu_batch": B, "global_batch": B * world, "tokens_per_sample": L, "parallelism": (f"fsdp{world} (sharded Adam state + update, reduce-scatter / all-gather)" if (args.shard and world > 1) else f"dp{world}"),
-                       "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB), no explicit flush"},
+                       "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB), no explicit flush",
+                       "dropout": args.drop},
             "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": (x_h.numel() + y_h.numel()) * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
@@ -349,6 +350,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--drop", type=float, default=0.0, help="drop_rate = drop_path (the reference YAMLs train at 0.1; the "
+                    "headline and every parity run use 0)")
     ap.add_argument("--shard", action="store_true", help="FSDP-style sharded optimizer instead of plain data parallel")
     ap.add_argument("--ref-grid", default=None, choices=["full", "sub"], help="force the CPU sample (default: by time budget)")
     args = ap.parse_args()

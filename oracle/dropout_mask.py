@@ -43,3 +43,23 @@ def scaled_mask(seed: int, site: int, shape, p: float, dtype=torch.float64) -> t
     for d in shape:
         n *= d
     return (keep_mask(seed, site, n, p).to(dtype) / (1.0 - p)).reshape(shape)
+
+
+def attn_scaled_mask(seed: int, site: int, B: int, heads: int, N: int, p: float, dtype=torch.float64) -> torch.Tensor:
+    """[B, heads, N, N] pre-scaled keep mask of the attention-probability dropout (orbit2_b200/csrc/common.cuh): one byte
+    of lowbias32(((q >> 1) * ceil(N / 2) + (k >> 1)) ^ key_bh) per element, byte index (q & 1) * 2 + (k & 1), keep iff
+    byte >= floor(p * 256); kept values scaled by 256 / (256 - floor(p * 256))."""
+    thr8 = math.floor(p * 256.0)
+    n2 = (N + 1) >> 1
+    q = torch.arange(N, dtype=torch.int64).view(N, 1)
+    k = torch.arange(N, dtype=torch.int64).view(1, N)
+    blk = ((q >> 1) * n2 + (k >> 1)) & M32
+    sh = ((q & 1) * 2 + (k & 1)) * 8
+    sk = site_key(seed, site)
+    out = torch.empty(B, heads, N, N, dtype=dtype)
+    for bh in range(B * heads):
+        key_bh = _lb(sk ^ ((bh * 0x9E3779B1) & M32))
+        h = lowbias32(blk ^ key_bh)
+        keep = ((h >> sh) & 0xFF) >= thr8
+        out[bh // heads, bh % heads] = keep.to(dtype) * (256.0 / (256.0 - thr8))
+    return out

@@ -18,7 +18,15 @@ struct AttnArgs {
   const float* qkv; float* out; float* lse;
   const float* dout; float* dqkv; float* delta;
   int B, N, heads, hd; float scale;
+  ptx::AttnDrop drop;        // thr8 == 0: no attention dropout
 };
+
+// scaled keep factor of element (q, k) of (batch, head) bh: 0 or 1 / keep_prob (mask function: common.cuh)
+__device__ __forceinline__ float drop_factor(const AttnArgs& a, uint32_t key_bh, int q, int k) {
+  const uint32_t h = ptx::lowbias32(((uint32_t)(q >> 1) * a.drop.n2 + (uint32_t)(k >> 1)) ^ key_bh);
+  const uint32_t byte = (h >> (((q & 1) * 2 + (k & 1)) * 8)) & 0xFFu;
+  return byte >= a.drop.thr8 ? a.drop.inv_keep : 0.f;
+}
 
 __device__ __forceinline__ const float* qkv_ptr(const AttnArgs& a, int b, int which, int h) {
   return a.qkv + ((size_t)b * a.N * 3 + which) * a.heads * a.hd + (size_t)h * a.hd;
@@ -98,6 +106,11 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnArgs a) {
       m[i] = mn;
 #pragma unroll
       for (int c = 0; c < DC; ++c) o[i][c] *= alpha;
+      if (a.drop.thr8 > 0) {                  // P V uses the masked probabilities, l the unmasked ones
+        const uint32_t key_bh = ptx::attn_drop_key(a.drop, blockIdx.y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] *= drop_factor(a, key_bh, q0 + ty * 4 + i, k0 + tx * 4 + j);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) pT[tx * 4 + j][ty * 4 + i] = s[i][j];
     }
@@ -174,7 +187,13 @@ __device__ __forceinline__ void recompute_p_ds(const AttnArgs& a, float (*qT)[BQ
     for (int j = 0; j < 4; ++j) {
       const bool ok = (q0 + ty * 4 + i < a.N) && (k0 + tx * 4 + j < a.N);
       p[i][j] = ok ? __expf(s[i][j] * a.scale - lse_s[ty * 4 + i]) : 0.f;
-      ds[i][j] = p[i][j] * (dp[i][j] - delta_s[ty * 4 + i]) * a.scale;
+      if (a.drop.thr8 > 0) {                  // dP = dP_drop o M; the returned p is the masked one (it feeds dV = P_drop^T dO)
+        const float f = drop_factor(a, ptx::attn_drop_key(a.drop, blockIdx.y), q0 + ty * 4 + i, k0 + tx * 4 + j);
+        ds[i][j] = p[i][j] * (dp[i][j] * f - delta_s[ty * 4 + i]) * a.scale;
+        p[i][j] *= f;
+      } else {
+        ds[i][j] = p[i][j] * (dp[i][j] - delta_s[ty * 4 + i]) * a.scale;
+      }
     }
 }
 
@@ -337,9 +356,20 @@ template <int HD> int run_bwd(const AttnArgs& a, cudaStream_t st) {
 
 }  // namespace
 
-int o2_attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, cudaStream_t st) {
+ptx::AttnDrop make_drop_simt(float p, uint64_t seed, uint32_t site, int N) {
+  ptx::AttnDrop d;
+  d.site_key = ptx::lowbias32((uint32_t)seed ^ ptx::lowbias32(site ^ (uint32_t)(seed >> 32)));
+  d.thr8 = (uint32_t)floor((double)p * 256.0);
+  d.n2 = (uint32_t)((N + 1) >> 1);
+  d.inv_keep = 256.f / (256.f - (float)d.thr8);
+  return d;
+}
+
+int o2_attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, float p_drop,
+                     uint64_t seed, uint32_t site, cudaStream_t st) {
   AttnArgs a;
   memset(&a, 0, sizeof(a));
+  a.drop = make_drop_simt(p_drop, seed, site, N);
   a.qkv = (const float*)qkv; a.out = (float*)out; a.lse = lse; a.B = B; a.N = N; a.heads = heads; a.hd = hd; a.scale = scale;
   O2_REQUIRE((long long)B * heads <= 65535, "attn: B*heads too large");
   if (hd == 32) return run_fwd<32>(a, st);
@@ -349,9 +379,10 @@ int o2_attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int h
 }
 
 int o2_attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B,
-                     int N, int heads, int hd, float scale, cudaStream_t st) {
+                     int N, int heads, int hd, float scale, float p_drop, uint64_t seed, uint32_t site, cudaStream_t st) {
   AttnArgs a;
   memset(&a, 0, sizeof(a));
+  a.drop = make_drop_simt(p_drop, seed, site, N);
   a.qkv = (const float*)qkv; a.out = (float*)const_cast<void*>(out); a.lse = const_cast<float*>(lse);
   a.dout = (const float*)dout; a.dqkv = (float*)dqkv; a.delta = delta;
   a.B = B; a.N = N; a.heads = heads; a.hd = hd; a.scale = scale;
@@ -362,31 +393,49 @@ int o2_attn_bwd_simt(const void* qkv, const void* out, const void* dout, const f
   O2_FAIL(O2_ERR_UNSUPPORTED, "attn_simt backward: head dim %d not in {32,64,128}", hd);
 }
 
-int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, cudaStream_t st);
+int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, float p_drop,
+                   uint64_t seed, uint32_t site, cudaStream_t st);
 int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B,
-                   int N, int heads, int hd, float scale, int parts, cudaStream_t st);
+                   int N, int heads, int hd, float scale, int parts, float p_drop, uint64_t seed, uint32_t site,
+                   cudaStream_t st);
+
+extern "C" int o2_attn_fwd_drop(int impl, const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale,
+                                float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  O2_REQUIRE(qkv && out && lse, "attn_fwd: null pointer");
+  O2_REQUIRE(B > 0 && N > 0 && heads > 0 && hd > 0, "attn_fwd: bad dims");
+  O2_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "attn_fwd: p_drop=%f outside [0, 1)", (double)p_drop);
+  if (impl == O2_GEMM_SIMT_F32)
+    return o2_attn_fwd_simt(qkv, out, lse, B, N, heads, hd, scale, p_drop, seed, site, (cudaStream_t)stream);
+  if (impl == O2_GEMM_TC_BF16)
+    return o2_attn_fwd_tc(qkv, out, lse, B, N, heads, hd, scale, p_drop, seed, site, (cudaStream_t)stream);
+  O2_FAIL(O2_ERR_ARG, "attn_fwd: unknown impl %d", impl);
+}
 
 extern "C" int o2_attn_fwd(int impl, const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale,
                            void* stream) {
-  O2_REQUIRE(qkv && out && lse, "attn_fwd: null pointer");
-  O2_REQUIRE(B > 0 && N > 0 && heads > 0 && hd > 0, "attn_fwd: bad dims");
-  if (impl == O2_GEMM_SIMT_F32) return o2_attn_fwd_simt(qkv, out, lse, B, N, heads, hd, scale, (cudaStream_t)stream);
-  if (impl == O2_GEMM_TC_BF16) return o2_attn_fwd_tc(qkv, out, lse, B, N, heads, hd, scale, (cudaStream_t)stream);
-  O2_FAIL(O2_ERR_ARG, "attn_fwd: unknown impl %d", impl);
+  return o2_attn_fwd_drop(impl, qkv, out, lse, B, N, heads, hd, scale, 0.f, 0, 0, stream);
+}
+
+extern "C" int o2_attn_bwd_parts_drop(int impl, int parts, const void* qkv, const void* out, const void* dout,
+                                      const float* lse, void* dqkv, float* delta, int B, int N, int heads, int hd,
+                                      float scale, float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  O2_REQUIRE(qkv && out && dout && lse && dqkv && delta, "attn_bwd: null pointer");
+  O2_REQUIRE(B > 0 && N > 0 && heads > 0 && hd > 0, "attn_bwd: bad dims");
+  O2_REQUIRE(parts > 0 && parts <= O2_ATTN_BWD_ALL, "attn_bwd: bad parts mask %d", parts);
+  O2_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "attn_bwd: p_drop=%f outside [0, 1)", (double)p_drop);
+  if (impl == O2_GEMM_SIMT_F32) {
+    O2_REQUIRE(parts == O2_ATTN_BWD_ALL, "attn_bwd: the fp32 SIMT path runs all parts in one call");
+    return o2_attn_bwd_simt(qkv, out, dout, lse, dqkv, delta, B, N, heads, hd, scale, p_drop, seed, site, (cudaStream_t)stream);
+  }
+  if (impl == O2_GEMM_TC_BF16)
+    return o2_attn_bwd_tc(qkv, out, dout, lse, dqkv, delta, B, N, heads, hd, scale, parts, p_drop, seed, site,
+                          (cudaStream_t)stream);
+  O2_FAIL(O2_ERR_ARG, "attn_bwd: unknown impl %d", impl);
 }
 
 extern "C" int o2_attn_bwd_parts(int impl, int parts, const void* qkv, const void* out, const void* dout, const float* lse,
                                  void* dqkv, float* delta, int B, int N, int heads, int hd, float scale, void* stream) {
-  O2_REQUIRE(qkv && out && dout && lse && dqkv && delta, "attn_bwd: null pointer");
-  O2_REQUIRE(B > 0 && N > 0 && heads > 0 && hd > 0, "attn_bwd: bad dims");
-  O2_REQUIRE(parts > 0 && parts <= O2_ATTN_BWD_ALL, "attn_bwd: bad parts mask %d", parts);
-  if (impl == O2_GEMM_SIMT_F32) {
-    O2_REQUIRE(parts == O2_ATTN_BWD_ALL, "attn_bwd: the fp32 SIMT path runs all parts in one call");
-    return o2_attn_bwd_simt(qkv, out, dout, lse, dqkv, delta, B, N, heads, hd, scale, (cudaStream_t)stream);
-  }
-  if (impl == O2_GEMM_TC_BF16)
-    return o2_attn_bwd_tc(qkv, out, dout, lse, dqkv, delta, B, N, heads, hd, scale, parts, (cudaStream_t)stream);
-  O2_FAIL(O2_ERR_ARG, "attn_bwd: unknown impl %d", impl);
+  return o2_attn_bwd_parts_drop(impl, parts, qkv, out, dout, lse, dqkv, delta, B, N, heads, hd, scale, 0.f, 0, 0, stream);
 }
 
 extern "C" int o2_attn_bwd(int impl, const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,

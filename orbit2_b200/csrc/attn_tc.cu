@@ -49,7 +49,17 @@ struct FwdArgs {
   float* lse;
   int B, N, heads, n_sub;   // n_sub = ceil(N / 64) key sub-tiles
   float scale_log2;         // softmax scale * log2(e)
+  ptx::AttnDrop drop;       // kDrop kernels only
 };
+
+// zero the dropped probabilities of one packed pair (columns k, k + 1 of row q share a hash: bytes 2 (q & 1) + {0, 1})
+__device__ __forceinline__ uint64_t drop_pair_row(uint64_t Pq, uint32_t h16, uint32_t thr8) {
+  float lo, hi;
+  ptx::unpack2(Pq, lo, hi);
+  lo = ((h16 & 0xFFu) >= thr8) ? lo : 0.f;
+  hi = (((h16 >> 8) & 0xFFu) >= thr8) ? hi : 0.f;
+  return ptx::pack2(lo, hi);
+}
 
 constexpr int BS = 64;            // key sub-tile (forward, dq) / query sub-tile (dkv) processed per MMA group
 constexpr uint32_t kHalfBytes = BS * kHD * 2;   // 8 KiB: byte offset of rows 64.. inside a 128-row tile
@@ -64,7 +74,7 @@ __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { retur
 
 // NH = head dim / 64: Q, K and V tiles are kept as NH separate 64-column (128-byte, one swizzle atom) half-tiles; S sums
 // over them (NH x 4 MMAs), O has NH 64-column accumulators per query tile.  NH = 2 fills TMEM exactly (4 x 64 + 4 x 64).
-template <int NH>
+template <int NH, bool kDrop>
 __global__ void __launch_bounds__(kThreadsB, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -241,6 +251,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t o_addr = lane_addr + 256 + t * NH * 64;
     const float sc = a.scale_log2;
+    // attention dropout: P V uses the masked probabilities, the normaliser l the unmasked ones (attention.py:73-76)
+    const uint32_t drop_key = kDrop ? ptx::attn_drop_key(a.drop, bh) : 0u;
+    const uint32_t drop_row = kDrop ? (uint32_t)((q0 + t * BQ + r) >> 1) * a.drop.n2 : 0u;
+    const uint32_t drop_sh = kDrop ? (uint32_t)((q0 + t * BQ + r) & 1) * 16u : 0u;
     float m_ref = -INFINITY;
     uint64_t lA = 0ull, lB = 0ull;          // packed partial row sums
     const int tail = a.N - (n_sub - 1) * BS;    // valid keys in the last sub-tile (1..64)
@@ -304,7 +318,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
         const uint64_t X = ptx::fma2(ptx::pack2u(v0[i], v0[i + 1]), sc2, nm2);
         const uint64_t Pq = (((i >> 1) % kPolyFwd) == kPolyFwd - 1) ? ptx::exp2_pair<true>(X) : ptx::exp2_pair<false>(X);
         if ((i >> 1) & 1) lB = ptx::add2(lB, Pq); else lA = ptx::add2(lA, Pq);
-        pk[i >> 1] = ptx::pack_bf16x2_pair(Pq);
+        if (kDrop) {
+          const uint32_t hh_ = ptx::lowbias32((drop_row + (uint32_t)(u * (BS / 2) + (i >> 1))) ^ drop_key) >> drop_sh;
+          pk[i >> 1] = ptx::pack_bf16x2_pair(drop_pair_row(Pq, hh_, a.drop.thr8));
+        } else {
+          pk[i >> 1] = ptx::pack_bf16x2_pair(Pq);
+        }
       }
       ptx::tmem_st_32x16(s_addr, pk);
 #pragma unroll
@@ -312,7 +331,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
         const uint64_t X = ptx::fma2(ptx::pack2u(v1[i], v1[i + 1]), sc2, nm2);
         const uint64_t Pq = (((i >> 1) % kPolyFwd) == kPolyFwd - 1) ? ptx::exp2_pair<true>(X) : ptx::exp2_pair<false>(X);
         if ((i >> 1) & 1) lB = ptx::add2(lB, Pq); else lA = ptx::add2(lA, Pq);
-        pk[i >> 1] = ptx::pack_bf16x2_pair(Pq);
+        if (kDrop) {
+          const uint32_t hh_ = ptx::lowbias32((drop_row + (uint32_t)(u * (BS / 2) + 16 + (i >> 1))) ^ drop_key) >> drop_sh;
+          pk[i >> 1] = ptx::pack_bf16x2_pair(drop_pair_row(Pq, hh_, a.drop.thr8));
+        } else {
+          pk[i >> 1] = ptx::pack_bf16x2_pair(Pq);
+        }
       }
       ptx::tmem_st_32x16(s_addr + 16, pk);
       if (quarter == 2) O2_TL(u, t, 7);
@@ -330,7 +354,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
     ptx::unpack2(lA, l0, l1);
     ptx::unpack2(lB, l2, l3);
     const float l = (l0 + l1) + (l2 + l3);
-    const float inv = 1.f / l;
+    const float inv = (kDrop ? a.drop.inv_keep : 1.f) / l;
     __nv_bfloat16* op = a.out + (((size_t)b * a.N + row) * a.heads + h) * (NH * 64);
 #pragma unroll 1
     for (int c = 0; c < NH * 2; ++c) {
@@ -389,7 +413,17 @@ struct BwdArgs {
   __nv_bfloat16* dqkv;    // [B, N, 3, heads, hd]
   int B, N, heads, n_sub; // n_sub = ceil(N / 64)
   float scale, scale_log2;
+  ptx::AttnDrop drop;     // kDrop kernels only
 };
+
+// dP of one packed pair through the dropout mask: kept -> dP / keep_prob, dropped -> 0 (row-owner layout, see drop_pair_row)
+__device__ __forceinline__ uint64_t drop_grad_pair_row(uint64_t dP, uint32_t h16, uint32_t thr8, float inv_keep) {
+  float lo, hi;
+  ptx::unpack2(dP, lo, hi);
+  lo = ((h16 & 0xFFu) >= thr8) ? lo * inv_keep : 0.f;
+  hi = (((h16 >> 8) & 0xFFu) >= thr8) ? hi * inv_keep : 0.f;
+  return ptx::pack2(lo, hi);
+}
 
 template <int NH>
 __global__ void attn_delta_bf16_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
@@ -425,7 +459,7 @@ __global__ void attn_delta_bf16_kernel(const __nv_bfloat16* __restrict__ out, co
 // TMEM columns of query tile t (base t*256): S buffers [0,64) / [64,128), dP [128,192), dQ [192, 192 + 64 NH).
 // S is double-buffered (S(u+2) is issued as soon as dQ(u) has consumed the dS written over S(u)); dP has one buffer
 // that the softmax warps release as soon as they have it in registers, so dP(u+1) is computed while they work on u.
-template <int NH>
+template <int NH, bool kDrop>
 __global__ void __launch_bounds__(BwdCfg<NH>::kDqThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                    const BwdArgs a) {
@@ -608,6 +642,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const float delta = (row < a.N) ? a.delta[stat] : 0.f;
     const float sc = a.scale_log2;
     const uint64_t sc2 = ptx::pack2(sc, sc), nl2 = ptx::pack2(neg_lse2, neg_lse2), nd2 = ptx::pack2(-delta, -delta);
+    const uint32_t drop_key = kDrop ? ptx::attn_drop_key(a.drop, bh) : 0u;
+    const uint32_t drop_row = kDrop ? (uint32_t)(row >> 1) * a.drop.n2 : 0u;
+    const uint32_t drop_sh = kDrop ? (uint32_t)(row & 1) * 16u : 0u;
     for (int u = 0; u < n_sub; ++u) {
       const int bb = u & 1;
       const uint32_t s_addr = lane_addr + bb * BS;
@@ -627,14 +664,24 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       for (int i = 0; i < 32; i += 2) {
         const uint64_t X = ptx::fma2(ptx::pack2u(s0[i], s0[i + 1]), sc2, nl2);
         const uint64_t Pq = (((i >> 1) % kPolyDq) == kPolyDq - 1) ? ptx::exp2_pair<true>(X) : ptx::exp2_pair<false>(X);
-        pk[i >> 1] = ptx::pack_bf16x2_pair(ptx::mul2(Pq, ptx::add2(ptx::pack2u(d0[i], d0[i + 1]), nd2)));
+        uint64_t dPq = ptx::pack2u(d0[i], d0[i + 1]);
+        if (kDrop) {
+          const uint32_t hh_ = ptx::lowbias32((drop_row + (uint32_t)(u * (BS / 2) + (i >> 1))) ^ drop_key) >> drop_sh;
+          dPq = drop_grad_pair_row(dPq, hh_, a.drop.thr8, a.drop.inv_keep);
+        }
+        pk[i >> 1] = ptx::pack_bf16x2_pair(ptx::mul2(Pq, ptx::add2(dPq, nd2)));
       }
       ptx::tmem_st_32x16(s_addr, pk);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const uint64_t X = ptx::fma2(ptx::pack2u(s1[i], s1[i + 1]), sc2, nl2);
         const uint64_t Pq = (((i >> 1) % kPolyDq) == kPolyDq - 1) ? ptx::exp2_pair<true>(X) : ptx::exp2_pair<false>(X);
-        pk[i >> 1] = ptx::pack_bf16x2_pair(ptx::mul2(Pq, ptx::add2(ptx::pack2u(d1[i], d1[i + 1]), nd2)));
+        uint64_t dPq = ptx::pack2u(d1[i], d1[i + 1]);
+        if (kDrop) {
+          const uint32_t hh_ = ptx::lowbias32((drop_row + (uint32_t)(u * (BS / 2) + 16 + (i >> 1))) ^ drop_key) >> drop_sh;
+          dPq = drop_grad_pair_row(dPq, hh_, a.drop.thr8, a.drop.inv_keep);
+        }
+        pk[i >> 1] = ptx::pack_bf16x2_pair(ptx::mul2(Pq, ptx::add2(dPq, nd2)));
       }
       ptx::tmem_st_32x16(s_addr + 16, pk);
       ptx::tmem_st_wait();
@@ -679,7 +726,7 @@ __device__ __forceinline__ uint4 neg_split3(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------- dK, dV
-template <int NH>
+template <int NH, bool kDrop>
 __global__ void __launch_bounds__(kThreadsF, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                     const BwdArgs a) {
@@ -801,6 +848,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         uint4* dst = reinterpret_cast<uint4*>(sStat + idx * 128);
         dst[(2 * stage) ^ (idx & 7)] = neg_split3(xs[e]);
         dst[(2 * stage + 1) ^ (idx & 7)] = neg_split3(ys[e]);
+        // dropout: dS = P o (dP o M - delta) needs delta outside the accumulator; raw fp32 copy in the unused k-slice 3
+        if (kDrop) reinterpret_cast<float*>(dst + (6 ^ (idx & 7)))[stage] = ys[e];
       }
       fetch_stats(i + 1);
       ptx::fence_proxy_async_smem();
@@ -840,7 +889,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
           for (int k = 1; k < NH * 4; ++k)
             ptx::umma_ss_acc(ds_ + 64, desc_add(va, (k >> 2) * kTileBytes + (k & 3) * 32),
                              desc_add(da, (k >> 2) * kTileBytes + (k & 3) * 32), idesc_s);
-          ptx::umma_ss_acc(ds_ + 64, desc_add(dones, 32), st, idesc_s);       // - delta
+          if (!kDrop) ptx::umma_ss_acc(ds_ + 64, desc_add(dones, 32), st, idesc_s);       // - delta
           ptx::umma_commit(&sd_full[t]);
         }
         __syncwarp();
@@ -917,6 +966,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float sc = a.scale_log2;
     const uint64_t sc2 = ptx::pack2(sc, sc);
+    static_assert(!kDrop || BwdCfg<NH>::kStages <= 3, "the raw delta copy lives in k-slice 3 of the statistics tile");
+    const uint32_t drop_key = kDrop ? ptx::attn_drop_key(a.drop, bh) : 0u;
+    int dstage = 0;                              // stage of the 128-query tile that holds sub-tile u
     for (int u = 0; u < n_sub; ++u) {
 #pragma unroll
       for (int t = 0; t < kTiles; ++t) {
@@ -932,12 +984,38 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         ptx::tmem_ld_wait();
         if (warp == 2) O2_TL(u, t, 6);          // TMEM loads landed
         uint32_t pk[16], dk[16];
+        if (kDrop) {
+          // thread = key row: queries (q, q + 1) of a pair share a hash, bytes (k & 1) and 2 + (k & 1)
+          const int key_ = k0 + t * BKV + r;
+          const int qb = u * BS + chalf * 32;
+          const uint32_t ksh = (uint32_t)(key_ & 1) * 8u;
+          uint32_t blk = (uint32_t)(qb >> 1) * a.drop.n2 + (uint32_t)(key_ >> 1);
+          const float* dl = reinterpret_cast<const float*>(sStat) + dstage;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const uint64_t X = ptx::mul2(ptx::pack2u(sv_[i], sv_[i + 1]), sc2);
-          const uint64_t Pq = (((i >> 1) % kPolyDkv) == kPolyDkv - 1) ? ptx::exp2_pair<true>(X) : ptx::exp2_pair<false>(X);
-          pk[i >> 1] = ptx::pack_bf16x2_pair(Pq);
-          dk[i >> 1] = ptx::pack_bf16x2_pair(ptx::mul2(Pq, ptx::pack2u(dv_[i], dv_[i + 1])));
+          for (int i = 0; i < 32; i += 2) {
+            const uint64_t X = ptx::mul2(ptx::pack2u(sv_[i], sv_[i + 1]), sc2);
+            const uint64_t Pq = ptx::exp2_pair<false>(X);
+            const uint32_t hh_ = ptx::lowbias32(blk ^ drop_key) >> ksh;
+            blk += a.drop.n2;
+            const bool k0_ = (hh_ & 0xFFu) >= a.drop.thr8, k1_ = ((hh_ >> 16) & 0xFFu) >= a.drop.thr8;
+            float p0, p1;
+            ptx::unpack2(Pq, p0, p1);
+            const int qi = (u & 1) * BS + chalf * 32 + i;            // row of the 128-query statistics tile
+            const float de0 = dl[(qi * 128 + ((6 ^ (qi & 7)) * 16)) >> 2];
+            const float de1 = dl[((qi + 1) * 128 + ((6 ^ ((qi + 1) & 7)) * 16)) >> 2];
+            const float g0 = k0_ ? __uint_as_float(dv_[i]) * a.drop.inv_keep : 0.f;
+            const float g1 = k1_ ? __uint_as_float(dv_[i + 1]) * a.drop.inv_keep : 0.f;
+            pk[i >> 1] = pack_bf16x2(k0_ ? p0 : 0.f, k1_ ? p1 : 0.f);
+            dk[i >> 1] = pack_bf16x2(p0 * (g0 - de0), p1 * (g1 - de1));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint64_t X = ptx::mul2(ptx::pack2u(sv_[i], sv_[i + 1]), sc2);
+            const uint64_t Pq = (((i >> 1) % kPolyDkv) == kPolyDkv - 1) ? ptx::exp2_pair<true>(X) : ptx::exp2_pair<false>(X);
+            pk[i >> 1] = ptx::pack_bf16x2_pair(Pq);
+            dk[i >> 1] = ptx::pack_bf16x2_pair(ptx::mul2(Pq, ptx::pack2u(dv_[i], dv_[i + 1])));
+          }
         }
         ptx::tmem_st_32x16(st_addr, pk);
         ptx::tmem_st_32x16(dp_addr, dk);
@@ -947,6 +1025,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         ptx::mbar_arrive(&pd_full[t]);
         if (warp == 2) O2_TL(u, t, 8);          // arrived on pd_full
       }
+      if (u & 1) { if (++dstage == kStagesB) dstage = 0; }
     }
     // epilogue.  Two key tiles: warps 2-5 drain tile 0, warps 6-9 tile 1 (dK then dV).  One key tile: warps 2-5 drain
     // dK, warps 6-9 dV.
@@ -959,7 +1038,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 #pragma unroll 1
     for (int which = w_lo; which <= w_hi; ++which) {    // 1: dK (scaled), 2: dV
       __nv_bfloat16* op = a.dqkv + ((((size_t)b * a.N + key) * 3 + which) * a.heads + h) * (NH * 64);
-      const float f = (which == 1) ? a.scale : 1.f;
+      const float f = (which == 1) ? a.scale : (kDrop ? a.drop.inv_keep : 1.f);   // dV = P_kept^T dO / keep_prob
 #pragma unroll 1
       for (int c = 0; c < NH * 2; ++c) {
         uint32_t o[32];
@@ -1000,36 +1079,46 @@ extern "C" int o2_debug_timeline(long long* host, int n) {
 }
 #endif
 
-template <int NH>
+template <int NH, bool kDrop>
 int launch_fwd(const CUtensorMap& tm, const FwdArgs& a, dim3 grid, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    O2_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    O2_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<NH, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)FwdCfg<NH>::kSmemBytes));
     attr_done = true;
   }
-  attn_fwd_tc_kernel<NH><<<grid, kThreadsB, FwdCfg<NH>::kSmemBytes, st>>>(tm, a);
+  attn_fwd_tc_kernel<NH, kDrop><<<grid, kThreadsB, FwdCfg<NH>::kSmemBytes, st>>>(tm, a);
   O2_LAUNCH_CHECK();
   return O2_OK;
 }
 
-template <int NH>
+// p -> (site key, 8-bit threshold, exact keep scale); p == 0 -> thr8 = 0 (kernels without the kDrop code are used)
+ptx::AttnDrop make_drop(float p, uint64_t seed, uint32_t site, int N) {
+  ptx::AttnDrop d;
+  d.site_key = ptx::lowbias32((uint32_t)seed ^ ptx::lowbias32(site ^ (uint32_t)(seed >> 32)));
+  d.thr8 = (uint32_t)floor((double)p * 256.0);
+  d.n2 = (uint32_t)((N + 1) >> 1);
+  d.inv_keep = 256.f / (256.f - (float)d.thr8);
+  return d;
+}
+
+template <int NH, bool kDrop>
 int launch_bwd(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const BwdArgs& a, int parts, cudaStream_t st) {
   using Cfg = BwdCfg<NH>;
   static bool attr_done = false;
   if (!attr_done) {
-    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kDqSmem));
-    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kDkvSmem));
+    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<NH, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kDqSmem));
+    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<NH, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kDkvSmem));
     attr_done = true;
   }
   const int rows_per_cta = Cfg::kTiles * BQ;
   dim3 grid((a.N + rows_per_cta - 1) / rows_per_cta, a.B * a.heads);
   if (parts & O2_ATTN_BWD_DKV) {
-    attn_bwd_dkv_kernel<NH><<<grid, kThreadsF, Cfg::kDkvSmem, st>>>(tm_qkv, tm_do, a);
+    attn_bwd_dkv_kernel<NH, kDrop><<<grid, kThreadsF, Cfg::kDkvSmem, st>>>(tm_qkv, tm_do, a);
     O2_LAUNCH_CHECK();
   }
   if (parts & O2_ATTN_BWD_DQ) {
-    attn_bwd_dq_kernel<NH><<<grid, Cfg::kDqThreads, Cfg::kDqSmem, st>>>(tm_qkv, tm_do, a);
+    attn_bwd_dq_kernel<NH, kDrop><<<grid, Cfg::kDqThreads, Cfg::kDqSmem, st>>>(tm_qkv, tm_do, a);
     O2_LAUNCH_CHECK();
   }
   return O2_OK;
@@ -1037,7 +1126,8 @@ int launch_bwd(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const BwdArg
 
 }  // namespace
 
-int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, cudaStream_t st) {
+int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, float p_drop,
+                   uint64_t seed, uint32_t site, cudaStream_t st) {
   O2_REQUIRE(hd == 64 || hd == 128, "attn_fwd_tc: head dim %d not supported (64 or 128)", hd);
   O2_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0, "attn_fwd_tc: pointers must be 16-byte aligned");
   O2_REQUIRE((long long)B * heads <= 65535, "attn_fwd_tc: B*heads too large");
@@ -1049,11 +1139,15 @@ int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int hea
   a.n_sub = (N + BS - 1) / BS;
   a.scale_log2 = scale * kLog2e;
   dim3 grid((N + 2 * BQ - 1) / (2 * BQ), B * heads);
-  return hd == 64 ? launch_fwd<1>(tm, a, grid, st) : launch_fwd<2>(tm, a, grid, st);
+  a.drop = make_drop(p_drop, seed, site, N);
+  O2_REQUIRE((long long)a.drop.n2 * a.drop.n2 < (1ll << 32), "attn_fwd_tc: N=%d too large for the dropout block index", N);
+  if (a.drop.thr8 > 0) return hd == 64 ? launch_fwd<1, true>(tm, a, grid, st) : launch_fwd<2, true>(tm, a, grid, st);
+  return hd == 64 ? launch_fwd<1, false>(tm, a, grid, st) : launch_fwd<2, false>(tm, a, grid, st);
 }
 
 int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B,
-                   int N, int heads, int hd, float scale, int parts, cudaStream_t st) {
+                   int N, int heads, int hd, float scale, int parts, float p_drop, uint64_t seed, uint32_t site,
+                   cudaStream_t st) {
   O2_REQUIRE(hd == 64 || hd == 128, "attn_bwd_tc: head dim %d not supported (64 or 128)", hd);
   O2_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dout % 16) == 0 &&
                  ((uintptr_t)dqkv % 16) == 0,
@@ -1083,5 +1177,9 @@ int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const flo
   a.lse = lse; a.delta = delta; a.dqkv = (__nv_bfloat16*)dqkv; a.B = B; a.N = N; a.heads = heads;
   a.n_sub = (N + BS - 1) / BS;
   a.scale = scale; a.scale_log2 = scale * kLog2e;
-  return hd == 64 ? launch_bwd<1>(tm_qkv, tm_do, a, parts, st) : launch_bwd<2>(tm_qkv, tm_do, a, parts, st);
+  a.drop = make_drop(p_drop, seed, site, N);
+  O2_REQUIRE((long long)a.drop.n2 * a.drop.n2 < (1ll << 32), "attn_bwd_tc: N=%d too large for the dropout block index", N);
+  if (a.drop.thr8 > 0)
+    return hd == 64 ? launch_bwd<1, true>(tm_qkv, tm_do, a, parts, st) : launch_bwd<2, true>(tm_qkv, tm_do, a, parts, st);
+  return hd == 64 ? launch_bwd<1, false>(tm_qkv, tm_do, a, parts, st) : launch_bwd<2, false>(tm_qkv, tm_do, a, parts, st);
 }

@@ -288,6 +288,25 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// ---- attention-probability dropout (components/attention.py:75 attn_drop): the keep decision of element (q, k) of one
+// (batch, head) is one byte of a counter-based hash shared by a 2 x 2 block of elements, so the forward kernel (thread =
+// query row) and the dK/dV kernel (thread = key row) both get two decisions per hash:
+//     h = lowbias32(((q >> 1) * ceil(N / 2) + (k >> 1)) ^ key_bh),  byte (q & 1) * 2 + (k & 1),  keep <=> byte >= thr8
+// key_bh = lowbias32(site_key ^ (b * heads + h) * 0x9E3779B1), thr8 = floor(p * 256); kept values are scaled by
+// 1 / (1 - thr8 / 256), the exact keep probability (oracle/dropout_mask.py restates this for the parity tests).
+struct AttnDrop {
+  uint32_t site_key, thr8, n2;
+  float inv_keep;
+};
+__host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16; x *= 0x21f0aaadu;
+  x ^= x >> 15; x *= 0x735a2d97u;
+  x ^= x >> 15;
+  return x;
+}
+__device__ __forceinline__ uint32_t attn_drop_key(const AttnDrop& d, int bh) {
+  return lowbias32(d.site_key ^ ((uint32_t)bh * 0x9E3779B1u));
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float y;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));

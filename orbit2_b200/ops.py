@@ -113,30 +113,35 @@ class _timed:
         return False
 
 
-def attn_fwd(qkv, B, N, heads, hd):
-    """qkv [B*N, 3*heads*hd] -> (out [B*N, heads*hd], lse [B,heads,N])."""
+def attn_fwd(qkv, B, N, heads, hd, drop=None):
+    """qkv [B*N, 3*heads*hd] -> (out [B*N, heads*hd], lse [B,heads,N]).  drop = (p, seed, site): attention-probability
+    dropout (training mode)."""
     lib = L.load()
     out = torch.empty(B * N, heads * hd, device=qkv.device, dtype=qkv.dtype)
     lse = torch.empty(B, heads, N, device=qkv.device, dtype=torch.float32)
+    p, seed, site = drop if drop is not None else (0.0, 0, 0)
     with _timed("attn_fwd"):
-        L.check(lib.o2_attn_fwd(impl_for(qkv.dtype), _ptr(qkv), _ptr(out), _ptr(lse), B, N, heads, hd, hd ** -0.5,
-                                _stream()), "o2_attn_fwd")
+        L.check(lib.o2_attn_fwd_drop(impl_for(qkv.dtype), _ptr(qkv), _ptr(out), _ptr(lse), B, N, heads, hd, hd ** -0.5,
+                                     float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF, _stream()),
+                "o2_attn_fwd")
     _count()
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, B, N, heads, hd):
+def attn_bwd(qkv, out, dout, lse, B, N, heads, hd, drop=None):
     lib = L.load()
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, heads, N, device=qkv.device, dtype=torch.float32)
     impl = impl_for(qkv.dtype)
-    args = (_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(delta), B, N, heads, hd, hd ** -0.5, _stream())
+    p, seed, site = drop if drop is not None else (0.0, 0, 0)
+    args = (_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(delta), B, N, heads, hd, hd ** -0.5, float(p),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF, _stream())
     if TIMERS is not None and impl == GEMM_TC_BF16:
         for name, part in (("attn_bwd_delta", 1), ("attn_bwd_dkv", 2), ("attn_bwd_dq", 4)):
             with _timed(name):
-                L.check(lib.o2_attn_bwd_parts(impl, part, *args), "o2_attn_bwd_parts")
+                L.check(lib.o2_attn_bwd_parts_drop(impl, part, *args), "o2_attn_bwd_parts")
     else:
-        L.check(lib.o2_attn_bwd(impl, *args), "o2_attn_bwd")
+        L.check(lib.o2_attn_bwd_parts_drop(impl, 7, *args), "o2_attn_bwd")
     _count(3)
     return dqkv
 

@@ -175,7 +175,8 @@ def reslim_forward(g: Geometry, P: Dict[str, torch.Tensor], Wc: Dict[str, torch.
         s = {"x": tok}
         y1, s["mean1"], s["rstd1"] = ops.layernorm_fwd(tok, P[b + "norm1.weight"], P[b + "norm1.bias"])
         qkv = gemm(y1, Wc[b + "attn.qkv.weight"], 3 * D, epi=EPI_BIAS, bias=P[b + "attn.qkv.bias"])
-        ao, s["lse"] = ops.attn_fwd(qkv, g.B, g.L, g.heads, g.hd)
+        adrop = (dp.rate, dp.seed, drop_site(i, SITE_ATTN)) if (dp is not None and dp.rate > 0) else None
+        ao, s["lse"] = ops.attn_fwd(qkv, g.B, g.L, g.heads, g.hd, adrop)                 # attention.py:75 attn_drop
         if dp is not None and dp.branch_active(i):
             # x + drop_path1(proj_drop(proj(.))): attention.py:81, vit_blocks.py:78
             br = gemm(ao, Wc[b + "attn.proj.weight"], D, epi=EPI_BIAS, bias=P[b + "attn.proj.bias"])
@@ -281,7 +282,8 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
         wgrad(dbr, s["ao"], b + "attn.proj")
         dao = dgrad(dbr, Wc[b + "attn.proj.weight"], D)
         del dbr
-        dqkv = ops.attn_bwd(s["qkv"], s["ao"], dao, s["lse"], g.B, g.L, g.heads, g.hd)
+        adrop = (dp.rate, dp.seed, drop_site(i, SITE_ATTN)) if (dp is not None and dp.rate > 0) else None
+        dqkv = ops.attn_bwd(s["qkv"], s["ao"], dao, s["lse"], g.B, g.L, g.heads, g.hd, adrop)
         wgrad(dqkv, s["y1"], b + "attn.qkv")
         dy1 = dgrad(dqkv, Wc[b + "attn.qkv.weight"], D)
         del dqkv
@@ -548,10 +550,6 @@ class Res_Slim_ViT(nn.Module):
             x = x.flatten(1, 2)
         if not x.is_cuda:
             raise RuntimeError("orbit2_b200.Res_Slim_ViT runs on sm_100a CUDA kernels only (no CPU fallback)")
-        if self.training and self.drop_rate > 0 and not self._warned_drop:
-            warnings.warn("orbit2_b200: attention-probability dropout (attention.py:75, attn_drop) is not applied by "
-                          "this build; pos_drop, proj_drop, the MLP dropouts and DropPath are")
-            self._warned_drop = True
         act = self._act_dtype()
         x = x.contiguous().float()
         in_variables, out_variables = list(in_variables), list(out_variables)

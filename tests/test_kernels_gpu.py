@@ -250,3 +250,36 @@ def test_attn_tc_hd128(B, N, heads):
     o.backward(dout.double())
     ref = t.grad.permute(1, 3, 0, 2, 4).reshape(B * N, 3 * D)
     assert rel(dqkv, ref) < 2e-2
+
+
+@pytest.mark.parametrize("dtype,hd,B,N,heads", [(torch.bfloat16, 64, 2, 300, 2), (torch.bfloat16, 64, 1, 1000, 1),
+                                                (torch.bfloat16, 128, 1, 333, 2), (torch.float32, 64, 2, 200, 2),
+                                                (torch.float32, 32, 1, 77, 3)])
+def test_attn_dropout(dtype, hd, B, N, heads):
+    """Attention-probability dropout inside the attention kernels (forward, dQ, dK/dV; tcgen05 and fp32 SIMT arms) against
+    float64 attention with the SAME mask rebuilt from the documented hash (oracle/dropout_mask.py)."""
+    from oracle import dropout_mask as DM
+    from orbit2_b200 import ops
+    p, seed, site = 0.1, 0x1234_5678_9ABC_DEF0, 17
+    g = torch.Generator(device="cuda").manual_seed(N + hd)
+    D = heads * hd
+    qkv = torch.randn(B * N, 3 * D, generator=g, device="cuda").to(dtype)
+    dout = torch.randn(B * N, D, generator=g, device="cuda").to(dtype)
+    out, lse = ops.attn_fwd(qkv, B, N, heads, hd, (p, seed, site))
+    M = DM.attn_scaled_mask(seed, site, B, heads, N, p).cuda()
+    assert 0.88 < float((M > 0).double().mean()) < 0.92
+    t = qkv.double().reshape(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4).requires_grad_(True)
+    q, k, v = t.unbind(0)
+    s = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    o = ((s.softmax(-1) * M) @ v).transpose(1, 2).reshape(B * N, D)
+    o.backward(dout.double())
+    ref = t.grad.permute(1, 3, 0, 2, 4).reshape(B * N, 3 * D)
+    ftol, gtol = (1.5e-2, 2e-2) if dtype == torch.bfloat16 else (2e-5, 5e-5)
+    assert rel(lse, torch.logsumexp(s, -1).detach()) < 1e-3
+    assert rel(out, o.detach()) < ftol
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, B, N, heads, hd, (p, seed, site))
+    assert rel(dqkv, ref) < gtol
+    # p = 0 through the same entry point is the plain kernel
+    out0, _ = ops.attn_fwd(qkv, B, N, heads, hd, (0.0, seed, site))
+    out1, _ = ops.attn_fwd(qkv, B, N, heads, hd)
+    assert torch.equal(out0, out1)

@@ -109,6 +109,7 @@ def oracle_masks_for(plan, cfg, B, attn=False):
     for i in range(cfg["depth"]):
         b = f"blocks.{i}."
         if plan.rate > 0:
+            masks[b + "attn"] = DM.attn_scaled_mask(plan.seed, R.drop_site(i, R.SITE_ATTN), B, cfg["num_heads"], L, plan.rate)
             masks[b + "proj"] = DM.scaled_mask(plan.seed, R.drop_site(i, R.SITE_PROJ), (B, L, D), plan.rate)
             masks[b + "drop1"] = DM.scaled_mask(plan.seed, R.drop_site(i, R.SITE_DROP1), (B, L, hid), plan.rate)
             masks[b + "drop2"] = DM.scaled_mask(plan.seed, R.drop_site(i, R.SITE_DROP2), (B, L, D), plan.rate)
@@ -123,7 +124,7 @@ def oracle_masks_for(plan, cfg, B, attn=False):
 def test_dropout_training_mode_vs_oracle(dtype, rate, path):
     """Training-mode forward/backward with dropout + stochastic depth (the reference's shipped drop_rate / drop_path,
     configs/interm_117m.yaml:44-45) against the float64 oracle fed the SAME masks (the oracle's mask placement is pinned
-    to the live reference in tests/test_oracle.py).  Attention-probability dropout is not part of this build yet."""
+    to the live reference in tests/test_oracle.py), attention-probability dropout included."""
     from oracle import cases, reslim_oracle as O
     from orbit2_b200 import losses, reslim as R
     cfg = cases.get_case("tiny")
