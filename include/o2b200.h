@@ -116,9 +116,11 @@ int o2_frontend_bwd(const float* x, const float* tab_s, const float* tab_v, cons
 
 /* ---- residual conv branch, first half (res_slimvit.py:107-109,233-242): gather the C+4 channels
  * ch_idx_host[0..cin) of x, conv3x3(cin -> c1, pad 1) + bias.  Writes the PRE-activation h1
- * [B, c1, Hx, Wx] in act dtype (GELU + PixelShuffle are applied on the fly by o2_headtail_*). */
-int o2_path2_conv1_fwd(const float* x, const int* ch_idx_host, const float* w1, const float* b1, void* h1,
-                       int dtype, int B, int V, int Hx, int Wx, int cin, int c1, void* stream);
+ * [B, c1, Hx, Wx] in act dtype and, when g1 != NULL, also g1 = PixelShuffle(mag)(GELU(h1))
+ * [B, c1/mag^2, Hx*mag, Wx*mag] (res_slimvit.py:109-110) for o2_headtail_* (g1 == NULL there: GELU +
+ * PixelShuffle are applied on the fly from h1). */
+int o2_path2_conv1_fwd(const float* x, const int* ch_idx_host, const float* w1, const float* b1, void* h1, void* g1,
+                       int dtype, int B, int V, int Hx, int Wx, int cin, int c1, int mag, void* stream);
 /* dw1 [c1,cin,3,3] / db1 [c1] "+=" from dh1 (gradient w.r.t. the pre-activation). */
 int o2_path2_conv1_bwd(const float* x, const int* ch_idx_host, const void* dh1, float* dw1, float* db1, int dtype,
                        int B, int V, int Hx, int Wx, int cin, int c1, void* stream);
@@ -126,12 +128,14 @@ int o2_path2_conv1_bwd(const float* x, const int* ch_idx_host, const void* dh1, 
 /* ---- head tail (res_slimvit.py:329-338): unpatchify (the reference's flat re-interpretation, see
  * SURVEY.md 8/a14) + conv_out 3x3 + [GELU -> PixelShuffle(mag) -> conv3x3(cr -> C)] of h1 + crop-add.
  * head_out [B, gh*gw, C*(mag*p)^2] act dtype; preds [B, C, Ho, Wo] act dtype, Ho = gh*p*mag, Wo = gw*p*mag;
- * h1 [B, cr*mag^2, Hx, Wx] with Hx*mag >= Ho, Wx*mag >= Wo (the branch is cropped to the ViT output). */
-int o2_headtail_fwd(const void* head_out, const void* h1, const float* w_out, const float* b_out, const float* w2,
+ * h1 [B, cr*mag^2, Hx, Wx] with Hx*mag >= Ho, Wx*mag >= Wo (the branch is cropped to the ViT output);
+ * g1 = the activated, shuffled branch written by o2_path2_conv1_fwd, or NULL. */
+int o2_headtail_fwd(const void* head_out, const void* h1, const void* g1, const float* w_out, const float* b_out, const float* w2,
                     const float* b2, void* preds, int dtype, int B, int C, int gh, int gw, int p, int mag, int cr,
                     int Hx, int Wx, void* stream);
 /* d_head_out / dh1 overwritten; dw_out [C,C,3,3], db_out [C], dw2 [C,cr,3,3], db2 [C] "+=". */
-int o2_headtail_bwd(const void* dpreds, const void* head_out, const void* h1, const float* w_out, const float* w2,
+int o2_headtail_bwd(const void* dpreds, const void* head_out, const void* h1, const void* g1, const float* w_out,
+                    const float* w2,
                     void* d_head_out, void* dh1, float* dw_out, float* db_out, float* dw2, float* db2, int dtype,
                     int B, int C, int gh, int gw, int p, int mag, int cr, int Hx, int Wx, void* stream);
 

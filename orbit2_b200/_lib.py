@@ -32,10 +32,10 @@ SIGNATURES = {
     "o2_attn_bwd_parts_drop": ([_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, C.c_uint64, _u, _p], _i),
     "o2_frontend_fwd": ([_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
     "o2_frontend_bwd": ([_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
-    "o2_path2_conv1_fwd": ([_p, C.POINTER(C.c_int), _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p], _i),
+    "o2_path2_conv1_fwd": ([_p, C.POINTER(C.c_int), _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
     "o2_path2_conv1_bwd": ([_p, C.POINTER(C.c_int), _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p], _i),
-    "o2_headtail_fwd": ([_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
-    "o2_headtail_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
+    "o2_headtail_fwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
+    "o2_headtail_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
     "o2_loss_fwd_bwd": ([_p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _u, _i, _i, _i, _i, _i, _i, _f, _p], _i),
     "o2_clip_replace": ([_p, _i, _p, _i, _u, _i, _i, _i, _i, _i, _i, _p], _i),
     "o2_scale_channels": ([_p, _i, _p, _i, _i, _l, _p], _i),

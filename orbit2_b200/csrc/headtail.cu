@@ -5,17 +5,14 @@
 // :333-336 crop-add.  o2_path2_conv1_* works on the low-res grid and keeps the PRE-activation h1; o2_headtail_* fuses
 // everything on the high-res grid (gather-unpatchify + conv_out + GELU/pixel-shuffle gather + conv2 + add) so that the
 // prediction is written exactly once and neither the unpatchified image nor the path2 output ever exist in HBM.
-#include "common.cuh"
+#include "headtail.cuh"
+
+using namespace o2ht;
 
 namespace {
 
 constexpr int TX = 32, TY = 8, NT = 256;
 constexpr int HXW = TX + 2, HYW = TY + 2;
-constexpr int MAXC = 8;      // output channels / cr
-constexpr int MAXCIN = 16;   // C + 4
-constexpr int MAXC1 = 64;    // cr * mag^2
-
-struct IdxList { int v[MAXCIN]; };
 
 // ------------------------------------------------------------------ path2 conv1 (low-res)
 template <typename T>
@@ -55,6 +52,18 @@ __global__ void __launch_bounds__(NT) conv1_fwd_kernel(const float* __restrict__
     for (int o = 0; o < 16; ++o)
       if (oc0 + o < c1) h1[(((size_t)b * c1 + oc0 + o) * Hx + gy) * Wx + gx] = from_f<T>(acc[o]);
   }
+}
+
+// g1 = PixelShuffle(mag)(GELU(h1)) for the generic path (the register-tiled conv1 kernel writes it from its epilogue)
+template <typename T>
+__global__ void gelu_shuffle_kernel(const T* __restrict__ h1, T* __restrict__ g1, int c1, int Hx, int Wx, int mag, size_t total) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int xl = (int)(i % Wx), yl = (int)((i / Wx) % Hx), ch = (int)((i / ((size_t)Wx * Hx)) % c1);
+  const size_t b = i / ((size_t)Wx * Hx * c1);
+  const int m2 = mag * mag, c4 = ch / m2, py = (ch % m2) / mag, px = ch % mag;
+  g1[((b * (c1 / m2) + c4) * ((size_t)Hx * mag) + (size_t)yl * mag + py) * ((size_t)Wx * mag) + (size_t)xl * mag + px] =
+      from_f<T>(gelu_f(to_f(h1[i])));
 }
 
 // dw1[oc][ci][tap] += sum dh1[b,oc,y,x] x7[b,ci,y+dy-1,x+dx-1]; db1[oc] += sum dh1.  Persistent CTAs, register partials.
@@ -132,13 +141,6 @@ __global__ void __launch_bounds__(NT) conv1_bwd_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------ head tail (high-res)
-struct HtArgs {
-  const void* head_out; const void* h1; const void* dpreds;
-  const float* w_out; const float* b_out; const float* w2; const float* b2;
-  void* preds; void* d_head_out; void* dh1;
-  float* dw_out; float* db_out; float* dw2; float* db2;
-  int B, C, gh, gw, p, mag, cr, Hx, Wx, Ho, Wo, Hs, Ws;   // Hs = Hx*mag, Ws = Wx*mag (extent of the shuffled branch)
-};
 
 // flat index of unpatchified pixel (c, y, x) inside one sample of head_out
 __device__ __forceinline__ size_t unpatch_idx(const HtArgs& a, int c, int y, int x) {
@@ -277,6 +279,12 @@ __global__ void __launch_bounds__(NT) headtail_bwd_kernel(const HtArgs a) {
   }
 }
 
+// O2_HEADTAIL_GENERIC=1 keeps the generic kernels (any p / mag / cr) on shapes the register-tiled ones would take: tests
+bool force_generic() {
+  const char* e = getenv("O2_HEADTAIL_GENERIC");
+  return e && e[0] == '1';
+}
+
 int fill_ht(HtArgs& a, int B, int C, int gh, int gw, int p, int mag, int cr, int Hx, int Wx) {
   O2_REQUIRE(B > 0 && C > 0 && C <= MAXC && cr > 0 && cr <= MAXC, "headtail: C=%d / cr=%d out of range (<=%d)", C, cr, MAXC);
   O2_REQUIRE(gh > 0 && gw > 0 && p > 0 && mag > 0, "headtail: bad dims");
@@ -292,18 +300,23 @@ int fill_ht(HtArgs& a, int B, int C, int gh, int gw, int p, int mag, int cr, int
 
 }  // namespace
 
-extern "C" int o2_path2_conv1_fwd(const float* x, const int* ch_idx_host, const float* w1, const float* b1, void* h1,
-                                  int dtype, int B, int V, int Hx, int Wx, int cin, int c1, void* stream) {
+extern "C" int o2_path2_conv1_fwd(const float* x, const int* ch_idx_host, const float* w1, const float* b1, void* h1, void* g1,
+                                  int dtype, int B, int V, int Hx, int Wx, int cin, int c1, int mag, void* stream) {
   O2_REQUIRE(x && ch_idx_host && w1 && b1 && h1, "conv1_fwd: null pointer");
   O2_REQUIRE(cin > 0 && cin <= MAXCIN && c1 > 0 && c1 <= MAXC1, "conv1_fwd: cin=%d / c1=%d out of range", cin, c1);
+  O2_REQUIRE(!g1 || (mag > 0 && c1 % (mag * mag) == 0), "conv1_fwd: g1 needs mag > 0 and c1 %% mag^2 == 0 (c1=%d mag=%d)", c1, mag);
   IdxList idx;
   for (int i = 0; i < cin; ++i) {
     O2_REQUIRE(ch_idx_host[i] >= 0 && ch_idx_host[i] < V, "conv1_fwd: channel index %d out of range", ch_idx_host[i]);
     idx.v[i] = ch_idx_host[i];
   }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!force_generic()) {
+    const int rc = conv1_fwd_fast(x, idx, w1, b1, h1, g1, dtype, B, V, Hx, Wx, cin, c1, mag, st);
+    if (rc != kNotApplicable) return rc;
+  }
   const size_t smem = sizeof(float) * ((size_t)cin * HYW * HXW + (size_t)c1 * cin * 9 + c1);
   dim3 grid((Wx + TX - 1) / TX, (Hx + TY - 1) / TY, B);
-  cudaStream_t st = (cudaStream_t)stream;
   if (dtype == O2_F32) {
     O2_CUDA(cudaFuncSetAttribute(conv1_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv1_fwd_kernel<float><<<grid, NT, smem, st>>>(x, idx, w1, b1, (float*)h1, B, V, Hx, Wx, cin, c1);
@@ -312,6 +325,13 @@ extern "C" int o2_path2_conv1_fwd(const float* x, const int* ch_idx_host, const 
     conv1_fwd_kernel<__nv_bfloat16><<<grid, NT, smem, st>>>(x, idx, w1, b1, (__nv_bfloat16*)h1, B, V, Hx, Wx, cin, c1);
   } else O2_FAIL(O2_ERR_ARG, "conv1_fwd: bad dtype %d", dtype);
   O2_LAUNCH_CHECK();
+  if (g1) {
+    const size_t total = (size_t)B * c1 * Hx * Wx;
+    const unsigned gsz = (unsigned)((total + 255) / 256);
+    if (dtype == O2_F32) gelu_shuffle_kernel<float><<<gsz, 256, 0, st>>>((const float*)h1, (float*)g1, c1, Hx, Wx, mag, total);
+    else gelu_shuffle_kernel<__nv_bfloat16><<<gsz, 256, 0, st>>>((const __nv_bfloat16*)h1, (__nv_bfloat16*)g1, c1, Hx, Wx, mag, total);
+    O2_LAUNCH_CHECK();
+  }
   return O2_OK;
 }
 
@@ -326,11 +346,15 @@ extern "C" int o2_path2_conv1_bwd(const float* x, const int* ch_idx_host, const 
     O2_REQUIRE(ch_idx_host[i] >= 0 && ch_idx_host[i] < V, "conv1_bwd: channel index out of range");
     idx.v[i] = ch_idx_host[i];
   }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!force_generic()) {
+    const int rc = conv1_bwd_fast(x, idx, dh1, dw1, db1, dtype, B, V, Hx, Wx, cin, c1, st);
+    if (rc != kNotApplicable) return rc;
+  }
   const size_t smem = sizeof(float) * ((size_t)cin * 10 * 18 + (size_t)c1 * 128);
   const long long ntiles = (long long)B * ((Wx + 15) / 16) * ((Hx + 7) / 8);
   long long grid = (long long)o2_num_sms() * 2;
   if (grid > ntiles) grid = ntiles;
-  cudaStream_t st = (cudaStream_t)stream;
   if (dtype == O2_F32) {
     O2_CUDA(cudaFuncSetAttribute(conv1_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv1_bwd_kernel<float><<<(unsigned)grid, NT, smem, st>>>(x, idx, (const float*)dh1, dw1, db1, B, V, Hx, Wx, cin, c1);
@@ -342,16 +366,20 @@ extern "C" int o2_path2_conv1_bwd(const float* x, const int* ch_idx_host, const 
   return O2_OK;
 }
 
-extern "C" int o2_headtail_fwd(const void* head_out, const void* h1, const float* w_out, const float* b_out,
+extern "C" int o2_headtail_fwd(const void* head_out, const void* h1, const void* g1, const float* w_out, const float* b_out,
                                const float* w2, const float* b2, void* preds, int dtype, int B, int C, int gh, int gw,
                                int p, int mag, int cr, int Hx, int Wx, void* stream) {
   HtArgs a;
   int rc = fill_ht(a, B, C, gh, gw, p, mag, cr, Hx, Wx);
   if (rc) return rc;
   O2_REQUIRE(head_out && h1 && w_out && b_out && w2 && b2 && preds, "headtail_fwd: null pointer");
-  a.head_out = head_out; a.h1 = h1; a.w_out = w_out; a.b_out = b_out; a.w2 = w2; a.b2 = b2; a.preds = preds;
+  a.head_out = head_out; a.h1 = h1; a.g1 = g1; a.w_out = w_out; a.b_out = b_out; a.w2 = w2; a.b2 = b2; a.preds = preds;
   dim3 grid((a.Wo + TX - 1) / TX, (a.Ho + TY - 1) / TY, B);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!force_generic()) {
+    rc = headtail_fwd_fast(a, dtype, st);
+    if (rc != kNotApplicable) return rc;
+  }
   if (dtype == O2_F32) headtail_fwd_kernel<float><<<grid, NT, 0, st>>>(a);
   else if (dtype == O2_BF16) headtail_fwd_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(a);
   else O2_FAIL(O2_ERR_ARG, "headtail_fwd: bad dtype %d", dtype);
@@ -359,7 +387,7 @@ extern "C" int o2_headtail_fwd(const void* head_out, const void* h1, const float
   return O2_OK;
 }
 
-extern "C" int o2_headtail_bwd(const void* dpreds, const void* head_out, const void* h1, const float* w_out,
+extern "C" int o2_headtail_bwd(const void* dpreds, const void* head_out, const void* h1, const void* g1, const float* w_out,
                                const float* w2, void* d_head_out, void* dh1, float* dw_out, float* db_out, float* dw2,
                                float* db2, int dtype, int B, int C, int gh, int gw, int p, int mag, int cr, int Hx, int Wx,
                                void* stream) {
@@ -368,12 +396,16 @@ extern "C" int o2_headtail_bwd(const void* dpreds, const void* head_out, const v
   if (rc) return rc;
   O2_REQUIRE(dpreds && head_out && h1 && w_out && w2 && d_head_out && dh1 && dw_out && db_out && dw2 && db2,
              "headtail_bwd: null pointer");
-  a.dpreds = dpreds; a.head_out = head_out; a.h1 = h1; a.w_out = w_out; a.w2 = w2; a.d_head_out = d_head_out; a.dh1 = dh1;
+  a.dpreds = dpreds; a.head_out = head_out; a.h1 = h1; a.g1 = g1; a.w_out = w_out; a.w2 = w2; a.d_head_out = d_head_out; a.dh1 = dh1;
   a.dw_out = dw_out; a.db_out = db_out; a.dw2 = dw2; a.db2 = db2;
   const long long ntiles = (long long)B * ((a.Ws + TX - 1) / TX) * ((a.Hs + TY - 1) / TY);
   long long grid = (long long)o2_num_sms() * 4;
   if (grid > ntiles) grid = ntiles;
   cudaStream_t st = (cudaStream_t)stream;
+  if (!force_generic()) {
+    rc = headtail_bwd_fast(a, dtype, st);
+    if (rc != kNotApplicable) return rc;
+  }
   if (dtype == O2_F32) headtail_bwd_kernel<float><<<(unsigned)grid, NT, 0, st>>>(a);
   else if (dtype == O2_BF16) headtail_bwd_kernel<__nv_bfloat16><<<(unsigned)grid, NT, 0, st>>>(a);
   else O2_FAIL(O2_ERR_ARG, "headtail_bwd: bad dtype %d", dtype);

@@ -230,17 +230,19 @@ def _idx(ch_idx):
     return (C.c_int * len(ch_idx))(*[int(i) for i in ch_idx])
 
 
-def path2_conv1_fwd(x, ch_idx, w1, b1, out_dtype):
-    """x [B,V,Hx,Wx] fp32 -> pre-activation h1 [B, c1, Hx, Wx]."""
+def path2_conv1_fwd(x, ch_idx, w1, b1, out_dtype, mag=0):
+    """x [B,V,Hx,Wx] fp32 -> pre-activation h1 [B, c1, Hx, Wx]; with mag > 0 also g1 = PixelShuffle(mag)(GELU(h1))
+    [B, c1/mag^2, Hx*mag, Wx*mag] and the return value is (h1, g1)."""
     lib = L.load()
     B, V, Hx, Wx = x.shape
     c1, cin = w1.shape[0], w1.shape[1]
     assert cin == len(ch_idx)
     h1 = torch.empty(B, c1, Hx, Wx, device=x.device, dtype=out_dtype)
-    L.check(lib.o2_path2_conv1_fwd(_ptr(x), _idx(ch_idx), _ptr(w1), _ptr(b1), _ptr(h1), dt(h1), B, V, Hx, Wx, cin, c1,
-                                   _stream()), "o2_path2_conv1_fwd")
+    g1 = torch.empty(B, c1 // (mag * mag), Hx * mag, Wx * mag, device=x.device, dtype=out_dtype) if mag else None
+    L.check(lib.o2_path2_conv1_fwd(_ptr(x), _idx(ch_idx), _ptr(w1), _ptr(b1), _ptr(h1), _ptr(g1) if mag else None, dt(h1),
+                                   B, V, Hx, Wx, cin, c1, mag, _stream()), "o2_path2_conv1_fwd")
     _count()
-    return h1
+    return (h1, g1) if mag else h1
 
 
 def path2_conv1_bwd(x, ch_idx, dh1, dw1, db1):
@@ -253,19 +255,19 @@ def path2_conv1_bwd(x, ch_idx, dh1, dw1, db1):
     _count()
 
 
-def headtail_fwd(head_out, h1, w_out, b_out, w2, b2, B, C_, gh, gw, p, mag):
+def headtail_fwd(head_out, h1, w_out, b_out, w2, b2, B, C_, gh, gw, p, mag, g1=None):
     """head_out [B*gh*gw, C*(mag*p)^2], h1 [B, cr*mag^2, Hx, Wx] -> preds [B, C, gh*p*mag, gw*p*mag]."""
     lib = L.load()
     cr = w2.shape[1]
     Hx, Wx = h1.shape[2], h1.shape[3]
     preds = torch.empty(B, C_, gh * p * mag, gw * p * mag, device=head_out.device, dtype=head_out.dtype)
-    L.check(lib.o2_headtail_fwd(_ptr(head_out), _ptr(h1), _ptr(w_out), _ptr(b_out), _ptr(w2), _ptr(b2), _ptr(preds),
+    L.check(lib.o2_headtail_fwd(_ptr(head_out), _ptr(h1), _ptr(g1) if g1 is not None else None, _ptr(w_out), _ptr(b_out), _ptr(w2), _ptr(b2), _ptr(preds),
                                 dt(preds), B, C_, gh, gw, p, mag, cr, Hx, Wx, _stream()), "o2_headtail_fwd")
     _count()
     return preds
 
 
-def headtail_bwd(dpreds, head_out, h1, w_out, w2, dw_out, db_out, dw2, db2, B, C_, gh, gw, p, mag):
+def headtail_bwd(dpreds, head_out, h1, w_out, w2, dw_out, db_out, dw2, db2, B, C_, gh, gw, p, mag, g1=None):
     """-> (d_head_out, dh1); the four weight gradients (fp32) are accumulated into."""
     lib = L.load()
     cr = w2.shape[1]
@@ -273,7 +275,8 @@ def headtail_bwd(dpreds, head_out, h1, w_out, w2, dw_out, db_out, dw2, db2, B, C
     dho = torch.empty_like(head_out)
     dh1 = torch.empty_like(h1)
     assert dpreds.is_contiguous() and dpreds.dtype == head_out.dtype
-    L.check(lib.o2_headtail_bwd(_ptr(dpreds), _ptr(head_out), _ptr(h1), _ptr(w_out), _ptr(w2), _ptr(dho), _ptr(dh1),
+    L.check(lib.o2_headtail_bwd(_ptr(dpreds), _ptr(head_out), _ptr(h1), _ptr(g1) if g1 is not None else None, _ptr(w_out),
+                                _ptr(w2), _ptr(dho), _ptr(dh1),
                                 _ptr(dw_out), _ptr(db_out), _ptr(dw2), _ptr(db2), dt(dpreds), B, C_, gh, gw, p, mag, cr,
                                 Hx, Wx, _stream()), "o2_headtail_bwd")
     _count()

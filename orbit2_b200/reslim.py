@@ -11,7 +11,7 @@ Execution plan of one forward (T = B*L tokens, act = fp32 | bf16):
       tab_s/tab_v  = exact collapse of patch-embed + var-embed + var-agg q/kv
       posres [L,D] = pos_embed (bicubic-resampled if the grid changed) + spatial_embed(resolution)
   kernels (one manual autograd node, ``ReslimFunction``):
-      h1    = o2_path2_conv1_fwd(x[:, idx7])                       residual branch, low-res, pre-GELU
+      h1,g1 = o2_path2_conv1_fwd(x[:, idx7])                       residual branch: low-res pre-GELU + activated/shuffled copy
       o     = o2_frontend_fwd(x, tab_s, tab_v)                     [T, D]
       tok   = o2_gemm(o, var_agg.proj) + bias + posres             BIAS_RES epilogue
       per block: LN -> qkv GEMM(+bias) -> flash attention -> proj GEMM(+bias+residual)
@@ -163,7 +163,7 @@ def reslim_forward(g: Geometry, P: Dict[str, torch.Tensor], Wc: Dict[str, torch.
         out = torch.empty(a.shape[0], n_out, device=dev, dtype=act)
         return ops.gemm(a, w, out, **kw)
 
-    S["h1"] = h1 = ops.path2_conv1_fwd(x, g.idx7, P["path2.0.weight"], P["path2.0.bias"], act)
+    S["h1"], S["g1"] = h1, g1 = ops.path2_conv1_fwd(x, g.idx7, P["path2.0.weight"], P["path2.0.bias"], act, mag=g.mag)
     S["o"] = o = ops.frontend_fwd(x, tab_s, tab_v, g.p, g.gh, g.gw, g.hd, act)
     tok = gemm(o, Wc["var_agg.proj.weight"], D, epi=EPI_BIAS_RES, bias=P["var_agg.proj.bias"], aux=posres, aux_rows=g.L)
     dp = getattr(g, "drop", None)
@@ -210,7 +210,7 @@ def reslim_forward(g: Geometry, P: Dict[str, torch.Tensor], Wc: Dict[str, torch.
     n_out = g.C * (g.mag * g.p) ** 2
     S["ho"] = ho = gemm(z, Wc[f"head.{2 * g.dec}.weight"], n_out, epi=EPI_BIAS, bias=P[f"head.{2 * g.dec}.bias"])
     preds = ops.headtail_fwd(ho, h1, P["conv_out.weight"], P["conv_out.bias"], P["path2.3.weight"], P["path2.3.bias"],
-                             g.B, g.C, g.gh, g.gw, g.p, g.mag)
+                             g.B, g.C, g.gh, g.gw, g.p, g.mag, g1=g1)
     return preds, S
 
 
@@ -239,7 +239,7 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
 
     dho, dh1 = ops.headtail_bwd(dpreds, S["ho"], S["h1"], P["conv_out.weight"], P["path2.3.weight"], G["conv_out.weight"],
                                 G["conv_out.bias"], G["path2.3.weight"], G["path2.3.bias"], g.B, g.C, g.gh, g.gw, g.p,
-                                g.mag)
+                                g.mag, g1=S["g1"])
     ops.path2_conv1_bwd(x, g.idx7, dh1, G["path2.0.weight"], G["path2.0.bias"])
     ready(["conv_out.weight", "conv_out.bias", "path2.3.weight", "path2.3.bias", "path2.0.weight", "path2.0.bias"])
     del dh1

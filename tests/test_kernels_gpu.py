@@ -165,11 +165,15 @@ def test_frontend(dtype, B, V, gh, gw, heads, hd, extra):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("B,C,gh,gw,extra", [(2, 3, 4, 8, 0), (1, 3, 6, 12, 1), (1, 1, 5, 21, 0)])
-def test_conv1_headtail(dtype, B, C, gh, gw, extra):
-    """residual branch + head tail against the oracle's path2 / unpatchify / conv_out (float64)."""
+@pytest.mark.parametrize("generic,with_g1", [(False, True), (False, False), (True, True)])
+@pytest.mark.parametrize("B,C,gh,gw,extra", [(2, 3, 4, 8, 0), (1, 3, 6, 12, 1), (1, 1, 5, 21, 0), (2, 3, 12, 20, 0),
+                                             (1, 2, 9, 17, 2)])
+def test_conv1_headtail(dtype, B, C, gh, gw, extra, generic, with_g1, monkeypatch):
+    """residual branch + head tail against the oracle's path2 / unpatchify / conv_out (float64); both the register-tiled
+    kernels (p 2 / mag 4 / cr 4: every reference config) and the generic ones (forced by O2_HEADTAIL_GENERIC=1)."""
     from oracle import reslim_oracle as O
     from orbit2_b200 import ops
+    monkeypatch.setenv("O2_HEADTAIL_GENERIC", "1" if generic else "0")
     p, mag, cr = 2, 4, 4
     V = C + 6
     Hx, Wx = gh * p + extra, gw * p + extra
@@ -183,8 +187,13 @@ def test_conv1_headtail(dtype, B, C, gh, gw, extra):
     ho = rn(B * gh * gw, C * (mag * p) ** 2).to(dtype)
     Ho, Wo = gh * p * mag, gw * p * mag
     dp = rn(B, C, Ho, Wo).to(dtype)
-    h1 = ops.path2_conv1_fwd(x, idx, w1, b1, dtype)
-    preds = ops.headtail_fwd(ho, h1, wo, bo, w2, b2, B, C, gh, gw, p, mag)
+    if with_g1:
+        h1, g1 = ops.path2_conv1_fwd(x, idx, w1, b1, dtype, mag=mag)
+        gref = torch.nn.functional.pixel_shuffle(torch.nn.functional.gelu(h1.double()), mag)
+        assert rel(g1, gref) < (1e-6 if dtype == torch.float32 else 5e-3)
+    else:
+        h1, g1 = ops.path2_conv1_fwd(x, idx, w1, b1, dtype), None
+    preds = ops.headtail_fwd(ho, h1, wo, bo, w2, b2, B, C, gh, gw, p, mag, g1=g1)
     d = lambda t: t.double().requires_grad_(True)
     w1d, b1d, w2d, b2d, wod, bod, hod = d(w1), d(b1), d(w2), d(b2), d(wo), d(bo), d(ho)
     sd = {"path2.0.weight": w1d, "path2.0.bias": b1d, "path2.3.weight": w2d, "path2.3.bias": b2d}
@@ -196,7 +205,7 @@ def test_conv1_headtail(dtype, B, C, gh, gw, extra):
     assert rel(preds, ref.detach()) < tol
     ref.backward(dp.double())
     G = {k: torch.zeros_like(v) for k, v in dict(w1=w1, b1=b1, w2=w2, b2=b2, wo=wo, bo=bo).items()}
-    dho, dh1 = ops.headtail_bwd(dp, ho, h1, wo, w2, G["wo"], G["bo"], G["w2"], G["b2"], B, C, gh, gw, p, mag)
+    dho, dh1 = ops.headtail_bwd(dp, ho, h1, wo, w2, G["wo"], G["bo"], G["w2"], G["b2"], B, C, gh, gw, p, mag, g1=g1)
     ops.path2_conv1_bwd(x, idx, dh1, G["w1"], G["b1"])
     gt = 2e-5 if dtype == torch.float32 else 2.5e-2
     assert rel(dho, hod.grad) < gt

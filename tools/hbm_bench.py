@@ -62,15 +62,18 @@ report("loss mse fwd+grad", lambda: ops.loss_fwd_bwd(pred, tgt, L.LOSS_MSE, ch_w
 idx = [21, 6, 5, 0, 1, 2, 3]
 w1, b1 = rn(64, 7, 3, 3) * 0.1, rn(64) * 0.1
 w2, b2, wo, bo = rn(C, 4, 3, 3) * 0.1, rn(C) * 0.1, rn(C, C, 3, 3) * 0.1, rn(C) * 0.1
-h1 = ops.path2_conv1_fwd(x, idx, w1, b1, bf)
+h1, g1 = ops.path2_conv1_fwd(x, idx, w1, b1, bf, mag=mag)
 ho = rn(T, C * (mag * p) ** 2).to(bf)
-report("path2 conv1 fwd (7->64 ch, low-res)", lambda: ops.path2_conv1_fwd(x, idx, w1, b1, bf), B * 7 * H * W * 4 + B * 64 * H * W * 2)
-report("head tail fwd (unpatchify+convs+add)", lambda: ops.headtail_fwd(ho, h1, wo, bo, w2, b2, B, C, gh, gw, p, mag),
+report("path2 conv1 fwd (7->64 ch, low-res)", lambda: ops.path2_conv1_fwd(x, idx, w1, b1, bf, mag=mag), B * 7 * H * W * 4 + 2 * B * 64 * H * W * 2)
+report("head tail fwd (unpatchify+convs+add)", lambda: ops.headtail_fwd(ho, h1, wo, bo, w2, b2, B, C, gh, gw, p, mag, g1=g1),
        ho.numel() * 2 + h1.numel() * 2 + B * C * Ho * Wo * 2)
 dp = rn(B, C, Ho, Wo).to(bf)
 G = [torch.zeros_like(t) for t in (wo, bo, w2, b2)]
-report("head tail bwd", lambda: ops.headtail_bwd(dp, ho, h1, wo, w2, *G, B, C, gh, gw, p, mag),
-       dp.numel() * 2 + 2 * ho.numel() * 2 + 2 * h1.numel() * 2)
+report("head tail bwd", lambda: ops.headtail_bwd(dp, ho, h1, wo, w2, *G, B, C, gh, gw, p, mag, g1=g1),
+       dp.numel() * 2 + 2 * ho.numel() * 2 + 3 * h1.numel() * 2)
+dh1 = torch.randn_like(h1)
+Gw = [torch.zeros_like(w1), torch.zeros_like(b1)]
+report("path2 conv1 bwd (weight grads)", lambda: ops.path2_conv1_bwd(x, idx, dh1, *Gw), B * 7 * H * W * 4 + B * 64 * H * W * 2)
 ts, tv = rn(V, heads, 5), rn(heads, V * 5, hd) * 0.1
 do = rn(T, D).to(bf)
 report("front end fwd (x -> o [T,D])", lambda: ops.frontend_fwd(x, ts, tv, p, gh, gw, hd, bf), x.numel() * 4 + T * D * 2)
