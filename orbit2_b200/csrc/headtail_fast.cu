@@ -562,25 +562,27 @@ __global__ void __launch_bounds__(FNT, 2) conv1_fwd_fast_kernel(const float* __r
 
 // backward (weight gradients): warp = 8 output channels, lane = (input plane ci, tap row dy) -> 8 x 3 private taps kept
 // over a persistent loop of 64 x 4 pixel tiles (FFMA2 over pixel pairs, the two halves are added at the end); nobody
-// shares a tap, so the CTA ends with plain atomics
+// shares a tap, so the CTA ends with plain atomics.  The bias gradient rides along for free: lane cin*3 runs the same
+// instruction stream on a row of ones, so its first tap accumulates sum(dh1).
 constexpr int RY = 4;
 template <typename T>
 __global__ void __launch_bounds__(FNT, 2) conv1_bwd_fast_kernel(const float* __restrict__ x, IdxList idx, const T* __restrict__ dh1,
                                                                float* __restrict__ dw1, float* __restrict__ db1, int B, int V,
                                                                int Hx, int Wx, int cin, int c1) {
   extern __shared__ __align__(16) float smem_f[];
-  float* sx = smem_f;                              // [cin][RY + 2][QW]
-  float* sd = sx + cin * (RY + 2) * QW;            // [c1][RY][QX]
+  float* sx = smem_f;                              // [cin][RY + 2][QW], then one row of ones
+  float* sones = sx + cin * (RY + 2) * QW;         // [QW]
+  float* sd = sones + QW;                          // [c1][RY][QX]
   const int og = threadIdx.x >> 5, cd = threadIdx.x & 31;   // warp = group of 8 output channels, lane = ci * 3 + dy
   const int ci = cd / 3, dy = cd % 3;
-  const bool active = (og < (c1 >> 3)) && (cd < cin * 3);
-  uint64_t acc[8][3], bacc[8];
+  const bool bias_lane = (cd == cin * 3);
+  const bool active = (og < (c1 >> 3)) && (cd <= cin * 3);
+  for (int i = threadIdx.x; i < QW; i += FNT) sones[i] = 1.f;
+  uint64_t acc[8][3];
 #pragma unroll
-  for (int o = 0; o < 8; ++o) {
-    bacc[o] = 0ull;
+  for (int o = 0; o < 8; ++o)
 #pragma unroll
     for (int d = 0; d < 3; ++d) acc[o][d] = 0ull;
-  }
   const int tiles_x = (Wx + QX - 1) / QX, tiles_y = (Hx + RY - 1) / RY;
   const long long ntiles = (long long)B * tiles_x * tiles_y;
   const size_t plane = (size_t)Hx * Wx;
@@ -619,7 +621,7 @@ __global__ void __launch_bounds__(FNT, 2) conv1_bwd_fast_kernel(const float* __r
     if (active) {
 #pragma unroll 1
       for (int r = 0; r < RY; ++r) {
-        const float* srow = sx + (ci * (RY + 2) + r + dy) * QW;
+        const float* srow = bias_lane ? sones : sx + (ci * (RY + 2) + r + dy) * QW;
         const float* drow = sd + ((og * 8) * RY + r) * QX;
 #pragma unroll 2
         for (int s = 0; s < QX / 4; ++s) {
@@ -636,7 +638,6 @@ __global__ void __launch_bounds__(FNT, 2) conv1_bwd_fast_kernel(const float* __r
               acc[o][d] = ptx::fma2(g.x, vp[d], acc[o][d]);
               acc[o][d] = ptx::fma2(g.y, vp[d + 2], acc[o][d]);
             }
-            if (cd == 0) bacc[o] = ptx::add2(bacc[o], ptx::add2(g.x, g.y));
           }
         }
       }
@@ -646,16 +647,17 @@ __global__ void __launch_bounds__(FNT, 2) conv1_bwd_fast_kernel(const float* __r
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
       const int oc = og * 8 + o;
+      if (bias_lane) {
+        float lo, hi;
+        ptx::unpack2(acc[o][0], lo, hi);
+        atomicAdd(&db1[oc], lo + hi);
+        continue;
+      }
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         float lo, hi;
         ptx::unpack2(acc[o][d], lo, hi);
         atomicAdd(&dw1[((size_t)oc * cin + ci) * 9 + dy * 3 + d], lo + hi);
-      }
-      if (cd == 0) {
-        float lo, hi;
-        ptx::unpack2(bacc[o], lo, hi);
-        atomicAdd(&db1[oc], lo + hi);
       }
     }
   }
@@ -704,8 +706,8 @@ int conv1_fwd_fast(const float* x, const IdxList& idx, const float* w1, const fl
 
 int conv1_bwd_fast(const float* x, const IdxList& idx, const void* dh1, float* dw1, float* db1, int dtype, int B, int V,
                    int Hx, int Wx, int cin, int c1, cudaStream_t st) {
-  if ((c1 & 7) != 0 || (c1 >> 3) > FNT / 32 || cin * 3 > 32) return kNotApplicable;
-  const size_t smem = sizeof(float) * ((size_t)cin * (RY + 2) * QW + (size_t)c1 * RY * QX);
+  if ((c1 & 7) != 0 || (c1 >> 3) > FNT / 32 || cin * 3 > 31) return kNotApplicable;
+  const size_t smem = sizeof(float) * ((size_t)cin * (RY + 2) * QW + QW + (size_t)c1 * RY * QX);
   if (smem > 100 * 1024) return kNotApplicable;
   const long long ntiles = (long long)B * ((Wx + QX - 1) / QX) * ((Hx + RY - 1) / RY);
   long long grid = (long long)o2_num_sms() * 2;

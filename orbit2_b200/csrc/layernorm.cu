@@ -7,6 +7,8 @@
 // streaming column reduction for dgamma / dbeta (a fused register-accumulator version ran at 222 registers, one CTA
 // per SM and 29 % of HBM peak).
 #include "common.cuh"
+#include <algorithm>
+#include <type_traits>
 
 namespace {
 
@@ -162,6 +164,231 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const T* __restrict__ dy
   }
 }
 
+// Fused backward for rows that fit ONE 16-byte vector per lane (NV = 1: D = 1024 bf16 with G = 4 warps per row,
+// D = 1024 fp32 with G = 8): dx and the column gradients in a single pass over dy / x (4 tensors moved instead of 6).
+// A lane owns the same VN columns for every row it sees, so dgamma / dbeta partials are 2 VN registers; the CTA walks
+// rows persistently, two per row-group per iteration (both rows' loads are in flight before the one barrier that
+// exchanges the row statistics, double-buffered), and ends with a shared-memory reduction over its row groups and one
+// atomic per column.
+template <typename T, int G>
+__global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const T* __restrict__ dres,
+                                                           T* __restrict__ dx, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, long long rows, int D) {
+  constexpr int VN = Vec<T>::N, RPC = 8 / G, R = 2;
+  __shared__ float sred[2][8][R][2];
+  __shared__ float scol[RPC > 1 ? RPC : 1][2][32 * G * VN];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & (32 * G - 1);
+  const int grp = threadIdx.x / (32 * G);
+  const bool col_ok = lane * VN < D;
+  float gm[VN], ag[VN], ab[VN];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) { gm[j] = 0.f; ag[j] = 0.f; ab[j] = 0.f; }
+  if (col_ok) {
+#pragma unroll
+    for (int j = 0; j < VN; j += 4) Vec<float>::load(gamma + lane * VN + j, reinterpret_cast<float(&)[4]>(gm[j]));
+  }
+  const float invD = 1.0f / D;
+  const long long stride = (long long)gridDim.x * RPC * R;
+  int buf = 0;
+  for (long long base = (long long)blockIdx.x * RPC * R; base < rows; base += stride) {
+    float xh[R][VN], gy[R][VN], rs[R];
+    long long row[R];
+    bool ok[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      row[q] = base + q * RPC + grp;
+      ok[q] = col_ok && row[q] < rows;
+      float xv[VN], dv[VN];
+#pragma unroll
+      for (int j = 0; j < VN; ++j) { xv[j] = 0.f; dv[j] = 0.f; }
+      float mu = 0.f;
+      rs[q] = 0.f;
+      if (ok[q]) {
+        Vec<T>::load(x + row[q] * D + lane * VN, xv);
+        Vec<T>::load(dy + row[q] * D + lane * VN, dv);
+        mu = mean[row[q]];
+        rs[q] = rstd[row[q]];
+      }
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        xh[q][j] = (xv[j] - mu) * rs[q];
+        gy[q][j] = dv[j] * gm[j];
+        s1 += gy[q][j];
+        s2 = fmaf(gy[q][j], xh[q][j], s2);
+        ag[j] = fmaf(dv[j], xh[q][j], ag[j]);
+        ab[j] += dv[j];
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if ((threadIdx.x & 31) == 0) { sred[buf][warp][q][0] = s1; sred[buf][warp][q][1] = s2; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < G; ++i) { s1 += sred[buf][grp * G + i][q][0]; s2 += sred[buf][grp * G + i][q][1]; }
+      s1 *= invD;
+      s2 *= invD;
+      if (ok[q]) {
+        float o[VN];
+        if (dres) Vec<T>::load(dres + row[q] * D + lane * VN, o);
+        else {
+#pragma unroll
+          for (int j = 0; j < VN; ++j) o[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o[j] += rs[q] * (gy[q][j] - s1 - xh[q][j] * s2);
+        Vec<T>::store(dx + row[q] * D + lane * VN, o);
+      }
+    }
+    buf ^= 1;
+  }
+  // column gradients: sum the CTA's row groups, one atomic per column
+  if (RPC > 1) {
+#pragma unroll
+    for (int j = 0; j < VN; ++j) { scol[grp][0][lane * VN + j] = ag[j]; scol[grp][1][lane * VN + j] = ab[j]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * 32 * G * VN; i += 256) {
+      const int which = i / (32 * G * VN), c = i % (32 * G * VN);
+      float s_ = 0.f;
+#pragma unroll
+      for (int r = 0; r < RPC; ++r) s_ += scol[r][which][c];
+      if (c < D) atomicAdd(which == 0 ? &dgamma[c] : &dbeta[c], s_);
+    }
+  } else if (col_ok) {
+#pragma unroll
+    for (int j = 0; j < VN; ++j) { atomicAdd(&dgamma[lane * VN + j], ag[j]); atomicAdd(&dbeta[lane * VN + j], ab[j]); }
+  }
+}
+
+// Fused backward for bf16 rows of up to 1024 columns (the 117M / 8m widths): dx AND the column gradients in one pass
+// over dy / x / dres (4 tensors moved instead of 6).  ONE WARP owns a row and keeps the dgamma / dbeta partials of its
+// NV x 8 columns in fp32 registers for the whole persistent loop.  Rows arrive through a private 2-stage shared-memory
+// ring filled by 1-D bulk copies (cp.async.bulk + mbarrier complete_tx): the bytes in flight live in shared memory, not
+// in registers -- the register-resident versions of this kernel (12 warps per SM at 168 registers, or 4 warps per row
+// with a CTA barrier) all stalled at 3.0 TB/s with ~48 KB in flight per SM; this one keeps 16 warps x 2 rows x 6 KB.
+constexpr int kLnWarps = 8, kLnStages = 2;
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(ptx::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(ptx::smem_u32(bar)) : "memory");
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32, 2) ln_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                                       const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dres,
+                                                                       __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                                       float* __restrict__ dbeta, long long rows, int D) {
+  constexpr int W = NV * 256;                       // padded row width (elements)
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(ln_smem);                 // [warp][stage][x | dy | dres][W]
+  float* sg = reinterpret_cast<float*>(ring + kLnWarps * kLnStages * 3 * W);        // [W]
+  float* scol = sg + W;                                                             // [2][W]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scol + 2 * W);                       // [warp][stage]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < W; i += kLnWarps * 32) { sg[i] = i < D ? gamma[i] : 0.f; scol[i] = 0.f; scol[W + i] = 0.f; }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kLnWarps * kLnStages; ++i) ptx::mbar_init(&bars[i], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int nvec = D >> 3;
+  const uint32_t row_bytes = (uint32_t)D * 2u;
+  const float invD = 1.0f / D;
+  const long long nw = (long long)gridDim.x * kLnWarps;
+  const long long row0 = (long long)blockIdx.x * kLnWarps + warp;
+  __nv_bfloat16* my = ring + (size_t)warp * kLnStages * 3 * W;
+  uint64_t* mybar = bars + warp * kLnStages;
+  auto issue = [&](long long row, int st) {         // lane 0 only
+    __nv_bfloat16* dst = my + (size_t)st * 3 * W;
+    ptx::mbar_expect_tx(&mybar[st], (dres ? 3u : 2u) * row_bytes);
+    bulk_g2s(dst, x + row * D, row_bytes, &mybar[st]);
+    bulk_g2s(dst + W, dy + row * D, row_bytes, &mybar[st]);
+    if (dres) bulk_g2s(dst + 2 * W, dres + row * D, row_bytes, &mybar[st]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < kLnStages; ++st)
+      if (row0 + st * nw < rows) issue(row0 + st * nw, st);
+  }
+  float ag[NV][8], ab[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; }
+  int st = 0;
+  uint32_t phase = 0;
+  for (long long row = row0; row < rows; row += nw) {
+    const float mu = mean[row], rs = rstd[row];
+    ptx::mbar_wait(&mybar[st], phase);
+    const __nv_bfloat16* sx = my + (size_t)st * 3 * W;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        float xv[8], dv[8], gm[8];
+        Vec<__nv_bfloat16>::load(sx + vi * 8, xv);
+        Vec<__nv_bfloat16>::load(sx + W + vi * 8, dv);
+        Vec<float>::load(sg + vi * 8, reinterpret_cast<float(&)[4]>(gm[0]));
+        Vec<float>::load(sg + vi * 8 + 4, reinterpret_cast<float(&)[4]>(gm[4]));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mu) * rs, gy = dv[j] * gm[j];
+          s1 += gy;
+          s2 = fmaf(gy, xh, s2);
+          ag[i][j] = fmaf(dv[j], xh, ag[i][j]);
+          ab[i][j] += dv[j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        float xv[8], dv[8], gm[8], o[8];
+        Vec<__nv_bfloat16>::load(sx + vi * 8, xv);
+        Vec<__nv_bfloat16>::load(sx + W + vi * 8, dv);
+        Vec<float>::load(sg + vi * 8, reinterpret_cast<float(&)[4]>(gm[0]));
+        Vec<float>::load(sg + vi * 8 + 4, reinterpret_cast<float(&)[4]>(gm[4]));
+        if (dres) Vec<__nv_bfloat16>::load(sx + 2 * W + vi * 8, o);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mu) * rs, gy = dv[j] * gm[j];
+          o[j] += rs * (gy - s1 - xh * s2);
+        }
+        Vec<__nv_bfloat16>::store(dx + row * D + vi * 8, o);
+      }
+    }
+    __syncwarp();                                   // every lane is done reading this stage
+    if (lane == 0 && row + kLnStages * nw < rows) {
+      ptx::fence_proxy_async_smem();
+      issue(row + kLnStages * nw, st);
+    }
+    if (++st == kLnStages) { st = 0; phase ^= 1; }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&scol[(lane + 32 * i) * 8 + j], ag[i][j]);
+      atomicAdd(&scol[W + (lane + 32 * i) * 8 + j], ab[i][j]);
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += kLnWarps * 32) { atomicAdd(&dgamma[c], scol[c]); atomicAdd(&dbeta[c], scol[W + c]); }
+}
+
 // dgamma[c] += sum_rows dy * (x - mean) * rstd, dbeta[c] += sum_rows dy: 32 column vectors x 8 row lanes per CTA,
 // grid-strided over rows, smem transpose-reduce, one atomic per column per CTA.
 template <typename T>
@@ -223,6 +450,42 @@ int ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
            void* dx, float* dgamma, float* dbeta, long long T_, int D, cudaStream_t st) {
   constexpr int VN = Vec<T>::N;
   const int nv = (D / VN + 31) / 32;
+  if (std::is_same<T, __nv_bfloat16>::value && nv <= 4 && !getenv("O2_LN_BWD_SPLIT")) {
+    auto launch = [&](auto kern, int nvt) -> int {
+      const size_t smem = (size_t)kLnWarps * kLnStages * 3 * nvt * 256 * 2 + (size_t)3 * nvt * 256 * 4 + kLnWarps * kLnStages * 8;
+      O2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLnWarps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+      const long long grid = std::min((long long)o2_num_sms() * per_sm, (T_ + kLnWarps - 1) / kLnWarps);
+      kern<<<(unsigned)grid, kLnWarps * 32, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, gamma, mean, rstd,
+                                                       (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, dgamma, dbeta, T_, D);
+      O2_LAUNCH_CHECK();
+      return O2_OK;
+    };
+    if (nv <= 1) return launch(ln_bwd_ring_kernel<1>, 1);
+    if (nv <= 2) return launch(ln_bwd_ring_kernel<2>, 2);
+    return launch(ln_bwd_ring_kernel<4>, 4);
+  }
+  if (nv <= 8 && nv > 2 && !getenv("O2_LN_BWD_SPLIT")) {      // one vector per lane with G = 4 / 8 warps per row
+    auto resident = [](const void* fn) {      // persistent grid = exactly the CTAs that are co-resident (one wave)
+      int n = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, 256, 0) != cudaSuccess || n < 1) n = 1;
+      return (long long)o2_num_sms() * n;
+    };
+    if (nv <= 4) {
+      const long long want = resident((const void*)ln_bwd_fused_kernel<T, 4>);
+      const long long per = 2 * 2, grid = std::min(want, (T_ + per - 1) / per);
+      ln_bwd_fused_kernel<T, 4><<<(unsigned)grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres,
+                                                              (T*)dx, dgamma, dbeta, T_, D);
+    } else {
+      const long long want = resident((const void*)ln_bwd_fused_kernel<T, 8>);
+      const long long per = 1 * 2, grid = std::min(want, (T_ + per - 1) / per);
+      ln_bwd_fused_kernel<T, 8><<<(unsigned)grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres,
+                                                              (T*)dx, dgamma, dbeta, T_, D);
+    }
+    O2_LAUNCH_CHECK();
+    return O2_OK;
+  }
 #define O2_LN_BWD(NV, G)                                                                                        \
   ln_bwd_dx_kernel<T, NV, G><<<(unsigned)((T_ + 8 / G - 1) / (8 / G)), 256, 0, st>>>(                            \
       (const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, T_, D)

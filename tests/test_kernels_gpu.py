@@ -14,7 +14,8 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("T,D", [(37, 256), (1000, 1024), (129, 128), (64, 2048), (67, 3072), (35, 8192)])
+@pytest.mark.parametrize("T,D", [(37, 256), (1000, 1024), (129, 128), (64, 2048), (67, 3072), (35, 8192), (5003, 768),
+                                 (3, 1024)])
 def test_layernorm(dtype, T, D):
     """D = 3072 / 8192 are the interm_1b / 10b widths (rows shared by 2-8 warps)."""
     from orbit2_b200 import ops
