@@ -78,7 +78,7 @@ template <int NH, bool kDrop>
 __global__ void __launch_bounds__(kThreadsB, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   constexpr int kStagesF = FwdCfg<NH>::kStages;
   constexpr uint32_t kQKV = NH * kTileBytes;        // bytes of one Q / K / V tile (NH half-tiles)
   uint8_t* sQ = smem;                               // 2 tiles
@@ -467,7 +467,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   constexpr int kTiles = BwdCfg<NH>::kTiles;
   constexpr uint32_t kT = BwdCfg<NH>::kT;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* sQ = smem;                               // kTiles tiles
   uint8_t* sdO = sQ + kTiles * kT;                  // kTiles tiles
   uint8_t* sK = sdO + kTiles * kT;                  // kStagesB tiles
@@ -735,7 +735,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   constexpr uint32_t kT = BwdCfg<NH>::kT;
   constexpr uint32_t kColDK = 128, kColDV = 128 + 64 * NH;   // TMEM columns inside a key tile's block
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* sK = smem;                               // kTiles tiles
   uint8_t* sV = sK + kTiles * kT;                   // kTiles tiles
   uint8_t* sQ = sV + kTiles * kT;                   // kStagesB tiles

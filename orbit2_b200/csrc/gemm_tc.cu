@@ -23,7 +23,7 @@ constexpr uint32_t kStageA = BM * BK * 2;  // 16 KiB
 
 struct GemmArgs {
   int M, N, K;
-  int epi, c_f32;
+  int epi, c_f32, wide_st, wide_ld;   // C (and aux_out) / aux rows are 32-byte aligned -> 256-bit stores / loads
   long long ldc, ld_aux, aux_rows, ld_aux_out;
   const float* bias;
   const __nv_bfloat16* aux;
@@ -46,51 +46,79 @@ template <int BN> struct Cfg {
 // the chunk's aux values (residual / pre-activation), fetched by the caller BEFORE it waited for the TMEM load so that
 // their L2 latency overlaps it (the first version loaded bias and aux here, per 8 columns: the epilogue warps then sat
 // in long-scoreboard stalls for 2/3 of the time and the tensor pipe idled at 58 %).
+// 32-byte (one full sector) store: with 16-byte stores every lane of a row-per-lane epilogue half-fills a sector per
+// request, and the LSU store path -- not the tensor pipe -- bounded the GELU / residual epilogues (ncu: LDS / FADD of
+// the next columns waiting on the previous STG's operand read, 32 sectors per request at 50 % efficiency).
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  return u;
+}
+// bf16 row piece of 16 columns starting at n (n % 8 == 0): one 256-bit store when it is in range and 32-byte aligned
+__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float* v, int n, int N, bool wide) {
+  const uint4 lo = pack8(v), hi = pack8(v + 8);
+  if (wide && n + 16 <= N) {
+    st_global_256(dst, lo, hi);
+  } else {
+    *reinterpret_cast<uint4*>(dst) = lo;
+    if (n + 8 < N) *reinterpret_cast<uint4*>(dst + 8) = hi;
+  }
+}
+
 template <int BN, int EPI, bool C_F32>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&r)[32], long long row, int n0,
                                                const float* sbias, const uint4 (&ax)[4]) {
   if (row >= g.M) return;
 #pragma unroll
-  for (int j0 = 0; j0 < 32; j0 += 8) {
+  for (int j0 = 0; j0 < 32; j0 += 16) {
     const int n = n0 + j0;
     if (n >= g.N) break;
-    float v[8];
+    float v[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j0 + j]);
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j0 + j]);
     if (EPI == O2_EPI_BIAS || EPI == O2_EPI_BIAS_GELU || EPI == O2_EPI_BIAS_RES) {
-      const float4 b0 = *reinterpret_cast<const float4*>(sbias + j0);
-      const float4 b1 = *reinterpret_cast<const float4*>(sbias + j0 + 4);
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+#pragma unroll
+      for (int q = 0; q < 16; q += 4) {
+        const float4 b0 = *reinterpret_cast<const float4*>(sbias + j0 + q);
+        v[q] += b0.x; v[q + 1] += b0.y; v[q + 2] += b0.z; v[q + 3] += b0.w;
+      }
     }
     if (EPI == O2_EPI_BIAS_GELU) {
-      uint4 u;
-      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-      u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(g.aux_out + row * g.ld_aux_out + n) = u;
+      store_bf16x16(g.aux_out + row * g.ld_aux_out + n, v, n, g.N, g.wide_st);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
+      for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
     }
     if (EPI == O2_EPI_BIAS_RES || EPI == O2_EPI_DGELU) {
-      const uint4 u = ax[j0 >> 3];
-      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-      const float a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (EPI == O2_EPI_BIAS_RES) ? (v[j] + a[j]) : (v[j] * dgelu_fast(a[j]));
+      for (int h = 0; h < 2; ++h) {
+        const uint4 u = ax[(j0 >> 3) + h];
+        const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+        const float a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          v[8 * h + j] = (EPI == O2_EPI_BIAS_RES) ? (v[8 * h + j] + a[j]) : (v[8 * h + j] * dgelu_fast(a[j]));
+      }
     }
     if (EPI == O2_EPI_ACCUM) {
       float* c = reinterpret_cast<float*>(g.C) + row * g.ldc + n;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(c + j, v[j]);
+      for (int h = 0; h < 16; h += 8)
+        if (n + h < g.N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(c + h + j, v[h + j]);
+        }
     } else if (C_F32) {
       float* c = reinterpret_cast<float*>(g.C) + row * g.ldc + n;
-      *reinterpret_cast<float4*>(c) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+      for (int q = 0; q < 16; q += 4)
+        if (n + q < g.N) *reinterpret_cast<float4*>(c + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
     } else {
-      uint4 u;
-      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-      u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.C) + row * g.ldc + n) = u;
+      store_bf16x16(reinterpret_cast<__nv_bfloat16*>(g.C) + row * g.ldc + n, v, n, g.N, g.wide_st);
     }
   }
 }
@@ -124,7 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                const GemmArgs g) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tfull_bar = empty_bar + C::kStages;
@@ -276,10 +304,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const long long arow = (g.epi == O2_EPI_BIAS_RES) ? (row % g.aux_rows) : row;
       auto load_aux = [&](int c, uint4 (&ax)[4]) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 4; j += 2) {
           const int n = n_blk * BN + c * 32 + j * 8;
           ax[j] = make_uint4(0u, 0u, 0u, 0u);
-          if (has_aux && row < g.M && n < g.N) ax[j] = *reinterpret_cast<const uint4*>(g.aux + arow * g.ld_aux + n);
+          ax[j + 1] = make_uint4(0u, 0u, 0u, 0u);
+          if (has_aux && row < g.M && n < g.N) {
+            const __nv_bfloat16* src = g.aux + arow * g.ld_aux + n;
+            if (g.wide_ld && n + 16 <= g.N) {           // one full 32-byte sector per lane and request
+              asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                           : "=r"(ax[j].x), "=r"(ax[j].y), "=r"(ax[j].z), "=r"(ax[j].w), "=r"(ax[j + 1].x), "=r"(ax[j + 1].y),
+                             "=r"(ax[j + 1].z), "=r"(ax[j + 1].w)
+                           : "l"(src));
+            } else {
+              ax[j] = *reinterpret_cast<const uint4*>(src);
+              if (n + 8 < g.N) ax[j + 1] = *reinterpret_cast<const uint4*>(src + 8);
+            }
+          }
         }
       };
       uint4 ax[4];
@@ -367,6 +407,9 @@ int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans
   g.epi = epilogue; g.c_f32 = (c_dtype == O2_F32);
   g.ldc = ldc; g.ld_aux = ld_aux; g.aux_rows = aux_rows > 0 ? aux_rows : M; g.ld_aux_out = ld_aux_out;
   g.bias = bias; g.aux = (const __nv_bfloat16*)aux; g.aux_out = (__nv_bfloat16*)aux_out; g.C = Cp;
+  g.wide_st = (ldc % 16 == 0) && ((uintptr_t)Cp % 32 == 0) && (!aux_out || (ld_aux_out % 16 == 0 && (uintptr_t)aux_out % 32 == 0)) &&
+              !getenv("O2_GEMM_NARROW_ST");
+  g.wide_ld = aux && (ld_aux % 16 == 0) && ((uintptr_t)aux % 32 == 0) && !getenv("O2_GEMM_NARROW_ST");
   g.a_mn = trans_a ? 1 : 0; g.b_mn = trans_b ? 1 : 0;
   g.kb_total = (int)((K + BK - 1) / BK);
   if (split_k > g.kb_total) split_k = g.kb_total;
