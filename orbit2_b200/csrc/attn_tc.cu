@@ -45,6 +45,7 @@ __device__ long long g_timeline[kTlCount * 2 * kTlSlots];
 #endif
 
 struct FwdArgs {
+  const __nv_bfloat16* qkv;  // [B, N, 3, heads, hd] (the Q rows are read straight from here when Q lives in TMEM)
   __nv_bfloat16* out;
   float* lse;
   int B, N, heads, n_sub;   // n_sub = ceil(N / 64) key sub-tiles
@@ -94,7 +95,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
   uint64_t* p_full = s_full + 4;                    // [tile][buffer] = 4 (128 arrivals)
   uint64_t* o_done = p_full + 4;                    // 2: one phase per sub-tile (gates the lazy rescale)
   uint64_t* o_final = o_done + 2;                   // 2: completes once, after the last P V of the tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
+  uint64_t* q_ready = o_final + 2;                  // 2: Q_t has been written to TMEM (128 arrivals; kQTmem only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 2);
+  // Head dim 64: Q_t (bf16, 32 packed columns) sits in the 128 TMEM columns that S / O leave free and is the A operand of
+  // S = Q K^T from there (TS-MMA), exactly like P for P V.  An SS-MMA of 128 x 64 x 16 reads 4 KiB of A + 2 KiB of B per
+  // instruction and runs at the shared-memory bandwidth (58 cycles instead of 32); with the constant operand in TMEM
+  // only the 2 KiB of K are read.  Head dim 128 has no spare columns and keeps Q in shared memory.
+  constexpr bool kQTmem = (NH == 1);
+  constexpr uint32_t kQCol = 384;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,6 +128,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
     for (int t = 0; t < 2; ++t) {
       ptx::mbar_init(&o_done[t], 1);
       ptx::mbar_init(&o_final[t], 1);
+      ptx::mbar_init(&q_ready[t], 128);
     }
     ptx::fence_barrier_init();
   }
@@ -133,11 +142,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      ptx::mbar_expect_tx(q_full, 2 * kQKV);
+      if (!kQTmem) {
+        ptx::mbar_expect_tx(q_full, 2 * kQKV);
 #pragma unroll
-      for (int hh = 0; hh < NH; ++hh) {
-        ptx::tma_load_4d(sQ + hh * kTileBytes, &tmap_qkv, q_full, hh * 64, h, q0, b);
-        ptx::tma_load_4d(sQ + kQKV + hh * kTileBytes, &tmap_qkv, q_full, hh * 64, h, q0 + BQ, b);
+        for (int hh = 0; hh < NH; ++hh) {
+          ptx::tma_load_4d(sQ + hh * kTileBytes, &tmap_qkv, q_full, hh * 64, h, q0, b);
+          ptx::tma_load_4d(sQ + kQKV + hh * kTileBytes, &tmap_qkv, q_full, hh * 64, h, q0 + BQ, b);
+        }
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -170,19 +181,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
       // S_t(u) = Q_t K_u^T into buffer (t, u & 1); K sub-tile u = rows [64 (u&1), +64) of K tile u >> 1
       auto issue_s = [&](int t, int u, int kstage) {
         if (ptx::elect_one()) {
-          const uint64_t qd = desc_add(dq0, t * kQKV);
           const uint64_t kd = desc_add(dk0, kstage * kQKV + (u & 1) * kHalfBytes);
           const uint32_t d = tmem_base + (2 * t + (u & 1)) * BS;
-          ptx::umma_ss_first(d, qd, kd, idesc_s);
+          if (kQTmem) {
+            const uint32_t qa = tmem_base + kQCol + t * 32;      // 8 packed columns per 16-wide K slice
+            ptx::umma_ts(d, qa, kd, idesc_s, 0u);
 #pragma unroll
-          for (int k = 1; k < NH * 4; ++k)          // 16-wide K slices: 4 per 64-column half-tile
-            ptx::umma_ss_acc(d, desc_add(qd, (k >> 2) * kTileBytes + (k & 3) * 32), desc_add(kd, (k >> 2) * kTileBytes + (k & 3) * 32),
-                             idesc_s);
+            for (int k = 1; k < 4; ++k) ptx::umma_ts_acc(d, qa + k * 8, desc_add(kd, k * 32), idesc_s);
+          } else {
+            const uint64_t qd = desc_add(dq0, t * kQKV);
+            ptx::umma_ss_first(d, qd, kd, idesc_s);
+#pragma unroll
+            for (int k = 1; k < NH * 4; ++k)          // 16-wide K slices: 4 per 64-column half-tile
+              ptx::umma_ss_acc(d, desc_add(qd, (k >> 2) * kTileBytes + (k & 3) * 32), desc_add(kd, (k >> 2) * kTileBytes + (k & 3) * 32),
+                               idesc_s);
+          }
           ptx::umma_commit(&s_full[2 * t + (u & 1)]);
         }
         __syncwarp();
       };
-      ptx::mbar_wait(q_full, 0);
+      if (kQTmem) ptx::mbar_wait(&q_ready[t], 0);
+      else ptx::mbar_wait(q_full, 0);
       ptx::mbar_wait(&k_full[0], 0);
       ptx::tc_fence_after();
       issue_s(t, 0, 0);
@@ -255,6 +274,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
     const uint32_t drop_key = kDrop ? ptx::attn_drop_key(a.drop, bh) : 0u;
     const uint32_t drop_row = kDrop ? (uint32_t)((q0 + t * BQ + r) >> 1) * a.drop.n2 : 0u;
     const uint32_t drop_sh = kDrop ? (uint32_t)((q0 + t * BQ + r) & 1) * 16u : 0u;
+    if (kQTmem) {                           // this thread's query row -> its TMEM lane, 64 bf16 = 32 packed columns
+      const int qrow = q0 + t * BQ + r;
+      uint32_t qw[32];
+      if (qrow < a.N) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.qkv + (((size_t)b * a.N + qrow) * 3 * a.heads + h) * kHD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = src[i];
+          qw[4 * i] = v.x; qw[4 * i + 1] = v.y; qw[4 * i + 2] = v.z; qw[4 * i + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) qw[i] = 0u;
+      }
+      ptx::tmem_st_32x32(lane_addr + kQCol + t * 32, qw);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&q_ready[t]);
+    }
     float m_ref = -INFINITY;
     uint64_t lA = 0ull, lB = 0ull;          // packed partial row sums
     const int tail = a.N - (n_sub - 1) * BS;    // valid keys in the last sub-tile (1..64)
@@ -1135,6 +1173,7 @@ int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int hea
   int rc = make_qkv_tmap(&tm, qkv, B, N, heads, hd, BQ);
   if (rc) return rc;
   FwdArgs a;
+  a.qkv = (const __nv_bfloat16*)qkv;
   a.out = (__nv_bfloat16*)out; a.lse = lse; a.B = B; a.N = N; a.heads = heads;
   a.n_sub = (N + BS - 1) / BS;
   a.scale_log2 = scale * kLog2e;
