@@ -16,7 +16,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # --use_fast_math would change erff/expf accuracy; we keep IEEE division/sqrt and only take ftz/fmad
-FLAGS = [f for f in FLAGS if f != "--use_fast_math"]
+FLAGS = [f for f in FLAGS if f != "--use_fast_math"] + os.environ.get("O2_NVCC_DEFS", "").split()
 
 
 def _digest(paths):

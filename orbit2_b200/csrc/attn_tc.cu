@@ -27,9 +27,12 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;
 // One pair of exponentials in every kPoly* pairs is evaluated by the FMA-pipe polynomial instead of MUFU.EX2 (measured
-// optima on B200 at N = 16200: forward 853 TFLOP/s @6 vs 794 without, dq 1107 @4 vs 989, dkv best without: it is
+// optima on B200 at N = 16200: forward 900 TFLOP/s @4 (with Q in TMEM; 857 @6, 808 @3), dq 1107 @4 vs 989, dkv best without: it is
 // bound by its MMA issue chain, not by MUFU).
-constexpr int kPolyFwd = 6, kPolyDq = 4, kPolyDkv = 1 << 20;
+#ifndef O2_POLY_FWD
+#define O2_POLY_FWD 4
+#endif
+constexpr int kPolyFwd = O2_POLY_FWD, kPolyDq = 4, kPolyDkv = 1 << 20;
 
 #ifdef O2_TIMELINE
 // Debug build only: CTA (0,0) records clock64() at the hand-off points of sub-tiles [kTlFirst, kTlFirst + kTlCount).
