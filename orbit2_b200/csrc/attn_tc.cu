@@ -32,7 +32,10 @@ constexpr float kRescaleThreshold = 8.0f;
 #ifndef O2_POLY_FWD
 #define O2_POLY_FWD 4
 #endif
-constexpr int kPolyFwd = O2_POLY_FWD, kPolyDq = 4, kPolyDkv = 1 << 20;
+#ifndef O2_POLY_DQ
+#define O2_POLY_DQ 4
+#endif
+constexpr int kPolyFwd = O2_POLY_FWD, kPolyDq = O2_POLY_DQ, kPolyDkv = 1 << 20;
 
 #ifdef O2_TIMELINE
 // Debug build only: CTA (0,0) records clock64() at the hand-off points of sub-tiles [kTlFirst, kTlFirst + kTlCount).
