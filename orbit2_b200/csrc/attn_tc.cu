@@ -452,6 +452,7 @@ template <int NH> struct BwdCfg {
 };
 
 struct BwdArgs {
+  const __nv_bfloat16* qkv;   // [B, N, 3, heads, hd] (K / V rows are copied straight from here into TMEM by the v2 dK/dV kernel)
   const float* lse;       // [B, heads, N] natural log
   const float* delta;     // [B, heads, N]
   __nv_bfloat16* dqkv;    // [B, N, 3, heads, hd]
@@ -1108,6 +1109,314 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------- dK, dV (hd 64, v2)
+// Same mathematics as attn_bwd_dkv_kernel, re-organised so that EVERY tensor-core instruction takes its A operand from
+// tensor memory.  A CTA owns ONE 128-key tile and keeps K and V themselves (bf16, 32 packed columns each) plus the
+// rank-1 "ones" slices in TMEM; S^T / dP^T are double-buffered over consecutive 64-query sub-tiles instead of over two
+// key tiles.  An SS-MMA of 128 x 64 x 16 reads 4 KiB of A and 2 KiB of B from shared memory and runs at the
+// shared-memory bandwidth (58 cycles instead of 32); here only the 2 KiB of Q / dO are read, so the 18 MMAs of a
+// (key tile, query sub-tile) block take 18 x 32 instead of 10 x 58 + 8 x 32 cycles of the tensor pipe.
+// TMEM columns: buffer b: S^T [128 b, +64) dP^T [128 b + 64, +64) | dK [256,320) dV [320,384) | K [384,416) V [416,448)
+// | ones slice 0 [448,456) slice 1 [456,464).
+template <bool kDrop>
+__global__ void __launch_bounds__(kThreadsB, 1)
+attn_bwd_dkv_tm_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                       const BwdArgs a) {
+  constexpr int kStagesB = kDrop ? 3 : 4;     // the dropout variant keeps a raw delta copy in k-slice 3 of the statistics tile
+  constexpr uint32_t kT = kTileBytes;
+  constexpr uint32_t kColDK = 256, kColDV = 320, kColK = 384, kColV = 416, kColOnes = 448;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                               // kStagesB tiles of 128 queries
+  uint8_t* sdO = sQ + kStagesB * kT;                // kStagesB tiles
+  uint8_t* sStat = sdO + kStagesB * kT;             // [128 q x 64]: k-slice `stage` = -(split lse/scale | split delta)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + kTileBytes);
+  uint64_t* kv_ready = bars;                        // 1 (256 arrivals: K, V and the ones are in TMEM)
+  uint64_t* qdo_full = kv_ready + 1;                // kStagesB (2 arrivals: TMA expect_tx + statistics)
+  uint64_t* qdo_empty = qdo_full + kStagesB;
+  uint64_t* sd_full = qdo_empty + kStagesB;         // 2 (per buffer)
+  uint64_t* pd_full = sd_full + 2;                  // 2 (256 arrivals)
+  uint64_t* dkv_done = pd_full + 2;                 // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dkv_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / a.heads, h = bh % a.heads;
+  const int k0 = blockIdx.x * BKV;
+  const int n_sub = a.n_sub;                        // 64-query sub-tiles
+  const int n_q = (n_sub + 1) / 2;                  // 128-query TMA tiles
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_qkv);
+    ptx::prefetch_tmap(&tmap_do);
+    ptx::mbar_init(kv_ready, 256);
+    for (int s = 0; s < kStagesB; ++s) {
+      ptx::mbar_init(&qdo_full[s], 2);
+      ptx::mbar_init(&qdo_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      ptx::mbar_init(&sd_full[t], 1);
+      ptx::mbar_init(&pd_full[t], 256);
+      ptx::mbar_init(&dkv_done[t], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (Q / dO tiles of 128 queries)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < n_q; ++i) {
+        ptx::mbar_wait(&qdo_empty[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&qdo_full[stage], 2 * kT);
+        ptx::tma_load_4d(sQ + stage * kT, &tmap_qkv, &qdo_full[stage], 0, h, i * BQ, b);
+        ptx::tma_load_4d(sdO + stage * kT, &tmap_do, &qdo_full[stage], 0, h, i * BQ, b);
+        if (++stage == kStagesB) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------ statistics warp: the second arrival on qdo_full.
+    // A 128-query tile lasts ~1.2 us here (one key tile per CTA); TMA issue + split + shared-memory stores + proxy fence
+    // in ONE warp took ~1.7 us per tile and paced the whole kernel, so the statistics have their own warp, and they are
+    // fetched two tiles ahead into alternating register sets.
+    int stage = 0;
+    uint32_t phase = 0;
+    const float* lse = a.lse + ((size_t)b * a.heads + h) * a.N;
+    const float* dlt = a.delta + ((size_t)b * a.heads + h) * a.N;
+    const float inv_scale = 1.f / a.scale;
+    float xa[4], ya[4], xb[4], yb[4];
+    auto fetch_stats = [&](int i, float (&xs)[4], float (&ys)[4]) {
+      float lv[4], dv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = i * BQ + e * 32 + lane;
+        const bool ok = row < a.N;
+        lv[e] = ok ? __ldg(lse + row) : 0.f;
+        dv[e] = ok ? __ldg(dlt + row) : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = i * BQ + e * 32 + lane;
+        xs[e] = (row < a.N) ? lv[e] * inv_scale : 1e30f;    // exp2((s - 1e30) * c) = 0 for rows past N
+        ys[e] = (row < a.N) ? dv[e] : 0.f;
+      }
+    };
+    auto produce = [&](const float (&xs)[4], const float (&ys)[4]) {
+      ptx::mbar_wait(&qdo_empty[stage], phase ^ 1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int idx = e * 32 + lane;
+        uint4* dst = reinterpret_cast<uint4*>(sStat + idx * 128);
+        dst[(2 * stage) ^ (idx & 7)] = neg_split3(xs[e]);
+        dst[(2 * stage + 1) ^ (idx & 7)] = neg_split3(ys[e]);
+        if (kDrop) reinterpret_cast<float*>(dst + (6 ^ (idx & 7)))[stage] = ys[e];
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&qdo_full[stage]);
+      if (++stage == kStagesB) { stage = 0; phase ^= 1; }
+    };
+    fetch_stats(0, xa, ya);
+    fetch_stats(1, xb, yb);
+    for (int i = 0; i < n_q; i += 2) {
+      produce(xa, ya);
+      fetch_stats(i + 2, xa, ya);
+      if (i + 1 < n_q) {
+        produce(xb, yb);
+        fetch_stats(i + 3, xb, yb);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = ptx::umma_idesc_bf16(BKV, BS, 0, 0);   // S^T / dP^T: N = 64 queries
+    const uint32_t idesc_g = ptx::umma_idesc_bf16(BKV, kHD, 0, 1);  // dV / dK: A (TMEM), B = dO / Q (MN-major)
+    const uint64_t dq0 = ptx::umma_smem_desc(ptx::smem_u32(sQ), 16, 1024);
+    const uint64_t ddo0 = ptx::umma_smem_desc(ptx::smem_u32(sdO), 16, 1024);
+    const uint64_t dqm0 = ptx::umma_smem_desc(ptx::smem_u32(sQ), 8192, 1024);    // Q as MN-major B
+    const uint64_t ddom0 = ptx::umma_smem_desc(ptx::smem_u32(sdO), 8192, 1024);  // dO as MN-major B
+    const uint64_t dstat0 = ptx::umma_smem_desc(ptx::smem_u32(sStat), 16, 1024);
+    // S^T / dP^T of the sub-tile that lives in rows [64 half, +64) of Q / dO stage `stage`, into buffer `buf`
+    auto issue_sd = [&](int buf, int stage, int half) {
+      if (ptx::elect_one()) {
+        const uint64_t qa = desc_add(dq0, stage * kT + half * kHalfBytes);
+        const uint64_t da = desc_add(ddo0, stage * kT + half * kHalfBytes);
+        const uint64_t st = desc_add(dstat0, half * kHalfBytes + stage * 32);
+        const uint32_t ds_ = tmem_base + buf * 128;
+        ptx::umma_ts(ds_, tmem_base + kColK, qa, idesc_s, 0u);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) ptx::umma_ts_acc(ds_, tmem_base + kColK + k * 8, desc_add(qa, k * 32), idesc_s);
+        ptx::umma_ts_acc(ds_, tmem_base + kColOnes, st, idesc_s);                    // - lse / scale
+        ptx::umma_ts(ds_ + 64, tmem_base + kColV, da, idesc_s, 0u);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) ptx::umma_ts_acc(ds_ + 64, tmem_base + kColV + k * 8, desc_add(da, k * 32), idesc_s);
+        if (!kDrop) ptx::umma_ts_acc(ds_ + 64, tmem_base + kColOnes + 8, st, idesc_s);   // - delta
+        ptx::umma_commit(&sd_full[buf]);
+      }
+      __syncwarp();
+    };
+    ptx::mbar_wait(kv_ready, 0);
+    ptx::mbar_wait(&qdo_full[0], 0);
+    ptx::tc_fence_after();
+    issue_sd(0, 0, 0);
+    if (n_sub > 1) issue_sd(1, 0, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = 0; u < n_sub; ++u) {
+      const int buf = u & 1;                          // = half: sub-tile u is rows [64 buf, +64) of its 128-query tile
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == kStagesB) { nstage = 0; nphase ^= 1; }
+      const uint64_t dam = desc_add(ddom0, stage * kT + buf * kHalfBytes);
+      const uint64_t qam = desc_add(dqm0, stage * kT + buf * kHalfBytes);
+      ptx::mbar_wait(&pd_full[buf], (u >> 1) & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t base = tmem_base + buf * 128;
+        ptx::umma_ts(tmem_base + kColDV, base, dam, idesc_g, u > 0 ? 1u : 0u);           // dV += P^T dO
+#pragma unroll
+        for (int k = 1; k < BS / 16; ++k)
+          ptx::umma_ts_acc(tmem_base + kColDV, base + (k >> 1) * 32 + (k & 1) * 8, desc_add(dam, k * 2048), idesc_g);
+        ptx::umma_ts(tmem_base + kColDK, base + 64, qam, idesc_g, u > 0 ? 1u : 0u);       // dK += dS^T Q
+#pragma unroll
+        for (int k = 1; k < BS / 16; ++k)
+          ptx::umma_ts_acc(tmem_base + kColDK, base + 64 + (k >> 1) * 32 + (k & 1) * 8, desc_add(qam, k * 2048), idesc_g);
+        ptx::umma_commit(&dkv_done[buf]);
+      }
+      __syncwarp();
+      if (u + 2 < n_sub) {                            // this buffer's next sub-tile (u + 2) lives in the next 128-query tile
+        if (buf == 0) {                               // first touch of that tile
+          ptx::mbar_wait(&qdo_full[nstage], nphase);
+          ptx::tc_fence_after();
+        }
+        issue_sd(buf, nstage, buf);
+      }
+      if (buf == 1 || u + 1 == n_sub) {               // both halves of this tile have been consumed
+        if (ptx::elect_one()) ptx::umma_commit(&qdo_empty[stage]);
+        __syncwarp();
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    // eight softmax warps, all on the same sub-tile: thread = one key row, 32 of the 64 query columns
+    const int quarter = warp & 3;
+    const int chalf = (warp - 2) >> 2;            // query columns [32 chalf, +32) of the sub-tile
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float sc = a.scale_log2;
+    const uint64_t sc2 = ptx::pack2(sc, sc);
+    const int key = k0 + r;
+    {   // K row (warps 2-5) / V row (warps 6-9) of this thread's key -> its TMEM lane; warps 2-5 also write the ones
+      uint32_t w[32];
+      if (key < a.N) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.qkv + ((((size_t)b * a.N + key) * 3 + 1 + chalf) * a.heads + h) * kHD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = src[i];
+          w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) w[i] = 0u;
+      }
+      ptx::tmem_st_32x32(lane_addr + (chalf == 0 ? kColK : kColV), w);
+      if (chalf == 0) {
+        // ones in K positions 0..2 of slice 0 and 8..10 of slice 1 (bf16 1.0 = 0x3F80)
+        const uint32_t ones[16] = {0x3F803F80u, 0x00003F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0x3F803F80u, 0x00003F80u, 0u, 0u};
+        ptx::tmem_st_32x16(lane_addr + kColOnes, ones);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(kv_ready);
+    }
+    const uint32_t drop_key = kDrop ? ptx::attn_drop_key(a.drop, bh) : 0u;
+    int dstage = 0;                              // stage of the 128-query tile that holds sub-tile u
+    for (int u = 0; u < n_sub; ++u) {
+      const int buf = u & 1;
+      const uint32_t st_addr = lane_addr + buf * 128 + chalf * 32;       // this thread's S^T columns; P^T goes over their head
+      const uint32_t dp_addr = st_addr + 64;
+      ptx::mbar_wait(&sd_full[buf], (u >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t sv_[32], dv_[32];
+      ptx::tmem_ld_32x32(st_addr, sv_);
+      ptx::tmem_ld_32x32(dp_addr, dv_);
+      ptx::tmem_ld_wait();
+      uint32_t pk[16], dk[16];
+      if (kDrop) {
+        const int qb = u * BS + chalf * 32;
+        const uint32_t ksh = (uint32_t)(key & 1) * 8u;
+        uint32_t blk = (uint32_t)(qb >> 1) * a.drop.n2 + (uint32_t)(key >> 1);
+        const float* dl = reinterpret_cast<const float*>(sStat) + dstage;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const uint64_t X = ptx::mul2(ptx::pack2u(sv_[i], sv_[i + 1]), sc2);
+          const uint64_t Pq = ptx::exp2_pair<false>(X);
+          const uint32_t hh_ = ptx::lowbias32(blk ^ drop_key) >> ksh;
+          blk += a.drop.n2;
+          const bool k0_ = (hh_ & 0xFFu) >= a.drop.thr8, k1_ = ((hh_ >> 16) & 0xFFu) >= a.drop.thr8;
+          float p0, p1;
+          ptx::unpack2(Pq, p0, p1);
+          const int qi = (u & 1) * BS + chalf * 32 + i;            // row of the 128-query statistics tile
+          const float de0 = dl[(qi * 128 + ((6 ^ (qi & 7)) * 16)) >> 2];
+          const float de1 = dl[((qi + 1) * 128 + ((6 ^ ((qi + 1) & 7)) * 16)) >> 2];
+          const float g0 = k0_ ? __uint_as_float(dv_[i]) * a.drop.inv_keep : 0.f;
+          const float g1 = k1_ ? __uint_as_float(dv_[i + 1]) * a.drop.inv_keep : 0.f;
+          pk[i >> 1] = pack_bf16x2(k0_ ? p0 : 0.f, k1_ ? p1 : 0.f);
+          dk[i >> 1] = pack_bf16x2(p0 * (g0 - de0), p1 * (g1 - de1));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const uint64_t X = ptx::mul2(ptx::pack2u(sv_[i], sv_[i + 1]), sc2);
+          const uint64_t Pq = (((i >> 1) % kPolyDkv) == kPolyDkv - 1) ? ptx::exp2_pair<true>(X) : ptx::exp2_pair<false>(X);
+          pk[i >> 1] = ptx::pack_bf16x2_pair(Pq);
+          dk[i >> 1] = ptx::pack_bf16x2_pair(ptx::mul2(Pq, ptx::pack2u(dv_[i], dv_[i + 1])));
+        }
+      }
+      ptx::tmem_st_32x16(st_addr, pk);
+      ptx::tmem_st_32x16(dp_addr, dk);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&pd_full[buf]);
+      if (u & 1) { if (++dstage == kStagesB) dstage = 0; }
+    }
+    // epilogue: warps 2-5 drain dK (scaled), warps 6-9 dV
+    ptx::mbar_wait(&dkv_done[(n_sub - 1) & 1], ((n_sub - 1) >> 1) & 1);
+    ptx::tc_fence_after();
+    const int which = 1 + chalf;
+    __nv_bfloat16* op = a.dqkv + ((((size_t)b * a.N + key) * 3 + which) * a.heads + h) * kHD;
+    const float f = (which == 1) ? a.scale : (kDrop ? a.drop.inv_keep : 1.f);   // dV = P_kept^T dO / keep_prob
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      ptx::tmem_ld_32x32(lane_addr + (which == 1 ? kColDK : kColDV) + c * 32, o);
+      ptx::tmem_ld_wait();
+      if (key < a.N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[i]) * f, __uint_as_float(o[i + 1]) * f);
+          w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * f, __uint_as_float(o[i + 3]) * f);
+          w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * f, __uint_as_float(o[i + 5]) * f);
+          w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * f, __uint_as_float(o[i + 7]) * f);
+          *reinterpret_cast<uint4*>(op + c * 32 + i) = w;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
+}
+constexpr uint32_t kDkvTmSmem = (2 * 4 + 1) * kTileBytes + 1024 + 256;
+
 int make_qkv_tmap(CUtensorMap* tm, const void* qkv, int B, int N, int heads, int hd, int box_rows) {
   uint64_t dims[4] = {(uint64_t)hd, (uint64_t)(3 * heads), (uint64_t)N, (uint64_t)B};
   uint64_t str[3] = {(uint64_t)hd * 2, (uint64_t)3 * heads * hd * 2, (uint64_t)N * 3 * heads * hd * 2};
@@ -1158,7 +1467,22 @@ int launch_bwd(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const BwdArg
   const int rows_per_cta = Cfg::kTiles * BQ;
   dim3 grid((a.N + rows_per_cta - 1) / rows_per_cta, a.B * a.heads);
   if (parts & O2_ATTN_BWD_DKV) {
-    attn_bwd_dkv_kernel<NH, kDrop><<<grid, kThreadsF, Cfg::kDkvSmem, st>>>(tm_qkv, tm_do, a);
+    // the all-TS kernel (K / V in TMEM, one key tile per CTA) measures the same as the two-tile kernel in isolation
+    // (1017 vs 1024 TFLOP/s) and inside the step (A/B on one box: 423.0 / 424.1 vs 424.2 / 422.3 ms) while doubling the
+    // L2 -> SM traffic for Q / dO, so it stays opt-in: both are bound by the 2-buffer softmax <-> MMA hand-off chain,
+    // not by the tensor pipe (54 % busy) or MUFU (51 %).  profiles/r01_attn_experiments.md
+    static const bool use_tm = getenv("O2_DKV_TM") != nullptr;
+    if (NH == 1 && use_tm) {
+      static bool attr2 = false;
+      if (!attr2) {
+        O2_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tm_kernel<kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDkvTmSmem));
+        attr2 = true;
+      }
+      dim3 grid2((a.N + BKV - 1) / BKV, a.B * a.heads);
+      attn_bwd_dkv_tm_kernel<kDrop><<<grid2, kThreadsB, kDkvTmSmem, st>>>(tm_qkv, tm_do, a);
+    } else {
+      attn_bwd_dkv_kernel<NH, kDrop><<<grid, kThreadsF, Cfg::kDkvSmem, st>>>(tm_qkv, tm_do, a);
+    }
     O2_LAUNCH_CHECK();
   }
   if (parts & O2_ATTN_BWD_DQ) {
@@ -1219,6 +1543,7 @@ int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const flo
     O2_LAUNCH_CHECK();
   }
   BwdArgs a;
+  a.qkv = (const __nv_bfloat16*)qkv;
   a.lse = lse; a.delta = delta; a.dqkv = (__nv_bfloat16*)dqkv; a.B = B; a.N = N; a.heads = heads;
   a.n_sub = (N + BS - 1) / BS;
   a.scale = scale; a.scale_log2 = scale * kLog2e;
