@@ -184,6 +184,7 @@ def run_ours(args):
         model.var_embed.normal_(0, 0.02)
         model.var_query.normal_(0, 0.02)
     model.spatial_resolution = cfg["spatial_resolution"]
+    model.activation_checkpointing = args.ckpt
     model = model.to(dev)
     n_params = sum(p.numel() for p in model.parameters())
     H_out = cfg["img_size"][0] * cfg["superres_mag"]
@@ -327,7 +328,7 @@ def run_ours(args):
                                    f", V={len(cfg['in_vars'])} in / {len(cfg['out_vars'])} out vars, fwd+clip+bayesian_tv+bwd+allreduce+AdamW",
                        "per_gpu_batch": B, "global_batch": B * world, "tokens_per_sample": L, "parallelism": (f"fsdp{world} (sharded Adam state + update, reduce-scatter / all-gather)" if (args.shard and world > 1) else f"dp{world}"),
                        "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB), no explicit flush",
-                       "dropout": args.drop},
+                       "dropout": args.drop, "activation_checkpointing": bool(args.ckpt)},
             "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": (x_h.numel() + y_h.numel()) * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
@@ -352,6 +353,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--drop", type=float, default=0.0, help="drop_rate = drop_path (the reference YAMLs train at 0.1; the "
                     "headline and every parity run use 0)")
+    ap.add_argument("--ckpt", action="store_true", help="per-Block activation recomputation (reference: checkpoint wrappers "
+                    "on every Block under FSDP); the recomputed forward FLOPs are NOT counted in the roofline")
     ap.add_argument("--shard", action="store_true", help="FSDP-style sharded optimizer instead of plain data parallel")
     ap.add_argument("--ref-grid", default=None, choices=["full", "sub"], help="force the CPU sample (default: by time budget)")
     args = ap.parse_args()

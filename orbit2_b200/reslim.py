@@ -97,7 +97,7 @@ def get_2d_sincos_pos_embed(embed_dim, gh, gw):
 # ------------------------------------------------------------------------------------------------
 class Geometry:
     __slots__ = ("B", "V", "Hx", "Wx", "p", "gh", "gw", "L", "T", "D", "heads", "hd", "depth", "dec", "mag", "C", "cr",
-                 "hidden", "idx7", "act", "drop")
+                 "hidden", "idx7", "act", "drop", "ckpt")
 
     def __repr__(self):
         return "Geometry(" + ", ".join(f"{k}={getattr(self, k)}" for k in self.__slots__ if hasattr(self, k)) + ")"
@@ -152,6 +152,45 @@ def _f32(t):
     return t if t.dtype == torch.float32 else t.float()
 
 
+def _block_forward(g: Geometry, P, Wc, i: int, tok):
+    """One pre-norm block (vit_blocks.py:76-81): returns (output tokens, tensors the block's backward needs).  Dropout /
+    drop-path masks are functions of (seed, site, element), so a re-run for activation checkpointing reproduces them."""
+    T, D, act = g.T, g.D, g.act
+    dev = tok.device
+    dp = getattr(g, "drop", None)
+
+    def gemm(a, w, n_out, **kw):
+        out = torch.empty(a.shape[0], n_out, device=dev, dtype=act)
+        return ops.gemm(a, w, out, **kw)
+
+    b = f"blocks.{i}."
+    s = {"x": tok}
+    y1, s["mean1"], s["rstd1"] = ops.layernorm_fwd(tok, P[b + "norm1.weight"], P[b + "norm1.bias"])
+    qkv = gemm(y1, Wc[b + "attn.qkv.weight"], 3 * D, epi=EPI_BIAS, bias=P[b + "attn.qkv.bias"])
+    adrop = (dp.rate, dp.seed, drop_site(i, SITE_ATTN)) if (dp is not None and dp.rate > 0) else None
+    ao, s["lse"] = ops.attn_fwd(qkv, g.B, g.L, g.heads, g.hd, adrop)                 # attention.py:75 attn_drop
+    if dp is not None and dp.branch_active(i):
+        # x + drop_path1(proj_drop(proj(.))): attention.py:81, vit_blocks.py:78
+        br = gemm(ao, Wc[b + "attn.proj.weight"], D, epi=EPI_BIAS, bias=P[b + "attn.proj.bias"])
+        xm = ops.dropout(br, dp.rate, dp.seed, drop_site(i, SITE_PROJ), res=tok, sample_scale=dp.path[i][0],
+                         rows_per_sample=g.L, out=br)
+    else:
+        xm = gemm(ao, Wc[b + "attn.proj.weight"], D, epi=EPI_BIAS_RES, bias=P[b + "attn.proj.bias"], aux=tok)
+    y2, s["mean2"], s["rstd2"] = ops.layernorm_fwd(xm, P[b + "norm2.weight"], P[b + "norm2.bias"])
+    pre = torch.empty(T, g.hidden, device=dev, dtype=act)
+    h = gemm(y2, Wc[b + "mlp.fc1.weight"], g.hidden, epi=EPI_BIAS_GELU, bias=P[b + "mlp.fc1.bias"], aux_out=pre)
+    if dp is not None and dp.rate > 0:
+        ops.dropout(h, dp.rate, dp.seed, drop_site(i, SITE_DROP1), out=h)       # mlp.py:65 drop1
+    if dp is not None and dp.branch_active(i):
+        br = gemm(h, Wc[b + "mlp.fc2.weight"], D, epi=EPI_BIAS, bias=P[b + "mlp.fc2.bias"])
+        out = ops.dropout(br, dp.rate, dp.seed, drop_site(i, SITE_DROP2), res=xm, sample_scale=dp.path[i][1],
+                          rows_per_sample=g.L, out=br)                          # mlp.py:68 drop2, vit_blocks.py:79
+    else:
+        out = gemm(h, Wc[b + "mlp.fc2.weight"], D, epi=EPI_BIAS_RES, bias=P[b + "mlp.fc2.bias"], aux=xm)
+    s.update(y1=y1, qkv=qkv, ao=ao, xm=xm, y2=y2, pre=pre, h=h)
+    return out, s
+
+
 def reslim_forward(g: Geometry, P: Dict[str, torch.Tensor], Wc: Dict[str, torch.Tensor], x, tab_s, tab_v, posres):
     """P: fp32 parameters (biases, LN affine, conv weights); Wc: GEMM weights in the activation dtype.
     Returns (preds, saved) where ``saved`` holds what reslim_backward needs."""
@@ -170,33 +209,13 @@ def reslim_forward(g: Geometry, P: Dict[str, torch.Tensor], Wc: Dict[str, torch.
     if dp is not None and dp.rate > 0:
         ops.dropout(tok, dp.rate, dp.seed, SITE_POS, out=tok)                       # pos_drop, res_slimvit.py:284
     blocks = []
+    ckpt = bool(getattr(g, "ckpt", False))
     for i in range(g.depth):
-        b = f"blocks.{i}."
-        s = {"x": tok}
-        y1, s["mean1"], s["rstd1"] = ops.layernorm_fwd(tok, P[b + "norm1.weight"], P[b + "norm1.bias"])
-        qkv = gemm(y1, Wc[b + "attn.qkv.weight"], 3 * D, epi=EPI_BIAS, bias=P[b + "attn.qkv.bias"])
-        adrop = (dp.rate, dp.seed, drop_site(i, SITE_ATTN)) if (dp is not None and dp.rate > 0) else None
-        ao, s["lse"] = ops.attn_fwd(qkv, g.B, g.L, g.heads, g.hd, adrop)                 # attention.py:75 attn_drop
-        if dp is not None and dp.branch_active(i):
-            # x + drop_path1(proj_drop(proj(.))): attention.py:81, vit_blocks.py:78
-            br = gemm(ao, Wc[b + "attn.proj.weight"], D, epi=EPI_BIAS, bias=P[b + "attn.proj.bias"])
-            xm = ops.dropout(br, dp.rate, dp.seed, drop_site(i, SITE_PROJ), res=tok, sample_scale=dp.path[i][0],
-                             rows_per_sample=g.L, out=br)
-        else:
-            xm = gemm(ao, Wc[b + "attn.proj.weight"], D, epi=EPI_BIAS_RES, bias=P[b + "attn.proj.bias"], aux=tok)
-        y2, s["mean2"], s["rstd2"] = ops.layernorm_fwd(xm, P[b + "norm2.weight"], P[b + "norm2.bias"])
-        pre = torch.empty(T, g.hidden, device=dev, dtype=act)
-        h = gemm(y2, Wc[b + "mlp.fc1.weight"], g.hidden, epi=EPI_BIAS_GELU, bias=P[b + "mlp.fc1.bias"], aux_out=pre)
-        if dp is not None and dp.rate > 0:
-            ops.dropout(h, dp.rate, dp.seed, drop_site(i, SITE_DROP1), out=h)       # mlp.py:65 drop1
-        if dp is not None and dp.branch_active(i):
-            br = gemm(h, Wc[b + "mlp.fc2.weight"], D, epi=EPI_BIAS, bias=P[b + "mlp.fc2.bias"])
-            tok = ops.dropout(br, dp.rate, dp.seed, drop_site(i, SITE_DROP2), res=xm, sample_scale=dp.path[i][1],
-                              rows_per_sample=g.L, out=br)                          # mlp.py:68 drop2, vit_blocks.py:79
-        else:
-            tok = gemm(h, Wc[b + "mlp.fc2.weight"], D, epi=EPI_BIAS_RES, bias=P[b + "mlp.fc2.bias"], aux=xm)
-        s.update(y1=y1, qkv=qkv, ao=ao, xm=xm, y2=y2, pre=pre, h=h)
-        blocks.append(s)
+        tok_in = tok
+        tok, s = _block_forward(g, P, Wc, i, tok_in)
+        # activation checkpointing (the reference wraps every Block, intermediate_downscaling.py:583-590, 635-637):
+        # keep only the block input, reslim_backward re-runs the block's forward kernels to rebuild the rest
+        blocks.append({"x": tok_in} if ckpt else s)
     S["blocks"] = blocks
     S["xf"] = tok
     z, S["meanf"], S["rstdf"] = ops.layernorm_fwd(tok, P["norm.weight"], P["norm.bias"])
@@ -263,6 +282,8 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
     for i in range(g.depth - 1, -1, -1):
         b = f"blocks.{i}."
         s = S["blocks"][i]
+        if "qkv" not in s:                       # checkpointed block: re-run its forward from the saved input
+            _, s = _block_forward(g, P, Wc, i, s["x"])
         branch_drop = dp is not None and dp.branch_active(i)
         # gradient entering the MLP branch = the stream gradient through drop_path2 / drop2 (same mask, same scale)
         dbr = ops.dropout(dx, dp.rate, dp.seed, drop_site(i, SITE_DROP2), sample_scale=dp.path[i][1],
@@ -394,6 +415,9 @@ class Res_Slim_ViT(nn.Module):
         self.tensor_par_group = tensor_par_group
         self.drop_rate, self.drop_path = float(drop_rate), float(drop_path)
         self.compute_dtype = compute_dtype
+        # per-Block activation recomputation (the reference applies checkpoint wrappers to every Block under FSDP,
+        # intermediate_downscaling.py:583-590, 635-637): set True to keep only each block's input for backward
+        self.activation_checkpointing = False
         assert embed_dim % num_heads == 0
 
         self.spatial_embed = nn.Linear(1, embed_dim)
@@ -534,6 +558,7 @@ class Res_Slim_ViT(nn.Module):
         g.hidden = self.blocks[0].mlp.fc1.weight.shape[0] if self.depth else 0
         g.idx7 = self.find_var_index(in_variables, out_variables)
         g.act = act
+        g.ckpt = bool(getattr(self, "activation_checkpointing", False))
         g.drop = None
         if self.training and (self.drop_rate > 0 or self.drop_path > 0):
             # seeds come from torch's CPU generator: reproducible under torch.manual_seed, no device sync

@@ -67,6 +67,9 @@ def build(conf: dict, data_key: str, img_size: Tuple[int, int], device, pos_grid
                          compute_dtype=dtype, **model_kwargs(conf))
     model.spatial_resolution = d["spatial_resolution"][data_key]
     model.img_size = tuple(img_size)
+    # the reference wraps every Block in a checkpoint wrapper (intermediate_downscaling.py:583-590, 635-637); with 180 GB
+    # per GPU the 117M / 1B activations fit, so recomputation is opt-in here (O2_ACT_CKPT=1 or trainer --act-ckpt)
+    model.activation_checkpointing = bool(int(os.environ.get("O2_ACT_CKPT", "0")))
     model = model.to(device)
     meta = losses.MetricsMetaInfo(in_vars, out_vars, None, None)
     loss = losses.METRICS_REGISTRY[t["train_loss"]](aggregate_only=True, metainfo=meta)
@@ -245,7 +248,10 @@ def main():
     ap.add_argument("--steps-per-epoch", type=int, default=10)
     ap.add_argument("--checkpoint-dir", default=None)
     ap.add_argument("--resume", default=None)
+    ap.add_argument("--act-ckpt", action="store_true", help="per-Block activation recomputation (the reference's default)")
     a = ap.parse_args()
+    if a.act_ckpt:
+        os.environ["O2_ACT_CKPT"] = "1"
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:

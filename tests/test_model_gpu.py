@@ -184,3 +184,39 @@ def test_errors_like_reference():
         m(x, iv, cfg["out_vars"])
     with pytest.raises(RuntimeError):
         m(x.cpu(), cfg["in_vars"], cfg["out_vars"])
+
+
+@pytest.mark.parametrize("dtype,drop", [(torch.float32, 0.0), (torch.bfloat16, 0.0), (torch.bfloat16, 0.1)])
+def test_activation_checkpointing(dtype, drop):
+    """Per-Block activation recomputation (reference: checkpoint wrappers on every Block, intermediate_downscaling.py:
+    583-590, 635-637): same prediction bit for bit, same gradients up to the order of the split-K / column-sum atomics,
+    less memory held between forward and backward; with dropout the re-run regenerates the same hash masks."""
+    from oracle import cases, reslim_oracle as O
+    from orbit2_b200 import losses
+    from tests.util import build_model
+    cfg = cases.get_case("8m")
+    sd = O.init_state_dict(cfg, 3)
+    x, y = O.synthetic_batch(cfg, 4, cfg["in_vars"], cfg["out_vars"], seed=5)
+    x, y = x.cuda(), y.cuda()
+    meta = losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None)
+    loss_fn = losses.METRICS_REGISTRY["bayesian_tv"](aggregate_only=True, metainfo=meta)
+    res = []
+    for ckpt in (False, True):
+        m = build_model(cfg, sd, "cuda", dtype, drop_rate=drop, drop_path=drop)
+        m.activation_checkpointing = ckpt
+        m.train()
+        torch.manual_seed(7)
+        torch.cuda.synchronize(); torch.cuda.reset_peak_memory_stats()
+        pred = m(x, cfg["in_vars"], cfg["out_vars"])
+        held = torch.cuda.memory_allocated()
+        loss = loss_fn(pred, y, var_names=cfg["out_vars"], var_weights=cfg["var_weights"], clip_out_variables=cfg["out_vars"])
+        loss.backward()
+        res.append((pred.detach().clone(), {k: p.grad.detach().double().clone() for k, p in m.named_parameters()
+                                            if p.grad is not None}, held))
+        del m, pred, loss
+    (p0, g0, h0), (p1, g1, h1) = res
+    assert torch.equal(p0, p1)
+    assert h1 < 0.75 * h0, (h0, h1)
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    bad = {k: rel(g1[k], g0[k]) for k in g0 if g0[k].abs().max() > 0 and rel(g1[k], g0[k]) > tol}
+    assert not bad, bad
