@@ -114,8 +114,8 @@ def cpu_reference_step_time(case_name, B, steps, warmup, threads):
 def pick_cpu_sample(workload, n_steps_total, threads, budget_s=260.0, force=None):
     """Bounded CPU sample of the workload: B=1 on the full 180x360 grid when (steps+warmup) of them fit the time budget
     (calibrated with one step on the quarter-area 90x180 sub-grid, full grid measured 5.9x, budgeted 6.5x), else the sub-grid itself."""
-    if workload == "1b":
-        return "1b", 1, None
+    if workload in ("1b", "10b"):
+        return workload, 1, None
     if workload != "117m":
         return "8m", 8, None
     if force in ("full", "sub"):
@@ -172,14 +172,15 @@ def run_ours(args):
     _lib.load(require_device=True)
 
     cfg = cases.get_case(args.workload)
-    B = args.batch or {"117m": 8, "1b": 8}.get(args.workload, 32)
+    B = args.batch or {"117m": 8, "1b": 8}.get(args.workload, 32)       # 8m / 10b: 32 per GPU (configs/interm_*.yaml:6)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     torch.manual_seed(0)
-    model = Res_Slim_ViT(cfg["default_vars"], cfg["img_size"], len(cfg["default_vars"]), cfg["out_channels"], 1,
-                         superres_mag=cfg["superres_mag"], cnn_ratio=cfg["cnn_ratio"], patch_size=cfg["patch_size"],
-                         drop_path=args.drop, drop_rate=args.drop, learn_pos_emb=True, embed_dim=cfg["embed_dim"], depth=cfg["depth"],
-                         decoder_depth=cfg["decoder_depth"], num_heads=cfg["num_heads"], mlp_ratio=cfg["mlp_ratio"],
-                         compute_dtype=dtype)
+    with torch.device(dev if args.workload == "10b" else "cpu"):     # 9.5 B parameters are initialised on the GPU
+        model = Res_Slim_ViT(cfg["default_vars"], cfg["img_size"], len(cfg["default_vars"]), cfg["out_channels"], 1,
+                             superres_mag=cfg["superres_mag"], cnn_ratio=cfg["cnn_ratio"], patch_size=cfg["patch_size"],
+                             drop_path=args.drop, drop_rate=args.drop, learn_pos_emb=True, embed_dim=cfg["embed_dim"],
+                             depth=cfg["depth"], decoder_depth=cfg["decoder_depth"], num_heads=cfg["num_heads"],
+                             mlp_ratio=cfg["mlp_ratio"], compute_dtype=dtype)
     with torch.no_grad():                                   # zeros would hide the front end
         model.var_embed.normal_(0, 0.02)
         model.var_query.normal_(0, 0.02)
@@ -347,7 +348,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="117m", choices=["117m", "8m", "117m_90x180", "1b"])
+    ap.add_argument("--workload", default="117m", choices=["117m", "8m", "117m_90x180", "1b", "10b"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -182,6 +182,8 @@ int o2_eval_stats(const void* pred, int dtype, const float* target, const float*
 
 /* ---- small HBM-bound helpers ---------------------------------------------------------------- */
 int o2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* bf16 -> fp32: operands of the fp32 attention arm for head dims the tcgen05 kernels do not cover (256, interm_10b). */
+int o2_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
 /* out[n] += sum_m X[m, n]  (bias gradients), X act dtype with row pitch ld. */
 int o2_colsum(const void* X, int dtype, float* out, int64_t M, int64_t N, int64_t ld, void* stream);
 /* fused AdamW (torch.optim.AdamW semantics, intermediate_downscaling.py:642-644) over a flat fp32

@@ -50,6 +50,12 @@ CASES = {
     # float64 oracle finishes in seconds, "1b" is the full model on a 64x128 PRISM-like grid
     "1b_small": lambda: _cfg(DEFAULT_VARS_23, (16, 32), 3072, 2, 1, 24, 18.0, in_vars=PRISM_VARS_7),
     "1b": lambda: _cfg(DEFAULT_VARS_23, (64, 128), 3072, 8, 4, 24, 18.0, in_vars=PRISM_VARS_7),
+    # BASELINE configs[3]: interm_10b head shape (configs/interm_10b.yaml:39-42: D=8192, 32 heads x 256, depth 11, dec 4);
+    # "10b_small" keeps head dim 256 (the shape no 64 / 128 kernel covers) at D=512 so the float64 oracle finishes in
+    # seconds; the full widths need the 8-GPU sharded engine
+    "10b_small": lambda: _cfg(DEFAULT_VARS_23, (16, 32), 512, 2, 1, 2, 4.0),
+    # the full interm_10b model (9.5 B parameters) on the 32x64 ERA5 5.625-degree grid of its YAML's first dataset
+    "10b": lambda: _cfg(DEFAULT_VARS_23, (32, 64), 8192, 11, 4, 32, 625.0),
     # reduced-grid 117M (same widths, L=4050) for bounded CPU timing
     "117m_90x180": lambda: _cfg(DEFAULT_VARS_23, (90, 180), 1024, 8, 4, 16, 111.0),
 }

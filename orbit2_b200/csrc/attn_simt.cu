@@ -327,6 +327,212 @@ __global__ void __launch_bounds__(NT) attn_bwd_q_kernel(const AttnArgs a) {
   }
 }
 
+// ---- wide heads (interm_10b: head dim 256).  The four transposed operand tiles of the S / dP recomputation would need
+// 256 KiB, so they are staged in chunks of HC head-dim columns and S / dP accumulate over the chunks; the row-major
+// tiles for the gradient contractions and the register accumulators keep the full head dim.
+template <int HC>
+__device__ __forceinline__ void accumulate_s_dp(float (*qT)[BQ], float (*kT)[BKV], float (*doT)[BQ], float (*vT)[BKV], int tx,
+                                                int ty, float (&s)[4][4], float (&dp)[4][4]) {
+#pragma unroll 8
+  for (int d = 0; d < HC; ++d) {
+    const float4 qv = *reinterpret_cast<const float4*>(&qT[d][ty * 4]);
+    const float4 kv = *reinterpret_cast<const float4*>(&kT[d][tx * 4]);
+    const float4 gv = *reinterpret_cast<const float4*>(&doT[d][ty * 4]);
+    const float4 vv = *reinterpret_cast<const float4*>(&vT[d][tx * 4]);
+    const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, ka[4] = {kv.x, kv.y, kv.z, kv.w};
+    const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[i][j] = fmaf(qa[i], ka[j], s[i][j]);
+        dp[i][j] = fmaf(ga[i], va[j], dp[i][j]);
+      }
+  }
+}
+__device__ __forceinline__ void finish_p_ds(const AttnArgs& a, const float* lse_s, const float* delta_s, int q0, int k0, int tx,
+                                            int ty, const float (&s)[4][4], const float (&dp)[4][4], float (&p)[4][4],
+                                            float (&ds)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool ok = (q0 + ty * 4 + i < a.N) && (k0 + tx * 4 + j < a.N);
+      p[i][j] = ok ? __expf(s[i][j] * a.scale - lse_s[ty * 4 + i]) : 0.f;
+      if (a.drop.thr8 > 0) {
+        const float f = drop_factor(a, ptx::attn_drop_key(a.drop, blockIdx.y), q0 + ty * 4 + i, k0 + tx * 4 + j);
+        ds[i][j] = p[i][j] * (dp[i][j] * f - delta_s[ty * 4 + i]) * a.scale;
+        p[i][j] *= f;
+      } else {
+        ds[i][j] = p[i][j] * (dp[i][j] - delta_s[ty * 4 + i]) * a.scale;
+      }
+    }
+}
+// [64 rows x HC] chunk (columns c0 ..) transposed into dst[d][row] (no padding)
+template <int HC>
+__device__ __forceinline__ void load_chunk_T(float (*dst)[BQ], const float* src, size_t row_stride, int row0, int N) {
+  for (int i = threadIdx.x; i < 64 * HC; i += NT) {
+    const int r = i / HC, d = i % HC;
+    const int gr = row0 + r;
+    dst[d][r] = (gr < N) ? src[(size_t)gr * row_stride + d] : 0.f;
+  }
+}
+
+template <int HD, int HC>
+__global__ void __launch_bounds__(NT) attn_bwd_kv_wide_kernel(const AttnArgs a) {
+  constexpr int DC = HD / 16;
+  extern __shared__ float smem[];
+  float (*qT)[BQ] = reinterpret_cast<float (*)[BQ]>(smem);      // chunk buffers [HC][64]
+  float (*kT)[BKV] = qT + HC;
+  float (*doT)[BQ] = kT + HC;
+  float (*vT)[BKV] = doT + HC;
+  float* after = smem + 4 * HC * BQ;
+  float (*qS)[HD] = reinterpret_cast<float (*)[HD]>(after);      // [64 row][HD]
+  float (*doS)[HD] = qS + BQ;
+  float (*pS)[BKV] = reinterpret_cast<float (*)[BKV]>(after + 2 * BQ * HD);   // [row][key]
+  float (*dsS)[BKV] = pS + BQ;
+  float* lse_s = reinterpret_cast<float*>(dsS + BQ);
+  float* delta_s = lse_s + BQ;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int b = blockIdx.y / a.heads, h = blockIdx.y % a.heads;
+  const int k0 = blockIdx.x * BKV;
+  const size_t rs = qkv_rs(a);
+  const size_t os = (size_t)a.heads * a.hd;
+  float dk[4][DC] = {}, dv[4][DC] = {};   // keys ty*4+i, dims tx*DC+c
+  const float* dob = a.dout + (size_t)b * a.N * os + (size_t)h * a.hd;
+  for (int q0 = 0; q0 < a.N; q0 += BQ) {
+    __syncthreads();
+    load_tile<HD>(reinterpret_cast<float (*)[HD + kPad<HD>]>(qS), qkv_ptr(a, b, 0, h), rs, q0, a.N);
+    load_tile<HD>(reinterpret_cast<float (*)[HD + kPad<HD>]>(doS), dob, os, q0, a.N);
+    if (threadIdx.x < BQ) {
+      const int r = q0 + threadIdx.x;
+      lse_s[threadIdx.x] = r < a.N ? a.lse[((size_t)b * a.heads + h) * a.N + r] : 0.f;
+      delta_s[threadIdx.x] = r < a.N ? a.delta[((size_t)b * a.heads + h) * a.N + r] : 0.f;
+    }
+    float s[4][4] = {}, dp[4][4] = {};
+    for (int c0 = 0; c0 < HD; c0 += HC) {
+      __syncthreads();
+      load_chunk_T<HC>(qT, qkv_ptr(a, b, 0, h) + c0, rs, q0, a.N);
+      load_chunk_T<HC>(kT, qkv_ptr(a, b, 1, h) + c0, rs, k0, a.N);
+      load_chunk_T<HC>(doT, dob + c0, os, q0, a.N);
+      load_chunk_T<HC>(vT, qkv_ptr(a, b, 2, h) + c0, rs, k0, a.N);
+      __syncthreads();
+      accumulate_s_dp<HC>(qT, kT, doT, vT, tx, ty, s, dp);
+    }
+    float p[4][4], ds[4][4];
+    finish_p_ds(a, lse_s, delta_s, q0, k0, tx, ty, s, dp, p, ds);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { pS[ty * 4 + i][tx * 4 + j] = p[i][j]; dsS[ty * 4 + i][tx * 4 + j] = ds[i][j]; }
+    __syncthreads();
+#pragma unroll 2
+    for (int r = 0; r < BQ; ++r) {
+      const float4 pv = *reinterpret_cast<const float4*>(&pS[r][ty * 4]);
+      const float4 sv = *reinterpret_cast<const float4*>(&dsS[r][ty * 4]);
+      const float pa[4] = {pv.x, pv.y, pv.z, pv.w}, sa[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+      for (int c = 0; c < DC; ++c) {
+        const float g = doS[r][tx * DC + c], qv = qS[r][tx * DC + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { dv[i][c] = fmaf(pa[i], g, dv[i][c]); dk[i][c] = fmaf(sa[i], qv, dk[i][c]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int key = k0 + ty * 4 + i;
+    if (key >= a.N) continue;
+    float* dkp = a.dqkv + (((size_t)b * a.N + key) * 3 + 1) * os + (size_t)h * a.hd + tx * DC;
+    float* dvp = a.dqkv + (((size_t)b * a.N + key) * 3 + 2) * os + (size_t)h * a.hd + tx * DC;
+#pragma unroll
+    for (int c = 0; c < DC; ++c) { dkp[c] = dk[i][c]; dvp[c] = dv[i][c]; }
+  }
+}
+
+template <int HD, int HC>
+__global__ void __launch_bounds__(NT) attn_bwd_q_wide_kernel(const AttnArgs a) {
+  constexpr int DC = HD / 16;
+  extern __shared__ float smem[];
+  float (*qT)[BQ] = reinterpret_cast<float (*)[BQ]>(smem);
+  float (*kT)[BKV] = qT + HC;
+  float (*doT)[BQ] = kT + HC;
+  float (*vT)[BKV] = doT + HC;
+  float* after = smem + 4 * HC * BQ;
+  float (*kS)[HD] = reinterpret_cast<float (*)[HD]>(after);                       // [64 key][HD]
+  float (*dsT)[BQ] = reinterpret_cast<float (*)[BQ]>(after + BKV * HD);           // [key][row]
+  float* lse_s = reinterpret_cast<float*>(dsT + BKV);
+  float* delta_s = lse_s + BQ;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int b = blockIdx.y / a.heads, h = blockIdx.y % a.heads;
+  const int q0 = blockIdx.x * BQ;
+  const size_t rs = qkv_rs(a);
+  const size_t os = (size_t)a.heads * a.hd;
+  const float* dob = a.dout + (size_t)b * a.N * os + (size_t)h * a.hd;
+  if (threadIdx.x < BQ) {
+    const int r = q0 + threadIdx.x;
+    lse_s[threadIdx.x] = r < a.N ? a.lse[((size_t)b * a.heads + h) * a.N + r] : 0.f;
+    delta_s[threadIdx.x] = r < a.N ? a.delta[((size_t)b * a.heads + h) * a.N + r] : 0.f;
+  }
+  float dq[4][DC] = {};
+  for (int k0 = 0; k0 < a.N; k0 += BKV) {
+    __syncthreads();
+    load_tile<HD>(reinterpret_cast<float (*)[HD + kPad<HD>]>(kS), qkv_ptr(a, b, 1, h), rs, k0, a.N);
+    float s[4][4] = {}, dp[4][4] = {};
+    for (int c0 = 0; c0 < HD; c0 += HC) {
+      __syncthreads();
+      load_chunk_T<HC>(qT, qkv_ptr(a, b, 0, h) + c0, rs, q0, a.N);
+      load_chunk_T<HC>(kT, qkv_ptr(a, b, 1, h) + c0, rs, k0, a.N);
+      load_chunk_T<HC>(doT, dob + c0, os, q0, a.N);
+      load_chunk_T<HC>(vT, qkv_ptr(a, b, 2, h) + c0, rs, k0, a.N);
+      __syncthreads();
+      accumulate_s_dp<HC>(qT, kT, doT, vT, tx, ty, s, dp);
+    }
+    float p[4][4], ds[4][4];
+    finish_p_ds(a, lse_s, delta_s, q0, k0, tx, ty, s, dp, p, ds);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dsT[tx * 4 + j][ty * 4 + i] = ds[i][j];
+    __syncthreads();
+#pragma unroll 2
+    for (int k = 0; k < BKV; ++k) {
+      const float4 sv = *reinterpret_cast<const float4*>(&dsT[k][ty * 4]);
+      const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+      for (int c = 0; c < DC; ++c) {
+        const float kv = kS[k][tx * DC + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dq[i][c] = fmaf(sa[i], kv, dq[i][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = q0 + ty * 4 + i;
+    if (row >= a.N) continue;
+    float* dqp = a.dqkv + (((size_t)b * a.N + row) * 3 + 0) * os + (size_t)h * a.hd + tx * DC;
+#pragma unroll
+    for (int c = 0; c < DC; ++c) dqp[c] = dq[i][c];
+  }
+}
+
+template <int HD, int HC> int run_bwd_wide(const AttnArgs& a, cudaStream_t st) {
+  constexpr size_t kv_smem = sizeof(float) * (4 * HC * BQ + 2 * BQ * HD + 2 * BQ * BKV + 2 * BQ);
+  constexpr size_t q_smem = sizeof(float) * (4 * HC * BQ + BKV * HD + BKV * BQ + 2 * BQ);
+  static_assert(kv_smem <= 227 * 1024 && kPad<HD> == 0, "wide-head tiles must fit the 227 KiB of shared memory");
+  O2_CUDA(cudaFuncSetAttribute(attn_bwd_kv_wide_kernel<HD, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kv_smem));
+  O2_CUDA(cudaFuncSetAttribute(attn_bwd_q_wide_kernel<HD, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q_smem));
+  const long long warps = (long long)a.B * a.N * a.heads;
+  attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(a.out, a.dout, a.delta, a.B, a.N, a.heads, a.hd);
+  O2_LAUNCH_CHECK();
+  attn_bwd_kv_wide_kernel<HD, HC><<<dim3((a.N + BKV - 1) / BKV, a.B * a.heads), NT, kv_smem, st>>>(a);
+  O2_LAUNCH_CHECK();
+  attn_bwd_q_wide_kernel<HD, HC><<<dim3((a.N + BQ - 1) / BQ, a.B * a.heads), NT, q_smem, st>>>(a);
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
+
 template <int HD> constexpr size_t fwd_smem() { return sizeof(float) * (2 * HD * (BQ + kPad<HD>) + BKV * (HD + kPad<HD>) + BKV * (BQ + kPad<HD>)); }
 template <int HD> constexpr size_t bwd_kv_smem() {
   return sizeof(float) * (4 * HD * (BQ + kPad<HD>) + 2 * BQ * (HD + kPad<HD>) + 2 * BQ * (BKV + kPad<HD>) + 2 * BQ);
@@ -375,7 +581,8 @@ int o2_attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int h
   if (hd == 32) return run_fwd<32>(a, st);
   if (hd == 64) return run_fwd<64>(a, st);
   if (hd == 128) return run_fwd<128>(a, st);
-  O2_FAIL(O2_ERR_UNSUPPORTED, "attn_simt: head dim %d not in {32,64,128}", hd);
+  if (hd == 256) return run_fwd<256>(a, st);          // interm_10b: 32 heads x 256 (208 KiB of tiles, no padding)
+  O2_FAIL(O2_ERR_UNSUPPORTED, "attn_simt: head dim %d not in {32,64,128,256}", hd);
 }
 
 int o2_attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B,
@@ -390,7 +597,8 @@ int o2_attn_bwd_simt(const void* qkv, const void* out, const void* dout, const f
   if (hd == 32) return run_bwd<32>(a, st);
   if (hd == 64) return run_bwd<64>(a, st);
   if (hd == 128) return run_bwd<128>(a, st);
-  O2_FAIL(O2_ERR_UNSUPPORTED, "attn_simt backward: head dim %d not in {32,64,128}", hd);
+  if (hd == 256) return run_bwd_wide<256, 64>(a, st);
+  O2_FAIL(O2_ERR_UNSUPPORTED, "attn_simt backward: head dim %d not in {32,64,128,256}", hd);
 }
 
 int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, float p_drop,

@@ -77,6 +77,26 @@ inline int grid_for(long long n, int per_block) {
 
 }  // namespace
 
+__global__ void uncast_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint2 t = reinterpret_cast<const uint2*>(src)[i];
+    const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y);
+    reinterpret_cast<float4*>(dst)[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[n4 * 4 + threadIdx.x] = __bfloat162float(src[n4 * 4 + threadIdx.x]);
+}
+
+/* bf16 -> fp32 (operands of the fp32 attention arm when the bf16 path has no tensor-core kernel for a head dim) */
+extern "C" int o2_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
+  O2_REQUIRE(src && dst && n >= 0, "uncast: bad args");
+  if (n == 0) return O2_OK;
+  O2_REQUIRE(((uintptr_t)src % 8) == 0 && ((uintptr_t)dst % 16) == 0, "uncast: misaligned pointers");
+  uncast_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst, n);
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
+
 extern "C" int o2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   O2_REQUIRE(src && dst && n >= 0, "cast: bad args");
   if (n == 0) return O2_OK;

@@ -113,10 +113,27 @@ class _timed:
         return False
 
 
+def cast_f32(src: torch.Tensor):
+    """bf16 -> fp32 copy (o2_cast_bf16_to_f32)."""
+    lib = L.load()
+    dst = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+    L.check(lib.o2_cast_bf16_to_f32(_ptr(src), _ptr(dst), src.numel(), _stream()), "o2_cast_bf16_to_f32")
+    _count()
+    return dst
+
+
+# head dims of the tcgen05 attention kernels; a bf16 call with another head dim (256: interm_10b) runs the fp32 SIMT arm
+# on up-cast operands and rounds the result back (attention is < 1 % of that model's FLOPs at its 512-token grids)
+TC_HEAD_DIMS = (64, 128)
+
+
 def attn_fwd(qkv, B, N, heads, hd, drop=None):
     """qkv [B*N, 3*heads*hd] -> (out [B*N, heads*hd], lse [B,heads,N]).  drop = (p, seed, site): attention-probability
     dropout (training mode)."""
     lib = L.load()
+    if qkv.dtype == torch.bfloat16 and hd not in TC_HEAD_DIMS:
+        out32, lse = attn_fwd(cast_f32(qkv), B, N, heads, hd, drop)
+        return cast_bf16(out32), lse
     out = torch.empty(B * N, heads * hd, device=qkv.device, dtype=qkv.dtype)
     lse = torch.empty(B, heads, N, device=qkv.device, dtype=torch.float32)
     p, seed, site = drop if drop is not None else (0.0, 0, 0)
@@ -130,6 +147,8 @@ def attn_fwd(qkv, B, N, heads, hd, drop=None):
 
 def attn_bwd(qkv, out, dout, lse, B, N, heads, hd, drop=None):
     lib = L.load()
+    if qkv.dtype == torch.bfloat16 and hd not in TC_HEAD_DIMS:
+        return cast_bf16(attn_bwd(cast_f32(qkv), cast_f32(out), cast_f32(dout), lse, B, N, heads, hd, drop))
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, heads, N, device=qkv.device, dtype=torch.float32)
     impl = impl_for(qkv.dtype)
@@ -200,9 +219,27 @@ def _heads_of(tab_s):
     return tab_s.shape[1]
 
 
+FE_MAX_HD = 128
+
+
+def _split_wide_heads(tab_s, tab_v, hd):
+    """Head dims above the front-end kernels' 128: the softmax over the variables depends on the head, the output columns
+    are independent, so a head of width hd is f = hd / 128 heads of width 128 that share one score table (tab_s rows
+    repeated, tab_v [heads, KK, hd] re-laid as [heads * f, KK, 128]); the output [T, heads * hd] is the same memory."""
+    f = hd // FE_MAX_HD
+    assert hd % FE_MAX_HD == 0
+    heads, KK = tab_v.shape[0], tab_v.shape[1]
+    ts = tab_s.repeat_interleave(f, dim=1).contiguous()
+    tv = tab_v.view(heads, KK, f, FE_MAX_HD).permute(0, 2, 1, 3).reshape(heads * f, KK, FE_MAX_HD).contiguous()
+    return ts, tv, f
+
+
 def frontend_fwd(x, tab_s, tab_v, p, gh, gw, hd, out_dtype):
     """x [B,V,Hx,Wx] fp32; tab_s [V,heads,PP+1]; tab_v [heads, V*(PP+1), hd] -> o [B*gh*gw, heads*hd]."""
     lib = L.load()
+    if hd > FE_MAX_HD:
+        ts, tv, _ = _split_wide_heads(tab_s, tab_v, hd)
+        return frontend_fwd(x, ts, tv, p, gh, gw, FE_MAX_HD, out_dtype)
     B, V, Hx, Wx = x.shape
     heads = _heads_of(tab_s)
     assert x.dtype == torch.float32 and x.is_contiguous() and tab_s.is_contiguous() and tab_v.is_contiguous()
@@ -216,6 +253,13 @@ def frontend_fwd(x, tab_s, tab_v, p, gh, gw, hd, out_dtype):
 def frontend_bwd(x, tab_s, tab_v, dout, p, gh, gw, hd):
     """-> (dtab_s, dtab_v) fp32."""
     lib = L.load()
+    if hd > FE_MAX_HD:
+        ts, tv, f = _split_wide_heads(tab_s, tab_v, hd)
+        dts, dtv = frontend_bwd(x, ts, tv, dout, p, gh, gw, FE_MAX_HD)
+        heads, KK = tab_v.shape[0], tab_v.shape[1]
+        dts = dts.view(tab_s.shape[0], heads, f, tab_s.shape[2]).sum(2)
+        dtv = dtv.view(heads, f, KK, FE_MAX_HD).permute(0, 2, 1, 3).reshape(heads, KK, hd)
+        return dts.contiguous(), dtv.contiguous()
     B, V, Hx, Wx = x.shape
     heads = _heads_of(tab_s)
     dts = torch.zeros_like(tab_s)

@@ -222,6 +222,27 @@ def _attn_ref(qkv, B, N, heads, hd):
     return t, o, torch.logsumexp(s, -1)
 
 
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,N,heads", [(1, 100, 1), (2, 512, 2), (1, 333, 1)])
+def test_attn_hd256(dtype, B, N, heads):
+    """head dim 256 (interm_10b: 32 heads x 256): chunked fp32 attention kernels, forward and backward; the bf16 entry
+    up-casts its operands for them and rounds the results."""
+    from orbit2_b200 import ops
+    hd = 256
+    g = torch.Generator(device="cuda").manual_seed(N + 11 * heads)
+    D = heads * hd
+    qkv = (torch.randn(B * N, 3 * D, generator=g, device="cuda") * 0.5).to(dtype)
+    dout = torch.randn(B * N, D, generator=g, device="cuda").to(dtype)
+    out, lse = ops.attn_fwd(qkv, B, N, heads, hd)
+    t, o, lse_ref = _attn_ref(qkv, B, N, heads, hd)
+    assert out.dtype == dtype and rel(lse, lse_ref.detach()) < 1e-4
+    assert rel(out, o.detach()) < (2e-5 if dtype == torch.float32 else 8e-3)
+    o.backward(dout.double())
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, B, N, heads, hd)
+    ref = t.grad.permute(1, 3, 0, 2, 4).reshape(B * N, 3 * D)
+    assert dqkv.dtype == dtype and rel(dqkv, ref) < (5e-5 if dtype == torch.float32 else 1.5e-2)
+
+
 @pytest.mark.parametrize("B,N,heads,scale_in", [(1, 128, 1, 1.0), (2, 256, 2, 1.0), (1, 300, 2, 2.0), (2, 1000, 3, 1.0),
                                                 (1, 72, 1, 4.0), (1, 2049, 1, 1.0)])
 def test_attn_tc(B, N, heads, scale_in):

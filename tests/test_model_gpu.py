@@ -96,6 +96,28 @@ def test_1b_widths_vs_oracle(dtype):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_10b_head_dim_vs_oracle(dtype):
+    """BASELINE configs[3] head shape (interm_10b: 32 heads x 256): head dim 256 runs the chunked fp32 attention kernels
+    (the bf16 arm up-casts q / k / v for them) and the head-dim-256 front end; reduced width / depth / grid, against the
+    float64 CPU oracle."""
+    from oracle import cases, reslim_oracle as O
+    cfg = cases.get_case("10b_small")
+    assert cfg["embed_dim"] // cfg["num_heads"] == 256
+    sd = O.init_state_dict(cfg, seed=4)
+    x, y = O.synthetic_batch(cfg, 2, cfg["in_vars"], cfg["out_vars"], seed=4)
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    loss = O.training_step(sd64, cfg, x.double(), y.double(), cfg["in_vars"], cfg["out_vars"], "bayesian_tv",
+                           cfg["var_weights"], None, {})
+    loss.backward()
+    pred, vec, grads = run_ours(cfg, sd, x, y, "bayesian_tv", False, dtype)
+    tol = TOL[dtype]
+    assert rel(vec[-1], loss) < tol
+    worst = {k: rel(grads[k], v.grad) for k, v in sd64.items() if v.grad is not None and v.grad.abs().max() > 0}
+    bad = {k: v for k, v in worst.items() if v > tol * (1 if dtype == torch.float32 else 2.5)}
+    assert not bad, bad
+
+
 def oracle_masks_for(plan, cfg, B, attn=False):
     """The masks a DropPlan implies, rebuilt on the CPU from the documented hash (oracle/dropout_mask.py)."""
     from oracle import dropout_mask as DM
