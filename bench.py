@@ -192,7 +192,8 @@ def run_ours(args):
     meta = losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None)
     loss_fn = losses.METRICS_REGISTRY["bayesian_tv"](aggregate_only=True, metainfo=meta)
     eng = engine.TrainEngine(model, loss_fn, cfg["in_vars"], cfg["out_vars"], cfg["var_weights"], lr=2e-4,
-                             betas=(0.9, 0.99), weight_decay=1e-5, shard_optimizer=args.shard)
+                             betas=(0.9, 0.99), weight_decay=1e-5, shard_optimizer=args.shard,
+                             shard_params=args.full_shard)
 
     x_h, y_h = O.synthetic_batch(cfg, B, cfg["in_vars"], cfg["out_vars"], seed=rank)
     x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
@@ -272,6 +273,13 @@ def run_ours(args):
         eng.optimizer_step()
         opt_state["loss"] = loss.item()                    # device -> host read of the step's result
 
+    def e2e_step_engine():                                 # FULL_SHARD: the module holds no full weights, the engine step
+        x = x_h.to(dev, non_blocking=True)                 # is the public call (trainer.py drives exactly this)
+        y = y_h.to(dev, non_blocking=True)
+        opt_state["loss"] = eng.step(x, y)[-1].item()
+
+    if args.full_shard:
+        e2e_step = e2e_step_engine
     model.external_wc = eng.Wc if dtype == torch.bfloat16 else None
     model.train()
     ms_e2e = timed(e2e_step, args.steps, max(1, args.warmup // 2))
@@ -311,7 +319,7 @@ def run_ours(args):
             kernels_ms[n + "_tflops"] = round(attn_fwd_flops_blk * mult * B * cfg["depth"] / (kern[n] * 1e-3) / 1e12, 1)
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and args.workload != "10b":      # 9.5 B fp32 parameters + gradients: no host fit
         threads = os.cpu_count() or 1
         case, cb, _ = pick_cpu_sample(args.workload, 1, threads, budget_s=60.0, force=args.ref_grid)
         sec, ccfg = cpu_reference_step_time(case, cb, 1, 0 if args.workload == "117m" else 1, threads)
@@ -327,7 +335,7 @@ def run_ours(args):
             "config": {"workload": f"interm_{args.workload} Res_Slim_ViT ({n_params / 1e6:.1f}M params) ERA5 "
                                    f"{cfg['img_size'][0]}x{cfg['img_size'][1]} -> {H_out}x{cfg['img_size'][1] * cfg['superres_mag']}"
                                    f", V={len(cfg['in_vars'])} in / {len(cfg['out_vars'])} out vars, fwd+clip+bayesian_tv+bwd+allreduce+AdamW",
-                       "per_gpu_batch": B, "global_batch": B * world, "tokens_per_sample": L, "parallelism": (f"fsdp{world} (sharded Adam state + update, reduce-scatter / all-gather)" if (args.shard and world > 1) else f"dp{world}"),
+                       "per_gpu_batch": B, "global_batch": B * world, "tokens_per_sample": L, "parallelism": (f"fsdp{world} FULL_SHARD (per-Block all-gather fwd+bwd, gradient reduce-scatter, sharded fp32 master + Adam)" if args.full_shard else f"fsdp{world} (sharded Adam state + update, reduce-scatter / all-gather)" if (args.shard and world > 1) else f"dp{world}"),
                        "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB), no explicit flush",
                        "dropout": args.drop, "activation_checkpointing": bool(args.ckpt)},
             "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e,
@@ -357,6 +365,9 @@ def main():
     ap.add_argument("--ckpt", action="store_true", help="per-Block activation recomputation (reference: checkpoint wrappers "
                     "on every Block under FSDP); the recomputed forward FLOPs are NOT counted in the roofline")
     ap.add_argument("--shard", action="store_true", help="FSDP-style sharded optimizer instead of plain data parallel")
+    ap.add_argument("--full-shard", action="store_true",
+                    help="FSDP FULL_SHARD: GEMM weights, fp32 masters, gradients and Adam state sharded per Block "
+                         "(all-gather in forward and backward, reduce-scatter of gradients)")
     ap.add_argument("--ref-grid", default=None, choices=["full", "sub"], help="force the CPU sample (default: by time budget)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .dp import BucketReducer, FlatLayout, ShardedReducer, shard_size
+from .dp import BucketReducer, ChainedMap, FlatLayout, FullShard, ShardedReducer, shard_size
 from .losses import Metric, clip_spec
 from .reslim import Res_Slim_ViT, reslim_backward, reslim_forward
 
@@ -28,7 +28,7 @@ class TrainEngine:
     def __init__(self, model: Res_Slim_ViT, loss: Metric, in_variables: Sequence[str], out_variables: Sequence[str],
                  var_weights: Optional[Dict[str, float]] = None, lr: float = 2e-4, betas=(0.9, 0.99),
                  weight_decay: float = 1e-5, eps: float = 1e-8, process_group=None, clip_constants: bool = True,
-                 shard_optimizer: bool = False):
+                 shard_optimizer: bool = False, shard_params: bool = False):
         self.model = model
         self.loss = loss
         self.in_variables, self.out_variables = list(in_variables), list(out_variables)
@@ -44,8 +44,28 @@ class TrainEngine:
             raise RuntimeError("TrainEngine needs the model on a CUDA device (no CPU fallback)")
         self.device = dev
 
-        # ---- flat buffers; parameters become views of the fp32 master
+        # ---- FULL_SHARD mode (interm_1b / interm_10b; reference: FSDP FULL_SHARD with one unit per Block,
+        # intermediate_downscaling.py:583-617): the GEMM weights of the kernel schedule -- 99.9 % of the parameters --
+        # leave the flat buffers and live as per-unit 1/world shards (dp.FullShard: all-gather per Block in forward and
+        # backward, reduce-scatter of the Block's gradient, sharded master / Adam state / update); everything else
+        # (biases, LayerNorm, convolutions, embeddings, the var_agg q / kv weights the host-side tables are built from)
+        # stays replicated below with an all-reduced gradient.  Works with world size 1 (gathers become copies).
         named = [(n, p) for n, p in model.named_parameters()]
+        self.fs: Optional[FullShard] = None
+        if shard_params:
+            if shard_optimizer:
+                raise ValueError("shard_params already shards the optimizer; pass only one of the two modes")
+            kernel = set(model._names)
+            big = {n: p for n, p in named if n in kernel and n.endswith(".weight") and p.dim() == 2 and p.requires_grad}
+            root = [n for n in big if not n.startswith("blocks.")]
+            units = [root] + [[n for n in big if n.startswith(f"blocks.{i}.")] for i in range(len(model.blocks))]
+            self.fs = FullShard(units, big, self.act, process_group)
+            for p in big.values():                      # the module keeps no full copy (engine.full_state_dict() gathers)
+                p.data = torch.empty(0, device=dev, dtype=p.dtype)
+                p.grad = None
+            named = [(n, p) for n, p in named if n not in big]
+
+        # ---- flat buffers; parameters become views of the fp32 master
         self.names = [n for n, _ in named]
         sizes = [p.numel() for _, p in named]
         self.layout = FlatLayout(self.names, sizes, align=8)
@@ -88,7 +108,18 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ pieces
     def _on_ready(self, names: List[str]):
+        if self.fs is not None:
+            self.fs.ready(names)
+            names = [n for n in names if n not in self.fs.where]
         self.reducer.ready(names)
+
+    def full_state_dict(self) -> Dict[str, torch.Tensor]:
+        """The module's state dict with the sharded weights gathered (collective in FULL_SHARD mode)."""
+        sd = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        if self.fs is not None:
+            for n in self.fs.where:
+                sd[n] = self.fs.full_tensor(n)
+        return sd
 
     def forward_backward(self, x: torch.Tensor, y: torch.Tensor):
         """x [B,V,H,W] fp32, y [B,C,H',W'] fp32 on the device.  Returns the [C+1] loss vector (device, fp32);
@@ -104,13 +135,19 @@ class TrainEngine:
         with torch.no_grad():
             posres_act = posres if self.act == torch.float32 else ops.cast_bf16(posres)
             Wc = self.P if self.act == torch.float32 else self.Wc
+            G = self.G
+            if self.fs is not None:                 # lookups in these mappings drive the gathers / gradient slots
+                Wc, G = self.fs.params, ChainedMap(self.G, self.fs.grads)
+                self.fs.begin(+1)
             preds, S = reslim_forward(g, self.P, Wc, x, tab_s.detach(), tab_v.detach(), posres_act)
             if self._lat is None:
                 self._lat = self.loss._lat(preds)
                 self._chw = self.loss._ch_w(preds, self.out_variables, self.var_weights)
             vec, dpred = ops.loss_fwd_bwd(preds, y, self.loss.kind, lat_w=self._lat, ch_w=self._chw, clamp_ch=self.clip[0],
                                           const_mask=self.clip[1])
-            dts, dtv, dpos = reslim_backward(g, self.P, Wc, x, tab_s.detach(), tab_v.detach(), S, dpred, self.G,
+            if self.fs is not None:
+                self.fs.begin(-1)
+            dts, dtv, dpos = reslim_backward(g, self.P, Wc, x, tab_s.detach(), tab_v.detach(), S, dpred, G,
                                              on_ready=self._on_ready)
         torch.autograd.backward([tab_s, tab_v, posres], [dts, dtv, dpos])
         for n in self.frozen:                       # e.g. pos_embed when learn_pos_emb=False
@@ -118,6 +155,8 @@ class TrainEngine:
         if self.world > 1:
             self._on_ready([n for n in self.names if not self._is_kernel_param(n)])
             self.reducer.finish()
+        if self.fs is not None:
+            self.fs.finish()
         return vec
 
     def _is_kernel_param(self, n):
@@ -142,6 +181,11 @@ class TrainEngine:
             ops.adamw(self.flat_p[lo:hi], self.flat_g[lo:hi], self.flat_m[lo - o0:hi - o0], self.flat_v[lo - o0:hi - o0],
                       self.flat_b[lo:hi] if self.flat_b is not None else None, self.lr, self.betas[0], self.betas[1],
                       self.eps, self.weight_decay, self.step_count, grad_scale)
+        if self.fs is not None:                         # FULL_SHARD units: each rank updates its slice of every unit
+            for p32, g32, m, v, low in self.fs.shards():
+                ops.adamw(p32, g32, m, v, low, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                          self.step_count, grad_scale)
+            self.fs.after_step()
         if self.sharded:                                # in-place all-gather of the updated shards
             dist.all_gather_into_tensor(self.flat_p, self.flat_p[o0:o1], group=self.pg)
             if self.flat_b is not None:

@@ -555,7 +555,7 @@ class Res_Slim_ViT(nn.Module):
         g.hd = g.D // g.heads
         g.depth, g.dec, g.mag = self.depth, self.decoder_depth, self.superres_mag
         g.C, g.cr = len(out_variables), self.cnn_ratio
-        g.hidden = self.blocks[0].mlp.fc1.weight.shape[0] if self.depth else 0
+        g.hidden = self.blocks[0].mlp.fc1.out_features if self.depth else 0
         g.idx7 = self.find_var_index(in_variables, out_variables)
         g.act = act
         g.ckpt = bool(getattr(self, "activation_checkpointing", False))

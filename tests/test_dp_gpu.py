@@ -19,12 +19,43 @@ def _free_port():
     return p
 
 
-def _make(cfg, sd, dev, shard=False, dtype=torch.float32):
+def _make(cfg, sd, dev, shard=False, dtype=torch.float32, full_shard=False, ckpt=False):
     from orbit2_b200 import engine, losses
     m = build_model(cfg, sd, dev, dtype)
+    m.activation_checkpointing = ckpt
     loss = losses.METRICS_REGISTRY["mse"](aggregate_only=True, metainfo=losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None))
     return engine.TrainEngine(m, loss, cfg["in_vars"], cfg["out_vars"], cfg["var_weights"], lr=1e-3, betas=(0.9, 0.99), weight_decay=1e-5,
-                              shard_optimizer=shard)
+                              shard_optimizer=shard, shard_params=full_shard)
+
+
+def _same_params(a, b, dtype):
+    """Engine b (FULL_SHARD) holds the same parameters as engine a (replicated): fp32 masters of the sharded weights
+    gathered from the shards, the replicated rest straight from the flat buffer."""
+    sa, sb = a.full_state_dict(), b.full_state_dict()
+    tol = 1e-5 if dtype == torch.float32 else 2e-3        # bf16 arm: split-K atomics order + bf16 operands
+    bad = {k: (sa[k] - sb[k]).abs().max().item() for k in sa
+           if (sa[k] - sb[k]).abs().max().item() > tol * sa[k].abs().max().item() + 1e-7}
+    return bad
+
+
+@pytest.mark.parametrize("dtype,ckpt", [(torch.float32, False), (torch.bfloat16, True)])
+def test_full_shard_world1_equals_replicated(dtype, ckpt):
+    """FULL_SHARD engine on one GPU (gathers are copies): the lookup-driven unit hand-over, the two rotating weight /
+    gradient slots and the per-shard AdamW reproduce the replicated engine step for step."""
+    from oracle import cases, reslim_oracle as O
+    cfg = cases.get_case("tiny")
+    sd = O.init_state_dict(cfg, seed=9)
+    x, y = O.synthetic_batch(cfg, 2, cfg["in_vars"], cfg["out_vars"], seed=9)
+    a = _make(cfg, sd, "cuda:0", dtype=dtype, ckpt=ckpt)
+    b = _make(cfg, sd, "cuda:0", dtype=dtype, full_shard=True, ckpt=ckpt)
+    assert b.fs is not None and len(b.fs.units) == cfg["depth"] + 1
+    assert b.model.blocks[0].mlp.fc1.weight.numel() == 0           # the module keeps no full copy of a sharded weight
+    for _ in range(3):
+        va = a.step(x.cuda(), y.cuda())
+        vb = b.step(x.cuda(), y.cuda())
+        assert abs(va[-1].item() - vb[-1].item()) <= (1e-5 if dtype == torch.float32 else 5e-3) * abs(va[-1].item())
+    bad = _same_params(a, b, dtype)
+    assert not bad, bad
 
 
 def _worker(rank, world, port, ret):
@@ -55,6 +86,18 @@ def _worker(rank, world, port, ret):
         ret[f"shard{rank}{dtype}"] = bool(torch.allclose(a.flat_p[:n], b.flat_p[:n], rtol=1e-5, atol=1e-7)) and \
             (a.flat_b is None or bool(torch.equal(a.flat_b[:n], b.flat_b[:n]) or
                                       (a.flat_b[:n].float() - b.flat_b[:n].float()).abs().max().item() < 1e-2))
+    # FULL_SHARD (per-Block all-gather / reduce-scatter, sharded master + Adam) against plain data parallel
+    for dtype, ckpt in ((torch.float32, False), (torch.bfloat16, True)):
+        a = _make(cfg, sd, f"cuda:{rank}", dtype=dtype, ckpt=ckpt)
+        b = _make(cfg, sd, f"cuda:{rank}", dtype=dtype, full_shard=True, ckpt=ckpt)
+        assert b.fs.world == 2 and b.fs.master[1].numel() * 2 == b.fs.S[1] * 2
+        for _ in range(3):
+            xa, ya = x[2 * rank:2 * rank + 2].cuda(), y[2 * rank:2 * rank + 2].cuda()
+            a.step(xa, ya)
+            b.step(xa, ya)
+        torch.cuda.synchronize()
+        bad = _same_params(a, b, dtype)
+        ret[f"shard-full{rank}{dtype}"] = not bad
     dist.destroy_process_group()
 
 
