@@ -114,7 +114,7 @@ def cpu_reference_step_time(case_name, B, steps, warmup, threads):
 def pick_cpu_sample(workload, n_steps_total, threads, budget_s=260.0, force=None):
     """Bounded CPU sample of the workload: B=1 on the full 180x360 grid when (steps+warmup) of them fit the time budget
     (calibrated with one step on the quarter-area 90x180 sub-grid, full grid measured 5.9x, budgeted 6.5x), else the sub-grid itself."""
-    if workload in ("1b", "10b"):
+    if workload in ("1b", "10b", "10b_d2"):
         return workload, 1, None
     if workload != "117m":
         return "8m", 8, None
@@ -175,7 +175,7 @@ def run_ours(args):
     B = args.batch or {"117m": 8, "1b": 8}.get(args.workload, 32)       # 8m / 10b: 32 per GPU (configs/interm_*.yaml:6)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     torch.manual_seed(0)
-    with torch.device(dev if args.workload == "10b" else "cpu"):     # 9.5 B parameters are initialised on the GPU
+    with torch.device(dev if args.workload.startswith("10b") else "cpu"):     # 9.5 B parameters are initialised on the GPU
         model = Res_Slim_ViT(cfg["default_vars"], cfg["img_size"], len(cfg["default_vars"]), cfg["out_channels"], 1,
                              superres_mag=cfg["superres_mag"], cnn_ratio=cfg["cnn_ratio"], patch_size=cfg["patch_size"],
                              drop_path=args.drop, drop_rate=args.drop, learn_pos_emb=True, embed_dim=cfg["embed_dim"],
@@ -319,7 +319,7 @@ def run_ours(args):
             kernels_ms[n + "_tflops"] = round(attn_fwd_flops_blk * mult * B * cfg["depth"] / (kern[n] * 1e-3) / 1e12, 1)
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline and args.workload != "10b":      # 9.5 B fp32 parameters + gradients: no host fit
+    if rank == 0 and not args.no_cpu_baseline and not args.workload.startswith("10b"):      # 9.5 B fp32 parameters + gradients: no host fit
         threads = os.cpu_count() or 1
         case, cb, _ = pick_cpu_sample(args.workload, 1, threads, budget_s=60.0, force=args.ref_grid)
         sec, ccfg = cpu_reference_step_time(case, cb, 1, 0 if args.workload == "117m" else 1, threads)
@@ -343,6 +343,7 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "step_tflops": step_tflops, "step_frac_of_bf16_peak": step_tflops / peaks["tf_sust"],
             "kernels_ms_per_step": kernels_ms, "loss": loss_val,
+            "hbm_peak_gib": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -356,7 +357,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="117m", choices=["117m", "8m", "117m_90x180", "1b", "10b"])
+    ap.add_argument("--workload", default="117m", choices=["117m", "8m", "117m_90x180", "1b", "10b", "10b_d2"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -56,6 +56,8 @@ CASES = {
     "10b_small": lambda: _cfg(DEFAULT_VARS_23, (16, 32), 512, 2, 1, 2, 4.0),
     # the full interm_10b model (9.5 B parameters) on the 32x64 ERA5 5.625-degree grid of its YAML's first dataset
     "10b": lambda: _cfg(DEFAULT_VARS_23, (32, 64), 8192, 11, 4, 32, 625.0),
+    # interm_10b widths with 2 of the 11 Blocks (2.0 B parameters): every kernel shape of the full model on a 1-2 GPU budget
+    "10b_d2": lambda: _cfg(DEFAULT_VARS_23, (32, 64), 8192, 2, 4, 32, 625.0),
     # reduced-grid 117M (same widths, L=4050) for bounded CPU timing
     "117m_90x180": lambda: _cfg(DEFAULT_VARS_23, (90, 180), 1024, 8, 4, 16, 111.0),
 }
