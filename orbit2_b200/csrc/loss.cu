@@ -7,6 +7,9 @@
 // One CTA stages a (TH+2) x (TW+2) halo tile of the *clipped* prediction in shared memory (coalesced reads along W),
 // then every thread produces 4 pixels: weighted error -> warp-shuffle/CTA reduction -> one fp64 atomic per CTA, and the
 // analytic gradient (gather form of the TV stencil, sign(0)=0 like torch.abs) written once.
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -233,6 +236,273 @@ __global__ void __launch_bounds__(NT) loss_stream_kernel(const LossArgs a) {
   }
 }
 
+// Band variant for bayesian_tv (the shipped train_loss): one thread owns an 8-column strip of RH consecutive rows and
+// slides a two-row register window down it, so DRAM / L1 see every prediction row (RH + 2) / RH times instead of 3, the
+// halo columns come from the neighbour lanes by warp shuffle (only lanes 0 / 31 load a scalar), and every TV difference
+// that lies inside the strip is evaluated ONCE and scattered to both of its end points (35 sign evaluations per 8
+// pixels instead of 64).  Pair ownership follows functional.py:141-160: pixel (h, w) owns |p(h+1,w)-p|, |p(h,w+1)-p|,
+// 0.7|p(h+1,w+1)-p|, 0.7|p(h+1,w-1)-p| and weights them with lat_w[h]; a pair whose end point lies outside the image
+// does not exist (the reference zero-pads the difference tensors).
+constexpr int RH = 8;
+
+// raw (not yet unpacked) CW-element row segments: the loads of the next row stay in flight while the current row computes
+template <typename S, int CW> struct RawN;
+template <> struct RawN<float, 8> { float4 a, b; };
+template <> struct RawN<__nv_bfloat16, 8> { uint4 a; };
+template <> struct RawN<float, 4> { float4 a; };
+template <> struct RawN<__nv_bfloat16, 4> { uint2 a; };
+__device__ __forceinline__ void ldraw(const float* p, RawN<float, 8>& r) {
+  r.a = __ldg(reinterpret_cast<const float4*>(p));
+  r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+}
+__device__ __forceinline__ void ldraw(const __nv_bfloat16* p, RawN<__nv_bfloat16, 8>& r) {
+  r.a = __ldg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void ldraw(const float* p, RawN<float, 4>& r) { r.a = __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void ldraw(const __nv_bfloat16* p, RawN<__nv_bfloat16, 4>& r) {
+  r.a = __ldg(reinterpret_cast<const uint2*>(p));
+}
+__device__ __forceinline__ void unpackN(const RawN<float, 8>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+__device__ __forceinline__ void unpackN(const RawN<__nv_bfloat16, 8>& r, float (&v)[8]) {
+  const float2 a = unpack_bf16x2(r.a.x), b = unpack_bf16x2(r.a.y), c = unpack_bf16x2(r.a.z), d = unpack_bf16x2(r.a.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void unpackN(const RawN<float, 4>& r, float (&v)[4]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w;
+}
+__device__ __forceinline__ void unpackN(const RawN<__nv_bfloat16, 4>& r, float (&v)[4]) {
+  const float2 a = unpack_bf16x2(r.a.x), b = unpack_bf16x2(r.a.y);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void storeN(float* p, const float (&v)[8]) { store8<float>(p, v); }
+__device__ __forceinline__ void storeN(__nv_bfloat16* p, const float (&v)[8]) { store8<__nv_bfloat16>(p, v); }
+__device__ __forceinline__ void storeN(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void storeN(__nv_bfloat16* p, const float (&v)[4]) {
+  uint2 t;
+  t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+template <typename T, bool CONST, int CW>     // CW columns per thread; CONST: the channel is overwritten with the target (no gradient, the TV term is the target's)
+__device__ __forceinline__ void loss_tv_band_body(const LossArgs& a, float* swarp) {
+  using S = typename std::conditional<CONST, float, T>::type;       // element type of the rows the TV stencil reads
+  const int bc = blockIdx.y;
+  const int c = bc % a.C;
+  const int W8 = a.W / CW;
+  const int warps_per_row = (W8 + 31) >> 5;
+  const int n_bands = (a.H + RH - 1) / RH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long gw = (long long)blockIdx.x * (NT / 32) + warp;
+  const bool warp_ok = gw < (long long)n_bands * warps_per_row;          // warp-uniform
+  const int band = warp_ok ? (int)(gw / warps_per_row) : 0;
+  const int grp = (warp_ok ? (int)(gw % warps_per_row) : 0) * 32 + lane;
+  const bool active = warp_ok && grp < W8;
+  const int w0 = active ? grp * CW : 0;                                   // idle lanes shadow group 0 (valid addresses)
+  const int h0 = band * RH;
+  const float* tgt = a.target + (size_t)bc * a.tgt_H * a.tgt_W + w0;
+  const S* src;
+  size_t sW;
+  if constexpr (CONST) { src = tgt; sW = (size_t)a.tgt_W; }
+  else { src = reinterpret_cast<const T*>(a.pred) + (size_t)bc * a.H * a.W + w0; sW = (size_t)a.W; }
+  const bool is_clamp = (c == a.clamp_ch);
+  const bool validL = w0 > 0, validR = w0 + CW < a.W;
+  const bool haloL = (lane == 0) && validL, haloR = (lane == 31) && validR;
+  const float chw = (a.ch_w ? a.ch_w[c] : 1.0f) * a.gscale;
+  const int Hm1 = a.H - 1;
+  float local = 0.f;
+
+  // issue the loads of row hh (clamped into the image; callers mask what a clamped row feeds): CW own columns + the halo
+  // columns w0 - 1 / w0 + CW that no neighbour lane holds
+  auto issue = [&](int hh, RawN<S, CW>& rw, float& l, float& r) {
+    hh = hh < 0 ? 0 : (hh > Hm1 ? Hm1 : hh);
+    const S* rowp = src + (size_t)hh * sW;
+    ldraw(rowp, rw);
+    l = 0.f; r = 0.f;
+    if (haloL) l = to_f(__ldg(rowp - 1));
+    if (haloR) r = to_f(__ldg(rowp + CW));
+  };
+  auto issue_t = [&](int hh, RawN<float, CW>& rt) {
+    hh = hh > Hm1 ? Hm1 : hh;
+    ldraw(tgt + (size_t)hh * a.tgt_W, rt);
+  };
+  // landed loads -> clipped values at columns w0-1 .. w0+CW and the gradient-pass bits of the CW own columns
+  auto finish = [&](const RawN<S, CW>& rw, float l, float r, float (&dst)[CW + 2], uint32_t& pass) {
+    float v[CW];
+    unpackN(rw, v);
+    pass = CONST ? 0u : ((1u << CW) - 1u);
+    if (is_clamp) {
+#pragma unroll
+      for (int i = 0; i < CW; ++i) {
+        if (v[i] < 0.f) { v[i] = 0.f; pass &= ~(1u << i); }
+      }
+      l = fmaxf(l, 0.f); r = fmaxf(r, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < CW; ++i) dst[i + 1] = v[i];
+    const float ls = __shfl_up_sync(0xffffffffu, v[CW - 1], 1), rs = __shfl_down_sync(0xffffffffu, v[0], 1);
+    dst[0] = lane == 0 ? l : ls;
+    dst[CW + 1] = lane == 31 ? r : rs;
+  };
+  // d|x|/dx with sign(0) = 0 (torch.abs): +-1 (FSET.BF + LOP3) and +-0.7
+  auto sgn1 = [](float x) {
+    return __uint_as_float(__float_as_uint(x != 0.f ? 1.f : 0.f) | (__float_as_uint(x) & 0x80000000u));
+  };
+  auto sgn07 = [](float x) {
+    return __uint_as_float(__float_as_uint(x != 0.f ? 0.7f : 0.f) | (__float_as_uint(x) & 0x80000000u));
+  };
+
+  if (warp_ok) {
+    const bool full = (h0 + RH < a.H);                   // every row of the band has a row below it (warp-uniform)
+    // lat_w[h0 - 1 + lane] (lanes 0 .. RH), broadcast by shuffle where a row needs it: no load on the per-row path
+    float lw_lane = 1.0f;
+    if (a.lat_w && lane <= RH) {
+      int hh = h0 - 1 + lane;
+      hh = hh < 0 ? 0 : (hh > Hm1 ? Hm1 : hh);
+      lw_lane = __ldg(a.lat_w + hh);
+    }
+    // pull the whole band towards L2 first: the register pipeline below runs one row ahead, which covers an L2 hit
+    // (~0.4 us) but not a DRAM miss under load (> 1 us)
+#pragma unroll
+    for (int k = 1; k <= RH + 2; ++k) {
+      int hh = h0 - 1 + k;
+      hh = hh > Hm1 ? Hm1 : hh;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)hh * sW));
+      if (!CONST && k <= RH) asm volatile("prefetch.global.L2 [%0];" ::"l"(tgt + (size_t)hh * a.tgt_W));
+    }
+    float cur[CW + 2], nxt[CW + 2], carry[CW];
+    uint32_t pc, pn;
+    RawN<S, CW> rp, rp2;
+    RawN<float, CW> rt;
+    float rl, rr, rl2, rr2;
+    issue(h0 - 1, rp, rl, rr);
+    issue(h0, rp2, rl2, rr2);
+    finish(rp, rl, rr, cur, pn);
+    issue(h0 + 1, rp, rl, rr);                           // stays in flight until the first row step
+    if (!CONST) issue_t(h0, rt);
+    finish(rp2, rl2, rr2, nxt, pc);
+#pragma unroll
+    for (int i = 0; i < CW; ++i) carry[i] = 0.f;
+    if (h0 > 0) {
+      // what the pairs owned by row h0 - 1 (another band's row) hand down to row h0
+      const float lwm = __shfl_sync(0xffffffffu, lw_lane, 0);
+#pragma unroll
+      for (int i = 0; i < CW; ++i) carry[i] = sgn1(nxt[i + 1] - cur[i + 1]);
+#pragma unroll
+      for (int j = 0; j <= CW - 1; ++j) {
+        float x = nxt[j + 1] - cur[j];
+        if (j == 0 && !validL) x = 0.f;
+        carry[j] += sgn07(x);
+      }
+#pragma unroll
+      for (int j = 2; j <= CW + 1; ++j) {
+        float x = nxt[j - 1] - cur[j];
+        if (j == CW + 1 && !validR) x = 0.f;
+        carry[j - 2] += sgn07(x);
+      }
+#pragma unroll
+      for (int i = 0; i < CW; ++i) carry[i] *= lwm;
+    }
+#pragma unroll
+    for (int i = 0; i < CW + 2; ++i) cur[i] = nxt[i];
+
+    // one row: cur = row h, rp = loads of row h + 1 (issued one step ago), rt = loads of the target of row h
+    auto row_step = [&](int h, bool below) {
+      finish(rp, rl, rr, nxt, pn);
+      float t[CW];
+      if (!CONST) unpackN(rt, t);
+      issue(h + 2, rp, rl, rr);                          // in flight while this row computes
+      if (!CONST) issue_t(h + 1, rt);
+      const float lw = __shfl_sync(0xffffffffu, lw_lane, h - h0 + 1);
+      float gs[CW], gn[CW];
+      float eA = 0.f, eB = 0.f;
+      {  // |p(h, w+1) - p(h, w)|: owner array index j (column w0 - 1 + j), other j + 1
+        float x = cur[1] - cur[0];
+        if (!validL) x = 0.f;
+        gs[0] = sgn1(x);
+#pragma unroll
+        for (int j = 1; j <= CW; ++j) {
+          x = cur[j + 1] - cur[j];
+          if (j == CW && !validR) x = 0.f;
+          const float s = sgn1(x);
+          eA += fabsf(x); gs[j - 1] -= s;
+          if (j <= CW - 1) gs[j] = s;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < CW; ++i) gn[i] = 0.f;
+      if (below) {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {                    // |p(h+1, w) - p(h, w)|
+          const float x = nxt[i + 1] - cur[i + 1];
+          const float s = sgn1(x);
+          eA += fabsf(x); gs[i] -= s; gn[i] = s;
+        }
+#pragma unroll
+        for (int j = 0; j <= CW; ++j) {                   // 0.7 |p(h+1, w+1) - p(h, w)|: owner j, other j + 1 in the row below
+          float x = nxt[j + 1] - cur[j];
+          if (j == 0 && !validL) x = 0.f;
+          if (j == CW && !validR) x = 0.f;
+          const float s = sgn07(x);
+          if (j >= 1) { eB += fabsf(x); gs[j - 1] -= s; }
+          if (j <= CW - 1) gn[j] += s;
+        }
+#pragma unroll
+        for (int j = 1; j <= CW + 1; ++j) {                   // 0.7 |p(h+1, w-1) - p(h, w)|: owner j, other j - 1 in the row below
+          float x = nxt[j - 1] - cur[j];
+          if (j == 1 && !validL) x = 0.f;
+          if (j == CW + 1 && !validR) x = 0.f;
+          const float s = sgn07(x);
+          if (j <= CW) { eB += fabsf(x); gs[j - 1] -= s; }
+          if (j >= 2) gn[j - 2] += s;
+        }
+      }
+      float gout[CW], e2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CW; ++i) {
+        const float d = CONST ? 0.f : cur[i + 1] - t[i];
+        e2 = fmaf(d, d, e2);
+        const float g = 2.f * d * lw + 0.02f * (lw * gs[i] + carry[i]);
+        gout[i] = ((pc >> i) & 1u) ? g * chw : 0.f;
+      }
+      if (active) {
+        local += lw * (e2 + 0.02f * (eA + 0.7f * eB));
+        if (a.dpred) storeN(reinterpret_cast<T*>(a.dpred) + (size_t)bc * a.H * a.W + (size_t)h * a.W + w0, gout);
+      }
+#pragma unroll
+      for (int i = 0; i < CW; ++i) carry[i] = lw * gn[i];
+#pragma unroll
+      for (int i = 0; i < CW + 2; ++i) cur[i] = nxt[i];
+      pc = pn;
+    };
+    if (full) {
+#pragma unroll
+      for (int k = 0; k < RH; ++k) row_step(h0 + k, true);
+    } else {
+#pragma unroll 1
+      for (int h = h0; h < a.H; ++h) row_step(h, h + 1 < a.H);
+    }
+  }
+  local = warp_sum(local);
+  if (lane == 0) swarp[warp] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s_ = 0.f;
+    for (int i = 0; i < NT / 32; ++i) s_ += swarp[i];
+    atomicAdd(&a.accum[c], (double)s_);
+  }
+}
+
+template <typename T, int CW>
+__global__ void __launch_bounds__(NT, CW == 4 ? 3 : 2) loss_tv_band_kernel(const LossArgs a) {
+  __shared__ float swarp[NT / 32];
+  if ((a.const_mask >> (blockIdx.y % a.C)) & 1u) loss_tv_band_body<T, true, CW>(a, swarp);     // CTA-uniform
+  else loss_tv_band_body<T, false, CW>(a, swarp);
+}
+
 __global__ void loss_finalize(const double* accum, const float* ch_w, float* loss_vec, int C, double inv_per_ch) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double tot = 0.0;
@@ -304,11 +574,23 @@ extern "C" int o2_loss_fwd_bwd(const void* pred, int dtype, const float* target,
                          (dpred == nullptr || (uintptr_t)dpred % 16 == 0) && (((size_t)H * W * esz) % 16 == 0) &&
                          (((size_t)tgt_H * tgt_W * 4) % 16 == 0);
   if (stream_ok) {
-    const long long items = (long long)H * (W / 8);
-    dim3 grid((unsigned)((items + NT - 1) / NT), B * C);
-    const bool tv = (kind == O2_LOSS_BAYESIAN_TV);
-    if (dtype == O2_F32) { if (tv) loss_stream_kernel<float, true><<<grid, NT, 0, st>>>(a); else loss_stream_kernel<float, false><<<grid, NT, 0, st>>>(a); }
-    else { if (tv) loss_stream_kernel<__nv_bfloat16, true><<<grid, NT, 0, st>>>(a); else loss_stream_kernel<__nv_bfloat16, false><<<grid, NT, 0, st>>>(a); }
+    if (kind == O2_LOSS_BAYESIAN_TV) {
+      static const int cw = getenv("O2_LOSS_CW") ? atoi(getenv("O2_LOSS_CW")) : 8;     // columns per thread (A/B switch: 4 | 8)
+      const long long warps = (long long)((H + RH - 1) / RH) * ((W / cw + 31) / 32);
+      dim3 grid((unsigned)((warps + NT / 32 - 1) / (NT / 32)), B * C);
+      if (cw == 8) {
+        if (dtype == O2_F32) loss_tv_band_kernel<float, 8><<<grid, NT, 0, st>>>(a);
+        else loss_tv_band_kernel<__nv_bfloat16, 8><<<grid, NT, 0, st>>>(a);
+      } else {
+        if (dtype == O2_F32) loss_tv_band_kernel<float, 4><<<grid, NT, 0, st>>>(a);
+        else loss_tv_band_kernel<__nv_bfloat16, 4><<<grid, NT, 0, st>>>(a);
+      }
+    } else {
+      const long long items = (long long)H * (W / 8);
+      dim3 grid((unsigned)((items + NT - 1) / NT), B * C);
+      if (dtype == O2_F32) loss_stream_kernel<float, false><<<grid, NT, 0, st>>>(a);
+      else loss_stream_kernel<__nv_bfloat16, false><<<grid, NT, 0, st>>>(a);
+    }
   } else {
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * C);
     if (dtype == O2_F32) loss_kernel<float><<<grid, NT, 0, st>>>(a);

@@ -86,7 +86,8 @@ def test_elementwise():
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("kind", ["mse", "mae", "bayesian_tv"])
 @pytest.mark.parametrize("use_lat", [False, True])
-@pytest.mark.parametrize("W,tW", [(150, 152), (152, 156)])      # tiled shared-memory path / streaming path (W % 8 == 0)
+# tiled shared-memory path / streaming + band paths (W % 8 == 0) / three warps per row (lane-0 and lane-31 halo loads)
+@pytest.mark.parametrize("W,tW", [(150, 152), (152, 156), (520, 524)])
 def test_loss_vs_oracle(dtype, kind, use_lat, W, tW):
     from oracle import cases, reslim_oracle as O
     from orbit2_b200 import _lib as L, ops

@@ -24,11 +24,35 @@ g = torch.Generator(device=dev).manual_seed(0)
 rn = lambda *s: torch.randn(*s, generator=g, device=dev)
 
 
-def timed(fn, n=10):
+def timed(fn, n=10, graph=True):
+    """Mean device time of fn: n back-to-back calls captured in one CUDA graph (so a 40 us kernel is not paced by the
+    Python / ctypes issue rate), replayed three times; eager event timing if the capture fails."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if graph and os.environ.get("O2_HBM_EAGER", "0") != "1":
+        try:
+            st = torch.cuda.Stream()
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                fn()
+            torch.cuda.current_stream().wait_stream(st)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for _ in range(n):
+                    fn()
+            gr.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / (3 * n)
+        except Exception as ex:          # noqa: BLE001
+            print(f"# graph capture failed ({type(ex).__name__}: {ex}); eager timing", file=sys.stderr)
+            torch.cuda.synchronize()
     e0.record()
     for _ in range(n):
         fn()
@@ -40,8 +64,8 @@ def timed(fn, n=10):
 rows = []
 
 
-def report(name, fn, nbytes):
-    ms = timed(fn)
+def report(name, fn, nbytes, graph=True):
+    ms = timed(fn, graph=graph)
     gbs = nbytes / ms / 1e6
     rows.append((name, ms, nbytes / 1e6, gbs, gbs / PEAK))
     print(f"{name:34s} {ms:8.3f} ms {nbytes / 1e6:9.1f} MB {gbs:8.0f} GB/s {100 * gbs / PEAK:5.1f}% of {SRC} peak {PEAK:.0f}")
@@ -85,7 +109,7 @@ P, Gd, M, Vv = (torch.zeros(n, device=dev) for _ in range(4))
 Pb = torch.zeros(n, device=dev, dtype=bf)
 report("fused AdamW 126.1M params", lambda: ops.adamw(P, Gd, M, Vv, Pb, 1e-3, 0.9, 0.99, 1e-8, 1e-5, 1), n * (4 * 4 + 3 * 4 + 2))
 a, b_ = torch.empty(1 << 29, device=dev, dtype=bf), torch.empty(1 << 29, device=dev, dtype=bf)
-report("torch copy 1 GiB bf16 (yardstick)", lambda: b_.copy_(a), 2 * a.numel() * 2)
+report("torch copy 1 GiB bf16 (yardstick)", lambda: b_.copy_(a), 2 * a.numel() * 2, graph=False)
 if len(sys.argv) > 1:
     with open(sys.argv[1], "w") as f:
         f.write(f"| kernel | ms | algorithmic MB | GB/s | of {SRC} HBM peak ({PEAK:.0f} GB/s) |\n|---|---|---|---|---|\n")
