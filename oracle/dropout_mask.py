@@ -45,21 +45,44 @@ def scaled_mask(seed: int, site: int, shape, p: float, dtype=torch.float64) -> t
     return (keep_mask(seed, site, n, p).to(dtype) / (1.0 - p)).reshape(shape)
 
 
+_KEEP_MUL = (0x9E3779B1, 0x85EBCA77, 0xC2B2AE3D, 0x27D4EB2F, 0x165667B1, 0xD3A2646D, 0xFD7046C5, 0xB55A4F09)
+
+
+def attn_keep_bit(k: torch.Tensor) -> torch.Tensor:
+    """bit of the 32-key keep word that belongs to key k (orbit2_b200/csrc/common.cuh attn_keep_bit)."""
+    kk = k & 31
+    return 7 - (kk >> 2) + 8 * (kk & 1) + 16 * ((kk >> 1) & 1)
+
+
 def attn_scaled_mask(seed: int, site: int, B: int, heads: int, N: int, p: float, dtype=torch.float64) -> torch.Tensor:
-    """[B, heads, N, N] pre-scaled keep mask of the attention-probability dropout (orbit2_b200/csrc/common.cuh): one byte
-    of lowbias32(((q >> 1) * ceil(N / 2) + (k >> 1)) ^ key_bh) per element, byte index (q & 1) * 2 + (k & 1), keep iff
-    byte >= floor(p * 256); kept values scaled by 256 / (256 - floor(p * 256))."""
+    """[B, heads, N, N] pre-scaled keep mask of the attention-probability dropout (orbit2_b200/csrc/common.cuh, bit-sliced):
+    one 32-bit keep word per (query q, 32-key block kb): base = lowbias32((q * ceil(N / 32) + kb) ^ key_bh), eight planes
+    w_i = lo32(base * K_i) ^ hi32(base * K_i) of a uniform byte U per key, keep iff U >= floor(p * 256) (LSB plane first:
+    ge = w_i & ge where the threshold bit is set, w_i | ge where it is clear); key k reads bit attn_keep_bit(k); kept
+    values are scaled by 256 / (256 - floor(p * 256))."""
     thr8 = math.floor(p * 256.0)
-    n2 = (N + 1) >> 1
+    nkb = (N + 31) >> 5
     q = torch.arange(N, dtype=torch.int64).view(N, 1)
-    k = torch.arange(N, dtype=torch.int64).view(1, N)
-    blk = ((q >> 1) * n2 + (k >> 1)) & M32
-    sh = ((q & 1) * 2 + (k & 1)) * 8
+    kb = torch.arange(nkb, dtype=torch.int64).view(1, nkb)
+    k = torch.arange(N, dtype=torch.int64)
+    bit = attn_keep_bit(k).view(1, N)
     sk = site_key(seed, site)
     out = torch.empty(B, heads, N, N, dtype=dtype)
+    lo16 = 0xFFFF
     for bh in range(B * heads):
         key_bh = _lb(sk ^ ((bh * 0x9E3779B1) & M32))
-        h = lowbias32(blk ^ key_bh)
-        keep = ((h >> sh) & 0xFF) >= thr8
+        base = lowbias32(((q * nkb + kb) & M32) ^ key_bh)                      # [N, nkb], < 2^32
+        ge = torch.full_like(base, M32)
+        for i, mul in enumerate(_KEEP_MUL):
+            # 32 x 32 -> 64-bit product in int64 pieces (int64 would overflow on the full product)
+            b_lo, b_hi = base & lo16, base >> 16
+            m_lo, m_hi = mul & lo16, mul >> 16
+            p0 = b_lo * m_lo
+            p1 = b_lo * m_hi + b_hi * m_lo + (p0 >> 16)                         # < 2^33
+            lo32 = ((p1 & lo16) << 16) | (p0 & lo16)
+            hi32 = (b_hi * m_hi + (p1 >> 16)) & M32
+            w = lo32 ^ hi32
+            ge = (w & ge) if (thr8 >> i) & 1 else (w | ge)
+        keep = (ge[:, k >> 5] >> bit) & 1                                       # [N, N]
         out[bh // heads, bh % heads] = keep.to(dtype) * (256.0 / (256.0 - thr8))
     return out

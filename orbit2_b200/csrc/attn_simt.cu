@@ -23,9 +23,8 @@ struct AttnArgs {
 
 // scaled keep factor of element (q, k) of (batch, head) bh: 0 or 1 / keep_prob (mask function: common.cuh)
 __device__ __forceinline__ float drop_factor(const AttnArgs& a, uint32_t key_bh, int q, int k) {
-  const uint32_t h = ptx::lowbias32(((uint32_t)(q >> 1) * a.drop.n2 + (uint32_t)(k >> 1)) ^ key_bh);
-  const uint32_t byte = (h >> (((q & 1) * 2 + (k & 1)) * 8)) & 0xFFu;
-  return byte >= a.drop.thr8 ? a.drop.inv_keep : 0.f;
+  const uint32_t w = ptx::attn_keep_word(a.drop, key_bh, (uint32_t)q, (uint32_t)k >> 5);
+  return ((w >> ptx::attn_keep_bit((uint32_t)k)) & 1u) ? a.drop.inv_keep : 0.f;
 }
 
 __device__ __forceinline__ const float* qkv_ptr(const AttnArgs& a, int b, int which, int h) {
@@ -562,14 +561,7 @@ template <int HD> int run_bwd(const AttnArgs& a, cudaStream_t st) {
 
 }  // namespace
 
-ptx::AttnDrop make_drop_simt(float p, uint64_t seed, uint32_t site, int N) {
-  ptx::AttnDrop d;
-  d.site_key = ptx::lowbias32((uint32_t)seed ^ ptx::lowbias32(site ^ (uint32_t)(seed >> 32)));
-  d.thr8 = (uint32_t)floor((double)p * 256.0);
-  d.n2 = (uint32_t)((N + 1) >> 1);
-  d.inv_keep = 256.f / (256.f - (float)d.thr8);
-  return d;
-}
+ptx::AttnDrop make_drop_simt(float p, uint64_t seed, uint32_t site, int N) { return ptx::make_attn_drop(p, seed, site, N); }
 
 int o2_attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, float p_drop,
                      uint64_t seed, uint32_t site, cudaStream_t st) {

@@ -60,12 +60,22 @@ struct FwdArgs {
 };
 
 // zero the dropped probabilities of one packed pair (columns k, k + 1 of row q share a hash: bytes 2 (q & 1) + {0, 1})
-__device__ __forceinline__ uint64_t drop_pair_row(uint64_t Pq, uint32_t h16, uint32_t thr8) {
-  float lo, hi;
-  ptx::unpack2(Pq, lo, hi);
-  lo = ((h16 & 0xFFu) >= thr8) ? lo : 0.f;
-  hi = (((h16 >> 8) & 0xFFu) >= thr8) ? hi : 0.f;
-  return ptx::pack2(lo, hi);
+// row-owner kernels: AND-mask of packed pair PAIR (keys 2 PAIR, 2 PAIR + 1 of a 32-key block) from its keep word
+template <int PAIR> __device__ __forceinline__ uint32_t drop_mask_bf16x2(uint32_t word) {
+  return ptx::keep_mask_bf16x2<PAIR & 1>(word << (PAIR >> 1));
+}
+template <int PAIR = 0> __device__ __forceinline__ void drop_apply_bf16x2(uint32_t (&pk)[16], uint32_t word) {
+  if constexpr (PAIR < 16) {
+    pk[PAIR] &= drop_mask_bf16x2<PAIR>(word);
+    drop_apply_bf16x2<PAIR + 1>(pk, word);
+  }
+}
+// dP of the 32 keys of a block through the dropout mask (fp32 bit patterns): kept -> unchanged, dropped -> +0
+template <int K = 0> __device__ __forceinline__ void drop_apply_f32(uint32_t (&d)[32], uint32_t word) {
+  if constexpr (K < 32) {
+    d[K] &= ptx::keep_mask_f32<(K >> 1) & 1, K & 1>(word << (K >> 2));
+    drop_apply_f32<K + 1>(d, word);
+  }
 }
 
 constexpr int BS = 64;            // key sub-tile (forward, dq) / query sub-tile (dkv) processed per MMA group
@@ -278,8 +288,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
     const float sc = a.scale_log2;
     // attention dropout: P V uses the masked probabilities, the normaliser l the unmasked ones (attention.py:73-76)
     const uint32_t drop_key = kDrop ? ptx::attn_drop_key(a.drop, bh) : 0u;
-    const uint32_t drop_row = kDrop ? (uint32_t)((q0 + t * BQ + r) >> 1) * a.drop.n2 : 0u;
-    const uint32_t drop_sh = kDrop ? (uint32_t)((q0 + t * BQ + r) & 1) * 16u : 0u;
+    const uint32_t drop_q = (uint32_t)(q0 + t * BQ + r);
     if (kQTmem) {                           // this thread's query row -> its TMEM lane, 64 bf16 = 32 packed columns
       const int qrow = q0 + t * BQ + r;
       uint32_t qw[32];
@@ -362,26 +371,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FwdArgs a
         const uint64_t X = ptx::fma2(ptx::pack2u(v0[i], v0[i + 1]), sc2, nm2);
         const uint64_t Pq = (((i >> 1) % kPolyFwd) == kPolyFwd - 1) ? ptx::exp2_pair<true>(X) : ptx::exp2_pair<false>(X);
         if ((i >> 1) & 1) lB = ptx::add2(lB, Pq); else lA = ptx::add2(lA, Pq);
-        if (kDrop) {
-          const uint32_t hh_ = ptx::lowbias32((drop_row + (uint32_t)(u * (BS / 2) + (i >> 1))) ^ drop_key) >> drop_sh;
-          pk[i >> 1] = ptx::pack_bf16x2_pair(drop_pair_row(Pq, hh_, a.drop.thr8));
-        } else {
-          pk[i >> 1] = ptx::pack_bf16x2_pair(Pq);
-        }
+        pk[i >> 1] = ptx::pack_bf16x2_pair(Pq);
       }
+      if (kDrop) drop_apply_bf16x2(pk, ptx::attn_keep_word(a.drop, drop_key, drop_q, (uint32_t)(2 * u)));
       ptx::tmem_st_32x16(s_addr, pk);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const uint64_t X = ptx::fma2(ptx::pack2u(v1[i], v1[i + 1]), sc2, nm2);
         const uint64_t Pq = (((i >> 1) % kPolyFwd) == kPolyFwd - 1) ? ptx::exp2_pair<true>(X) : ptx::exp2_pair<false>(X);
         if ((i >> 1) & 1) lB = ptx::add2(lB, Pq); else lA = ptx::add2(lA, Pq);
-        if (kDrop) {
-          const uint32_t hh_ = ptx::lowbias32((drop_row + (uint32_t)(u * (BS / 2) + 16 + (i >> 1))) ^ drop_key) >> drop_sh;
-          pk[i >> 1] = ptx::pack_bf16x2_pair(drop_pair_row(Pq, hh_, a.drop.thr8));
-        } else {
-          pk[i >> 1] = ptx::pack_bf16x2_pair(Pq);
-        }
+        pk[i >> 1] = ptx::pack_bf16x2_pair(Pq);
       }
+      if (kDrop) drop_apply_bf16x2(pk, ptx::attn_keep_word(a.drop, drop_key, drop_q, (uint32_t)(2 * u + 1)));
       ptx::tmem_st_32x16(s_addr + 16, pk);
       if (quarter == 2) O2_TL(u, t, 7);
       ptx::tmem_st_wait();
@@ -460,15 +461,6 @@ struct BwdArgs {
   float scale, scale_log2;
   ptx::AttnDrop drop;     // kDrop kernels only
 };
-
-// dP of one packed pair through the dropout mask: kept -> dP / keep_prob, dropped -> 0 (row-owner layout, see drop_pair_row)
-__device__ __forceinline__ uint64_t drop_grad_pair_row(uint64_t dP, uint32_t h16, uint32_t thr8, float inv_keep) {
-  float lo, hi;
-  ptx::unpack2(dP, lo, hi);
-  lo = ((h16 & 0xFFu) >= thr8) ? lo * inv_keep : 0.f;
-  hi = (((h16 >> 8) & 0xFFu) >= thr8) ? hi * inv_keep : 0.f;
-  return ptx::pack2(lo, hi);
-}
 
 template <int NH>
 __global__ void attn_delta_bf16_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
@@ -688,8 +680,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const float sc = a.scale_log2;
     const uint64_t sc2 = ptx::pack2(sc, sc), nl2 = ptx::pack2(neg_lse2, neg_lse2), nd2 = ptx::pack2(-delta, -delta);
     const uint32_t drop_key = kDrop ? ptx::attn_drop_key(a.drop, bh) : 0u;
-    const uint32_t drop_row = kDrop ? (uint32_t)(row >> 1) * a.drop.n2 : 0u;
-    const uint32_t drop_sh = kDrop ? (uint32_t)(row & 1) * 16u : 0u;
+    const uint64_t ik2 = ptx::pack2(kDrop ? a.drop.inv_keep : 1.f, kDrop ? a.drop.inv_keep : 1.f);
     for (int u = 0; u < n_sub; ++u) {
       const int bb = u & 1;
       const uint32_t s_addr = lane_addr + bb * BS;
@@ -705,28 +696,24 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       ptx::tc_fence_before();
       ptx::mbar_arrive(&dp_free[t]);
       uint32_t pk[16];
+      if (kDrop) {        // dS = P (M dP / keep_prob - delta): mask the raw dP bits, the scale rides on the FFMA2 below
+        drop_apply_f32(d0, ptx::attn_keep_word(a.drop, drop_key, (uint32_t)row, (uint32_t)(2 * u)));
+        drop_apply_f32(d1, ptx::attn_keep_word(a.drop, drop_key, (uint32_t)row, (uint32_t)(2 * u + 1)));
+      }
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const uint64_t X = ptx::fma2(ptx::pack2u(s0[i], s0[i + 1]), sc2, nl2);
         const uint64_t Pq = (((i >> 1) % kPolyDq) == kPolyDq - 1) ? ptx::exp2_pair<true>(X) : ptx::exp2_pair<false>(X);
-        uint64_t dPq = ptx::pack2u(d0[i], d0[i + 1]);
-        if (kDrop) {
-          const uint32_t hh_ = ptx::lowbias32((drop_row + (uint32_t)(u * (BS / 2) + (i >> 1))) ^ drop_key) >> drop_sh;
-          dPq = drop_grad_pair_row(dPq, hh_, a.drop.thr8, a.drop.inv_keep);
-        }
-        pk[i >> 1] = ptx::pack_bf16x2_pair(ptx::mul2(Pq, ptx::add2(dPq, nd2)));
+        const uint64_t dPq = ptx::pack2u(d0[i], d0[i + 1]);
+        pk[i >> 1] = ptx::pack_bf16x2_pair(ptx::mul2(Pq, kDrop ? ptx::fma2(dPq, ik2, nd2) : ptx::add2(dPq, nd2)));
       }
       ptx::tmem_st_32x16(s_addr, pk);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const uint64_t X = ptx::fma2(ptx::pack2u(s1[i], s1[i + 1]), sc2, nl2);
         const uint64_t Pq = (((i >> 1) % kPolyDq) == kPolyDq - 1) ? ptx::exp2_pair<true>(X) : ptx::exp2_pair<false>(X);
-        uint64_t dPq = ptx::pack2u(d1[i], d1[i + 1]);
-        if (kDrop) {
-          const uint32_t hh_ = ptx::lowbias32((drop_row + (uint32_t)(u * (BS / 2) + 16 + (i >> 1))) ^ drop_key) >> drop_sh;
-          dPq = drop_grad_pair_row(dPq, hh_, a.drop.thr8, a.drop.inv_keep);
-        }
-        pk[i >> 1] = ptx::pack_bf16x2_pair(ptx::mul2(Pq, ptx::add2(dPq, nd2)));
+        const uint64_t dPq = ptx::pack2u(d1[i], d1[i + 1]);
+        pk[i >> 1] = ptx::pack_bf16x2_pair(ptx::mul2(Pq, kDrop ? ptx::fma2(dPq, ik2, nd2) : ptx::add2(dPq, nd2)));
       }
       ptx::tmem_st_32x16(s_addr + 16, pk);
       ptx::tmem_st_wait();
@@ -1030,19 +1017,19 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         if (warp == 2) O2_TL(u, t, 6);          // TMEM loads landed
         uint32_t pk[16], dk[16];
         if (kDrop) {
-          // thread = key row: queries (q, q + 1) of a pair share a hash, bytes (k & 1) and 2 + (k & 1)
+          // thread = key row: lane l builds the keep word of query qb + l for this warp's 32-key block, every thread
+          // reads the words of its 32 queries by shuffle and tests its own key's bit
           const int key_ = k0 + t * BKV + r;
           const int qb = u * BS + chalf * 32;
-          const uint32_t ksh = (uint32_t)(key_ & 1) * 8u;
-          uint32_t blk = (uint32_t)(qb >> 1) * a.drop.n2 + (uint32_t)(key_ >> 1);
+          const uint32_t kbit = 1u << ptx::attn_keep_bit((uint32_t)key_);
+          const uint32_t my_word = ptx::attn_keep_word(a.drop, drop_key, (uint32_t)(qb + lane), (uint32_t)(key_ >> 5));
           const float* dl = reinterpret_cast<const float*>(sStat) + dstage;
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const uint64_t X = ptx::mul2(ptx::pack2u(sv_[i], sv_[i + 1]), sc2);
             const uint64_t Pq = ptx::exp2_pair<false>(X);
-            const uint32_t hh_ = ptx::lowbias32(blk ^ drop_key) >> ksh;
-            blk += a.drop.n2;
-            const bool k0_ = (hh_ & 0xFFu) >= a.drop.thr8, k1_ = ((hh_ >> 16) & 0xFFu) >= a.drop.thr8;
+            const bool k0_ = (__shfl_sync(0xffffffffu, my_word, i) & kbit) != 0u;
+            const bool k1_ = (__shfl_sync(0xffffffffu, my_word, i + 1) & kbit) != 0u;
             float p0, p1;
             ptx::unpack2(Pq, p0, p1);
             const int qi = (u & 1) * BS + chalf * 32 + i;            // row of the 128-query statistics tile
@@ -1350,16 +1337,15 @@ attn_bwd_dkv_tm_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gri
       uint32_t pk[16], dk[16];
       if (kDrop) {
         const int qb = u * BS + chalf * 32;
-        const uint32_t ksh = (uint32_t)(key & 1) * 8u;
-        uint32_t blk = (uint32_t)(qb >> 1) * a.drop.n2 + (uint32_t)(key >> 1);
+        const uint32_t kbit = 1u << ptx::attn_keep_bit((uint32_t)key);
+        const uint32_t my_word = ptx::attn_keep_word(a.drop, drop_key, (uint32_t)(qb + lane), (uint32_t)(key >> 5));
         const float* dl = reinterpret_cast<const float*>(sStat) + dstage;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const uint64_t X = ptx::mul2(ptx::pack2u(sv_[i], sv_[i + 1]), sc2);
           const uint64_t Pq = ptx::exp2_pair<false>(X);
-          const uint32_t hh_ = ptx::lowbias32(blk ^ drop_key) >> ksh;
-          blk += a.drop.n2;
-          const bool k0_ = (hh_ & 0xFFu) >= a.drop.thr8, k1_ = ((hh_ >> 16) & 0xFFu) >= a.drop.thr8;
+          const bool k0_ = (__shfl_sync(0xffffffffu, my_word, i) & kbit) != 0u;
+          const bool k1_ = (__shfl_sync(0xffffffffu, my_word, i + 1) & kbit) != 0u;
           float p0, p1;
           ptx::unpack2(Pq, p0, p1);
           const int qi = (u & 1) * BS + chalf * 32 + i;            // row of the 128-query statistics tile
@@ -1445,15 +1431,8 @@ int launch_fwd(const CUtensorMap& tm, const FwdArgs& a, dim3 grid, cudaStream_t 
   return O2_OK;
 }
 
-// p -> (site key, 8-bit threshold, exact keep scale); p == 0 -> thr8 = 0 (kernels without the kDrop code are used)
-ptx::AttnDrop make_drop(float p, uint64_t seed, uint32_t site, int N) {
-  ptx::AttnDrop d;
-  d.site_key = ptx::lowbias32((uint32_t)seed ^ ptx::lowbias32(site ^ (uint32_t)(seed >> 32)));
-  d.thr8 = (uint32_t)floor((double)p * 256.0);
-  d.n2 = (uint32_t)((N + 1) >> 1);
-  d.inv_keep = 256.f / (256.f - (float)d.thr8);
-  return d;
-}
+// p -> (site key, 8-bit threshold + its plane masks, exact keep scale); p == 0 -> thr8 = 0 (kernels without the kDrop code)
+ptx::AttnDrop make_drop(float p, uint64_t seed, uint32_t site, int N) { return ptx::make_attn_drop(p, seed, site, N); }
 
 template <int NH, bool kDrop>
 int launch_bwd(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const BwdArgs& a, int parts, cudaStream_t st) {
@@ -1509,7 +1488,7 @@ int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int hea
   a.scale_log2 = scale * kLog2e;
   dim3 grid((N + 2 * BQ - 1) / (2 * BQ), B * heads);
   a.drop = make_drop(p_drop, seed, site, N);
-  O2_REQUIRE((long long)a.drop.n2 * a.drop.n2 < (1ll << 32), "attn_fwd_tc: N=%d too large for the dropout block index", N);
+  O2_REQUIRE((long long)N * a.drop.nkb < (1ll << 32), "attn_fwd_tc: N=%d too large for the dropout word index", N);
   if (a.drop.thr8 > 0) return hd == 64 ? launch_fwd<1, true>(tm, a, grid, st) : launch_fwd<2, true>(tm, a, grid, st);
   return hd == 64 ? launch_fwd<1, false>(tm, a, grid, st) : launch_fwd<2, false>(tm, a, grid, st);
 }
@@ -1548,7 +1527,7 @@ int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const flo
   a.n_sub = (N + BS - 1) / BS;
   a.scale = scale; a.scale_log2 = scale * kLog2e;
   a.drop = make_drop(p_drop, seed, site, N);
-  O2_REQUIRE((long long)a.drop.n2 * a.drop.n2 < (1ll << 32), "attn_bwd_tc: N=%d too large for the dropout block index", N);
+  O2_REQUIRE((long long)N * a.drop.nkb < (1ll << 32), "attn_bwd_tc: N=%d too large for the dropout word index", N);
   if (a.drop.thr8 > 0)
     return hd == 64 ? launch_bwd<1, true>(tm_qkv, tm_do, a, parts, st) : launch_bwd<2, true>(tm_qkv, tm_do, a, parts, st);
   return hd == 64 ? launch_bwd<1, false>(tm_qkv, tm_do, a, parts, st) : launch_bwd<2, false>(tm_qkv, tm_do, a, parts, st);

@@ -288,15 +288,22 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
-// ---- attention-probability dropout (components/attention.py:75 attn_drop): the keep decision of element (q, k) of one
-// (batch, head) is one byte of a counter-based hash shared by a 2 x 2 block of elements, so the forward kernel (thread =
-// query row) and the dK/dV kernel (thread = key row) both get two decisions per hash:
-//     h = lowbias32(((q >> 1) * ceil(N / 2) + (k >> 1)) ^ key_bh),  byte (q & 1) * 2 + (k & 1),  keep <=> byte >= thr8
+// ---- attention-probability dropout (components/attention.py:75 attn_drop), bit-sliced: ONE 32-bit keep word serves the
+// 32 keys [32 kb, 32 kb + 32) of one query row q of one (batch, head):
+//     base   = lowbias32((q * nkb + kb) ^ key_bh)                       nkb = ceil(N / 32)
+//     w_i    = lo32(base * K_i) ^ hi32(base * K_i)    i = 0..7         (eight bit planes of a uniform byte U per key)
+//     keep   = (U >= thr8), evaluated on all 32 lanes of the planes at once, LSB plane first:
+//              ge = ~0;  ge = thr8 bit i ? (w_i & ge) : (w_i | ge)       -> one LOP3 per plane (tm[i] = bit i ? ~0 : 0)
+//     key kk = k & 31 reads bit 7 - (kk >> 2) + 8 (kk & 1) + 16 ((kk >> 1) & 1): the byte-msb order that lets PRMT's
+//     sign-replicate mode expand four decisions of (word << s) into bf16x2 / fp32 AND-masks.
 // key_bh = lowbias32(site_key ^ (b * heads + h) * 0x9E3779B1), thr8 = floor(p * 256); kept values are scaled by
 // 1 / (1 - thr8 / 256), the exact keep probability (oracle/dropout_mask.py restates this for the parity tests).
+// Row-owner kernels (forward, dQ: thread = query row) build one word per 32 keys; the dK/dV kernels (thread = key row)
+// let lane l build the word of query q0 + l and read the others' by shuffle.
 struct AttnDrop {
-  uint32_t site_key, thr8, n2;
+  uint32_t site_key, thr8, nkb;
   float inv_keep;
+  uint32_t tm[8];
 };
 __host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
   x ^= x >> 16; x *= 0x21f0aaadu;
@@ -306,6 +313,44 @@ __host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
 }
 __device__ __forceinline__ uint32_t attn_drop_key(const AttnDrop& d, int bh) {
   return lowbias32(d.site_key ^ ((uint32_t)bh * 0x9E3779B1u));
+}
+__device__ __forceinline__ uint32_t attn_keep_word(const AttnDrop& d, uint32_t key_bh, uint32_t q, uint32_t kb) {
+  constexpr uint32_t kMul[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu,
+                                0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+  const uint32_t base = lowbias32((q * d.nkb + kb) ^ key_bh);
+  uint32_t ge = 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint64_t m = (uint64_t)base * kMul[i];
+    const uint32_t w = (uint32_t)m ^ (uint32_t)(m >> 32);
+    ge = (w & ge) | (~d.tm[i] & (w | ge));
+  }
+  return ge;
+}
+// bit of the keep word that belongs to key k (see above)
+__host__ __device__ __forceinline__ uint32_t attn_keep_bit(uint32_t k) {
+  const uint32_t kk = k & 31u;
+  return 7u - (kk >> 2) + 8u * (kk & 1u) + 16u * ((kk >> 1) & 1u);
+}
+// AND-masks of keys (4 s + 2 t, 4 s + 2 t + 1) of a keep word, given ws = word << s: a bf16x2 mask, or two fp32 masks
+template <int T2> __device__ __forceinline__ uint32_t keep_mask_bf16x2(uint32_t ws) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(m) : "r"(ws), "n"(T2 ? 0xBBAA : 0x9988));
+  return m;
+}
+template <int T2, int E> __device__ __forceinline__ uint32_t keep_mask_f32(uint32_t ws) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(m) : "r"(ws), "n"(T2 ? (E ? 0xBBBB : 0xAAAA) : (E ? 0x9999 : 0x8888)));
+  return m;
+}
+inline AttnDrop make_attn_drop(float p, uint64_t seed, uint32_t site, int N) {
+  AttnDrop d;
+  d.site_key = lowbias32((uint32_t)seed ^ lowbias32(site ^ (uint32_t)(seed >> 32)));
+  d.thr8 = (uint32_t)floor((double)p * 256.0);
+  d.nkb = (uint32_t)((N + 31) >> 5);
+  d.inv_keep = 256.f / (256.f - (float)d.thr8);
+  for (int i = 0; i < 8; ++i) d.tm[i] = ((d.thr8 >> i) & 1u) ? 0xFFFFFFFFu : 0u;
+  return d;
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float y;
