@@ -90,9 +90,9 @@ int o2_attn_bwd_parts(int impl, int parts, const void* qkv, const void* out, con
 
 /* Training-mode variants with attention-probability dropout (attention.py:56,69,75: attn_drop on softmax(QK^T)): the output
  * uses P o keep / keep_prob, the softmax normaliser the unmasked P; the backward regenerates the same mask from
- * (seed, site) -- it is never stored.  keep(b, h, q, k) is one byte of a counter-based hash shared by a 2 x 2 block of
- * (q, k) (csrc/common.cuh, restated in oracle/dropout_mask.py); p is quantised to floor(p * 256) / 256 and kept values are
- * scaled by the exact keep probability.  p_drop = 0 is identical to the plain entry points. */
+ * (seed, site) -- it is never stored.  keep(b, h, q, k) is one bit of a counter-based, bit-sliced 32-bit keep word per
+ * (q, 32-key block) (csrc/common.cuh, restated in oracle/dropout_mask.py); p is quantised to floor(p * 256) / 256 and kept
+ * values are scaled by the exact keep probability.  p_drop = 0 is identical to the plain entry points. */
 int o2_attn_fwd_drop(int impl, const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale,
                      float p_drop, uint64_t seed, uint32_t site, void* stream);
 int o2_attn_bwd_parts_drop(int impl, int parts, const void* qkv, const void* out, const void* dout, const float* lse,
