@@ -117,10 +117,10 @@ __global__ void __launch_bounds__(NT) loss_kernel(const LossArgs a) {
 }
 
 
-// Streaming variant (no shared memory, no barriers): one thread owns 8 consecutive pixels of one row, reads the three
-// prediction rows it needs with 16-byte loads (the two neighbour rows come out of L1/L2: DRAM sees every byte once),
-// the target with two 16-byte loads, and writes its 8 gradients with one 16/32-byte store.  Used when W % 8 == 0 and
-// the rows are 16-byte aligned; loss_kernel (tiled through shared memory) handles every other shape.
+// Streaming variant for mse / mae (no shared memory, no barriers): one thread owns 8 consecutive pixels of one row, reads
+// them with 16-byte loads (prediction) and two 16-byte loads (target) and writes its 8 gradients with one 16/32-byte
+// store.  Used when W % 8 == 0 and the rows are 16-byte aligned; loss_kernel (tiled through shared memory) handles every
+// other shape, loss_tv_band_kernel the bayesian_tv stencil.
 template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
 template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -142,7 +142,7 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
   *reinterpret_cast<uint4*>(p) = t;
 }
 
-template <typename T, bool TV>
+template <typename T>
 __global__ void __launch_bounds__(NT) loss_stream_kernel(const LossArgs a) {
   __shared__ float swarp[NT / 32];
   const int bc = blockIdx.y;
@@ -158,71 +158,27 @@ __global__ void __launch_bounds__(NT) loss_stream_kernel(const LossArgs a) {
   const bool is_clamp = (c == a.clamp_ch);
   float local = 0.f;
   if (active) {
-    // clipped prediction rows h-1, h, h+1 at columns w0-1 .. w0+8
-    float pv[TV ? 3 : 1][10];
-    bool pass[8];
-    auto load_row = [&](int hh, float (&dst)[10], bool centre) {
-      float v[8];
-      if (is_const) load8<float>(tgt + (size_t)hh * a.tgt_W + w0, v);
-      else load8<T>(pred + (size_t)hh * a.W + w0, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        bool ok = !is_const;
-        if (is_clamp && v[i] < 0.f) { v[i] = 0.f; ok = false; }
-        dst[i + 1] = v[i];
-        if (centre) pass[i] = ok;
-      }
-      if (TV) {
-        float l = 0.f, r = 0.f;
-        if (w0 > 0) l = is_const ? tgt[(size_t)hh * a.tgt_W + w0 - 1] : to_f(pred[(size_t)hh * a.W + w0 - 1]);
-        if (w0 + 8 < a.W) r = is_const ? tgt[(size_t)hh * a.tgt_W + w0 + 8] : to_f(pred[(size_t)hh * a.W + w0 + 8]);
-        if (is_clamp) { l = fmaxf(l, 0.f); r = fmaxf(r, 0.f); }
-        dst[0] = l; dst[9] = r;
-      }
-    };
-    constexpr int CR = TV ? 1 : 0;        // index of the centre row in pv
-    load_row(h, pv[CR], true);
-    if (TV) {
-      if (h >= 1) load_row(h - 1, pv[0], false);
-      if (h + 1 < a.H) load_row(h + 1, pv[TV ? 2 : 0], false);
-    }
-    float t[8];
+    float t[8], pv[8], gout[8];
     load8<float>(tgt + (size_t)h * a.tgt_W + w0, t);
+    if (is_const) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pv[i] = t[i];
+    } else {
+      load8<T>(pred + (size_t)h * a.W + w0, pv);
+    }
     const float lw = a.lat_w ? a.lat_w[h] : 1.0f;
-    const float lwm = (a.lat_w && h >= 1) ? a.lat_w[h - 1] : 1.0f;
     const float chw = a.ch_w ? a.ch_w[c] : 1.0f;
-    const bool hb = (h + 1 < a.H), ht = (h >= 1);
-    auto sgn = [](float x) { return (x > 0.f) ? 1.f : (x < 0.f ? -1.f : 0.f); };
-    float gout[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int w = w0 + i;
-      const float p = pv[CR][i + 1];
+      bool pass = !is_const;
+      float p = pv[i];
+      if (is_clamp && p < 0.f) { p = 0.f; pass = false; }       // clamp_(min=0): gradient only where raw >= 0
       const float d = p - t[i];
       float err, g;
-      if (a.kind == O2_LOSS_MAE) { err = fabsf(d); g = sgn(d); }
+      if (a.kind == O2_LOSS_MAE) { err = fabsf(d); g = (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f); }
       else { err = d * d; g = 2.f * d; }
-      g *= lw;
-      if (TV) {
-        const bool wr = (w + 1 < a.W), wl = (w >= 1);
-        float e = 0.f, gs = 0.f;
-        if (hb) { const float x = pv[2][i + 1] - p; e += fabsf(x); gs -= sgn(x); }
-        if (wr) { const float x = pv[1][i + 2] - p; e += fabsf(x); gs -= sgn(x); }
-        if (hb && wr) { const float x = pv[2][i + 2] - p; e += 0.7f * fabsf(x); gs -= 0.7f * sgn(x); }
-        if (hb && wl) { const float x = pv[2][i] - p; e += 0.7f * fabsf(x); gs -= 0.7f * sgn(x); }
-        err += 0.02f * e;
-        float gn = lw * gs;
-        if (wl) gn += lw * sgn(p - pv[1][i]);
-        if (ht) {
-          float s_ = sgn(p - pv[0][i + 1]);
-          if (wl) s_ += 0.7f * sgn(p - pv[0][i]);
-          if (wr) s_ += 0.7f * sgn(p - pv[0][i + 2]);
-          gn += lwm * s_;
-        }
-        g += 0.02f * gn;
-      }
       local += err * lw;
-      gout[i] = pass[i] ? g * chw * a.gscale : 0.f;
+      gout[i] = pass ? g * lw * chw * a.gscale : 0.f;
     }
     if (a.dpred) store8<T>(reinterpret_cast<T*>(a.dpred) + (size_t)bc * a.H * a.W + (size_t)h * a.W + w0, gout);
   }
@@ -588,8 +544,8 @@ extern "C" int o2_loss_fwd_bwd(const void* pred, int dtype, const float* target,
     } else {
       const long long items = (long long)H * (W / 8);
       dim3 grid((unsigned)((items + NT - 1) / NT), B * C);
-      if (dtype == O2_F32) loss_stream_kernel<float, false><<<grid, NT, 0, st>>>(a);
-      else loss_stream_kernel<__nv_bfloat16, false><<<grid, NT, 0, st>>>(a);
+      if (dtype == O2_F32) loss_stream_kernel<float><<<grid, NT, 0, st>>>(a);
+      else loss_stream_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(a);
     }
   } else {
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * C);

@@ -113,3 +113,35 @@ def test_flat_layout_runs():
     assert lay.runs(["a", "b"]) == [[0, 24]]
     assert lay.runs(["d", "a", "b"]) == [[0, 24], [32, 40]]
     assert lay.runs(["c"]) == [[24, 32]]
+
+
+def test_attn_keep_mask_restatement():
+    """oracle/dropout_mask.py restates the bit-sliced attention keep mask of csrc/common.cuh: checked here against a
+    scalar Python evaluation of the documented formula, plus its keep rate and the bit <-> key bijection."""
+    import math
+    from oracle import dropout_mask as DM
+    M32 = 0xFFFFFFFF
+
+    def lb(x):
+        x &= M32; x ^= x >> 16; x = (x * 0x21F0AAAD) & M32; x ^= x >> 15; x = (x * 0x735A2D97) & M32; x ^= x >> 15
+        return x
+
+    seed, site, N, heads = 0x1234_5678_9ABC_DEF0, 17, 70, 2
+    for p in (0.1, 0.35):
+        thr8 = math.floor(p * 256)
+        m = DM.attn_scaled_mask(seed, site, 1, heads, N, p)
+        nkb = (N + 31) // 32
+        key = lb(DM.site_key(seed, site) ^ ((1 * 0x9E3779B1) & M32))          # (b, h) = (0, 1)
+        for q, k in ((0, 0), (3, 31), (5, 32), (69, 69), (17, 40), (64, 2)):
+            base, ge = lb(((q * nkb + (k >> 5)) & M32) ^ key), M32
+            for i, mul in enumerate(DM._KEEP_MUL):
+                w = ((base * mul) & M32) ^ ((base * mul) >> 32)
+                ge = (w & ge) if (thr8 >> i) & 1 else (w | ge)
+            kk = k & 31
+            bit = 7 - (kk >> 2) + 8 * (kk & 1) + 16 * ((kk >> 1) & 1)
+            want = ((ge >> bit) & 1) * 256.0 / (256.0 - thr8)
+            assert float(m[0, 1, q, k]) == want
+    assert sorted(int(b) for b in DM.attn_keep_bit(torch.arange(32))) == list(range(32))
+    big = DM.attn_scaled_mask(seed, site, 1, 1, 512, 0.1)
+    assert abs(float((big > 0).double().mean()) - (1 - 25 / 256)) < 3e-3
+    assert abs(float(big.mean()) - 1.0) < 4e-3                                  # E[mask] = 1: kept values carry 1 / keep_prob
