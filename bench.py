@@ -247,6 +247,25 @@ def run_ours(args):
     timers, ops.TIMERS = ops.TIMERS, None
     launches = (ops.LAUNCHES - launches0) // args.steps
     loss_val = float(vec[-1].item())
+    eager_ms = None
+    if args.graph:
+        # launch-bound workloads (interm_8m): the same step captured once as a CUDA graph and replayed.  The per-kernel
+        # events above come from the eager pass (events cannot be read back from a capture); `value` is the replayed step.
+        eager_ms = ms_step
+        eng.enable_graph(warm_steps=1)
+        for _ in range(max(args.warmup, 1)):
+            dev_step()
+        sync_all()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0.record()
+        for _ in range(args.steps):
+            vec = dev_step()
+        e1.record()
+        sync_all()
+        clocks = sampler.summary()
+        ms_step = e0.elapsed_time(e1) / args.steps
+        loss_val = float(vec[-1].item())
 
     kern = {}
     for name, evs in timers.items():
@@ -337,7 +356,8 @@ def run_ours(args):
                                    f", V={len(cfg['in_vars'])} in / {len(cfg['out_vars'])} out vars, fwd+clip+bayesian_tv+bwd+allreduce+AdamW",
                        "per_gpu_batch": B, "global_batch": B * world, "tokens_per_sample": L, "parallelism": (f"fsdp{world} FULL_SHARD (per-Block all-gather fwd+bwd, gradient reduce-scatter, sharded fp32 master + Adam)" if args.full_shard else f"fsdp{world} (sharded Adam state + update, reduce-scatter / all-gather)" if (args.shard and world > 1) else f"dp{world}"),
                        "l2_policy": "inputs larger than L2 (activations of one step >> 126 MB), no explicit flush",
-                       "dropout": args.drop, "activation_checkpointing": bool(args.ckpt)},
+                       "dropout": args.drop, "activation_checkpointing": bool(args.ckpt),
+                       **({"cuda_graph": True, "eager_ms_per_step": eager_ms} if args.graph else {})},
             "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": (x_h.numel() + y_h.numel()) * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
@@ -365,6 +385,8 @@ def main():
                     "headline and every parity run use 0)")
     ap.add_argument("--ckpt", action="store_true", help="per-Block activation recomputation (reference: checkpoint wrappers "
                     "on every Block under FSDP); the recomputed forward FLOPs are NOT counted in the roofline")
+    ap.add_argument("--graph", action="store_true", help="replay the device-resident step as one captured CUDA graph "
+                    "(single GPU, dropout 0; for launch-bound workloads such as 8m)")
     ap.add_argument("--shard", action="store_true", help="FSDP-style sharded optimizer instead of plain data parallel")
     ap.add_argument("--full-shard", action="store_true",
                     help="FSDP FULL_SHARD: GEMM weights, fp32 masters, gradients and Adam state sharded per Block "

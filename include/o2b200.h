@@ -190,6 +190,11 @@ int o2_colsum(const void* X, int dtype, float* out, int64_t M, int64_t N, int64_
  * buffer; g is multiplied by grad_scale first; optionally refreshes the bf16 compute copy. */
 int o2_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
              float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* the same update with the step-dependent scalars read from DEVICE memory, so that a captured CUDA graph of the whole
+ * training step can be replayed while the host rewrites them: scalars fp32 [8] = {lr, beta1, beta2, eps, weight_decay,
+ * 1 - beta1^step, sqrt(1 - beta2^step), grad_scale}. */
+int o2_adamw_dev(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, const float* scalars,
+                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,9 +50,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, fl
   }
 }
 
-__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                             float* __restrict__ v, __nv_bfloat16* __restrict__ pb, long long n, float lr, float b1,
-                             float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+__device__ __forceinline__ void adamw_update(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                             float* __restrict__ v, __nv_bfloat16* __restrict__ pb, long long n, float lr,
+                                             float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                                             float gscale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
     float pi = p[i];
@@ -66,6 +67,20 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     p[i] = pi;
     if (pb) pb[i] = __float2bfloat16_rn(pi);
   }
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, __nv_bfloat16* __restrict__ pb, long long n, float lr, float b1,
+                             float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  adamw_update(p, g, m, v, pb, n, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+}
+
+// same update with the step-dependent scalars in device memory: a captured CUDA graph of the step stays valid while the
+// host rewrites {lr, beta1, beta2, eps, weight_decay, 1 - beta1^t, sqrt(1 - beta2^t), grad_scale} between replays
+__global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, __nv_bfloat16* __restrict__ pb, long long n,
+                                 const float* __restrict__ sc) {
+  adamw_update(p, g, m, v, pb, n, sc[0], sc[1], sc[2], sc[3], sc[4], sc[5], sc[6], sc[7]);
 }
 
 inline int grid_for(long long n, int per_block) {
@@ -134,6 +149,15 @@ extern "C" int o2_adamw(float* p, const float* g, float* m, float* v, void* p_bf
   adamw_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1,
                                                                        beta2, eps, weight_decay, bc1, bc2_sqrt,
                                                                        grad_scale);
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
+
+extern "C" int o2_adamw_dev(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, const float* scalars,
+                            void* stream) {
+  O2_REQUIRE(p && g && m && v && scalars && n >= 0, "adamw_dev: bad args");
+  if (n == 0) return O2_OK;
+  adamw_dev_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, scalars);
   O2_LAUNCH_CHECK();
   return O2_OK;
 }

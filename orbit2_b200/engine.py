@@ -105,6 +105,10 @@ class TrainEngine:
         self._train_runs = None
         self._lat = None
         self._chw = None
+        # CUDA-graph mode (enable_graph): the whole step is captured once and replayed; see graph_step
+        self._graph = None
+        self._graph_warm = 0
+        self._sc_dev = None
 
     # ------------------------------------------------------------------ pieces
     def _on_ready(self, names: List[str]):
@@ -169,6 +173,11 @@ class TrainEngine:
             s = self._ks = set(self.model._names)
         return s
 
+    def _adam_scalars(self, grad_scale: float = 1.0):
+        t = self.step_count
+        return [self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 - self.betas[0] ** t,
+                (1.0 - self.betas[1] ** t) ** 0.5, grad_scale]
+
     def optimizer_step(self, grad_scale: float = 1.0):
         self.step_count += 1
         if self._train_runs is None:                # frozen parameters get neither an update nor weight decay
@@ -177,6 +186,11 @@ class TrainEngine:
         for lo, hi in self._train_runs:
             lo, hi = max(lo, o0), min(hi, o1)           # sharded mode: only this rank's part of every run
             if lo >= hi:
+                continue
+            if self._sc_dev is not None:                # graph mode: step-dependent scalars come from device memory
+                ops.adamw_dev(self.flat_p[lo:hi], self.flat_g[lo:hi], self.flat_m[lo - o0:hi - o0],
+                              self.flat_v[lo - o0:hi - o0], self.flat_b[lo:hi] if self.flat_b is not None else None,
+                              self._sc_dev)
                 continue
             ops.adamw(self.flat_p[lo:hi], self.flat_g[lo:hi], self.flat_m[lo - o0:hi - o0], self.flat_v[lo - o0:hi - o0],
                       self.flat_b[lo:hi] if self.flat_b is not None else None, self.lr, self.betas[0], self.betas[1],
@@ -192,6 +206,46 @@ class TrainEngine:
                 dist.all_gather_into_tensor(self.flat_b, self.flat_b[o0:o1], group=self.pg)
 
     def step(self, x, y):
+        if self._graph_warm:
+            return self.graph_step(x, y)
         vec = self.forward_backward(x, y)
         self.optimizer_step()
         return vec
+
+    # ------------------------------------------------------------------ CUDA-graph mode
+    def enable_graph(self, warm_steps: int = 3):
+        """Replay the whole step (forward, loss, backward, AdamW) as ONE captured CUDA graph from step ``warm_steps`` + 1
+        on.  For launch-bound configurations (interm_8m: ~180 kernels of a few microseconds each, paced by the host's
+        issue rate when launched one by one).  Restrictions: one GPU (world size 1), replicated parameters, dropout 0
+        (the dropout counters are kernel arguments and would be frozen into the graph), fixed batch shape.  ``lr`` may
+        change between steps: AdamW reads its scalars from device memory (o2_adamw_dev)."""
+        if self.world > 1 or self.fs is not None or self.sharded:
+            raise RuntimeError("enable_graph: single-GPU, replicated-parameter engines only")
+        if self.model.training and (self.model.drop_rate > 0 or self.model.drop_path > 0):
+            raise RuntimeError("enable_graph: dropout / drop-path must be 0 (their counters are frozen into a graph)")
+        self._graph_warm = max(1, int(warm_steps))
+
+    def graph_step(self, x, y):
+        if self._graph is None and self.step_count < self._graph_warm:       # lazy initialisation happens eagerly
+            vec = self.forward_backward(x, y)
+            self.optimizer_step()
+            return vec
+        if self._graph is None:
+            self._gx, self._gy = x.clone(), y.clone()
+            self._sc_dev = torch.zeros(8, device=self.device, dtype=torch.float32)
+            g = torch.cuda.CUDAGraph()
+            count = self.step_count
+            with torch.cuda.graph(g):
+                self._gvec = self.forward_backward(self._gx, self._gy)
+                self.optimizer_step()
+            self.step_count = count                     # capture executes nothing
+            self._graph = g
+        if x.shape != self._gx.shape or y.shape != self._gy.shape:
+            raise RuntimeError("graph_step: the batch shape changed after the graph was captured")
+        self._gx.copy_(x, non_blocking=True)
+        self._gy.copy_(y, non_blocking=True)
+        self.step_count += 1
+        # pageable source: the driver stages it before the call returns, so the next step cannot overwrite it in flight
+        self._sc_dev.copy_(torch.tensor(self._adam_scalars(), dtype=torch.float32), non_blocking=True)
+        self._graph.replay()
+        return self._gvec

@@ -189,6 +189,16 @@ def adamw(p, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
     _count()
 
 
+def adamw_dev(p, g, m, v, p_bf16, scalars):
+    """AdamW with {lr, beta1, beta2, eps, wd, 1 - beta1^t, sqrt(1 - beta2^t), grad_scale} read from the device tensor
+    ``scalars`` (fp32 [8]) -- the form a captured CUDA graph of the step replays."""
+    lib = L.load()
+    assert scalars.is_cuda and scalars.dtype == torch.float32 and scalars.numel() >= 8
+    L.check(lib.o2_adamw_dev(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), p.numel(), _ptr(scalars), _stream()),
+            "o2_adamw_dev")
+    _count()
+
+
 def loss_fwd_bwd(pred, target, kind, *, lat_w=None, ch_w=None, clamp_ch=-1, const_mask=0, want_grad=True,
                  grad_scale=1.0):
     """pred [B,C,H,W] act dtype (raw); target fp32 [B,C,tH,tW].  Returns (loss_vec [C+1] fp32, dpred or None)."""

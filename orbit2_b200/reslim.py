@@ -476,6 +476,16 @@ class Res_Slim_ViT(nn.Module):
         in_variables = list(in_variables)
         return [in_variables.index(v) for v in out_variables] + [in_variables.index(v) for v in STATIC_VARS]
 
+    def _dev_const(self, key, values, dtype):
+        """Small host constants of the parameter prep, uploaded once per (key, device): no host->device copy on the
+        per-step path (also what lets a CUDA-graph capture of the step run through the prep)."""
+        dev = self.var_embed.device
+        cache = self.__dict__.setdefault("_dev_consts", {})
+        t = cache.get((key, dev))
+        if t is None:
+            t = cache[(key, dev)] = torch.tensor(values, dtype=dtype, device=dev)
+        return t
+
     def get_var_ids(self, variables):
         return [self.var_map[v] for v in variables]        # KeyError for unknown variables, like the reference
 
@@ -488,7 +498,8 @@ class Res_Slim_ViT(nn.Module):
         V = len(var_ids)
         f = torch.float32
         Wt = torch.stack([self.token_embeds[i].proj.weight.to(f).reshape(D, PP) for i in var_ids])        # V,D,PP
-        c = torch.stack([self.token_embeds[i].proj.bias.to(f) for i in var_ids]) + self.var_embed.to(f)[0, list(var_ids)]
+        c = torch.stack([self.token_embeds[i].proj.bias.to(f) for i in var_ids]) + \
+            self.var_embed.to(f)[0].index_select(0, self._dev_const(("ids", tuple(var_ids)), list(var_ids), torch.long))
         Wp = torch.cat([Wt, c.unsqueeze(-1)], dim=-1)                                                       # V,D,PP+1
         q = (self.var_agg.q.weight.to(f) @ self.var_query.to(f)[0, 0]).reshape(heads, hd) * hd ** -0.5
         Wk, Wv = self.var_agg.kv.weight.to(f)[:D].reshape(heads, hd, D), self.var_agg.kv.weight.to(f)[D:]
@@ -507,7 +518,7 @@ class Res_Slim_ViT(nn.Module):
             t = pe.reshape(-1, oh, 2 * oh, self.embed_dim).permute(0, 3, 1, 2)
             t = F.interpolate(t, size=(gh, gw), mode="bicubic", align_corners=False)
             pe = t.permute(0, 2, 3, 1).flatten(1, 2)
-        res = torch.tensor([float(self.spatial_resolution)], dtype=torch.float32, device=pe.device)
+        res = self._dev_const(("res", float(self.spatial_resolution)), [float(self.spatial_resolution)], torch.float32)
         se = F.linear(res, self.spatial_embed.weight.to(torch.float32), self.spatial_embed.bias.to(torch.float32))
         return (pe[0] + se[None]).contiguous()           # fp32; the kernel schedule casts it to the activation dtype
 

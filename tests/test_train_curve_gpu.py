@@ -50,3 +50,38 @@ def test_loss_curve_100_steps(dtype, tol):
     assert ref[-1] < 0.95 * ref[0], "the oracle did not train: test is not meaningful"
     print("max rel deviation over 100 steps:", float(rel.max()), "first", ours[0], ref[0], "last", ours[-1], ref[-1])
     assert rel.max() < tol, (float(rel.max()), int(rel.argmax()), ours[:3], ref[:3], ours[-3:], ref[-3:])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cuda_graph_step_equals_eager(dtype):
+    """TrainEngine.enable_graph: the step captured once as a CUDA graph (AdamW scalars read from device memory, batch
+    copied into the static buffers) follows the eager engine step by step -- same kernels, same order -- also across a
+    learning-rate change between replays."""
+    from oracle import cases, reslim_oracle as O
+    from orbit2_b200 import engine, losses
+    cfg = cases.get_case("tiny")
+    sd0 = O.init_state_dict(cfg, seed=7)
+    batches = [tuple(t.cuda() for t in O.synthetic_batch(cfg, 2, cfg["in_vars"], cfg["out_vars"], seed=s)) for s in range(3)]
+    curves, params = [], []
+    for graph in (False, True):
+        m = build_model(cfg, sd0, "cuda", dtype)
+        loss_fn = losses.METRICS_REGISTRY["bayesian_tv"](
+            aggregate_only=True, metainfo=losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None))
+        eng = engine.TrainEngine(m, loss_fn, cfg["in_vars"], cfg["out_vars"], cfg["var_weights"], lr=1e-3,
+                                 betas=(0.9, 0.99), weight_decay=1e-5)
+        if graph:
+            eng.enable_graph(warm_steps=2)
+        out = []
+        for i in range(12):
+            if i == 8:
+                eng.lr = 3e-4
+            x, y = batches[i % 3]
+            out.append(eng.step(x, y)[-1].clone())
+        assert (eng._graph is not None) == graph
+        curves.append(torch.stack(out).double().cpu())
+        params.append(eng.flat_p.clone())
+    tol = 1e-6 if dtype == torch.float32 else 1e-3           # same kernels; only atomics ordering may differ
+    assert ((curves[0] - curves[1]).abs() / curves[0].abs()).max().item() < tol
+    assert (params[0] - params[1]).abs().max().item() / params[0].abs().max().item() < tol
+    with pytest.raises(RuntimeError):
+        eng.step(batches[0][0][:1], batches[0][1][:1])       # batch shape is frozen into the graph
