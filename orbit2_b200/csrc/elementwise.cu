@@ -50,21 +50,44 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, fl
   }
 }
 
+__device__ __forceinline__ float adamw_one(float& pi, float gi, float& mi, float& vi, float lr, float b1, float b2,
+                                          float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  gi *= gscale;
+  pi *= (1.f - lr * wd);                       // decoupled weight decay (torch.optim.AdamW)
+  mi = b1 * mi + (1.f - b1) * gi;
+  vi = b2 * vi + (1.f - b2) * gi * gi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  pi -= (lr / bc1) * (mi / denom);
+  return pi;
+}
+
+// 16-byte vectors when every buffer is 16-byte aligned (the flat layout aligns every slice to 8 elements), scalar tail
 __device__ __forceinline__ void adamw_update(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                              float* __restrict__ v, __nv_bfloat16* __restrict__ pb, long long n, float lr,
                                              float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
                                              float gscale) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * gscale;
-    float pi = p[i];
-    pi *= (1.f - lr * wd);                       // decoupled weight decay (torch.optim.AdamW)
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= (lr / bc1) * (mi / denom);
-    p[i] = pi;
+  const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)pb & 7) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    adamw_one(p4.x, g4.x, m4.x, v4.x, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    adamw_one(p4.y, g4.y, m4.y, v4.y, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    adamw_one(p4.z, g4.z, m4.z, v4.z, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    adamw_one(p4.w, g4.w, m4.w, v4.w, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    reinterpret_cast<float4*>(p)[i] = p4;
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    if (pb) {
+      uint2 t;
+      t.x = pack_bf16x2(p4.x, p4.y); t.y = pack_bf16x2(p4.z, p4.w);
+      reinterpret_cast<uint2*>(pb)[i] = t;
+    }
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    adamw_one(pi, g[i], mi, vi, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    p[i] = pi; m[i] = mi; v[i] = vi;
     if (pb) pb[i] = __float2bfloat16_rn(pi);
   }
 }

@@ -81,6 +81,17 @@ def test_elementwise():
         pr.grad = gr.clone(); opt.step()
     assert rel(p, pr.detach()) < 1e-6
     assert torch.equal(pb, p.to(torch.bfloat16))
+    # vector body + scalar tail (n % 4 != 0) and a slice at a 4-byte offset (all-scalar path) give the same update
+    n = 5003
+    src = [torch.randn(n, generator=g, device="cuda") for _ in range(3)]          # p, g, v (made non-negative)
+    res = []
+    for off in (0, 1):
+        p_, g_, m_, v_ = (torch.empty(n + off, device="cuda")[off:] for _ in range(4))
+        p_.copy_(src[0]); g_.copy_(src[1]); m_.zero_(); v_.copy_(src[2].abs())
+        ops.adamw(p_, g_, m_, v_, None, 5e-4, 0.9, 0.99, 1e-8, 1e-5, 2)
+        res.append((p_.clone(), m_.clone(), v_.clone()))
+    for a_, b_ in zip(*res):
+        assert torch.equal(a_, b_)
 
 
 @pytest.mark.parametrize("dtype", DT)
