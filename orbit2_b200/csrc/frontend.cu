@@ -25,6 +25,7 @@ struct FeArgs {
   const float* x; const float* tab_s; const float* tab_v;
   void* out; const void* dout; float* dtab_s; float* dtab_v;
   int B, V, Hx, Wx, p, gh, gw, heads, hd, PP, KK;
+  int VP, fast;     // bf16 arm, p = 2: coefficient columns / table rows in (k', v) order, kk' = k' * VP + v (VP = V rounded up to even)
   long long T;
 };
 
@@ -274,6 +275,35 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 // pixels of one token tile for all variables (head independent)
 __device__ __forceinline__ void stage_pixels(const FeArgs& a, long long t0, float* sP) {
   const int V = a.V, PP = a.PP, L = a.gh * a.gw;
+  if (a.p == 2) {
+    // p = 2: a thread keeps its token (NT is a multiple of TT) and walks the variables: one coordinate computation, two
+    // 8-byte loads per (token, variable) when the rows are 8-byte aligned, one 16-byte shared store
+    static_assert(NT % TT == 0, "a thread must keep its token across the variable loop");
+    const int tl = threadIdx.x % TT;
+    const long long t = t0 + tl;
+    float4* dst = reinterpret_cast<float4*>(sP) + tl * V;
+    if (t < a.T) {
+      const int b = (int)(t / L), l = (int)(t - (long long)b * L);
+      const int gy = l / a.gw, gx = l - gy * a.gw;
+      const size_t plane = (size_t)a.Hx * a.Wx;
+      const float* xp = a.x + (size_t)b * V * plane + (size_t)(2 * gy) * a.Wx + 2 * gx;
+      const bool vec = ((a.Wx & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 7) == 0);
+      for (int v = threadIdx.x / TT; v < V; v += NT / TT) {
+        const float* q = xp + (size_t)v * plane;
+        float4 px;
+        if (vec) {
+          const float2 r0 = __ldg(reinterpret_cast<const float2*>(q)), r1 = __ldg(reinterpret_cast<const float2*>(q + a.Wx));
+          px = make_float4(r0.x, r0.y, r1.x, r1.y);
+        } else {
+          px = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + a.Wx), __ldg(q + a.Wx + 1));
+        }
+        dst[v] = px;
+      }
+    } else {
+      for (int v = threadIdx.x / TT; v < V; v += NT / TT) dst[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < TT * V; i += NT) {
     const int tl = i % TT, v = i / TT;
     const long long t = t0 + tl;
@@ -302,6 +332,55 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
 __device__ __forceinline__ void head_coefficients(const FeArgs& a, int h, long long t0, const float* sP, float* sa,
                                                   __nv_bfloat16* sC) {
   const int V = a.V, PP = a.PP, P1 = PP + 1;
+  if (a.fast) {
+    // p = 2 (PP = 4): pixels as one 16-byte load per (token, variable), coefficients of two neighbouring variables packed
+    // into one bf16x2 store per k' (columns kk' = k' * VP + v, so that the pair is adjacent), everything unrolled
+    const float4* sP4 = reinterpret_cast<const float4*>(sP);
+    {
+      const int tl = threadIdx.x >> 2, sub = threadIdx.x & 3;
+      float mx = -INFINITY;
+      for (int v = sub; v < V; v += 4) {
+        const float* ts = a.tab_s + ((size_t)v * a.heads + h) * 5;
+        const float4 px = sP4[tl * V + v];
+        float sc = __ldg(ts + 4);
+        sc = fmaf(px.x, __ldg(ts + 0), sc);
+        sc = fmaf(px.y, __ldg(ts + 1), sc);
+        sc = fmaf(px.z, __ldg(ts + 2), sc);
+        sc = fmaf(px.w, __ldg(ts + 3), sc);
+        sa[tl * V + v] = sc;
+        mx = fmaxf(mx, sc);
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+      for (int v = sub; v < V; v += 4) {
+        const float e = __expf(sa[tl * V + v] - mx);
+        sa[tl * V + v] = e;
+        sum += e;
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = (t0 + tl < a.T) ? 1.f / sum : 0.f;
+      for (int v = sub; v < V; v += 4) sa[tl * V + v] *= inv;
+    }
+    __syncthreads();
+    const int VP = a.VP, VH = VP >> 1;
+    for (int i = threadIdx.x; i < TT * VH; i += NT) {
+      const int vp = i % VH, tl = i / VH;
+      const int v0 = 2 * vp, v1 = v0 + 1;
+      const bool has1 = v1 < V;
+      const float w0 = sa[tl * V + v0], w1 = has1 ? sa[tl * V + v1] : 0.f;
+      const float4 p0 = sP4[tl * V + v0];
+      const float4 p1 = has1 ? sP4[tl * V + v1] : make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t* c = reinterpret_cast<uint32_t*>(sC + tl * LDS_) + vp;
+      c[0 * VH] = pack_bf16x2(w0 * p0.x, w1 * p1.x);
+      c[1 * VH] = pack_bf16x2(w0 * p0.y, w1 * p1.y);
+      c[2 * VH] = pack_bf16x2(w0 * p0.z, w1 * p1.z);
+      c[3 * VH] = pack_bf16x2(w0 * p0.w, w1 * p1.w);
+      c[4 * VH] = pack_bf16x2(w0, w1);
+    }
+    return;
+  }
   {   // four threads per token: scores of every 4th variable, max / sum combined with two shuffles
     const int tl = threadIdx.x >> 2, sub = threadIdx.x & 3;
     float mx = -INFINITY;
@@ -360,7 +439,7 @@ __global__ void __launch_bounds__(NT) frontend_fwd_mma_kernel(const FeArgs a) {
       uint2 pk;
       pk.x = pack_bf16x2(v4.x, v4.y);
       pk.y = pack_bf16x2(v4.z, v4.w);
-      *reinterpret_cast<uint2*>(sB + kk * LDB_ + e4 * 4) = pk;
+      *reinterpret_cast<uint2*>(sB + (a.fast ? (kk % 5) * a.VP + kk / 5 : kk) * LDB_ + e4 * 4) = pk;
     }
     __syncthreads();
     float acc[4][4];
@@ -411,7 +490,7 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_r
 //   dM[kk][e] += sum_t C[t][kk] dO[t][e]   (warp w owns rows 16w..16w+15 of dM in registers for the whole kernel)
 //   dC[t][kk]  = sum_e dO[t][e] M[kk][e]
 // then the small SIMT tail (da, ds, d tab_s) of the fp32 kernel.
-__global__ void __launch_bounds__(NT) frontend_bwd_mma_kernel(const FeArgs a) {
+__global__ void __launch_bounds__(NT, 2) frontend_bwd_mma_kernel(const FeArgs a) {
   constexpr int HD = 64;
   constexpr int LDC_ = KKP + 4;                       // fp32 pitch of the dC tile
   extern __shared__ float smem[];
@@ -433,7 +512,7 @@ __global__ void __launch_bounds__(NT) frontend_bwd_mma_kernel(const FeArgs a) {
     uint2 pk;
     pk.x = pack_bf16x2(v4.x, v4.y);
     pk.y = pack_bf16x2(v4.z, v4.w);
-    *reinterpret_cast<uint2*>(sM + kk * LDB_ + e4 * 4) = pk;
+    *reinterpret_cast<uint2*>(sM + (a.fast ? (kk % 5) * a.VP + kk / 5 : kk) * LDB_ + e4 * 4) = pk;
   }
   float dM[8][4];
 #pragma unroll
@@ -496,8 +575,19 @@ __global__ void __launch_bounds__(NT) frontend_bwd_mma_kernel(const FeArgs a) {
     // ---- SIMT tail: da[t][v] = <dC[t][v,:], P'[t][v,:]>,  ds = a (da - <a, da>),  d tab_s[v][k'] += sum_t ds P'
     for (int i = threadIdx.x; i < TT * V; i += NT) {
       const int tl = i % TT, v = i / TT;
-      float da = sdC[tl * LDC_ + v * P1 + PP];
-      for (int k = 0; k < PP; ++k) da = fmaf(sdC[tl * LDC_ + v * P1 + k], sP[(tl * V + v) * PP + k], da);
+      float da;
+      if (a.fast) {
+        const float* dc_ = sdC + tl * LDC_ + v;
+        const float4 px = reinterpret_cast<const float4*>(sP)[tl * V + v];
+        da = dc_[4 * a.VP];
+        da = fmaf(dc_[0], px.x, da);
+        da = fmaf(dc_[a.VP], px.y, da);
+        da = fmaf(dc_[2 * a.VP], px.z, da);
+        da = fmaf(dc_[3 * a.VP], px.w, da);
+      } else {
+        da = sdC[tl * LDC_ + v * P1 + PP];
+        for (int k = 0; k < PP; ++k) da = fmaf(sdC[tl * LDC_ + v * P1 + k], sP[(tl * V + v) * PP + k], da);
+      }
       ssc[tl * V + v] = da;
     }
     __syncthreads();
@@ -510,18 +600,20 @@ __global__ void __launch_bounds__(NT) frontend_bwd_mma_kernel(const FeArgs a) {
       for (int v = sub; v < V; v += 4) ssc[tl * V + v] = sa[tl * V + v] * (ssc[tl * V + v] - dot);
     }
     __syncthreads();
-    if (threadIdx.x < KK) {
-      const int v = threadIdx.x / P1, k = threadIdx.x % P1;
+    if ((threadIdx.x & 127) < KK) {                   // two threads per table entry, half of the tile's tokens each
+      const int vk = threadIdx.x & 127, v = vk / P1, k = vk % P1;
+      const int tl0 = (threadIdx.x >> 7) * (TT / 2);
       float sum = 0.f;
-      for (int tl = 0; tl < TT; ++tl) {
+#pragma unroll 4
+      for (int tl = tl0; tl < tl0 + TT / 2; ++tl) {
         const float pk = (k < PP) ? sP[(tl * V + v) * PP + k] : 1.f;
         sum = fmaf(ssc[tl * V + v], pk, sum);
       }
       dS += sum;
     }
   }
-  if (threadIdx.x < KK) {
-    const int v = threadIdx.x / P1, k = threadIdx.x % P1;
+  if ((threadIdx.x & 127) < KK) {
+    const int vk = threadIdx.x & 127, v = vk / P1, k = vk % P1;
     atomicAdd(&a.dtab_s[((size_t)v * a.heads + h) * P1 + k], dS);
   }
 #pragma unroll
@@ -529,7 +621,11 @@ __global__ void __launch_bounds__(NT) frontend_bwd_mma_kernel(const FeArgs a) {
     const int col = nt * 8 + tig * 2;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      const int kk = warp * 16 + g + half * 8;
+      int kk = warp * 16 + g + half * 8;
+      if (a.fast) {                                   // row kk' = k' * VP + v of the permuted tile -> table row v * 5 + k'
+        const int kq = kk / a.VP, v = kk % a.VP;
+        kk = (kq < 5 && v < V) ? v * 5 + kq : KK;
+      }
       if (kk < KK) {
         float* dst = a.dtab_v + ((size_t)h * KK + kk) * HD + col;
         atomicAdd(dst, dM[nt][half * 2]);
@@ -551,6 +647,8 @@ int fill(FeArgs& a, const float* x, const float* tab_s, const float* tab_v, int 
   a.x = x; a.tab_s = tab_s; a.tab_v = tab_v;
   a.B = B; a.V = V; a.Hx = Hx; a.Wx = Wx; a.p = p; a.gh = gh; a.gw = gw; a.heads = heads; a.hd = hd;
   a.PP = p * p; a.KK = V * (p * p + 1);
+  a.VP = (V + 1) & ~1;
+  a.fast = (a.PP == 4 && 5 * a.VP <= 128) ? 1 : 0;   // read by the bf16 (mma) kernels only
   a.T = (long long)B * gh * gw;
   return O2_OK;
 }
