@@ -329,8 +329,14 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
 
 // softmax weights a[t][v] of head h from the staged pixels (NT == 4 * TT: four threads per token), then the bf16 coefficient tile
 // sC[t][kk] = a[t][v] * [pixels, 1] (kk = v*(PP+1)+k'; columns >= KK stay zero from the caller's one-time clear)
+// this head's score table tab_s[:, h, :] -> shared memory [V][5] (fast path only: V * 5 <= 128 floats)
+__device__ __forceinline__ void stage_tab_s(const FeArgs& a, int h, float* sTs) {
+  for (int i = threadIdx.x; i < a.V * 5; i += NT) sTs[i] = __ldg(a.tab_s + ((size_t)(i / 5) * a.heads + h) * 5 + i % 5);
+}
+
+// sTs holds head h's score table on entry (fast path); h_next >= 0: it is refilled for that head once the scores are done
 __device__ __forceinline__ void head_coefficients(const FeArgs& a, int h, long long t0, const float* sP, float* sa,
-                                                  __nv_bfloat16* sC) {
+                                                  __nv_bfloat16* sC, float* sTs, int h_next) {
   const int V = a.V, PP = a.PP, P1 = PP + 1;
   if (a.fast) {
     // p = 2 (PP = 4): pixels as one 16-byte load per (token, variable), coefficients of two neighbouring variables packed
@@ -340,13 +346,13 @@ __device__ __forceinline__ void head_coefficients(const FeArgs& a, int h, long l
       const int tl = threadIdx.x >> 2, sub = threadIdx.x & 3;
       float mx = -INFINITY;
       for (int v = sub; v < V; v += 4) {
-        const float* ts = a.tab_s + ((size_t)v * a.heads + h) * 5;
+        const float* ts = sTs + v * 5;
         const float4 px = sP4[tl * V + v];
-        float sc = __ldg(ts + 4);
-        sc = fmaf(px.x, __ldg(ts + 0), sc);
-        sc = fmaf(px.y, __ldg(ts + 1), sc);
-        sc = fmaf(px.z, __ldg(ts + 2), sc);
-        sc = fmaf(px.w, __ldg(ts + 3), sc);
+        float sc = ts[4];
+        sc = fmaf(px.x, ts[0], sc);
+        sc = fmaf(px.y, ts[1], sc);
+        sc = fmaf(px.z, ts[2], sc);
+        sc = fmaf(px.w, ts[3], sc);
         sa[tl * V + v] = sc;
         mx = fmaxf(mx, sc);
       }
@@ -364,6 +370,7 @@ __device__ __forceinline__ void head_coefficients(const FeArgs& a, int h, long l
       for (int v = sub; v < V; v += 4) sa[tl * V + v] *= inv;
     }
     __syncthreads();
+    if (h_next >= 0) stage_tab_s(a, h_next, sTs);       // visible to the next head's scores through the barriers in between
     const int VP = a.VP, VH = VP >> 1;
     for (int i = threadIdx.x; i < TT * VH; i += NT) {
       const int vp = i % VH, tl = i / VH;
@@ -424,15 +431,17 @@ __global__ void __launch_bounds__(NT) frontend_fwd_mma_kernel(const FeArgs a) {
   __nv_bfloat16* sC = reinterpret_cast<__nv_bfloat16*>(sa + TT * V);   // [TT][LDS_]  coefficients
   __nv_bfloat16* sB = sC + TT * LDS_;                 // [KKP][LDB_] tab_v[h] (row kk, e contiguous; rows >= KK zero)
   __nv_bfloat16* sO = sB + KKP * LDB_;                // [TT][LDB_]  output tile
+  float* sTs = reinterpret_cast<float*>(sO + TT * LDB_);   // [V][5] score table of the current head (fast path)
   const long long t0 = (long long)blockIdx.x * TT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
   const int mt = warp & 3, nh = warp >> 2;            // 16-token row tile, 32-column half
   stage_pixels(a, t0, sP);
+  if (a.fast) stage_tab_s(a, 0, sTs);
   for (int i = threadIdx.x; i < TT * LDS_ / 2; i += NT) reinterpret_cast<uint32_t*>(sC)[i] = 0u;
   for (int i = threadIdx.x; i < KKP * LDB_ / 2; i += NT) reinterpret_cast<uint32_t*>(sB)[i] = 0u;
   __syncthreads();
   for (int h = 0; h < a.heads; ++h) {
-    head_coefficients(a, h, t0, sP, sa, sC);
+    head_coefficients(a, h, t0, sP, sa, sC, sTs, h + 1 < a.heads ? h + 1 : -1);
     for (int i = threadIdx.x; i < KK * (HD / 4); i += NT) {          // fp32 table -> bf16 tile, 16-byte reads
       const int kk = i / (HD / 4), e4 = i % (HD / 4);
       const float4 v4 = *reinterpret_cast<const float4*>(a.tab_v + ((size_t)h * KK + kk) * HD + e4 * 4);
@@ -502,7 +511,9 @@ __global__ void __launch_bounds__(NT, 2) frontend_bwd_mma_kernel(const FeArgs a)
   __nv_bfloat16* sC = reinterpret_cast<__nv_bfloat16*>(sdC);
   __nv_bfloat16* sdO = reinterpret_cast<__nv_bfloat16*>(sdC + TT * LDC_);   // [TT][LDB_]
   __nv_bfloat16* sM = sdO + TT * LDB_;                // [KKP][LDB_]  tab_v[h] (rows >= KK zero)
+  float* sTs = reinterpret_cast<float*>(sM + KKP * LDB_);   // [V][5] score table of this head (fast path)
   const int h = blockIdx.y;
+  if (a.fast) stage_tab_s(a, h, sTs);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
   for (int i = threadIdx.x; i < KKP * LDB_ / 2; i += NT) reinterpret_cast<uint32_t*>(sM)[i] = 0u;
   __syncthreads();
@@ -535,7 +546,7 @@ __global__ void __launch_bounds__(NT, 2) frontend_bwd_mma_kernel(const FeArgs a)
       *reinterpret_cast<uint4*>(sdO + tl * LDB_ + c8 * 8) = v;
     }
     __syncthreads();
-    head_coefficients(a, h, t0, sP, sa, sC);
+    head_coefficients(a, h, t0, sP, sa, sC, sTs, -1);
     __syncthreads();
     // ---- dM += C^T dO   (M = kk rows 16*warp.., N = e, K = t)
 #pragma unroll
@@ -699,7 +710,7 @@ extern "C" int o2_frontend_fwd(const float* x, const float* tab_s, const float* 
   O2_REQUIRE(out, "frontend_fwd: null out");
   a.out = out;
   if (out_dtype == O2_BF16 && hd == 64 && ((uintptr_t)out % 16) == 0 && !getenv("O2_FRONTEND_SIMT")) {
-    const size_t smem = sizeof(float) * ((size_t)TT * a.V * a.PP + (size_t)TT * a.V) + 2 * ((size_t)TT * LDS_ + (size_t)(KKP + TT) * LDB_);
+    const size_t smem = sizeof(float) * ((size_t)TT * a.V * a.PP + (size_t)TT * a.V + 128) + 2 * ((size_t)TT * LDS_ + (size_t)(KKP + TT) * LDB_);
     O2_CUDA(cudaFuncSetAttribute(frontend_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     frontend_fwd_mma_kernel<<<(unsigned)((a.T + TT - 1) / TT), NT, smem, (cudaStream_t)stream>>>(a);
     O2_LAUNCH_CHECK();
@@ -717,7 +728,7 @@ extern "C" int o2_frontend_bwd(const float* x, const float* tab_s, const float* 
   O2_REQUIRE(dout && dtab_s && dtab_v, "frontend_bwd: null pointer");
   a.dout = dout; a.dtab_s = dtab_s; a.dtab_v = dtab_v;
   if (dtype == O2_BF16 && hd == 64 && ((uintptr_t)dout % 16) == 0 && !getenv("O2_FRONTEND_SIMT")) {
-    const size_t smem = sizeof(float) * ((size_t)TT * a.V * a.PP + 2 * (size_t)TT * a.V + (size_t)TT * (KKP + 4)) +
+    const size_t smem = sizeof(float) * ((size_t)TT * a.V * a.PP + 2 * (size_t)TT * a.V + (size_t)TT * (KKP + 4) + 128) +
                         2 * ((size_t)TT + KKP) * LDB_;
     O2_CUDA(cudaFuncSetAttribute(frontend_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = (a.T + TT - 1) / TT;
