@@ -77,6 +77,10 @@ def build(conf: dict, data_key: str, img_size: Tuple[int, int], device, pos_grid
     eng = TrainEngine(model, loss, in_vars, out_vars, d["var_weights"], lr=float(m["lr"]),
                       betas=(float(m["beta_1"]), float(m["beta_2"])), weight_decay=float(m["weight_decay"]),
                       shard_optimizer=int(conf["parallelism"].get("fsdp", 1)) > 1)     # fsdp > 1 in the YAML -> sharded mode
+    # launch-bound configurations (interm_8m): replay the step as one CUDA graph (trainer --graph / O2_GRAPH=1); only
+    # where the engine allows it: one GPU, replicated parameters, dropout / drop-path 0
+    if int(os.environ.get("O2_GRAPH", "0")):
+        eng.enable_graph()
     return model, loss, eng
 
 
@@ -249,9 +253,13 @@ def main():
     ap.add_argument("--checkpoint-dir", default=None)
     ap.add_argument("--resume", default=None)
     ap.add_argument("--act-ckpt", action="store_true", help="per-Block activation recomputation (the reference's default)")
+    ap.add_argument("--graph", action="store_true", help="replay the training step as one captured CUDA graph (one GPU, "
+                    "dropout 0; for launch-bound configurations such as interm_8m)")
     a = ap.parse_args()
     if a.act_ckpt:
         os.environ["O2_ACT_CKPT"] = "1"
+    if a.graph:
+        os.environ["O2_GRAPH"] = "1"
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
