@@ -100,10 +100,22 @@ def test_elementwise():
 # tiled shared-memory path / streaming + band paths (W % 8 == 0) / three warps per row (lane-0 and lane-31 halo loads)
 @pytest.mark.parametrize("W,tW", [(150, 152), (152, 156), (520, 524)])
 def test_loss_vs_oracle(dtype, kind, use_lat, W, tW):
+    _loss_case(dtype, kind, use_lat, 45, 47, W, tW)
+
+
+@pytest.mark.parametrize("H,W", [(1, 8), (2, 16), (3, 8), (8, 8), (9, 24), (16, 256), (17, 264)])
+def test_loss_tv_band_edges(H, W):
+    """bayesian_tv band kernel at its edges: fewer rows than one 8-row band, exactly one band, one row into the next band,
+    a single 8-column strip, exactly one full warp per row, one strip into the second warp."""
+    for dtype in DT:
+        _loss_case(dtype, "bayesian_tv", True, H, H + 1, W, W + 4)
+
+
+def _loss_case(dtype, kind, use_lat, H, tH, W, tW):
     from oracle import cases, reslim_oracle as O
     from orbit2_b200 import _lib as L, ops
     g = torch.Generator().manual_seed(3)
-    B, C, H, tH = 2, 3, 45, 47
+    B, C = 2, 3
     pred = torch.randn(B, C, H, W, generator=g).to(dtype)
     y = torch.randn(B, C, tH, tW, generator=g)
     out_vars = ["total_precipitation_24hr", "orography", "2m_temperature_max"]   # ch0 clamped, ch1 constant
