@@ -195,6 +195,9 @@ int o2_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t
  * 1 - beta1^step, sqrt(1 - beta2^step), grad_scale}. */
 int o2_adamw_dev(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, const float* scalars,
                  void* stream);
+/* *flag |= 1 if any of g[0..n) is inf or NaN: the found_inf test of the reference's bf16 branch
+ * (ShardedGradScaler.step, examples/intermediate_downscaling.py:733-742).  The caller zero-fills flag. */
+int o2_nonfinite(const float* g, int64_t n, int* flag, void* stream);
 
 #ifdef __cplusplus
 }

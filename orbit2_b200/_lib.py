@@ -47,6 +47,7 @@ SIGNATURES = {
     "o2_colsum": ([_p, _i, _p, _l, _l, _l, _p], _i),
     "o2_adamw": ([_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _f, _p], _i),
     "o2_adamw_dev": ([_p, _p, _p, _p, _p, _l, _p, _p], _i),
+    "o2_nonfinite": ([_p, _l, _p, _p], _i),
 }
 
 _lib = None

@@ -184,3 +184,30 @@ extern "C" int o2_adamw_dev(float* p, const float* g, float* m, float* v, void* 
   O2_LAUNCH_CHECK();
   return O2_OK;
 }
+
+namespace {
+__device__ __forceinline__ bool nonfinite_bits(float x) {      // exponent all ones: inf or NaN (integer test: immune to fast-math folding)
+  return (__float_as_uint(x) & 0x7f800000u) == 0x7f800000u;
+}
+__global__ void nonfinite_kernel(const float* __restrict__ g, long long n, int* __restrict__ flag) {
+  bool bad = false;
+  const long long n4 = (((uintptr_t)g & 15) == 0) ? n / 4 : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    bad |= nonfinite_bits(v.x) | nonfinite_bits(v.y) | nonfinite_bits(v.z) | nonfinite_bits(v.w);
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    bad |= nonfinite_bits(g[i]);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+}  // namespace
+
+/* flag |= 1 if any of g[0..n) is inf or NaN (the found_inf test of torch's GradScaler.step, intermediate_downscaling.py:733-742);
+ * the caller zero-fills flag.  One streaming pass, HBM-bound. */
+extern "C" int o2_nonfinite(const float* g, int64_t n, int* flag, void* stream) {
+  O2_REQUIRE(g && flag && n >= 0, "nonfinite: bad args");
+  if (n == 0) return O2_OK;
+  nonfinite_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(g, n, flag);
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}

@@ -24,12 +24,46 @@ from .losses import Metric, clip_spec
 from .reslim import Res_Slim_ViT, reslim_backward, reslim_forward
 
 
+class GradScaler:
+    """Dynamic loss scaling with the semantics of the reference's bf16 branch (examples/intermediate_downscaling.py:493-495,
+    733-742: ``ShardedGradScaler(init_scale=8192, growth_interval=100)`` + the ``min_scale = 128`` floor; torch defaults
+    growth_factor 2, backoff_factor 0.5): gradients are produced pre-multiplied by ``scale``; a step whose gradients contain
+    inf / NaN on ANY rank is skipped and halves the scale, ``growth_interval`` clean steps in a row double it."""
+
+    def __init__(self, init_scale: float = 8192.0, growth_interval: int = 100, min_scale: float = 128.0,
+                 growth_factor: float = 2.0, backoff_factor: float = 0.5):
+        self.scale, self.growth_interval, self.min_scale = float(init_scale), int(growth_interval), float(min_scale)
+        self.growth_factor, self.backoff_factor = float(growth_factor), float(backoff_factor)
+        self.growth_tracker = 0
+        self.skipped = 0
+
+    def update(self, found_inf: bool):
+        if found_inf:
+            self.scale *= self.backoff_factor
+            self.growth_tracker = 0
+            self.skipped += 1
+        else:
+            self.growth_tracker += 1
+            if self.growth_tracker == self.growth_interval:
+                self.scale *= self.growth_factor
+                self.growth_tracker = 0
+        if self.scale < self.min_scale:                      # intermediate_downscaling.py:741-742
+            self.scale = self.min_scale
+
+    def state_dict(self):
+        return {"scale": self.scale, "growth_tracker": self.growth_tracker}
+
+    def load_state_dict(self, sd):
+        self.scale, self.growth_tracker = float(sd["scale"]), int(sd["growth_tracker"])
+
+
 class TrainEngine:
     def __init__(self, model: Res_Slim_ViT, loss: Metric, in_variables: Sequence[str], out_variables: Sequence[str],
                  var_weights: Optional[Dict[str, float]] = None, lr: float = 2e-4, betas=(0.9, 0.99),
                  weight_decay: float = 1e-5, eps: float = 1e-8, process_group=None, clip_constants: bool = True,
-                 shard_optimizer: bool = False, shard_params: bool = False):
+                 shard_optimizer: bool = False, shard_params: bool = False, grad_scaler: Optional[GradScaler] = None):
         self.model = model
+        self.scaler = grad_scaler
         self.loss = loss
         self.in_variables, self.out_variables = list(in_variables), list(out_variables)
         self.var_weights = dict(var_weights or {})
@@ -148,7 +182,8 @@ class TrainEngine:
                 self._lat = self.loss._lat(preds)
                 self._chw = self.loss._ch_w(preds, self.out_variables, self.var_weights)
             vec, dpred = ops.loss_fwd_bwd(preds, y, self.loss.kind, lat_w=self._lat, ch_w=self._chw, clamp_ch=self.clip[0],
-                                          const_mask=self.clip[1])
+                                          const_mask=self.clip[1],
+                                          grad_scale=self.scaler.scale if self.scaler is not None else 1.0)
             if self.fs is not None:
                 self.fs.begin(-1)
             dts, dtv, dpos = reslim_backward(g, self.P, Wc, x, tab_s.detach(), tab_v.detach(), S, dpred, G,
@@ -205,11 +240,30 @@ class TrainEngine:
             if self.flat_b is not None:
                 dist.all_gather_into_tensor(self.flat_b, self.flat_b[o0:o1], group=self.pg)
 
+    def grads_nonfinite(self) -> bool:
+        """inf / NaN anywhere in this step's (reduced) gradients, agreed on by all ranks (one streaming pass + one sync,
+        like GradScaler.step's found_inf.item())."""
+        flag = torch.zeros(1, device=self.device, dtype=torch.int32)
+        o0, o1 = self.own
+        ops.nonfinite(self.flat_g[o0:o1], flag)
+        if self.fs is not None:
+            for _, g32, _, _, _ in self.fs.shards():
+                ops.nonfinite(g32, flag)
+        if self.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.pg)
+        return bool(flag.item())
+
     def step(self, x, y):
         if self._graph_warm:
             return self.graph_step(x, y)
         vec = self.forward_backward(x, y)
-        self.optimizer_step()
+        if self.scaler is None:
+            self.optimizer_step()
+            return vec
+        found_inf = self.grads_nonfinite()                   # gradients carry the factor scaler.scale
+        if not found_inf:
+            self.optimizer_step(grad_scale=1.0 / self.scaler.scale)
+        self.scaler.update(found_inf)
         return vec
 
     # ------------------------------------------------------------------ CUDA-graph mode
@@ -221,6 +275,8 @@ class TrainEngine:
         change between steps: AdamW reads its scalars from device memory (o2_adamw_dev)."""
         if self.world > 1 or self.fs is not None or self.sharded:
             raise RuntimeError("enable_graph: single-GPU, replicated-parameter engines only")
+        if self.scaler is not None:
+            raise RuntimeError("enable_graph: the dynamic grad scaler decides on the host whether to step")
         if self.model.training and (self.model.drop_rate > 0 or self.model.drop_path > 0):
             raise RuntimeError("enable_graph: dropout / drop-path must be 0 (their counters are frozen into a graph)")
         self._graph_warm = max(1, int(warm_steps))

@@ -189,6 +189,14 @@ def adamw(p, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
     _count()
 
 
+def nonfinite(g, flag):
+    """flag (int32 [1], device, zero-filled by the caller) |= 1 if any element of the fp32 tensor g is inf / NaN."""
+    lib = L.load()
+    assert g.dtype == torch.float32 and g.is_contiguous() and flag.dtype == torch.int32
+    L.check(lib.o2_nonfinite(_ptr(g), g.numel(), _ptr(flag), _stream()), "o2_nonfinite")
+    _count()
+
+
 def adamw_dev(p, g, m, v, p_bf16, scalars):
     """AdamW with {lr, beta1, beta2, eps, wd, 1 - beta1^t, sqrt(1 - beta2^t), grad_scale} read from the device tensor
     ``scalars`` (fp32 [8]) -- the form a captured CUDA graph of the step replays."""

@@ -28,7 +28,7 @@ import torch
 import torch.distributed as dist
 
 from . import losses
-from .engine import TrainEngine
+from .engine import GradScaler, TrainEngine
 from .reslim import Res_Slim_ViT
 
 
@@ -76,7 +76,11 @@ def build(conf: dict, data_key: str, img_size: Tuple[int, int], device, pos_grid
     m = conf["model"]
     eng = TrainEngine(model, loss, in_vars, out_vars, d["var_weights"], lr=float(m["lr"]),
                       betas=(float(m["beta_1"]), float(m["beta_2"])), weight_decay=float(m["weight_decay"]),
-                      shard_optimizer=int(conf["parallelism"].get("fsdp", 1)) > 1)     # fsdp > 1 in the YAML -> sharded mode
+                      shard_optimizer=int(conf["parallelism"].get("fsdp", 1)) > 1,     # fsdp > 1 in the YAML -> sharded mode
+                      # bf16 branch of the reference: ShardedGradScaler(init_scale=8192, growth_interval=100), floor 128
+                      # (intermediate_downscaling.py:493-495, 733-742)
+                      grad_scaler=GradScaler() if (dtype == torch.bfloat16 and not int(os.environ.get("O2_GRAPH", "0")))
+                      else None)
     # launch-bound configurations (interm_8m): replay the step as one CUDA graph (trainer --graph / O2_GRAPH=1); only
     # where the engine allows it: one GPU, replicated parameters, dropout / drop-path 0
     if int(os.environ.get("O2_GRAPH", "0")):

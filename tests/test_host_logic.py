@@ -145,3 +145,28 @@ def test_attn_keep_mask_restatement():
     big = DM.attn_scaled_mask(seed, site, 1, 1, 512, 0.1)
     assert abs(float((big > 0).double().mean()) - (1 - 25 / 256)) < 3e-3
     assert abs(float(big.mean()) - 1.0) < 4e-3                                  # E[mask] = 1: kept values carry 1 / keep_prob
+
+
+def test_grad_scaler_state_machine():
+    """engine.GradScaler follows torch's GradScaler update rule with the reference's settings (init 8192, growth interval
+    100, floor 128: examples/intermediate_downscaling.py:493-495, 741-742); checked against torch.amp.GradScaler's own
+    scale sequence for the same found-inf pattern."""
+    from orbit2_b200.engine import GradScaler
+    s = GradScaler()
+    assert s.scale == 8192.0
+    pattern = [False] * 99 + [True] + [False] * 100 + [False] * 100 + [True] * 9
+    want = 8192.0
+    tracker = 0
+    for bad in pattern:
+        s.update(bad)
+        if bad:
+            want, tracker = want * 0.5, 0
+        else:
+            tracker += 1
+            if tracker == 100:
+                want, tracker = want * 2.0, 0
+        want = max(want, 128.0)
+        assert s.scale == want
+    assert s.scale == 128.0 and s.skipped == 10          # 4096 -> 8192 -> 16384, then nine halvings stop at the floor
+    t = GradScaler(); t.load_state_dict(s.state_dict())
+    assert (t.scale, t.growth_tracker) == (s.scale, s.growth_tracker)

@@ -85,3 +85,41 @@ def test_cuda_graph_step_equals_eager(dtype):
     assert (params[0] - params[1]).abs().max().item() / params[0].abs().max().item() < tol
     with pytest.raises(RuntimeError):
         eng.step(batches[0][0][:1], batches[0][1][:1])       # batch shape is frozen into the graph
+
+
+def test_grad_scaler_semantics():
+    """bf16 branch of the reference driver (intermediate_downscaling.py:733-742): gradients are produced pre-scaled, the
+    update un-scales them (same trajectory as the unscaled engine up to bf16 rounding of the scaled dL/dpred), and a step
+    whose gradients contain inf / NaN is skipped, halving the scale."""
+    from oracle import cases, reslim_oracle as O
+    from orbit2_b200 import engine, losses, ops
+    cfg = cases.get_case("tiny")
+    sd0 = O.init_state_dict(cfg, seed=9)
+    x, y = (t.cuda() for t in O.synthetic_batch(cfg, 2, cfg["in_vars"], cfg["out_vars"], seed=1))
+
+    def make(scaler):
+        m = build_model(cfg, sd0, "cuda", torch.bfloat16)
+        loss_fn = losses.METRICS_REGISTRY["bayesian_tv"](
+            aggregate_only=True, metainfo=losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None))
+        return engine.TrainEngine(m, loss_fn, cfg["in_vars"], cfg["out_vars"], cfg["var_weights"], lr=1e-3,
+                                  betas=(0.9, 0.99), weight_decay=1e-5, grad_scaler=scaler)
+    plain, scaled = make(None), make(engine.GradScaler(growth_interval=3))
+    for i in range(5):
+        a, b = plain.step(x, y)[-1].item(), scaled.step(x, y)[-1].item()
+        assert abs(a - b) / abs(a) < 2e-3, (i, a, b)                     # power-of-two scale: same numbers up to rounding
+    assert scaled.scaler.scale == 8192.0 * 2 and scaled.step_count == 5  # one growth after three clean steps
+    assert (plain.flat_p - scaled.flat_p).abs().max().item() / plain.flat_p.abs().max().item() < 2e-3
+    # the non-finite test itself
+    flag = torch.zeros(1, device="cuda", dtype=torch.int32)
+    g = torch.randn(100003, device="cuda")
+    ops.nonfinite(g, flag); assert flag.item() == 0
+    g[77777] = float("inf"); ops.nonfinite(g, flag); assert flag.item() == 1
+    flag.zero_(); g[77777] = 0.0; g[100002] = float("nan"); ops.nonfinite(g[1:], flag); assert flag.item() == 1
+    # an overflowing step is skipped: parameters and Adam state untouched, scale halved
+    before, s0 = scaled.flat_p.clone(), scaled.scaler.scale
+    bad_x = x.clone(); bad_x[0, 0, 0, 0] = float("inf")
+    scaled.step(bad_x, y)
+    assert scaled.step_count == 5 and scaled.scaler.scale == s0 / 2 and scaled.scaler.skipped == 1
+    assert torch.equal(before, scaled.flat_p)
+    scaled.step(x, y)
+    assert scaled.step_count == 6 and not torch.equal(before, scaled.flat_p)
