@@ -141,6 +141,55 @@ def load_checkpoint(path: str, eng: TrainEngine) -> int:
     return int(ck["epoch"]) + 1
 
 
+def interpolate_pos_embed(pos_embed: torch.Tensor, patch_size: int, new_size: Tuple[int, int]) -> torch.Tensor:
+    """Checkpoint pos_embed [1, L0, D] (stored grid h x 2h, the reference's fixed W / H = 2 assumption) -> the token grid
+    of ``new_size`` (pixels) by bicubic resampling (components/pos_embed.py:73-99); unchanged when the row counts agree."""
+    n, d = pos_embed.shape[-2], pos_embed.shape[-1]
+    oh = int((n // 2) ** 0.5)
+    ow = 2 * oh
+    nh, nw = new_size[0] // patch_size, new_size[1] // patch_size
+    if oh == nh:
+        return pos_embed
+    t = pos_embed.reshape(-1, oh, ow, d).permute(0, 3, 1, 2)
+    t = torch.nn.functional.interpolate(t, size=(nh, nw), mode="bicubic", align_corners=False)
+    return t.permute(0, 2, 3, 1).flatten(1, 2)
+
+
+def load_pretrained_weights(model, state: Dict[str, torch.Tensor], log=print) -> Dict[str, list]:
+    """``trainer.pretrain`` (examples/intermediate_downscaling.py:116-153): keys the model does not have are dropped, keys
+    whose shape differs are dropped EXCEPT ``pos_embed``, which is resampled to the model's grid; the rest is copied in
+    (``strict=False``).  Works on a plain module or on one whose parameters are views of an engine's flat buffer (copies
+    are in place).  Returns {"loaded", "dropped", "missing"}."""
+    own = model.state_dict()
+    state = dict(state)
+    dropped = []
+    for k in list(state.keys()):
+        if k not in own:
+            log(f"Removing key {k} from pretrained checkpoint: no exist")
+            dropped.append(k); del state[k]
+        elif state[k].shape != own[k].shape:
+            if k == "pos_embed":
+                state[k] = interpolate_pos_embed(state[k], model.patch_size, tuple(model.img_size))
+                if state[k].shape != own[k].shape:
+                    dropped.append(k); del state[k]
+            else:
+                log(f"Removing key {k} from pretrained checkpoint: no matching shape {tuple(state[k].shape)} {tuple(own[k].shape)}")
+                dropped.append(k); del state[k]
+    with torch.no_grad():
+        for k, v in state.items():
+            own[k].copy_(v.to(own[k].device, own[k].dtype))
+    return {"loaded": sorted(state), "dropped": dropped, "missing": sorted(set(own) - set(state))}
+
+
+def load_pretrain_checkpoint(path: str, eng: TrainEngine, log=print):
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    rep = load_pretrained_weights(eng.model, ck["model_state_dict"], log)
+    if eng.flat_b is not None:                             # refresh the bf16 operand copy of the flat master buffer
+        from . import ops
+        ops.cast_bf16(eng.flat_p, eng.flat_b)
+    return rep
+
+
 # ------------------------------------------------------------------------------------------------ loop
 def synthetic_loader(conf, data_key, grid, batch, steps, device, seed):
     d = conf["data"]
@@ -212,6 +261,13 @@ def train(conf: dict, data_key: str, grid, epochs: int, steps_per_epoch: int, ck
     m = conf["model"]
     sched = dict(warmup_epochs=m["warmup_epochs"], max_epochs=conf["trainer"]["max_epochs"],
                  warmup_start_lr=float(m["warmup_start_lr"]), eta_min=float(m["eta_min"]), base_lr=float(m["lr"]))
+    pre = conf["trainer"].get("pretrain")
+    if pre and not resume:                                 # like the reference: a resumed checkpoint wins over the pretrain path
+        if not os.path.exists(pre):
+            raise FileNotFoundError(f"trainer.pretrain = {pre}: pretrain path does not exist")
+        rep = load_pretrain_checkpoint(pre, eng, log if rank == 0 else (lambda *_: None))
+        if rank == 0:
+            log(f"pretrained weights: {len(rep['loaded'])} loaded, {len(rep['dropped'])} dropped, {len(rep['missing'])} kept from init")
     epoch0 = load_checkpoint(resume, eng) if resume else 0
     B = conf["trainer"]["batch_size"]
     hist = []

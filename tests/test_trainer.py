@@ -118,3 +118,59 @@ def test_npz_shards_training_and_validation(tmp_path):
     val = trainer.validate(eng, dm)
     assert set(val) == {"rmse", "pearson", "mean_bias"} and all(math.isfinite(v) for v in val.values())
     assert -1.0 <= val["pearson"] <= 1.0 and val["rmse"] > 0
+
+
+def test_pretrain_loader_semantics():
+    """trainer.load_pretrained_weights follows examples/intermediate_downscaling.py:116-153: unknown keys dropped, shape
+    mismatches dropped except pos_embed, which is resampled bicubically to the model's token grid
+    (components/pos_embed.py:73-99); everything else copied in place."""
+    import torch.nn.functional as F
+    from oracle import cases
+    from orbit2_b200 import trainer
+    from orbit2_b200.reslim import Res_Slim_ViT
+    cfg = cases.get_case("tiny")
+
+    def make(img, out_ch):
+        return Res_Slim_ViT(cfg["default_vars"], img, len(cfg["default_vars"]), out_ch, 1, superres_mag=cfg["superres_mag"],
+                            cnn_ratio=cfg["cnn_ratio"], patch_size=cfg["patch_size"], drop_path=0.0, drop_rate=0.0,
+                            learn_pos_emb=True, embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                            decoder_depth=cfg["decoder_depth"], num_heads=cfg["num_heads"], mlp_ratio=cfg["mlp_ratio"])
+    torch.manual_seed(0)
+    src = make((16, 32), 2)                      # pretrained on a coarser grid, with a different number of output channels
+    torch.manual_seed(1)
+    dst = make((32, 64), 3)
+    sd = {k: v.detach().clone() for k, v in src.state_dict().items()}
+    sd["pos_embed"] = torch.randn_like(sd["pos_embed"])
+    sd["not_in_the_model.weight"] = torch.zeros(3)
+    before = {k: v.detach().clone() for k, v in dst.state_dict().items()}
+    rep = trainer.load_pretrained_weights(dst, sd, log=lambda *_: None)
+    after = dst.state_dict()
+    p = cfg["patch_size"]
+    oh, ow = 16 // p, 32 // p
+    want = F.interpolate(sd["pos_embed"].reshape(1, oh, ow, -1).permute(0, 3, 1, 2), size=(32 // p, 64 // p), mode="bicubic",
+                         align_corners=False).permute(0, 2, 3, 1).flatten(1, 2)
+    assert torch.equal(after["pos_embed"], want)
+    assert "not_in_the_model.weight" in rep["dropped"]
+    mism = [k for k in sd if k in before and sd[k].shape != before[k].shape and k != "pos_embed"]
+    assert mism and all(k in rep["dropped"] and torch.equal(after[k], before[k]) for k in mism)   # head.8 / path2.3 / conv_out
+    same = [k for k in sd if k in before and sd[k].shape == before[k].shape]
+    assert same and all(torch.equal(after[k], sd[k]) for k in same)
+    assert set(rep["loaded"]) == set(same) | {"pos_embed"}
+
+
+@pytest.mark.reference
+def test_pos_embed_interpolation_matches_live_reference(monkeypatch):
+    from oracle import ref_shim
+    from orbit2_b200 import trainer
+    ref_shim.load_reference()
+    import importlib
+    pe = importlib.import_module("climate_learn.models.hub.components.pos_embed")
+    monkeypatch.setattr(torch.distributed, "get_rank", lambda: 1)
+    ck = {"pos_embed": torch.randn(1, 8 * 16, 24)}
+
+    class M:
+        patch_size = 2
+    want = dict(ck)
+    pe.interpolate_pos_embed(M(), want, new_size=(24, 48))
+    got = trainer.interpolate_pos_embed(ck["pos_embed"], 2, (24, 48))
+    assert torch.equal(got, want["pos_embed"])
