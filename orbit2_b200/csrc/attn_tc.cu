@@ -1018,27 +1018,37 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         uint32_t pk[16], dk[16];
         if (kDrop) {
           // thread = key row: lane l builds the keep word of query qb + l for this warp's 32-key block, every thread
-          // reads the words of its 32 queries by shuffle and tests its own key's bit
+          // reads the words of its 32 queries and tests its own key's bit
           const int key_ = k0 + t * BKV + r;
           const int qb = u * BS + chalf * 32;
           const uint32_t kbit = 1u << ptx::attn_keep_bit((uint32_t)key_);
-          const uint32_t my_word = ptx::attn_keep_word(a.drop, drop_key, (uint32_t)(qb + lane), (uint32_t)(key_ >> 5));
+          // the 32 words of this warp's (32 keys x 32 queries) block go through a private 128-byte shared-memory slot:
+          // one store + eight 16-byte broadcast loads instead of 32 shuffles
+          uint32_t* wslot = reinterpret_cast<uint32_t*>(smem + (BwdCfg<NH>::kDkvSmem - 1024)) + (warp - 2) * 32;
+          __syncwarp();                                 // the previous block's loads of this slot are done
+          wslot[lane] = ptx::attn_keep_word(a.drop, drop_key, (uint32_t)(qb + lane), (uint32_t)(key_ >> 5));
+          __syncwarp();
           const float* dl = reinterpret_cast<const float*>(sStat) + dstage;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const uint64_t X = ptx::mul2(ptx::pack2u(sv_[i], sv_[i + 1]), sc2);
-            const uint64_t Pq = ptx::exp2_pair<false>(X);
-            const bool k0_ = (__shfl_sync(0xffffffffu, my_word, i) & kbit) != 0u;
-            const bool k1_ = (__shfl_sync(0xffffffffu, my_word, i + 1) & kbit) != 0u;
-            float p0, p1;
-            ptx::unpack2(Pq, p0, p1);
-            const int qi = (u & 1) * BS + chalf * 32 + i;            // row of the 128-query statistics tile
-            const float de0 = dl[(qi * 128 + ((6 ^ (qi & 7)) * 16)) >> 2];
-            const float de1 = dl[((qi + 1) * 128 + ((6 ^ ((qi + 1) & 7)) * 16)) >> 2];
-            const float g0 = k0_ ? __uint_as_float(dv_[i]) * a.drop.inv_keep : 0.f;
-            const float g1 = k1_ ? __uint_as_float(dv_[i + 1]) * a.drop.inv_keep : 0.f;
-            pk[i >> 1] = pack_bf16x2(k0_ ? p0 : 0.f, k1_ ? p1 : 0.f);
-            dk[i >> 1] = pack_bf16x2(p0 * (g0 - de0), p1 * (g1 - de1));
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const uint4 w4 = reinterpret_cast<const uint4*>(wslot)[i4];        // keep words of queries qb + 4 i4 .. + 3
+#pragma unroll
+            for (int hp = 0; hp < 2; ++hp) {
+              const int i = 4 * i4 + 2 * hp;
+              const uint64_t X = ptx::mul2(ptx::pack2u(sv_[i], sv_[i + 1]), sc2);
+              const uint64_t Pq = ptx::exp2_pair<false>(X);
+              const bool k0_ = ((hp ? w4.z : w4.x) & kbit) != 0u;
+              const bool k1_ = ((hp ? w4.w : w4.y) & kbit) != 0u;
+              float p0, p1;
+              ptx::unpack2(Pq, p0, p1);
+              const int qi = (u & 1) * BS + chalf * 32 + i;            // row of the 128-query statistics tile
+              const float de0 = dl[(qi * 128 + ((6 ^ (qi & 7)) * 16)) >> 2];
+              const float de1 = dl[((qi + 1) * 128 + ((6 ^ ((qi + 1) & 7)) * 16)) >> 2];
+              const float g0 = k0_ ? __uint_as_float(dv_[i]) * a.drop.inv_keep : 0.f;
+              const float g1 = k1_ ? __uint_as_float(dv_[i + 1]) * a.drop.inv_keep : 0.f;
+              pk[i >> 1] = pack_bf16x2(k0_ ? p0 : 0.f, k1_ ? p1 : 0.f);
+              dk[i >> 1] = pack_bf16x2(p0 * (g0 - de0), p1 * (g1 - de1));
+            }
           }
         } else {
 #pragma unroll
@@ -1440,7 +1450,8 @@ int launch_bwd(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const BwdArg
   static bool attr_done = false;
   if (!attr_done) {
     O2_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<NH, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kDqSmem));
-    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<NH, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kDkvSmem));
+    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<NH, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)Cfg::kDkvSmem + (kDrop ? 1024 : 0)));       // + the keep-word slots of the 8 softmax warps
     attr_done = true;
   }
   const int rows_per_cta = Cfg::kTiles * BQ;
@@ -1460,7 +1471,7 @@ int launch_bwd(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const BwdArg
       dim3 grid2((a.N + BKV - 1) / BKV, a.B * a.heads);
       attn_bwd_dkv_tm_kernel<kDrop><<<grid2, kThreadsB, kDkvTmSmem, st>>>(tm_qkv, tm_do, a);
     } else {
-      attn_bwd_dkv_kernel<NH, kDrop><<<grid, kThreadsF, Cfg::kDkvSmem, st>>>(tm_qkv, tm_do, a);
+      attn_bwd_dkv_kernel<NH, kDrop><<<grid, kThreadsF, Cfg::kDkvSmem + (kDrop ? 1024 : 0), st>>>(tm_qkv, tm_do, a);
     }
     O2_LAUNCH_CHECK();
   }
