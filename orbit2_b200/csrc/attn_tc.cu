@@ -59,7 +59,7 @@ struct FwdArgs {
   ptx::AttnDrop drop;       // kDrop kernels only
 };
 
-// zero the dropped probabilities of one packed pair (columns k, k + 1 of row q share a hash: bytes 2 (q & 1) + {0, 1})
+// attention-probability dropout, row-owner side (mask function: common.cuh attn_keep_word)
 // row-owner kernels: AND-mask of packed pair PAIR (keys 2 PAIR, 2 PAIR + 1 of a 32-key block) from its keep word
 template <int PAIR> __device__ __forceinline__ uint32_t drop_mask_bf16x2(uint32_t word) {
   return ptx::keep_mask_bf16x2<PAIR & 1>(word << (PAIR >> 1));
