@@ -33,13 +33,45 @@ __device__ __forceinline__ const float* qkv_ptr(const AttnArgs& a, int b, int wh
 // row stride of q/k/v inside qkv
 __device__ __forceinline__ size_t qkv_rs(const AttnArgs& a) { return (size_t)3 * a.heads * a.hd; }
 
+// Unpadded transposed tiles of the wide-head kernels (pitch 64 floats = 0 mod 32 banks, no room for padding at head dim
+// 256): a thread that stored dst[d][row] element-wise with consecutive d would hit ONE bank 32 times.  Instead every
+// thread moves a 4 x 4 block -- four 16-byte global loads along d, transposed in registers, four 16-byte shared stores --
+// and the 4-row group g of column d lives at group g ^ ((d >> 2) & 15): the 32 threads of a warp (consecutive d groups)
+// then cover all banks (4 wavefronts of 128 bytes, the minimum for 512 bytes).  Readers XOR their row-group index with tswz.
+template <int HD> constexpr bool kSwz = (HD >= 256);
+__device__ __forceinline__ int tswz(int d) { return (d >> 2) & 15; }
+template <int W>     // W = number of columns (head-dim elements) of the chunk; dst is [W][64] floats, unpadded
+__device__ __forceinline__ void load_T_swizzled(float* dst, const float* src, size_t row_stride, int row0, int N) {
+  static_assert(W % 4 == 0, "4-column groups");
+  for (int it = threadIdx.x; it < 16 * (W / 4); it += NT) {
+    const int dq = it % (W / 4), rq = it / (W / 4);
+    const int d0 = dq * 4, r0 = rq * 4;
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int gr = row0 + r0 + k;
+      v[k] = (gr < N) ? *reinterpret_cast<const float4*>(src + (size_t)gr * row_stride + d0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float* base = dst + (size_t)d0 * 64 + ((rq ^ (dq & 15)) << 2);          // tswz(d0 + c) == dq & 15 for c = 0..3
+    *reinterpret_cast<float4*>(base) = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+    *reinterpret_cast<float4*>(base + 64) = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+    *reinterpret_cast<float4*>(base + 128) = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
+    *reinterpret_cast<float4*>(base + 192) = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+  }
+}
+
 // load a [64 rows x HD] tile transposed into smem: dst[d][row] (row pitch 64+pad), rows >= n_valid zero
 template <int HD>
 __device__ __forceinline__ void load_tile_T(float (*dst)[BQ + kPad<HD>], const float* src, size_t row_stride, int row0, int N) {
-  for (int i = threadIdx.x; i < 64 * HD; i += NT) {
-    const int r = i / HD, d = i % HD;
-    const int gr = row0 + r;
-    dst[d][r] = (gr < N) ? src[(size_t)gr * row_stride + d] : 0.f;
+  if constexpr (kSwz<HD>) {
+    static_assert(kPad<HD> == 0, "the swizzled layout assumes a 64-float pitch");
+    load_T_swizzled<HD>(&dst[0][0], src, row_stride, row0, N);
+  } else {
+    for (int i = threadIdx.x; i < 64 * HD; i += NT) {
+      const int r = i / HD, d = i % HD;
+      const int gr = row0 + r;
+      dst[d][r] = (gr < N) ? src[(size_t)gr * row_stride + d] : 0.f;
+    }
   }
 }
 template <int HD>
@@ -76,8 +108,9 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnArgs a) {
     float s[4][4] = {};
 #pragma unroll 8
     for (int d = 0; d < HD; ++d) {
-      const float4 qv = *reinterpret_cast<const float4*>(&qT[d][ty * 4]);
-      const float4 kv = *reinterpret_cast<const float4*>(&kT[d][tx * 4]);
+      const int sw = kSwz<HD> ? tswz(d) : 0;               // wide-head tiles are stored swizzled (load_T_swizzled)
+      const float4 qv = *reinterpret_cast<const float4*>(&qT[d][(ty ^ sw) * 4]);
+      const float4 kv = *reinterpret_cast<const float4*>(&kT[d][(tx ^ sw) * 4]);
       const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, ka[4] = {kv.x, kv.y, kv.z, kv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -120,7 +153,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnArgs a) {
       const float pa[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
       for (int c = 0; c < DC; ++c) {
-        const float vv = vS[k][tx * DC + c];
+        const float vv = vS[k][c * 16 + tx];            // thread tx owns head-dim columns c * 16 + tx: 16 banks, no conflict
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[i][c] = fmaf(pa[i], vv, o[i][c]);
       }
@@ -131,9 +164,9 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnArgs a) {
     const int row = q0 + ty * 4 + i;
     if (row >= a.N) continue;
     const float inv = 1.f / l[i];
-    float* op = a.out + ((size_t)b * a.N + row) * a.heads * a.hd + (size_t)h * a.hd + tx * DC;
+    float* op = a.out + ((size_t)b * a.N + row) * a.heads * a.hd + (size_t)h * a.hd + tx;
 #pragma unroll
-    for (int c = 0; c < DC; ++c) op[c] = o[i][c] * inv;
+    for (int c = 0; c < DC; ++c) op[c * 16] = o[i][c] * inv;
     if (tx == 0) a.lse[((size_t)b * a.heads + h) * a.N + row] = m[i] + __logf(l[i]);
   }
 }
@@ -334,10 +367,11 @@ __device__ __forceinline__ void accumulate_s_dp(float (*qT)[BQ], float (*kT)[BKV
                                                 int ty, float (&s)[4][4], float (&dp)[4][4]) {
 #pragma unroll 8
   for (int d = 0; d < HC; ++d) {
-    const float4 qv = *reinterpret_cast<const float4*>(&qT[d][ty * 4]);
-    const float4 kv = *reinterpret_cast<const float4*>(&kT[d][tx * 4]);
-    const float4 gv = *reinterpret_cast<const float4*>(&doT[d][ty * 4]);
-    const float4 vv = *reinterpret_cast<const float4*>(&vT[d][tx * 4]);
+    const int sw = tswz(d);                                 // chunk tiles are stored swizzled (load_T_swizzled)
+    const float4 qv = *reinterpret_cast<const float4*>(&qT[d][(ty ^ sw) * 4]);
+    const float4 kv = *reinterpret_cast<const float4*>(&kT[d][(tx ^ sw) * 4]);
+    const float4 gv = *reinterpret_cast<const float4*>(&doT[d][(ty ^ sw) * 4]);
+    const float4 vv = *reinterpret_cast<const float4*>(&vT[d][(tx ^ sw) * 4]);
     const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, ka[4] = {kv.x, kv.y, kv.z, kv.w};
     const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
@@ -367,14 +401,10 @@ __device__ __forceinline__ void finish_p_ds(const AttnArgs& a, const float* lse_
       }
     }
 }
-// [64 rows x HC] chunk (columns c0 ..) transposed into dst[d][row] (no padding)
+// [64 rows x HC] chunk (columns c0 ..) transposed into dst[d][row] (no padding, swizzled row groups: load_T_swizzled)
 template <int HC>
 __device__ __forceinline__ void load_chunk_T(float (*dst)[BQ], const float* src, size_t row_stride, int row0, int N) {
-  for (int i = threadIdx.x; i < 64 * HC; i += NT) {
-    const int r = i / HC, d = i % HC;
-    const int gr = row0 + r;
-    dst[d][r] = (gr < N) ? src[(size_t)gr * row_stride + d] : 0.f;
-  }
+  load_T_swizzled<HC>(&dst[0][0], src, row_stride, row0, N);
 }
 
 template <int HD, int HC>
@@ -432,7 +462,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_kv_wide_kernel(const AttnArgs a) 
       const float pa[4] = {pv.x, pv.y, pv.z, pv.w}, sa[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
       for (int c = 0; c < DC; ++c) {
-        const float g = doS[r][tx * DC + c], qv = qS[r][tx * DC + c];
+        const float g = doS[r][c * 16 + tx], qv = qS[r][c * 16 + tx];   // columns c * 16 + tx: conflict-free
 #pragma unroll
         for (int i = 0; i < 4; ++i) { dv[i][c] = fmaf(pa[i], g, dv[i][c]); dk[i][c] = fmaf(sa[i], qv, dk[i][c]); }
       }
@@ -442,10 +472,10 @@ __global__ void __launch_bounds__(NT) attn_bwd_kv_wide_kernel(const AttnArgs a) 
   for (int i = 0; i < 4; ++i) {
     const int key = k0 + ty * 4 + i;
     if (key >= a.N) continue;
-    float* dkp = a.dqkv + (((size_t)b * a.N + key) * 3 + 1) * os + (size_t)h * a.hd + tx * DC;
-    float* dvp = a.dqkv + (((size_t)b * a.N + key) * 3 + 2) * os + (size_t)h * a.hd + tx * DC;
+    float* dkp = a.dqkv + (((size_t)b * a.N + key) * 3 + 1) * os + (size_t)h * a.hd + tx;
+    float* dvp = a.dqkv + (((size_t)b * a.N + key) * 3 + 2) * os + (size_t)h * a.hd + tx;
 #pragma unroll
-    for (int c = 0; c < DC; ++c) { dkp[c] = dk[i][c]; dvp[c] = dv[i][c]; }
+    for (int c = 0; c < DC; ++c) { dkp[c * 16] = dk[i][c]; dvp[c * 16] = dv[i][c]; }
   }
 }
 
@@ -500,7 +530,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_q_wide_kernel(const AttnArgs a) {
       const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
       for (int c = 0; c < DC; ++c) {
-        const float kv = kS[k][tx * DC + c];
+        const float kv = kS[k][c * 16 + tx];
 #pragma unroll
         for (int i = 0; i < 4; ++i) dq[i][c] = fmaf(sa[i], kv, dq[i][c]);
       }
@@ -510,9 +540,9 @@ __global__ void __launch_bounds__(NT) attn_bwd_q_wide_kernel(const AttnArgs a) {
   for (int i = 0; i < 4; ++i) {
     const int row = q0 + ty * 4 + i;
     if (row >= a.N) continue;
-    float* dqp = a.dqkv + (((size_t)b * a.N + row) * 3 + 0) * os + (size_t)h * a.hd + tx * DC;
+    float* dqp = a.dqkv + (((size_t)b * a.N + row) * 3 + 0) * os + (size_t)h * a.hd + tx;
 #pragma unroll
-    for (int c = 0; c < DC; ++c) dqp[c] = dq[i][c];
+    for (int c = 0; c < DC; ++c) dqp[c * 16] = dq[i][c];
   }
 }
 

@@ -1,0 +1,34 @@
+"""fp32 head-dim-256 attention arm (interm_10b: 32 heads x 256, L = 512) forward / backward timing."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from orbit2_b200 import ops  # noqa: E402
+
+B, N, heads, hd = (int(v) for v in (sys.argv[1:5] if len(sys.argv) >= 5 else (8, 512, 32, 256)))
+D = heads * hd
+g = torch.Generator(device="cuda").manual_seed(0)
+qkv = torch.randn(B * N, 3 * D, generator=g, device="cuda")
+dout = torch.randn(B * N, D, generator=g, device="cuda")
+
+
+def timed(fn, n=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+out, lse = ops.attn_fwd(qkv, B, N, heads, hd)
+fl = 4.0 * B * heads * N * N * hd
+tf = timed(lambda: ops.attn_fwd(qkv, B, N, heads, hd))
+tb = timed(lambda: ops.attn_bwd(qkv, out, dout, lse, B, N, heads, hd))
+print(f"hd={hd} B={B} N={N} heads={heads}: fwd {tf:.3f} ms {fl / tf / 1e9:.1f} TFLOP/s   bwd {tb:.3f} ms {2.5 * fl / tb / 1e9:.1f} TFLOP/s")
