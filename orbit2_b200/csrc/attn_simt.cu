@@ -76,6 +76,16 @@ __device__ __forceinline__ void load_tile_T(float (*dst)[BQ + kPad<HD>], const f
 }
 template <int HD>
 __device__ __forceinline__ void load_tile(float (*dst)[HD + kPad<HD>], const float* src, size_t row_stride, int row0, int N) {
+  static_assert(HD % 4 == 0 && kPad<HD> % 4 == 0, "16-byte rows");
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (row_stride & 3) == 0) {       // 16-byte vectors (block-uniform branch)
+    for (int i = threadIdx.x; i < 64 * (HD / 4); i += NT) {
+      const int r = i / (HD / 4), d = (i % (HD / 4)) * 4;
+      const int gr = row0 + r;
+      *reinterpret_cast<float4*>(&dst[r][d]) =
+          (gr < N) ? *reinterpret_cast<const float4*>(src + (size_t)gr * row_stride + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < 64 * HD; i += NT) {
     const int r = i / HD, d = i % HD;
     const int gr = row0 + r;
@@ -603,7 +613,10 @@ int o2_attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int h
   if (hd == 32) return run_fwd<32>(a, st);
   if (hd == 64) return run_fwd<64>(a, st);
   if (hd == 128) return run_fwd<128>(a, st);
-  if (hd == 256) return run_fwd<256>(a, st);          // interm_10b: 32 heads x 256 (208 KiB of tiles, no padding)
+  if (hd == 256) {                                    // interm_10b: 32 heads x 256 (208 KiB of tiles, no padding)
+    O2_REQUIRE(((uintptr_t)qkv & 15) == 0, "attn_simt: head dim 256 needs a 16-byte aligned qkv (vector tile loads)");
+    return run_fwd<256>(a, st);
+  }
   O2_FAIL(O2_ERR_UNSUPPORTED, "attn_simt: head dim %d not in {32,64,128,256}", hd);
 }
 
@@ -619,7 +632,10 @@ int o2_attn_bwd_simt(const void* qkv, const void* out, const void* dout, const f
   if (hd == 32) return run_bwd<32>(a, st);
   if (hd == 64) return run_bwd<64>(a, st);
   if (hd == 128) return run_bwd<128>(a, st);
-  if (hd == 256) return run_bwd_wide<256, 64>(a, st);
+  if (hd == 256) {
+    O2_REQUIRE((((uintptr_t)qkv | (uintptr_t)dout) & 15) == 0, "attn_simt: head dim 256 needs 16-byte aligned qkv / dout");
+    return run_bwd_wide<256, 64>(a, st);
+  }
   O2_FAIL(O2_ERR_UNSUPPORTED, "attn_simt backward: head dim %d not in {32,64,128,256}", hd);
 }
 
