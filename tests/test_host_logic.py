@@ -170,3 +170,15 @@ def test_grad_scaler_state_machine():
     assert s.scale == 128.0 and s.skipped == 10          # 4096 -> 8192 -> 16384, then nine halvings stop at the floor
     t = GradScaler(); t.load_state_dict(s.state_dict())
     assert (t.scale, t.growth_tracker) == (s.scale, s.growth_tracker)
+
+
+def test_keep_masks_known_answer(golden_dir):
+    """the dropout mask restatements (oracle/dropout_mask.py) against the committed known-answer bits
+    (tests/golden/keep_masks.npz, written by oracle/make_mask_golden.py)."""
+    import os
+    from oracle import make_mask_golden as G
+    z = np.load(os.path.join(golden_dir, "keep_masks.npz"))
+    got = G.build()
+    assert sorted(z.files) == sorted(got)
+    for k in z.files:
+        assert np.array_equal(z[k], got[k]), k

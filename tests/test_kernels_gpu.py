@@ -339,3 +339,24 @@ def test_attn_dropout(dtype, hd, B, N, heads, p):
     out0, _ = ops.attn_fwd(qkv, B, N, heads, hd, (0.0, seed, site))
     out1, _ = ops.attn_fwd(qkv, B, N, heads, hd)
     assert torch.equal(out0, out1)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("p", [0.1, 0.35])
+def test_attn_dropout_mask_bits(dtype, p):
+    """The keep mask of the attention kernels read back bit by bit: with Q = K = 0 the probabilities are uniform (1 / N)
+    and with V = identity the output row q IS the masked probability row, so out * N > 0.5 <=> keep(q, k).  Compared with
+    the restatement in oracle/dropout_mask.py (itself pinned by tests/golden/keep_masks.npz) for both arms."""
+    from oracle import dropout_mask as DM
+    from orbit2_b200 import ops
+    seed, site = 0x1234_5678_9ABC_DEF0, 17
+    B, N, heads, hd = 2, 64, 3, 64
+    qkv = torch.zeros(B, N, 3, heads, hd, device="cuda")
+    qkv[:, torch.arange(N), 2, :, torch.arange(N)] = 1.0              # V[b, n, h, :] = e_n
+    qkv = qkv.reshape(B * N, 3 * heads * hd).to(dtype)
+    out, _ = ops.attn_fwd(qkv, B, N, heads, hd, (p, seed, site))
+    got = out.float().reshape(B, N, heads, hd).permute(0, 2, 1, 3)[..., :N] * N
+    M = DM.attn_scaled_mask(seed, site, B, heads, N, p).cuda()
+    assert torch.equal(got > 0.5, M > 0)
+    kept = got[got > 0.5]
+    assert (kept - 256.0 / (256 - int(p * 256))).abs().max().item() < (1e-5 if dtype == torch.float32 else 1e-2)
