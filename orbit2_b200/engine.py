@@ -272,7 +272,8 @@ class TrainEngine:
         on.  For launch-bound configurations (interm_8m: ~180 kernels of a few microseconds each, paced by the host's
         issue rate when launched one by one).  Restrictions: one GPU (world size 1), replicated parameters, dropout 0
         (the dropout counters are kernel arguments and would be frozen into the graph), fixed batch shape.  ``lr`` may
-        change between steps: AdamW reads its scalars from device memory (o2_adamw_dev)."""
+        change between steps: AdamW reads its scalars from device memory (o2_adamw_dev).  The loss vector returned by
+        ``step`` is then ONE static tensor that every replay overwrites (read or clone it before the next step)."""
         if self.world > 1 or self.fs is not None or self.sharded:
             raise RuntimeError("enable_graph: single-GPU, replicated-parameter engines only")
         if self.scaler is not None:
