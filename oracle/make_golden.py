@@ -85,8 +85,39 @@ def run_case(name: str, B: int, loss_name: str, seed: int = 0, use_lat: bool = F
     return out
 
 
+# BASELINE.json configs[0] (interm_8m, 5.5 M parameters): the full fixture would be 40+ MB, so this one keeps the inputs,
+# the prediction, the loss vector and the gradients of a parameter subset that touches every part of the path; the weights
+# are the seeded reference init (O.init_state_dict) and only their checksum is stored.
+COMPACT_GRADS = ["var_query", "var_embed", "spatial_embed.weight", "token_embeds.3.proj.weight", "var_agg.kv.weight",
+                 "var_agg.proj.bias", "blocks.0.norm1.weight", "blocks.0.attn.qkv.bias", "blocks.2.attn.proj.weight",
+                 "blocks.5.mlp.fc1.bias", "blocks.5.mlp.fc2.weight", "norm.bias", "head.0.weight", "head.8.bias",
+                 "path2.0.weight", "path2.3.bias", "conv_out.weight"]
+
+
+def weight_checksum(sd) -> np.ndarray:
+    return np.array([float(v.double().abs().sum()) for _, v in sorted(sd.items())])
+
+
+def run_case_compact(name: str, B: int, loss_name: str, seed: int, use_lat: bool):
+    full = run_case(name, B, loss_name, seed, use_lat)
+    out = {k: full[k] for k in ("x", "y", "pred", "loss_vec", "lat", "meta")}
+    out["pred"] = out["pred"].astype(np.float32)
+    for k in COMPACT_GRADS:                   # matrices: the first 8 rows only ("g8/"), everything else in full ("g/")
+        g = full["g/" + k]
+        if g.ndim == 2 and g.shape[0] > 8 and g.size > 4096:
+            out["g8/" + k] = g[:8].copy()
+        else:
+            out["g/" + k] = g
+    out["w_checksum"] = weight_checksum({k[2:]: torch.from_numpy(v) for k, v in full.items() if k.startswith("w/")})
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    out = run_case_compact("8m", 1, "bayesian_tv", 0, True)
+    fn = os.path.join(OUT, "8m_bayesian_tv_lat_compact.npz")
+    np.savez_compressed(fn, **out)
+    print(fn, os.path.getsize(fn) // 1024, "KiB", "loss", out["loss_vec"])
     jobs = [("tiny", 2, "mse", False), ("tiny", 2, "bayesian_tv", True), ("tiny_prism", 1, "mae", True)]
     for name, B, loss_name, use_lat in jobs:
         out = run_case(name, B, loss_name, 0, use_lat)

@@ -172,3 +172,31 @@ def test_reference_bugs_documented():
     x, _ = O.synthetic_batch(cfg, 1, cfg["in_vars"], cfg["out_vars"], 0)
     with pytest.raises(RuntimeError):
         m.forward(x, list(cfg["in_vars"]), list(cfg["out_vars"]))
+
+
+def test_oracle_matches_8m_golden(golden_dir):
+    """BASELINE.json configs[0] (interm_8m, 23 variables, 32x64 -> 128x256) pinned to the LIVE reference: compact fixture
+    written by oracle/make_golden.py (inputs, prediction, loss vector, gradients of a parameter subset that touches the
+    front end, attention, MLP, head, residual branch and conv tail; weights = the seeded reference init, checksummed)."""
+    from oracle import make_golden
+    z = np.load(os.path.join(golden_dir, "8m_bayesian_tv_lat_compact.npz"))
+    cfg = cases.get_case("8m")
+    sd = {k: v.double() for k, v in O.init_state_dict(cfg, 0).items()}
+    np.testing.assert_allclose(make_golden.weight_checksum(sd), z["w_checksum"], rtol=1e-6)   # fp32-stored weights
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    taps = {}
+    loss = O.training_step(sd, cfg, torch.from_numpy(z["x"]).double(), torch.from_numpy(z["y"]).double(), cfg["in_vars"],
+                           cfg["out_vars"], "bayesian_tv", cfg["var_weights"], O.lat_weights(z["lat"]), taps)
+    loss.backward()
+    assert abs(loss.item() - z["loss_vec"][-1]) <= 1e-6 * abs(z["loss_vec"][-1])
+    np.testing.assert_allclose(taps["preds"].detach().numpy(), z["pred"], rtol=2e-5, atol=2e-6)
+    n = 0
+    for k in z.files:
+        if not k.startswith("g"):
+            continue
+        name = k.split("/", 1)[1]
+        got = sd[name].grad[:8] if k.startswith("g8/") else sd[name].grad
+        want = torch.from_numpy(z[k]).double()
+        assert (got - want).abs().max().item() <= 2e-6 * (want.abs().max().item() + 1e-12), k
+        n += 1
+    assert n == len(make_golden.COMPACT_GRADS)
