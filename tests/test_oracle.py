@@ -88,7 +88,7 @@ def test_reference_error_paths():
 
 
 @pytest.mark.reference
-@pytest.mark.parametrize("case,B", [("tiny", 2), ("tiny_prism", 1)])
+@pytest.mark.parametrize("case,B", [("tiny", 2), ("tiny_prism", 1), ("8m", 1), ("1b_small", 1), ("10b_small", 1)])
 def test_oracle_matches_live_reference(case, B):
     from oracle import make_golden, ref_shim
     ref = ref_shim.load_reference()
@@ -200,3 +200,27 @@ def test_oracle_matches_8m_golden(golden_dir):
         assert (got - want).abs().max().item() <= 2e-6 * (want.abs().max().item() + 1e-12), k
         n += 1
     assert n == len(make_golden.COMPACT_GRADS)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("case", ["8m", "1b_small", "10b_small"])
+def test_oracle_gradients_match_live_reference(case):
+    """Forward + clip + latitude-weighted bayesian_tv + backward of the LIVE reference (float64) against the restatement
+    at the BASELINE widths the tiny fixtures do not cover: interm_8m (23 variables), interm_1b (head dim 128, PRISM
+    7-variable batch), interm_10b (head dim 256).  Every parameter gradient."""
+    from oracle import make_golden
+    ref = make_golden.run_case(case, 1, "bayesian_tv", 3, True)
+    cfg = cases.get_case(case)
+    sd = {k[2:]: torch.from_numpy(v).double().requires_grad_(True) for k, v in ref.items() if k.startswith("w/")}
+    loss = O.training_step(sd, cfg, torch.from_numpy(ref["x"]).double(), torch.from_numpy(ref["y"]).double(), cfg["in_vars"],
+                           cfg["out_vars"], "bayesian_tv", cfg["var_weights"], O.lat_weights(ref["lat"]), {})
+    loss.backward()
+    # run_case stores weights / gradients as float32 of the float64 run: compare at that resolution
+    assert abs(loss.item() - ref["loss_vec"][-1]) <= 2e-6 * abs(ref["loss_vec"][-1])
+    for k, v in ref.items():
+        if not k.startswith("g/"):
+            continue
+        g = sd[k[2:]].grad
+        got = g if g is not None else torch.zeros_like(sd[k[2:]])
+        want = torch.from_numpy(v).double()
+        assert (got - want).abs().max().item() <= 5e-6 * (want.abs().max().item() + 1e-12), k
