@@ -89,8 +89,10 @@ def flops_per_sample(cfg):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_step_time(case_name, B, steps, warmup, threads):
-    """Seconds per step of the CPU restatement (fp32, SDPA attention) of forward+clip+loss+backward."""
+def cpu_reference_step_time(case_name, B, steps, warmup, threads, budget_s=None):
+    """Seconds per step of the CPU restatement (fp32, SDPA attention) of forward+clip+loss+backward.  With ``budget_s`` the
+    number of warm-up / timed steps is cut (never the grid) so that the whole call ends inside the budget; returns
+    (seconds per step, cfg, timed steps, warm-up steps actually run)."""
     import torch
     from oracle import cases, reslim_oracle as O
     torch.set_num_threads(threads)
@@ -98,57 +100,60 @@ def cpu_reference_step_time(case_name, B, steps, warmup, threads):
     cfg = cases.get_case(case_name)
     sd = {k: v.requires_grad_(True) for k, v in O.init_state_dict(cfg, 0).items()}
     x, y = O.synthetic_batch(cfg, B, cfg["in_vars"], cfg["out_vars"], 0)
-    times = []
-    for i in range(warmup + steps):
+
+    def one():
         t0 = time.perf_counter()
         loss = O.training_step(sd, cfg, x, y, cfg["in_vars"], cfg["out_vars"], "bayesian_tv", cfg["var_weights"])
         loss.backward()
         for v in sd.values():
             v.grad = None
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    return sum(times) / len(times), cfg
+        return time.perf_counter() - t0
+
+    t_begin = time.perf_counter()
+    times, done_w = [], 0
+    for _ in range(warmup):
+        last = one()
+        done_w += 1
+        if budget_s is not None and (time.perf_counter() - t_begin) + last * (1 + steps) > budget_s:
+            break                                   # the remaining warm-up steps would eat the timed ones
+    for _ in range(steps):
+        times.append(one())
+        if budget_s is not None and (time.perf_counter() - t_begin) + times[-1] > budget_s:
+            break
+    return sum(times) / len(times), cfg, len(times), done_w
 
 
-def pick_cpu_sample(workload, n_steps_total, threads, budget_s=260.0, force=None):
-    """Bounded CPU sample of the workload: B=1 on the full 180x360 grid when (steps+warmup) of them fit the time budget
-    (calibrated with one step on the quarter-area 90x180 sub-grid, full grid measured 5.9x, budgeted 6.5x), else the sub-grid itself."""
-    if workload in ("1b", "10b", "10b_d2"):
-        return workload, 1, None
-    if workload != "117m":
-        return "8m", 8, None
-    if force in ("full", "sub"):
-        return ("117m" if force == "full" else "117m_90x180"), 1, None
-    sec, _ = cpu_reference_step_time("117m_90x180", 1, 1, 0, threads)
-    if 6.5 * sec * n_steps_total <= budget_s:
-        return "117m", 1, sec
-    return "117m_90x180", 1, sec
+REF_CASE = {"117m": ("117m", 1), "117m_90x180": ("117m_90x180", 1), "8m": ("8m", 8), "1b": ("1b", 1), "10b": ("10b", 1),
+            "10b_d2": ("10b_d2", 1)}
 
 
-def sample_note(case, cfg, B):
-    g = f"{cfg['img_size'][0]}x{cfg['img_size'][1]}"
-    if case == "117m_90x180":
-        return (f"B={B} on a {g} sub-grid (1/4 of the 180x360 field, L=4050): samples here are quarter-area samples, "
-                "not extrapolated")
-    return f"B={B} on the full {g} grid"
+def sample_note(cfg, B):
+    return f"B={B} on the full {cfg['img_size'][0]}x{cfg['img_size'][1]} grid of the workload (the GPU arm's grid)"
 
 
 def run_reference(args):
+    """CPU arm.  ALWAYS the GPU arm's grid (interm_117m: 180x360 -> 720x1440, L = 16200), B = 1 per step (a B = 8 step is
+    8 x 26 s on 16 cores and samples/s does not depend on B on the host); when K + W steps do not fit ``--ref-budget``
+    seconds the NUMBER of steps is cut and reported, the grid never changes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    case, B, _ = pick_cpu_sample(args.workload, args.steps + args.warmup, threads, force=args.ref_grid)
-    sec, cfg = cpu_reference_step_time(case, B, args.steps, args.warmup, threads)
+    case, B = REF_CASE[args.workload]
+    sec, cfg, n_timed, n_warm = cpu_reference_step_time(case, B, args.steps, args.warmup, threads, budget_s=args.ref_budget)
     val = B / sec
-    sample = (f"CPU restatement of the reference (oracle/, fp32, SDPA attention), forward+clip+bayesian_tv+backward, "
-              + sample_note(case, cfg, B) + f", {args.steps} steps after {args.warmup} warm-up")
+    L = (cfg["img_size"][0] // cfg["patch_size"]) * (cfg["img_size"][1] // cfg["patch_size"])
+    sample = ("CPU restatement of the reference (oracle/, fp32, SDPA attention = the reference's FusedAttn.DEFAULT path), "
+              "forward+clip+bayesian_tv+backward, " + sample_note(cfg, B) +
+              f", {n_timed} timed steps after {n_warm} warm-up (requested {args.steps}+{args.warmup}, budget {args.ref_budget:.0f} s)")
+    H_out = cfg["img_size"][0] * cfg["superres_mag"]
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "steps": n_timed, "warmup": n_warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "interm_117m ERA5 1.0->0.25 (reference arm: CPU sample, see cpu_baseline.sample)"
-                       if args.workload == "117m" else "interm_8m"},
+            "config": {"workload": f"interm_{args.workload} Res_Slim_ViT ERA5 {cfg['img_size'][0]}x{cfg['img_size'][1]} -> "
+                                   f"{H_out}x{cfg['img_size'][1] * cfg['superres_mag']}, V={len(cfg['in_vars'])} in / "
+                                   f"{len(cfg['out_vars'])} out vars, fwd+clip+bayesian_tv+bwd (host cores)",
+                       "per_gpu_batch": B, "tokens_per_sample": L, "same_grid_as_gpu_arm": True},
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -299,7 +304,6 @@ def run_ours(args):
 
     if args.full_shard:
         e2e_step = e2e_step_engine
-    model.external_wc = eng.Wc if dtype == torch.bfloat16 else None
     model.train()
     ms_e2e = timed(e2e_step, args.steps, max(1, args.warmup // 2))
 
@@ -340,11 +344,11 @@ def run_ours(args):
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and not args.workload.startswith("10b"):      # 9.5 B fp32 parameters + gradients: no host fit
         threads = os.cpu_count() or 1
-        case, cb, _ = pick_cpu_sample(args.workload, 1, threads, budget_s=60.0, force=args.ref_grid)
-        sec, ccfg = cpu_reference_step_time(case, cb, 1, 0 if args.workload == "117m" else 1, threads)
+        case, cb = REF_CASE[args.workload]
+        sec, ccfg, nt, nw = cpu_reference_step_time(case, cb, 1, 1, threads)
         cpu = {"value": cb / sec, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": "CPU restatement of the reference (oracle/, fp32, SDPA attention), 1 fwd+clip+bayesian_tv+bwd step, "
-                         + sample_note(case, ccfg, cb)}
+               "sample": f"CPU restatement of the reference (oracle/, fp32, SDPA attention), {nt} fwd+clip+bayesian_tv+bwd "
+                         f"step after {nw} warm-up, " + sample_note(ccfg, cb)}
 
     if rank == 0:
         line = {
@@ -391,7 +395,8 @@ def main():
     ap.add_argument("--full-shard", action="store_true",
                     help="FSDP FULL_SHARD: GEMM weights, fp32 masters, gradients and Adam state sharded per Block "
                          "(all-gather in forward and backward, reduce-scatter of gradients)")
-    ap.add_argument("--ref-grid", default=None, choices=["full", "sub"], help="force the CPU sample (default: by time budget)")
+    ap.add_argument("--ref-budget", type=float, default=1500.0, help="--impl reference: seconds the CPU arm may take; the "
+                    "number of steps is cut to fit, the grid is always the GPU arm's")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":

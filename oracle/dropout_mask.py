@@ -57,10 +57,13 @@ def attn_keep_bit(k: torch.Tensor) -> torch.Tensor:
 def attn_scaled_mask(seed: int, site: int, B: int, heads: int, N: int, p: float, dtype=torch.float64) -> torch.Tensor:
     """[B, heads, N, N] pre-scaled keep mask of the attention-probability dropout (orbit2_b200/csrc/common.cuh, bit-sliced):
     one 32-bit keep word per (query q, 32-key block kb): base = lowbias32((q * ceil(N / 32) + kb) ^ key_bh), eight planes
-    w_i = lo32(base * K_i) ^ hi32(base * K_i) of a uniform byte U per key, keep iff U >= floor(p * 256) (LSB plane first:
-    ge = w_i & ge where the threshold bit is set, w_i | ge where it is clear); key k reads bit attn_keep_bit(k); kept
-    values are scaled by 256 / (256 - floor(p * 256))."""
-    thr8 = math.floor(p * 256.0)
+    w_i = lo32(base * K_i) ^ hi32(base * K_i) of a uniform byte U per key, keep iff U >= thr (LSB plane first:
+    ge = w_i & ge where the threshold bit is set, w_i | ge where it is clear); key k reads bit attn_keep_bit(k).
+    16-bit drop probability thr16 = floor(p * 65536) = 256 hi8 + frac8: the byte threshold of a word is hi8 + 1 when its
+    dither byte lowbias32(base ^ 0x68E31DA4) >> 24 is below frac8, else hi8; kept values are scaled by
+    65536 / (65536 - thr16)."""
+    thr16 = math.floor(min(p, 0.99) * 65536.0) if p > 0 else 0
+    hi8, frac8 = thr16 >> 8, thr16 & 0xFF
     nkb = (N + 31) >> 5
     q = torch.arange(N, dtype=torch.int64).view(N, 1)
     kb = torch.arange(nkb, dtype=torch.int64).view(1, nkb)
@@ -73,6 +76,7 @@ def attn_scaled_mask(seed: int, site: int, B: int, heads: int, N: int, p: float,
         key_bh = _lb(sk ^ ((bh * 0x9E3779B1) & M32))
         base = lowbias32(((q * nkb + kb) & M32) ^ key_bh)                      # [N, nkb], < 2^32
         ge = torch.full_like(base, M32)
+        gh = torch.full_like(base, M32)
         for i, mul in enumerate(_KEEP_MUL):
             # 32 x 32 -> 64-bit product in int64 pieces (int64 would overflow on the full product)
             b_lo, b_hi = base & lo16, base >> 16
@@ -82,7 +86,9 @@ def attn_scaled_mask(seed: int, site: int, B: int, heads: int, N: int, p: float,
             lo32 = ((p1 & lo16) << 16) | (p0 & lo16)
             hi32 = (b_hi * m_hi + (p1 >> 16)) & M32
             w = lo32 ^ hi32
-            ge = (w & ge) if (thr8 >> i) & 1 else (w | ge)
-        keep = (ge[:, k >> 5] >> bit) & 1                                       # [N, N]
-        out[bh // heads, bh % heads] = keep.to(dtype) * (256.0 / (256.0 - thr8))
+            ge = (w & ge) if (hi8 >> i) & 1 else (w | ge)
+            gh = (w & gh) if ((hi8 + 1) >> i) & 1 else (w | gh)
+        word = torch.where((lowbias32(base ^ 0x68E31DA4) >> 24) < frac8, gh, ge)
+        keep = (word[:, k >> 5] >> bit) & 1                                     # [N, N]
+        out[bh // heads, bh % heads] = keep.to(dtype) * (65536.0 / (65536.0 - thr16))
     return out

@@ -109,3 +109,50 @@ def load_reference():
 
 # examples/intermediate_downscaling.py:267-278 cannot be imported (pulls the whole package), and
 # it is 10 lines; era5_constants.py:83 gives CONSTANTS.  The oracle restates it.
+
+
+def load_reference_loaders():
+    """Imports the reference's ``climate_learn.utils.loaders`` UNMODIFIED (``load_architecture`` :259-378, ``load_loss``
+    :436-450 -- the construction seam of the drop-in) on top of ``load_reference()``.  Its package-level
+    imports pull the whole library, so the sub-packages are assembled by hand: the reference's own files are imported from
+    where they lie, only the data package (mpi4py / xarray readers) is a stand-in exposing the one name ``loaders`` needs."""
+    if "loaders" in _loaded:
+        return _loaded["loaders"]
+    ns = load_reference()
+    R = os.path.join(ns.root, "src", "climate_learn")
+    # third-party names the other hub models import (timm ViT blocks); never instantiated here
+    vt = sys.modules["timm.models.vision_transformer"]
+    for n in ("Block", "PatchEmbed"):
+        if not hasattr(vt, n):
+            setattr(vt, n, type(n, (nn.Module,), {}))
+    data = sys.modules.get("climate_learn.data") or _mod("climate_learn.data")
+    data.__path__ = [R + "/data"]
+    if not hasattr(data, "IterDataModule"):
+        data.IterDataModule = type("IterDataModule", (), {})
+    if "climate_learn.data.processing" not in sys.modules:
+        _mod("climate_learn.data.processing").__path__ = [R + "/data/processing"]
+    hub = sys.modules["climate_learn.models.hub"]
+    for sub, names in (("utils", ["MODEL_REGISTRY"]), ("climatology", ["Climatology"]), ("interpolation", ["Interpolation"]),
+                       ("linear_regression", ["LinearRegression"]), ("persistence", ["Persistence"]), ("resnet", ["ResNet"]),
+                       ("unet", ["Unet"]), ("vit", ["VisionTransformer"]), ("res_slimvit", ["Res_Slim_ViT"])):
+        m = importlib.import_module("climate_learn.models.hub." + sub)
+        for n in names:
+            setattr(hub, n, getattr(m, n))
+    models = sys.modules["climate_learn.models"]
+    models.MODEL_REGISTRY = hub.MODEL_REGISTRY
+    models.hub = hub
+    importlib.import_module("climate_learn.models.lr_scheduler")
+    if "climate_learn.transforms" not in sys.modules:
+        _mod("climate_learn.transforms").__path__ = [R + "/transforms"]
+    tr = sys.modules["climate_learn.transforms"]
+    tr.TRANSFORMS_REGISTRY = importlib.import_module("climate_learn.transforms.registry").TRANSFORMS_REGISTRY
+    for sub in ("denormalize", "mask"):
+        importlib.import_module("climate_learn.transforms." + sub)
+    met = sys.modules["climate_learn.metrics"]
+    mu = importlib.import_module("climate_learn.metrics.utils")
+    met.MetricsMetaInfo, met.METRICS_REGISTRY = mu.MetricsMetaInfo, mu.METRICS_REGISTRY
+    if ns.metrics is None:
+        raise RuntimeError("reference metrics module not importable: " + getattr(ns, "metrics_import_error", "?"))
+    loaders = importlib.import_module("climate_learn.utils.loaders")
+    _loaded["loaders"] = loaders
+    return loaders

@@ -18,7 +18,7 @@ struct AttnArgs {
   const float* qkv; float* out; float* lse;
   const float* dout; float* dqkv; float* delta;
   int B, N, heads, hd; float scale;
-  ptx::AttnDrop drop;        // thr8 == 0: no attention dropout
+  ptx::AttnDrop drop;        // thr16 == 0: no attention dropout
 };
 
 // scaled keep factor of element (q, k) of (batch, head) bh: 0 or 1 / keep_prob (mask function: common.cuh)
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const AttnArgs a) {
       m[i] = mn;
 #pragma unroll
       for (int c = 0; c < DC; ++c) o[i][c] *= alpha;
-      if (a.drop.thr8 > 0) {                  // P V uses the masked probabilities, l the unmasked ones
+      if (a.drop.thr16 > 0) {                  // P V uses the masked probabilities, l the unmasked ones
         const uint32_t key_bh = ptx::attn_drop_key(a.drop, blockIdx.y);
 #pragma unroll
         for (int j = 0; j < 4; ++j) s[i][j] *= drop_factor(a, key_bh, q0 + ty * 4 + i, k0 + tx * 4 + j);
@@ -229,7 +229,7 @@ __device__ __forceinline__ void recompute_p_ds(const AttnArgs& a, float (*qT)[BQ
     for (int j = 0; j < 4; ++j) {
       const bool ok = (q0 + ty * 4 + i < a.N) && (k0 + tx * 4 + j < a.N);
       p[i][j] = ok ? __expf(s[i][j] * a.scale - lse_s[ty * 4 + i]) : 0.f;
-      if (a.drop.thr8 > 0) {                  // dP = dP_drop o M; the returned p is the masked one (it feeds dV = P_drop^T dO)
+      if (a.drop.thr16 > 0) {                  // dP = dP_drop o M; the returned p is the masked one (it feeds dV = P_drop^T dO)
         const float f = drop_factor(a, ptx::attn_drop_key(a.drop, blockIdx.y), q0 + ty * 4 + i, k0 + tx * 4 + j);
         ds[i][j] = p[i][j] * (dp[i][j] * f - delta_s[ty * 4 + i]) * a.scale;
         p[i][j] *= f;
@@ -402,7 +402,7 @@ __device__ __forceinline__ void finish_p_ds(const AttnArgs& a, const float* lse_
     for (int j = 0; j < 4; ++j) {
       const bool ok = (q0 + ty * 4 + i < a.N) && (k0 + tx * 4 + j < a.N);
       p[i][j] = ok ? __expf(s[i][j] * a.scale - lse_s[ty * 4 + i]) : 0.f;
-      if (a.drop.thr8 > 0) {
+      if (a.drop.thr16 > 0) {
         const float f = drop_factor(a, ptx::attn_drop_key(a.drop, blockIdx.y), q0 + ty * 4 + i, k0 + tx * 4 + j);
         ds[i][j] = p[i][j] * (dp[i][j] * f - delta_s[ty * 4 + i]) * a.scale;
         p[i][j] *= f;

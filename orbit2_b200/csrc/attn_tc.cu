@@ -1430,30 +1430,20 @@ extern "C" int o2_debug_timeline(long long* host, int n) {
 
 template <int NH, bool kDrop>
 int launch_fwd(const CUtensorMap& tm, const FwdArgs& a, dim3 grid, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    O2_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<NH, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)FwdCfg<NH>::kSmemBytes));
-    attr_done = true;
-  }
+  O2_SET_SMEM_ONCE((attn_fwd_tc_kernel<NH, kDrop>), FwdCfg<NH>::kSmemBytes);
   attn_fwd_tc_kernel<NH, kDrop><<<grid, kThreadsB, FwdCfg<NH>::kSmemBytes, st>>>(tm, a);
   O2_LAUNCH_CHECK();
   return O2_OK;
 }
 
-// p -> (site key, 8-bit threshold + its plane masks, exact keep scale); p == 0 -> thr8 = 0 (kernels without the kDrop code)
+// p -> (site key, 16-bit drop threshold as two byte comparators + dither, exact keep scale); p == 0 -> thr16 = 0 (kernels without the kDrop code)
 ptx::AttnDrop make_drop(float p, uint64_t seed, uint32_t site, int N) { return ptx::make_attn_drop(p, seed, site, N); }
 
 template <int NH, bool kDrop>
 int launch_bwd(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const BwdArgs& a, int parts, cudaStream_t st) {
   using Cfg = BwdCfg<NH>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<NH, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kDqSmem));
-    O2_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<NH, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)Cfg::kDkvSmem + (kDrop ? 1024 : 0)));       // + the keep-word slots of the 8 softmax warps
-    attr_done = true;
-  }
+  O2_SET_SMEM_ONCE((attn_bwd_dq_kernel<NH, kDrop>), Cfg::kDqSmem);
+  O2_SET_SMEM_ONCE((attn_bwd_dkv_kernel<NH, kDrop>), Cfg::kDkvSmem + (kDrop ? 1024 : 0));   // + the keep-word slots of the 8 softmax warps
   const int rows_per_cta = Cfg::kTiles * BQ;
   dim3 grid((a.N + rows_per_cta - 1) / rows_per_cta, a.B * a.heads);
   if (parts & O2_ATTN_BWD_DKV) {
@@ -1463,11 +1453,7 @@ int launch_bwd(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const BwdArg
     // not by the tensor pipe (54 % busy) or MUFU (51 %).  profiles/r01_attn_experiments.md
     static const bool use_tm = getenv("O2_DKV_TM") != nullptr;
     if (NH == 1 && use_tm) {
-      static bool attr2 = false;
-      if (!attr2) {
-        O2_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tm_kernel<kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDkvTmSmem));
-        attr2 = true;
-      }
+      O2_SET_SMEM_ONCE((attn_bwd_dkv_tm_kernel<kDrop>), kDkvTmSmem);
       dim3 grid2((a.N + BKV - 1) / BKV, a.B * a.heads);
       attn_bwd_dkv_tm_kernel<kDrop><<<grid2, kThreadsB, kDkvTmSmem, st>>>(tm_qkv, tm_do, a);
     } else {
@@ -1500,7 +1486,7 @@ int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int hea
   dim3 grid((N + 2 * BQ - 1) / (2 * BQ), B * heads);
   a.drop = make_drop(p_drop, seed, site, N);
   O2_REQUIRE((long long)N * a.drop.nkb < (1ll << 32), "attn_fwd_tc: N=%d too large for the dropout word index", N);
-  if (a.drop.thr8 > 0) return hd == 64 ? launch_fwd<1, true>(tm, a, grid, st) : launch_fwd<2, true>(tm, a, grid, st);
+  if (a.drop.thr16 > 0) return hd == 64 ? launch_fwd<1, true>(tm, a, grid, st) : launch_fwd<2, true>(tm, a, grid, st);
   return hd == 64 ? launch_fwd<1, false>(tm, a, grid, st) : launch_fwd<2, false>(tm, a, grid, st);
 }
 
@@ -1539,7 +1525,7 @@ int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const flo
   a.scale = scale; a.scale_log2 = scale * kLog2e;
   a.drop = make_drop(p_drop, seed, site, N);
   O2_REQUIRE((long long)N * a.drop.nkb < (1ll << 32), "attn_bwd_tc: N=%d too large for the dropout word index", N);
-  if (a.drop.thr8 > 0)
+  if (a.drop.thr16 > 0)
     return hd == 64 ? launch_bwd<1, true>(tm_qkv, tm_do, a, parts, st) : launch_bwd<2, true>(tm_qkv, tm_do, a, parts, st);
   return hd == 64 ? launch_bwd<1, false>(tm_qkv, tm_do, a, parts, st) : launch_bwd<2, false>(tm_qkv, tm_do, a, parts, st);
 }

@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/o2b200.h"
 
 // ---------------------------------------------------------------- error plumbing
@@ -27,6 +29,18 @@ void o2_set_error(const char* fmt, ...);
       O2_FAIL(O2_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
   } while (0)
 #define O2_LAUNCH_CHECK() O2_CUDA(cudaGetLastError())
+// opt a kernel into > 48 KiB of dynamic shared memory exactly once per process, safely from concurrent host threads
+// (the header promises re-entrant entry points; one process drives one GPU)
+#define O2_SET_SMEM_ONCE(kernel, bytes)                                                                     \
+  do {                                                                                                      \
+    static std::once_flag once__;                                                                           \
+    static cudaError_t err__ = cudaSuccess;                                                                 \
+    std::call_once(once__, [&] {                                                                            \
+      err__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));      \
+    });                                                                                                     \
+    if (err__ != cudaSuccess)                                                                               \
+      O2_FAIL(O2_ERR_CUDA, "%s:%d cudaFuncSetAttribute(%s) -> %s", __FILE__, __LINE__, #kernel, cudaGetErrorString(err__)); \
+  } while (0)
 
 static inline int o2_num_sms() {
   static int n = 0;
@@ -292,18 +306,22 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 // 32 keys [32 kb, 32 kb + 32) of one query row q of one (batch, head):
 //     base   = lowbias32((q * nkb + kb) ^ key_bh)                       nkb = ceil(N / 32)
 //     w_i    = lo32(base * K_i) ^ hi32(base * K_i)    i = 0..7         (eight bit planes of a uniform byte U per key)
-//     keep   = (U >= thr8), evaluated on all 32 lanes of the planes at once, LSB plane first:
-//              ge = ~0;  ge = thr8 bit i ? (w_i & ge) : (w_i | ge)       -> one LOP3 per plane (tm[i] = bit i ? ~0 : 0)
+//     keep   = (U >= thr), evaluated on all 32 lanes of the planes at once, LSB plane first:
+//              ge = ~0;  ge = thr bit i ? (w_i & ge) : (w_i | ge)        -> one LOP3 per plane (tm[i] = bit i ? ~0 : 0)
 //     key kk = k & 31 reads bit 7 - (kk >> 2) + 8 (kk & 1) + 16 ((kk >> 1) & 1): the byte-msb order that lets PRMT's
 //     sign-replicate mode expand four decisions of (word << s) into bf16x2 / fp32 AND-masks.
-// key_bh = lowbias32(site_key ^ (b * heads + h) * 0x9E3779B1), thr8 = floor(p * 256); kept values are scaled by
-// 1 / (1 - thr8 / 256), the exact keep probability (oracle/dropout_mask.py restates this for the parity tests).
+// The drop probability has 16-bit resolution (like the token-stream dropout of dropout.cu): thr16 = floor(p * 65536) =
+// 256 hi8 + frac8, and the byte threshold of a WORD is hi8 + 1 with probability frac8 / 256 (dither byte
+// d = lowbias32(base ^ 0x68E31DA4) >> 24, d < frac8) and hi8 otherwise, so that P(drop) = thr16 / 65536 exactly
+// (p = 0.1 -> 0.099991, not 25 / 256 = 0.0977); both comparators are evaluated on the planes (8 more LOP3 per 32 keys).
+// key_bh = lowbias32(site_key ^ (b * heads + h) * 0x9E3779B1); kept values are scaled by 65536 / (65536 - thr16), the
+// exact keep probability (oracle/dropout_mask.py restates this for the parity tests).
 // Row-owner kernels (forward, dQ: thread = query row) build one word per 32 keys; the dK/dV kernels (thread = key row)
 // let lane l build the word of query q0 + l and read the others' by shuffle.
 struct AttnDrop {
-  uint32_t site_key, thr8, nkb;
+  uint32_t site_key, thr16, nkb, frac8;
   float inv_keep;
-  uint32_t tm[8];
+  uint32_t tm[8], tn[8];      // plane masks of the byte thresholds hi8 and hi8 + 1
 };
 __host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
   x ^= x >> 16; x *= 0x21f0aaadu;
@@ -318,14 +336,15 @@ __device__ __forceinline__ uint32_t attn_keep_word(const AttnDrop& d, uint32_t k
   constexpr uint32_t kMul[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu,
                                 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
   const uint32_t base = lowbias32((q * d.nkb + kb) ^ key_bh);
-  uint32_t ge = 0xFFFFFFFFu;
+  uint32_t ge = 0xFFFFFFFFu, gh = 0xFFFFFFFFu;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const uint64_t m = (uint64_t)base * kMul[i];
     const uint32_t w = (uint32_t)m ^ (uint32_t)(m >> 32);
     ge = (w & ge) | (~d.tm[i] & (w | ge));
+    gh = (w & gh) | (~d.tn[i] & (w | gh));
   }
-  return ge;
+  return ((lowbias32(base ^ 0x68E31DA4u) >> 24) < d.frac8) ? gh : ge;
 }
 // bit of the keep word that belongs to key k (see above)
 __host__ __device__ __forceinline__ uint32_t attn_keep_bit(uint32_t k) {
@@ -346,10 +365,17 @@ template <int T2, int E> __device__ __forceinline__ uint32_t keep_mask_f32(uint3
 inline AttnDrop make_attn_drop(float p, uint64_t seed, uint32_t site, int N) {
   AttnDrop d;
   d.site_key = lowbias32((uint32_t)seed ^ lowbias32(site ^ (uint32_t)(seed >> 32)));
-  d.thr8 = (uint32_t)floor((double)p * 256.0);
+  double pc = (double)p;
+  if (pc > 0.99) pc = 0.99;                                   // hi8 + 1 must stay a byte
+  d.thr16 = pc > 0.0 ? (uint32_t)floor(pc * 65536.0) : 0u;
+  d.frac8 = d.thr16 & 0xFFu;
+  const uint32_t hi8 = d.thr16 >> 8;
   d.nkb = (uint32_t)((N + 31) >> 5);
-  d.inv_keep = 256.f / (256.f - (float)d.thr8);
-  for (int i = 0; i < 8; ++i) d.tm[i] = ((d.thr8 >> i) & 1u) ? 0xFFFFFFFFu : 0u;
+  d.inv_keep = 65536.f / (65536.f - (float)d.thr16);
+  for (int i = 0; i < 8; ++i) {
+    d.tm[i] = ((hi8 >> i) & 1u) ? 0xFFFFFFFFu : 0u;
+    d.tn[i] = (((hi8 + 1u) >> i) & 1u) ? 0xFFFFFFFFu : 0u;
+  }
   return d;
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {

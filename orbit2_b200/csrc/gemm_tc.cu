@@ -353,11 +353,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 template <int BN, int MC>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& g, cudaStream_t st) {
   using C = Cfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    O2_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
-    attr_done = true;
-  }
+  O2_SET_SMEM_ONCE((gemm_tc_kernel<BN, MC>), C::kSmemBytes);
   const int num_work = ((g.num_m_blk + MC - 1) / MC) * g.num_n_blk * g.split_k;
   int ctas = num_work * MC < o2_num_sms() ? num_work * MC : o2_num_sms() / MC * MC;
   cudaLaunchConfig_t cfg;

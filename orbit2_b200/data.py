@@ -59,20 +59,25 @@ class NpzShardStream:
 
     def __init__(self, inp_files: Sequence[str], out_files: Sequence[str], in_vars: Sequence[str], out_vars: Sequence[str],
                  rank: int = 0, world: int = 1, div: int = 1, overlap: int = 4, subsample: int = 1, shuffle: bool = False,
-                 buffer_size: int = 0, seed: Optional[int] = None):
+                 buffer_size: int = 0, seed: Optional[int] = None, file_seed: int = 0):
         assert len(inp_files) == len(out_files)
         self.inp_files = [f for f in inp_files if "climatology" not in f]
         self.out_files = [f for f in out_files if "climatology" not in f]
         self.in_vars, self.out_vars = list(in_vars), list(out_vars)
         self.rank, self.world, self.div, self.overlap = rank, world, div, overlap
         self.subsample, self.shuffle, self.buffer_size = subsample, shuffle, buffer_size
+        # Two generators.  The FILE order must be the same permutation on every rank, otherwise the per-rank slices
+        # below overlap and some files are never read (the reference shuffles after seed_everything(0) on all ranks,
+        # iterdataset.py:46-80); it is seeded by ``file_seed`` alone and advances once per pass, so every epoch draws a
+        # new order that all ranks agree on.  The shuffle BUFFER is private to the rank (``seed``).
         self.rng = random.Random(seed)
+        self.file_rng = random.Random(file_seed)
 
     def _files(self):
         inp, out = list(self.inp_files), list(self.out_files)
         if self.shuffle:
             order = list(range(len(inp)))
-            self.rng.shuffle(order)
+            self.file_rng.shuffle(order)
             inp, out = [inp[i] for i in order], [out[i] for i in order]
         n = len(inp)
         if n < self.world:                          # wrap the list around when there are fewer files than ranks
@@ -189,7 +194,8 @@ class DownscalingData:
 
     def __init__(self, inp_root_dir: str, out_root_dir: str, in_vars: Sequence[str], out_vars: Sequence[str],
                  batch_size: int, device, rank: int = 0, world: int = 1, div: int = 1, overlap: int = 4, subsample: int = 1,
-                 buffer_size: int = 0, seed: Optional[int] = 0):
+                 buffer_size: int = 0, seed: Optional[int] = 0, file_seed: int = 0):
+        self.file_seed, self._epoch = file_seed, {}
         self.inp_root_dir, self.out_root_dir = inp_root_dir, out_root_dir
         self.in_vars, self.out_vars = list(in_vars), list(out_vars)
         self.batch_size, self.device, self.rank, self.world = batch_size, device, rank, world
@@ -224,5 +230,7 @@ class DownscalingData:
         inp, out = self._lists(split)
         stream = NpzShardStream(inp, out, self.in_vars, self.out_vars, self.rank, self.world, self.div, self.overlap,
                                 self.subsample, shuffle=train if shuffle is None else shuffle,
-                                buffer_size=self.buffer_size if train else 0, seed=self.seed)
+                                buffer_size=self.buffer_size if train else 0, seed=self.seed,
+                                file_seed=self.file_seed + 7919 * self._epoch.get(split, 0))
+        self._epoch[split] = self._epoch.get(split, 0) + 1            # same count on every rank -> same file order
         return DeviceCollator(stream, self.batch_size, self.in_stats, self.out_stats, self.device)

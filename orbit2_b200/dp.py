@@ -3,7 +3,7 @@ bucketed, overlapped gradient all-reduce (reference: FSDP NO_SHARD, examples/int
 gradients averaged over the data-parallel group)."""
 from __future__ import annotations
 
-from typing import Dict, List, Sequence, Tuple
+from typing import Optional, Dict, List, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -313,6 +313,39 @@ class FullShard:
         else:
             full.copy_(self.master[u])
         return full[lo:lo + shape.numel()].view(shape).clone()
+
+    def _gather_unit(self, shard: torch.Tensor, u: int) -> torch.Tensor:
+        full = torch.empty(self.S[u] * self.world, device=self.device, dtype=shard.dtype)
+        if self.world > 1:
+            dist.all_gather_into_tensor(full, shard, group=self.group)
+        else:
+            full.copy_(shard)
+        return full
+
+    def full_adam_state(self) -> Dict[str, Tuple[torch.Tensor, torch.Tensor]]:
+        """name -> (exp_avg, exp_avg_sq), fp32 on the host, gathered unit by unit (checkpoints); collective."""
+        out = {}
+        for u, names in enumerate(self.units):
+            m, v = self._gather_unit(self.m[u], u).cpu(), self._gather_unit(self.v[u], u).cpu()
+            for n in names:
+                _, lo, shape = self.where[n]
+                out[n] = (m[lo:lo + shape.numel()].view(shape).clone(), v[lo:lo + shape.numel()].view(shape).clone())
+        return out
+
+    def load_tensor(self, name: str, value: Optional[torch.Tensor] = None, exp_avg: Optional[torch.Tensor] = None,
+                    exp_avg_sq: Optional[torch.Tensor] = None):
+        """Overwrite this rank's slice of a weight (and / or its Adam moments) from FULL tensors (checkpoint resume);
+        local, every rank calls it with the same values.  ``after_step()`` must follow to re-gather the operands."""
+        u, lo, shape = self.where[name]
+        S, r = self.S[u], self.rank
+        a, b = max(lo, r * S), min(lo + shape.numel(), (r + 1) * S)      # overlap of the tensor with this rank's slice
+        if a >= b:
+            return
+        for src, dst in ((value, self.master[u]), (exp_avg, self.m[u]), (exp_avg_sq, self.v[u])):
+            if src is not None:
+                dst[a - r * S:b - r * S].copy_(src.reshape(-1)[a - lo:b - lo].to(dst.device, torch.float32))
+        if value is not None and self.lowp:
+            self.low[u][a - r * S:b - r * S].copy_(self.master[u][a - r * S:b - r * S])
 
     def persistent_bytes(self) -> int:
         per = sum(self.S) * (16 + (2 if self.lowp else 0))

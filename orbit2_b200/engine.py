@@ -139,6 +139,16 @@ class TrainEngine:
         self._train_runs = None
         self._lat = None
         self._chw = None
+        # The module's own forward (validation, tiled inference, the public-API training path) must see the operands
+        # this engine maintains: the fused AdamW updates the flat fp32 master through raw pointers, so neither
+        # ``_version`` nor ``data_ptr()`` of a parameter changes and a bf16 copy cached by the module would go stale
+        # after the first optimizer step.  Replicated bf16: the flat bf16 buffer AdamW refreshes.  FULL_SHARD: lookups
+        # gather the unit (``external_begin`` restarts the forward prefetch order before every module forward).
+        if self.fs is not None:
+            model.external_wc = ChainedMap(self.Wc if self.flat_b is not None else self.P, self.fs.params)
+            model.external_begin = lambda: self.fs.begin(+1)
+        elif self.flat_b is not None:
+            model.external_wc = self.Wc
         # CUDA-graph mode (enable_graph): the whole step is captured once and replayed; see graph_step
         self._graph = None
         self._graph_warm = 0

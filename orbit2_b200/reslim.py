@@ -351,10 +351,10 @@ class ReslimFunction(torch.autograd.Function):
             p = p.detach()
             is_gemm_w = n.endswith(".weight") and p.dim() == 2
             P[n] = p if (is_gemm_w and lowp) else _f32(p)        # big GEMM weights are never up-cast
-        if not lowp:
-            Wc = P
-        elif Wc_in is not None:
+        if Wc_in is not None:                  # operands maintained by a training engine (bf16 copy / sharded units)
             Wc = Wc_in
+        elif not lowp:
+            Wc = P
         else:
             Wc = {n: (P[n] if P[n].dtype == g.act else ops.cast_bf16(P[n].contiguous()))
                   for n in names if n.endswith(".weight") and P[n].dim() == 2}
@@ -443,7 +443,9 @@ class Res_Slim_ViT(nn.Module):
         self.initialize_weights()
         self._names = kernel_param_names(depth, decoder_depth)
         self._wc_cache = None           # (versions, dict) bf16 copies of the GEMM weights
-        self.external_wc = None         # set by the training engine (flat bf16 buffer refreshed by fused AdamW)
+        self.external_wc = None         # set by TrainEngine.__init__: the operands it keeps fresh (flat bf16 buffer
+                                        # refreshed by the fused AdamW, or the FULL_SHARD gather-on-lookup mapping)
+        self.external_begin = None      # FULL_SHARD: called before every module forward (restarts the unit prefetch)
         self._warned_drop = False
 
     # res_slimvit.py:125-145
@@ -532,10 +534,12 @@ class Res_Slim_ViT(nn.Module):
         return sd
 
     def gemm_weights(self, act, params: Dict[str, torch.Tensor]):
+        if self.external_wc is not None:
+            if self.external_begin is not None:
+                self.external_begin()
+            return self.external_wc
         if act == torch.float32:
             return None
-        if self.external_wc is not None:
-            return self.external_wc
         names = [n for n in self._names if n.endswith(".weight") and params[n].dim() == 2]
         vers = tuple(params[n]._version for n in names) + tuple(params[n].data_ptr() for n in names)
         if self._wc_cache is not None and self._wc_cache[0] == vers:

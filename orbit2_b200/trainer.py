@@ -74,9 +74,13 @@ def build(conf: dict, data_key: str, img_size: Tuple[int, int], device, pos_grid
     meta = losses.MetricsMetaInfo(in_vars, out_vars, None, None)
     loss = losses.METRICS_REGISTRY[t["train_loss"]](aggregate_only=True, metainfo=meta)
     m = conf["model"]
+    full_shard = bool(int(os.environ.get("O2_FULL_SHARD", "0")))
     eng = TrainEngine(model, loss, in_vars, out_vars, d["var_weights"], lr=float(m["lr"]),
                       betas=(float(m["beta_1"]), float(m["beta_2"])), weight_decay=float(m["weight_decay"]),
-                      shard_optimizer=int(conf["parallelism"].get("fsdp", 1)) > 1,     # fsdp > 1 in the YAML -> sharded mode
+                      # fsdp > 1 in the YAML -> sharded Adam state + update; O2_FULL_SHARD=1 / trainer --full-shard ->
+                      # FSDP FULL_SHARD (per-Block weight shards, needed for interm_10b: intermediate_downscaling.py:615-617)
+                      shard_optimizer=int(conf["parallelism"].get("fsdp", 1)) > 1 and not full_shard,
+                      shard_params=full_shard,
                       # bf16 branch of the reference: ShardedGradScaler(init_scale=8192, growth_interval=100), floor 128
                       # (intermediate_downscaling.py:493-495, 733-742)
                       grad_scaler=GradScaler() if (dtype == torch.bfloat16 and not int(os.environ.get("O2_GRAPH", "0")))
@@ -89,22 +93,41 @@ def build(conf: dict, data_key: str, img_size: Tuple[int, int], device, pos_grid
 
 
 # ------------------------------------------------------------------------------------------------ checkpoints
-def optimizer_state_dict(eng: TrainEngine) -> dict:
-    """torch.optim.AdamW.state_dict() layout for the engine's flat Adam state."""
+def _adam_moments(eng: TrainEngine) -> Dict[str, Tuple[torch.Tensor, torch.Tensor]]:
+    """name -> (exp_avg, exp_avg_sq) on the host for EVERY trained parameter, whatever the sharding mode.  Collective
+    when the Adam state is sharded (``shard_optimizer``: one all-gather of the flat m / v; FULL_SHARD: one per unit)."""
     if eng.sharded:
-        raise NotImplementedError("checkpointing the sharded Adam state (gather to rank 0) is not implemented yet")
-    state, ids = {}, []
-    for i, n in enumerate(eng.names):
-        ids.append(i)
-        if n in eng.frozen or eng.step_count == 0:
+        m = torch.empty(eng.shard * eng.world, device=eng.device, dtype=torch.float32)
+        v = torch.empty_like(m)
+        dist.all_gather_into_tensor(m, eng.flat_m, group=eng.pg)
+        dist.all_gather_into_tensor(v, eng.flat_v, group=eng.pg)
+    else:
+        m, v = eng.flat_m, eng.flat_v
+    out = {}
+    for n in eng.names:
+        if n in eng.frozen:
             continue
         lo, hi = eng.layout.range[n]
         shape = eng.P[n].shape
-        state[i] = {"step": torch.tensor(float(eng.step_count)), "exp_avg": eng.flat_m[lo:hi].view(shape).clone(),
-                    "exp_avg_sq": eng.flat_v[lo:hi].view(shape).clone()}
+        out[n] = (m[lo:hi].view(shape).cpu().clone(), v[lo:hi].view(shape).cpu().clone())
+    if eng.fs is not None:
+        out.update(eng.fs.full_adam_state())
+    return out
+
+
+def optimizer_state_dict(eng: TrainEngine) -> dict:
+    """torch.optim.AdamW.state_dict() layout (parameter ids in ``model.named_parameters()`` order, like an optimizer
+    built from ``model.parameters()``: intermediate_downscaling.py:642-644) for the engine's Adam state.  Collective in
+    the sharded modes: every rank calls it, the result is complete on every rank."""
+    order = [n for n, _ in eng.model.named_parameters()]
+    mom = _adam_moments(eng) if eng.step_count > 0 else {}
+    state = {}
+    for i, n in enumerate(order):
+        if n in mom:
+            state[i] = {"step": torch.tensor(float(eng.step_count)), "exp_avg": mom[n][0], "exp_avg_sq": mom[n][1]}
     group = {"lr": eng.lr, "betas": tuple(eng.betas), "eps": eng.eps, "weight_decay": eng.weight_decay, "amsgrad": False,
              "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
-             "params": ids}
+             "params": list(range(len(order)))}
     return {"state": state, "param_groups": [group]}
 
 
@@ -113,17 +136,27 @@ def load_optimizer_state_dict(eng: TrainEngine, sd: dict):
     eng.lr, eng.betas, eng.eps, eng.weight_decay = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
     steps = [int(float(s["step"])) for s in sd["state"].values()]
     eng.step_count = max(steps) if steps else 0
+    order = [n for n, _ in eng.model.named_parameters()]
+    o0, o1 = eng.own
     for i, st in sd["state"].items():
-        n = eng.names[int(i)]
+        n = order[int(i)]
+        if eng.fs is not None and n in eng.fs.where:
+            eng.fs.load_tensor(n, exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"])
+            continue
         lo, hi = eng.layout.range[n]
-        eng.flat_m[lo:hi].copy_(st["exp_avg"].reshape(-1))
-        eng.flat_v[lo:hi].copy_(st["exp_avg_sq"].reshape(-1))
+        a, b = max(lo, o0), min(hi, o1)                    # sharded optimizer: this rank keeps its slice of the moments
+        if a < b:
+            eng.flat_m[a - o0:b - o0].copy_(st["exp_avg"].reshape(-1)[a - lo:b - lo])
+            eng.flat_v[a - o0:b - o0].copy_(st["exp_avg_sq"].reshape(-1)[a - lo:b - lo])
 
 
 def save_checkpoint(path: str, epoch: int, eng: TrainEngine, sched: dict):
-    torch.save({"epoch": epoch, "model_state_dict": {k: v.detach().cpu().clone() for k, v in eng.model.state_dict().items()},
-                "optimizer_state_dict": None if eng.sharded else optimizer_state_dict(eng),   # sharded: model only for now
-                "scheduler_state_dict": dict(sched)}, path)
+    """The reference's checkpoint (intermediate_downscaling.py:775-791).  EVERY rank calls this (the sharded modes gather
+    the weights and the Adam moments collectively); rank 0 writes the file."""
+    ck = {"epoch": epoch, "model_state_dict": {k: v.detach().cpu() for k, v in eng.full_state_dict().items()},
+          "optimizer_state_dict": optimizer_state_dict(eng), "scheduler_state_dict": dict(sched)}
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        torch.save(ck, path)
 
 
 def load_checkpoint(path: str, eng: TrainEngine) -> int:
@@ -132,12 +165,17 @@ def load_checkpoint(path: str, eng: TrainEngine) -> int:
     with torch.no_grad():
         sd = ck["model_state_dict"]
         for n, p in eng.model.named_parameters():
-            p.copy_(sd[n].to(p.device))                    # parameters are views of the flat master buffer
+            if eng.fs is not None and n in eng.fs.where:
+                eng.fs.load_tensor(n, value=sd[n])
+            else:
+                p.copy_(sd[n].to(p.device))                # parameters are views of the flat master buffer
         if eng.flat_b is not None:
             from . import ops
             ops.cast_bf16(eng.flat_p, eng.flat_b)
-    if "optimizer_state_dict" in ck:
+    if ck.get("optimizer_state_dict") is not None:         # model-only checkpoints (older sharded runs) resume the weights
         load_optimizer_state_dict(eng, ck["optimizer_state_dict"])
+    if eng.fs is not None:
+        eng.fs.after_step()                                # the gathered operand copies are stale
     return int(ck["epoch"]) + 1
 
 
@@ -294,9 +332,9 @@ def train(conf: dict, data_key: str, grid, epochs: int, steps_per_epoch: int, ck
         if rank == 0:
             log(f"epoch {epoch} lr {eng.lr:.3e} loss {mean:.5f} {n * B * world / dt:.2f} samples/s"
                 + ("" if val is None else " val " + " ".join(f"{k} {v:.5f}" for k, v in val.items())), flush=True)
-            if ckpt_dir:
-                os.makedirs(ckpt_dir, exist_ok=True)
-                save_checkpoint(os.path.join(ckpt_dir, f"interm_epoch_{epoch}.ckpt"), epoch, eng, dict(sched, last_epoch=epoch + 1))
+        if ckpt_dir:                                       # every rank: the sharded modes gather collectively
+            os.makedirs(ckpt_dir, exist_ok=True)
+            save_checkpoint(os.path.join(ckpt_dir, f"interm_epoch_{epoch}.ckpt"), epoch, eng, dict(sched, last_epoch=epoch + 1))
         if dist.is_initialized():
             dist.barrier()
     return hist, eng
@@ -313,6 +351,8 @@ def main():
     ap.add_argument("--checkpoint-dir", default=None)
     ap.add_argument("--resume", default=None)
     ap.add_argument("--act-ckpt", action="store_true", help="per-Block activation recomputation (the reference's default)")
+    ap.add_argument("--full-shard", action="store_true", help="FSDP FULL_SHARD: per-Block weight / gradient / Adam shards "
+                    "(interm_1b / interm_10b); default is the YAML's parallelism.fsdp -> sharded optimizer")
     ap.add_argument("--graph", action="store_true", help="replay the training step as one captured CUDA graph (one GPU, "
                     "dropout 0; for launch-bound configurations such as interm_8m)")
     a = ap.parse_args()
@@ -320,6 +360,8 @@ def main():
         os.environ["O2_ACT_CKPT"] = "1"
     if a.graph:
         os.environ["O2_GRAPH"] = "1"
+    if a.full_shard:
+        os.environ["O2_FULL_SHARD"] = "1"
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:

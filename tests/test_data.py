@@ -113,6 +113,19 @@ def test_rank_partition_and_wraparound(tmp_path):
         assert all(len(g) == max(1, 3 // world) for g in got)
         if world <= 3:
             assert sorted(sum(got, [])) == fi[:len(sum(got, []))]
+    # shuffled training lists: every rank must slice the SAME permutation even though each rank has its own sample
+    # seed (trainer.npz_data passes seed=rank), so the shards are disjoint and cover every file (iterdataset.py:46-80)
+    inp8, out8 = make_shards(str(tmp_path / "eight"), n_files=8, n_t=1)
+    f8i, f8o = sorted(glob.glob(inp8 + "/train/*.npz")), sorted(glob.glob(out8 + "/train/*.npz"))
+    for world in (2, 4, 8):
+        streams = [D.NpzShardStream(f8i, f8o, IN_VARS, OUT_VARS, rank=r, world=world, shuffle=True, seed=r)
+                   for r in range(world)]
+        orders = []
+        for epoch in range(3):
+            got = [s._files()[0] for s in streams]
+            assert sorted(sum(got, [])) == f8i, (world, epoch, got)
+            orders.append(sum(got, []))
+        assert orders[0] != orders[1] or orders[1] != orders[2]          # the order changes between epochs
     dm = D.DownscalingData(inp, out, IN_VARS, OUT_VARS, batch_size=2, device="cpu", div=2, overlap=2)
     (_, V, h, w), (_, C, H, W) = dm.get_data_dims()
     x, y = next(iter(D.NpzShardStream(fi, fo, IN_VARS, OUT_VARS, div=2, overlap=2)))

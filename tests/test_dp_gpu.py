@@ -39,7 +39,7 @@ def _same_params(a, b, dtype):
 
 
 @pytest.mark.parametrize("dtype,ckpt", [(torch.float32, False), (torch.bfloat16, True)])
-def test_full_shard_world1_equals_replicated(dtype, ckpt):
+def test_full_shard_world1_equals_replicated(dtype, ckpt, tmp_path):
     """FULL_SHARD engine on one GPU (gathers are copies): the lookup-driven unit hand-over, the two rotating weight /
     gradient slots and the per-shard AdamW reproduce the replicated engine step for step."""
     from oracle import cases, reslim_oracle as O
@@ -56,9 +56,33 @@ def test_full_shard_world1_equals_replicated(dtype, ckpt):
         assert abs(va[-1].item() - vb[-1].item()) <= (1e-5 if dtype == torch.float32 else 5e-3) * abs(va[-1].item())
     bad = _same_params(a, b, dtype)
     assert not bad, bad
+    assert _ckpt_roundtrip(b, lambda: _make(cfg, sd, "cuda:0", dtype=dtype, full_shard=True, ckpt=ckpt), x.cuda(), y.cuda(),
+                           str(tmp_path))
 
 
-def _worker(rank, world, port, ret):
+def _ckpt_roundtrip(eng, make, x, y, ckdir):
+    """save_checkpoint (collective gathers in the sharded modes, rank 0 writes) -> a fresh engine of the same mode resumes
+    and takes the same next step: weights, Adam moments, step count and bias correction all survived."""
+    from orbit2_b200 import trainer
+    path = os.path.join(ckdir, f"ck_{eng.sharded}_{eng.fs is not None}_{eng.act}.ckpt")
+    trainer.save_checkpoint(path, 4, eng, {"last_epoch": 5})
+    if dist.is_initialized():
+        dist.barrier()
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    ok = ck["optimizer_state_dict"] is not None and len(ck["optimizer_state_dict"]["state"]) > 0
+    opt = torch.optim.AdamW([torch.nn.Parameter(v.clone()) for v in ck["model_state_dict"].values()], lr=1.0)
+    opt.load_state_dict(ck["optimizer_state_dict"])        # the reference's optimizer accepts it (param order + shapes)
+    eng2 = make()
+    ok = ok and trainer.load_checkpoint(path, eng2) == 5 and eng2.step_count == eng.step_count
+    va, vb = eng.step(x, y), eng2.step(x, y)
+    torch.cuda.synchronize()
+    sa, sb = eng.full_state_dict(), eng2.full_state_dict()
+    tol = 1e-6 if eng.act == torch.float32 else 2e-3
+    bad = [k for k in sa if (sa[k] - sb[k]).abs().max().item() > tol * sa[k].abs().max().item() + 1e-8]
+    return ok and not bad and abs(va[-1].item() - vb[-1].item()) <= 5e-3 * abs(va[-1].item())
+
+
+def _worker(rank, world, port, ret, ckdir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -86,6 +110,8 @@ def _worker(rank, world, port, ret):
         ret[f"shard{rank}{dtype}"] = bool(torch.allclose(a.flat_p[:n], b.flat_p[:n], rtol=1e-5, atol=1e-7)) and \
             (a.flat_b is None or bool(torch.equal(a.flat_b[:n], b.flat_b[:n]) or
                                       (a.flat_b[:n].float() - b.flat_b[:n].float()).abs().max().item() < 1e-2))
+        ret[f"shard-ckpt{rank}{dtype}"] = _ckpt_roundtrip(b, lambda: _make(cfg, sd, f"cuda:{rank}", shard=True, dtype=dtype),
+                                                          x[2 * rank:2 * rank + 2].cuda(), y[2 * rank:2 * rank + 2].cuda(), ckdir)
     # FULL_SHARD (per-Block all-gather / reduce-scatter, sharded master + Adam) against plain data parallel
     for dtype, ckpt in ((torch.float32, False), (torch.bfloat16, True)):
         a = _make(cfg, sd, f"cuda:{rank}", dtype=dtype, ckpt=ckpt)
@@ -98,15 +124,18 @@ def _worker(rank, world, port, ret):
         torch.cuda.synchronize()
         bad = _same_params(a, b, dtype)
         ret[f"shard-full{rank}{dtype}"] = not bad
+        ret[f"shard-full-ckpt{rank}{dtype}"] = _ckpt_roundtrip(
+            b, lambda: _make(cfg, sd, f"cuda:{rank}", dtype=dtype, full_shard=True, ckpt=ckpt),
+            x[2 * rank:2 * rank + 2].cuda(), y[2 * rank:2 * rank + 2].cuda(), ckdir)
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_ranks_equal_one_rank_full_batch():
+def test_two_ranks_equal_one_rank_full_batch(tmp_path):
     from oracle import cases, reslim_oracle as O
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), ret, str(tmp_path)), nprocs=2, join=True)
     cfg = cases.get_case("tiny")
     sd = O.init_state_dict(cfg, seed=9)
     x, y = O.synthetic_batch(cfg, 4, cfg["in_vars"], cfg["out_vars"], seed=9)

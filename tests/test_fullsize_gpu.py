@@ -187,3 +187,57 @@ def test_model_117m_batch_independence_and_grad_linearity():
         if e > 2e-2:
             bad[k] = e
     assert not bad, bad
+
+
+def test_model_117m_whole_model_vs_oracle():
+    """BASELINE configs[1] itself -- interm_117m on its full 180x360 -> 720x1440 grid (L = 16200 tokens, 126 M parameters),
+    B = 1, the shipped Bayesian-TV training loss -- against the CPU oracle (res_slimvit.py:312-338 forward,
+    intermediate_downscaling.py:281-306 training_step; fp32 with SDPA attention, the reference's FusedAttn.DEFAULT path:
+    the explicit-softmax float64 path needs 16.8 GB per block at this length) on the SAME seeded weights and batch:
+    prediction, loss vector and EVERY parameter gradient, fp32 arm at 1e-4 and bf16 arm at 2e-2 (north_star)."""
+    import os
+    from oracle import cases, reslim_oracle as O
+    cfg = cases.get_case("117m")
+    sd = O.init_state_dict(cfg, seed=0)
+    x, y = O.synthetic_batch(cfg, 1, cfg["in_vars"], cfg["out_vars"], seed=0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    old = O.USE_SDPA
+    O.USE_SDPA = True
+    try:
+        sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        taps = {}
+        loss = O.training_step(sdr, cfg, x, y, cfg["in_vars"], cfg["out_vars"], "bayesian_tv", cfg["var_weights"], None, taps)
+        loss.backward()
+    finally:
+        O.USE_SDPA = old
+    pred_ref = taps["preds"].detach()
+    gref = {k: v.grad for k, v in sdr.items() if v.grad is not None and v.grad.abs().max() > 0}
+    assert len(gref) >= 150                                  # 23 patch embeds, 8 blocks x 12, head, convs, embeddings
+    from orbit2_b200 import losses
+    from tests.util import build_model
+    report = {}
+    for dtype, tol, gtol in ((torch.float32, 1e-4, 1e-4), (torch.bfloat16, 2e-2, 2e-2)):
+        m = build_model(cfg, sd, "cuda", dtype)
+        m.train()
+        meta = losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None)
+        loss_fn = losses.METRICS_REGISTRY["bayesian_tv"](aggregate_only=False, metainfo=meta)
+        pred = m(x.cuda(), cfg["in_vars"], cfg["out_vars"])
+        vec = loss_fn(pred, y.cuda(), var_names=cfg["out_vars"], var_weights=cfg["var_weights"],
+                      clip_out_variables=cfg["out_vars"])
+        vec[-1].backward()
+        torch.cuda.synchronize()
+        # the oracle's tap is the clipped prediction; clip ours the same way (channel 0 = precipitation, clamp at 0)
+        pc = pred.detach().float().clone()
+        pc[:, 0].clamp_(min=0)
+        e_pred = rel(pc, pred_ref)
+        e_loss = abs(vec[-1].item() - loss.item()) / abs(loss.item())
+        grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+        worst = {k: rel(grads[k], g) for k, g in gref.items()}
+        top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+        report[str(dtype)] = dict(pred=e_pred, loss=e_loss, worst_grads=top)
+        print(f"117m whole-model parity {dtype}: pred {e_pred:.3e} loss {e_loss:.3e} worst grads {top}")
+        assert e_pred < tol and e_loss < tol, report
+        bad = {k: v for k, v in worst.items() if v > gtol}
+        assert not bad, (dtype, bad)
+        del m, pred, vec, grads
+        torch.cuda.empty_cache()

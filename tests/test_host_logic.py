@@ -128,22 +128,35 @@ def test_attn_keep_mask_restatement():
 
     seed, site, N, heads = 0x1234_5678_9ABC_DEF0, 17, 70, 2
     for p in (0.1, 0.35):
-        thr8 = math.floor(p * 256)
+        thr16 = math.floor(p * 65536)
+        hi8, frac8 = thr16 >> 8, thr16 & 0xFF
         m = DM.attn_scaled_mask(seed, site, 1, heads, N, p)
         nkb = (N + 31) // 32
         key = lb(DM.site_key(seed, site) ^ ((1 * 0x9E3779B1) & M32))          # (b, h) = (0, 1)
         for q, k in ((0, 0), (3, 31), (5, 32), (69, 69), (17, 40), (64, 2)):
-            base, ge = lb(((q * nkb + (k >> 5)) & M32) ^ key), M32
+            base = lb(((q * nkb + (k >> 5)) & M32) ^ key)
+            thr, ge = hi8 + (1 if (lb(base ^ 0x68E31DA4) >> 24) < frac8 else 0), M32      # dithered byte threshold
             for i, mul in enumerate(DM._KEEP_MUL):
                 w = ((base * mul) & M32) ^ ((base * mul) >> 32)
-                ge = (w & ge) if (thr8 >> i) & 1 else (w | ge)
+                ge = (w & ge) if (thr >> i) & 1 else (w | ge)
             kk = k & 31
             bit = 7 - (kk >> 2) + 8 * (kk & 1) + 16 * ((kk >> 1) & 1)
-            want = ((ge >> bit) & 1) * 256.0 / (256.0 - thr8)
+            want = ((ge >> bit) & 1) * 65536.0 / (65536.0 - thr16)
             assert float(m[0, 1, q, k]) == want
     assert sorted(int(b) for b in DM.attn_keep_bit(torch.arange(32))) == list(range(32))
     big = DM.attn_scaled_mask(seed, site, 1, 1, 512, 0.1)
-    assert abs(float((big > 0).double().mean()) - (1 - 25 / 256)) < 3e-3
+    assert abs(float((big > 0).double().mean()) - (1 - math.floor(0.1 * 65536) / 65536)) < 2e-3   # 0.1 to 16 bits, not 25 / 256
+    # the exact byte decision U >= thr: the keep word must equal a direct comparison of the reconstructed bytes
+    nkb = 512 // 32
+    key0 = lb(DM.site_key(seed, site))
+    for q, kb in ((0, 0), (100, 7), (511, 15)):
+        base = lb(((q * nkb + kb) & M32) ^ key0)
+        planes = [(((base * mul) & M32) ^ ((base * mul) >> 32)) for mul in DM._KEEP_MUL]
+        thr = (math.floor(0.1 * 65536) >> 8) + (1 if (lb(base ^ 0x68E31DA4) >> 24) < (math.floor(0.1 * 65536) & 0xFF) else 0)
+        for kk in range(32):
+            bit = 7 - (kk >> 2) + 8 * (kk & 1) + 16 * ((kk >> 1) & 1)
+            U = sum(((planes[i] >> bit) & 1) << i for i in range(8))
+            assert (float(big[0, 0, q, 32 * kb + kk]) > 0) == (U >= thr)
     assert abs(float(big.mean()) - 1.0) < 4e-3                                  # E[mask] = 1: kept values carry 1 / keep_prob
 
 

@@ -95,6 +95,51 @@ def test_short_run_and_checkpoint_roundtrip(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["replicated", "full_shard"])
+def test_module_forward_sees_engine_updates(mode):
+    """The engine's fused AdamW updates the parameters through raw pointers (no ``_version`` bump): the module's own
+    forward (validation, tiled inference) must still run on the CURRENT weights.  Regression test for a stale bf16 operand
+    cache: module forward after further engine steps == a fresh module loaded from ``full_state_dict()``."""
+    from oracle import cases, reslim_oracle as O
+    from orbit2_b200 import engine, losses
+    from orbit2_b200.reslim import Res_Slim_ViT
+    cfg = cases.get_case("tiny")
+
+    def make():
+        m = Res_Slim_ViT(cfg["default_vars"], cfg["init_img_size"], len(cfg["default_vars"]), cfg["out_channels"], 1,
+                         patch_size=cfg["patch_size"], drop_path=0.0, drop_rate=0.0, learn_pos_emb=True,
+                         embed_dim=cfg["embed_dim"], depth=cfg["depth"], decoder_depth=cfg["decoder_depth"],
+                         num_heads=cfg["num_heads"], compute_dtype=torch.bfloat16)
+        m.spatial_resolution = cfg["spatial_resolution"]
+        return m
+    model = make()
+    model.load_state_dict(O.init_state_dict(cfg, seed=3))
+    model = model.cuda()
+    meta = losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None)
+    eng = engine.TrainEngine(model, losses.METRICS_REGISTRY["mse"](aggregate_only=True, metainfo=meta), cfg["in_vars"],
+                             cfg["out_vars"], cfg["var_weights"], lr=1e-2, shard_params=(mode == "full_shard"))
+    x, y = O.synthetic_batch(cfg, 2, cfg["in_vars"], cfg["out_vars"], seed=3)
+    x, y = x.cuda(), y.cuda()
+    eng.step(x, y)
+    model.eval()
+    with torch.no_grad():
+        first = model(x, cfg["in_vars"], cfg["out_vars"]).float().clone()       # a validation pass in between
+    model.train()
+    for _ in range(3):
+        eng.step(x, y)
+    model.eval()
+    with torch.no_grad():
+        got = model(x, cfg["in_vars"], cfg["out_vars"]).float()
+    fresh = make()
+    fresh.load_state_dict(eng.full_state_dict())
+    fresh = fresh.cuda().eval()
+    with torch.no_grad():
+        want = fresh(x, cfg["in_vars"], cfg["out_vars"]).float()
+    assert (want - first).abs().max() > 1e-3                  # the weights did move (lr 1e-2)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.gpu
 def test_npz_shards_training_and_validation(tmp_path):
     """The reference's shard layout end to end: raw npz -> GPU normalisation -> training steps -> validation metrics."""
     from orbit2_b200 import trainer
