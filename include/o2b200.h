@@ -91,13 +91,28 @@ int o2_attn_bwd_parts(int impl, int parts, const void* qkv, const void* out, con
 /* Training-mode variants with attention-probability dropout (attention.py:56,69,75: attn_drop on softmax(QK^T)): the output
  * uses P o keep / keep_prob, the softmax normaliser the unmasked P; the backward regenerates the same mask from
  * (seed, site) -- it is never stored.  keep(b, h, q, k) is one bit of a counter-based, bit-sliced 32-bit keep word per
- * (q, 32-key block) (csrc/common.cuh, restated in oracle/dropout_mask.py); p is quantised to floor(p * 256) / 256 and kept
- * values are scaled by the exact keep probability.  p_drop = 0 is identical to the plain entry points. */
+ * (q, 32-key block) (csrc/common.cuh, restated in oracle/dropout_mask.py); p is quantised to floor(p * 65536) / 65536 (a
+ * dithered byte threshold per keep word) and kept values are scaled by the exact keep probability.  p_drop = 0 is identical to the plain entry points. */
 int o2_attn_fwd_drop(int impl, const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale,
                      float p_drop, uint64_t seed, uint32_t site, void* stream);
 int o2_attn_bwd_parts_drop(int impl, int parts, const void* qkv, const void* out, const void* dout, const float* lse,
                            void* dqkv, float* delta, int B, int N, int heads, int hd, float scale, float p_drop,
                            uint64_t seed, uint32_t site, void* stream);
+
+/* One-pass backward for head dim 64 on the tcgen05 arm (bf16): S = QK^T and dP = dO V^T are computed ONCE per (key tile,
+ * query tile) pair -- 5 GEMMs and one softmax pass instead of the 7 + 2 of the two-kernel path above.  dK / dV accumulate
+ * in tensor memory (single owner, exact); the dQ partial of every 128-key tile is added into `workspace` (fp32
+ * [B, heads, N, hd], zero-filled by the call) by TMA reduce (L2 fp32 atomics: dQ is reproducible to fp32 rounding, not
+ * bit for bit -- o2_attn_bwd_parts remains the deterministic option) and a last pass writes dQ = scale * workspace as
+ * bf16.  Same dropout contract as o2_attn_bwd_parts_drop.  `parts` selects the launches so that a caller can time them:
+ * O2_ATTN_BWD_DELTA, O2_ATTN_BWD_FUSED (workspace memset + the fused kernel), O2_ATTN_BWD_DQ_FINISH.
+ * o2_attn_bwd_fused_workspace() = bytes the caller must provide (the reference has no counterpart: attention.py:54-78
+ * leaves the backward to autograd / the FMHA library). */
+enum { O2_ATTN_BWD_FUSED = 8, O2_ATTN_BWD_DQ_FINISH = 16, O2_ATTN_BWD_FUSED_ALL = 1 | 8 | 16 };
+size_t o2_attn_bwd_fused_workspace(int B, int N, int heads, int hd);
+int o2_attn_bwd_fused(int parts, const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                      float* delta, void* workspace, size_t ws_bytes, int B, int N, int heads, int hd, float scale,
+                      float p_drop, uint64_t seed, uint32_t site, void* stream);
 
 /* ---- front end: per-variable patch embedding + variable embedding + variable aggregation ---------
  * replaces res_slimvit.py:254-265 (23x PatchEmbed conv, var_embed add, aggregate_variables) and

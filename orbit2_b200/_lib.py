@@ -30,6 +30,8 @@ SIGNATURES = {
     "o2_attn_bwd_parts": ([_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p], _i),
     "o2_attn_fwd_drop": ([_i, _p, _p, _p, _i, _i, _i, _i, _f, _f, C.c_uint64, _u, _p], _i),
     "o2_attn_bwd_parts_drop": ([_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, C.c_uint64, _u, _p], _i),
+    "o2_attn_bwd_fused_workspace": ([_i, _i, _i, _i], C.c_size_t),
+    "o2_attn_bwd_fused": ([_i, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _i, _i, _i, _i, _f, _f, C.c_uint64, _u, _p], _i),
     "o2_frontend_fwd": ([_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
     "o2_frontend_bwd": ([_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
     "o2_path2_conv1_fwd": ([_p, C.POINTER(C.c_int), _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),

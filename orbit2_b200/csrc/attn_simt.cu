@@ -679,6 +679,25 @@ extern "C" int o2_attn_bwd_parts_drop(int impl, int parts, const void* qkv, cons
   O2_FAIL(O2_ERR_ARG, "attn_bwd: unknown impl %d", impl);
 }
 
+int o2_attn_bwd_fused_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
+                         float* dq_accum, int B, int N, int heads, int hd, float scale, int parts, float p_drop,
+                         uint64_t seed, uint32_t site, cudaStream_t st);
+
+extern "C" size_t o2_attn_bwd_fused_workspace(int B, int N, int heads, int hd) {
+  return (size_t)B * heads * N * hd * sizeof(float);
+}
+
+extern "C" int o2_attn_bwd_fused(int parts, const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                 float* delta, void* workspace, size_t ws_bytes, int B, int N, int heads, int hd, float scale,
+                                 float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  O2_REQUIRE(B > 0 && N > 0 && heads > 0, "attn_bwd_fused: bad dims");
+  O2_REQUIRE(workspace != nullptr && ws_bytes >= o2_attn_bwd_fused_workspace(B, N, heads, hd),
+             "attn_bwd_fused: workspace of %zu bytes needed (o2_attn_bwd_fused_workspace), got %zu",
+             o2_attn_bwd_fused_workspace(B, N, heads, hd), ws_bytes);
+  return o2_attn_bwd_fused_tc(qkv, out, dout, lse, dqkv, delta, (float*)workspace, B, N, heads, hd, scale, parts, p_drop, seed,
+                              site, (cudaStream_t)stream);
+}
+
 extern "C" int o2_attn_bwd_parts(int impl, int parts, const void* qkv, const void* out, const void* dout, const float* lse,
                                  void* dqkv, float* delta, int B, int N, int heads, int hd, float scale, void* stream) {
   return o2_attn_bwd_parts_drop(impl, parts, qkv, out, dout, lse, dqkv, delta, B, N, heads, hd, scale, 0.f, 0, 0, stream);

@@ -35,7 +35,10 @@ constexpr float kRescaleThreshold = 8.0f;
 #ifndef O2_POLY_DQ
 #define O2_POLY_DQ 4
 #endif
-constexpr int kPolyFwd = O2_POLY_FWD, kPolyDq = O2_POLY_DQ, kPolyDkv = 1 << 20;
+#ifndef O2_POLY_FUSED
+#define O2_POLY_FUSED (1 << 20)
+#endif
+constexpr int kPolyFwd = O2_POLY_FWD, kPolyDq = O2_POLY_DQ, kPolyDkv = 1 << 20, kPolyFused = O2_POLY_FUSED;
 
 #ifdef O2_TIMELINE
 // Debug build only: CTA (0,0) records clock64() at the hand-off points of sub-tiles [kTlFirst, kTlFirst + kTlCount).
@@ -1468,6 +1471,18 @@ int launch_bwd(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const BwdArg
   return O2_OK;
 }
 
+#include "attn_bwd_fused.cuh"
+
+template <bool kDrop>
+int launch_bwd_fused(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const CUtensorMap& tm_dq, const BwdArgs& a,
+                     cudaStream_t st) {
+  O2_SET_SMEM_ONCE((attn_bwd_fused_kernel<kDrop>), kFusedSmem);
+  dim3 grid((a.N + BKV - 1) / BKV, a.B * a.heads);
+  attn_bwd_fused_kernel<kDrop><<<grid, kFusedThreads, kFusedSmem, st>>>(tm_qkv, tm_do, tm_dq, a);
+  O2_LAUNCH_CHECK();
+  return O2_OK;
+}
+
 }  // namespace
 
 int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, float p_drop,
@@ -1528,4 +1543,56 @@ int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const flo
   if (a.drop.thr16 > 0)
     return hd == 64 ? launch_bwd<1, true>(tm_qkv, tm_do, a, parts, st) : launch_bwd<2, true>(tm_qkv, tm_do, a, parts, st);
   return hd == 64 ? launch_bwd<1, false>(tm_qkv, tm_do, a, parts, st) : launch_bwd<2, false>(tm_qkv, tm_do, a, parts, st);
+}
+
+// One-pass backward (head dim 64): delta, then the fused dK / dV / dQ kernel (dQ partials reduced into dq_accum by TMA),
+// then dQ = scale * dq_accum.  parts: O2_ATTN_BWD_DELTA | O2_ATTN_BWD_FUSED | O2_ATTN_BWD_DQ_FINISH.
+int o2_attn_bwd_fused_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
+                         float* dq_accum, int B, int N, int heads, int hd, float scale, int parts, float p_drop,
+                         uint64_t seed, uint32_t site, cudaStream_t st) {
+  O2_REQUIRE(hd == 64, "attn_bwd_fused: head dim %d not supported (64)", hd);
+  O2_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dout % 16) == 0 &&
+                 ((uintptr_t)dqkv % 16) == 0 && ((uintptr_t)dq_accum % 16) == 0,
+             "attn_bwd_fused: pointers must be 16-byte aligned");
+  O2_REQUIRE((long long)B * heads <= 65535, "attn_bwd_fused: B*heads too large");
+  const long long rows = (long long)B * N * heads;
+  if (parts & O2_ATTN_BWD_DELTA) {
+    attn_delta_bf16_kernel<1><<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(
+        (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, B, N, heads);
+    O2_LAUNCH_CHECK();
+  }
+  if (parts & O2_ATTN_BWD_FUSED) {
+    CUtensorMap tm_qkv, tm_do, tm_dq;
+    int rc = make_qkv_tmap(&tm_qkv, qkv, B, N, heads, hd, BQ);
+    if (rc) return rc;
+    {
+      uint64_t dims[4] = {(uint64_t)hd, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
+      uint64_t str[3] = {(uint64_t)hd * 2, (uint64_t)heads * hd * 2, (uint64_t)N * heads * hd * 2};
+      uint32_t box[4] = {64, 1, (uint32_t)BQ, 1};
+      rc = o2_make_tmap(&tm_do, dout, 2, 4, dims, str, box, 1);
+      if (rc) return rc;
+    }
+    {   // dq_accum [B * heads, N, 64] fp32; box = 32 queries x 32 columns (128-byte rows, 128B swizzle) per drain warp
+      uint64_t dims[3] = {64, (uint64_t)N, (uint64_t)B * heads};
+      uint64_t str[2] = {64 * 4, (uint64_t)N * 64 * 4};
+      uint32_t box[3] = {32, 32, 1};
+      rc = o2_make_tmap(&tm_dq, dq_accum, 4, 3, dims, str, box, 1);
+      if (rc) return rc;
+    }
+    O2_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)rows * 64 * sizeof(float), st));
+    BwdArgs a;
+    a.qkv = (const __nv_bfloat16*)qkv;
+    a.lse = lse; a.delta = delta; a.dqkv = (__nv_bfloat16*)dqkv; a.B = B; a.N = N; a.heads = heads;
+    a.n_sub = (N + BS - 1) / BS;
+    a.scale = scale; a.scale_log2 = scale * kLog2e;
+    a.drop = make_drop(p_drop, seed, site, N);
+    O2_REQUIRE((long long)N * a.drop.nkb < (1ll << 32), "attn_bwd_fused: N=%d too large for the dropout word index", N);
+    rc = a.drop.thr16 > 0 ? launch_bwd_fused<true>(tm_qkv, tm_do, tm_dq, a, st) : launch_bwd_fused<false>(tm_qkv, tm_do, tm_dq, a, st);
+    if (rc) return rc;
+  }
+  if (parts & O2_ATTN_BWD_DQ_FINISH) {
+    attn_dq_finish_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(dq_accum, (__nv_bfloat16*)dqkv, B, N, heads, scale);
+    O2_LAUNCH_CHECK();
+  }
+  return O2_OK;
 }

@@ -3,6 +3,7 @@ and raises O2Error on failure.  No op has a PyTorch/CPU fallback."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -145,7 +146,14 @@ def attn_fwd(qkv, B, N, heads, hd, drop=None):
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, B, N, heads, hd, drop=None):
+# head dims of the one-pass backward (5 GEMMs, dQ partials reduced through the L2 by TMA); O2_ATTN_BWD_TWO_PASS=1 keeps the
+# deterministic two-kernel backward (7 GEMMs, no atomics)
+FUSED_BWD_HEAD_DIMS = (64,)
+ATTN_BWD_TWO_PASS = bool(int(os.environ.get("O2_ATTN_BWD_TWO_PASS", "0")))
+
+
+def attn_bwd(qkv, out, dout, lse, B, N, heads, hd, drop=None, two_pass=None):
+    """-> dqkv.  bf16, head dim 64: the one-pass kernel unless ``two_pass`` (default: O2_ATTN_BWD_TWO_PASS)."""
     lib = L.load()
     if qkv.dtype == torch.bfloat16 and hd not in TC_HEAD_DIMS:
         return cast_bf16(attn_bwd(cast_f32(qkv), cast_f32(out), cast_f32(dout), lse, B, N, heads, hd, drop))
@@ -153,6 +161,21 @@ def attn_bwd(qkv, out, dout, lse, B, N, heads, hd, drop=None):
     delta = torch.empty(B, heads, N, device=qkv.device, dtype=torch.float32)
     impl = impl_for(qkv.dtype)
     p, seed, site = drop if drop is not None else (0.0, 0, 0)
+    if two_pass is None:
+        two_pass = ATTN_BWD_TWO_PASS
+    if impl == GEMM_TC_BF16 and hd in FUSED_BWD_HEAD_DIMS and not two_pass:
+        ws_bytes = int(lib.o2_attn_bwd_fused_workspace(B, N, heads, hd))
+        ws = torch.empty(ws_bytes // 4, device=qkv.device, dtype=torch.float32)        # caller-owned scratch (dQ accumulator)
+        fargs = (_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(delta), _ptr(ws), ws_bytes, B, N, heads, hd,
+                 hd ** -0.5, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF, _stream())
+        if TIMERS is not None:
+            for name, part in (("attn_bwd_delta", 1), ("attn_bwd_fused", 8), ("attn_bwd_dq_finish", 16)):
+                with _timed(name):
+                    L.check(lib.o2_attn_bwd_fused(part, *fargs), "o2_attn_bwd_fused")
+        else:
+            L.check(lib.o2_attn_bwd_fused(1 | 8 | 16, *fargs), "o2_attn_bwd_fused")
+        _count(4)
+        return dqkv
     args = (_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(delta), B, N, heads, hd, hd ** -0.5, float(p),
             int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF, _stream())
     if TIMERS is not None and impl == GEMM_TC_BF16:

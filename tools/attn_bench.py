@@ -15,6 +15,7 @@ ap.add_argument("--heads", type=int, default=16)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--hd", type=int, default=64)
 ap.add_argument("--fwd-only", action="store_true")
+ap.add_argument("--two-pass", action="store_true", help="time the deterministic two-kernel backward instead of the one-pass kernel")
 a = ap.parse_args()
 hd = a.hd
 D = a.heads * hd
@@ -25,15 +26,16 @@ fl = 4.0 * a.N * a.N * D * a.B
 for it in range(2):
     out, lse = ops.attn_fwd(qkv, a.B, a.N, a.heads, hd)
     if not a.fwd_only:
-        ops.attn_bwd(qkv, out, dout, lse, a.B, a.N, a.heads, hd)
+        ops.attn_bwd(qkv, out, dout, lse, a.B, a.N, a.heads, hd, two_pass=a.two_pass)
 torch.cuda.synchronize()
 ops.TIMERS = {}
 for it in range(a.iters):
     out, lse = ops.attn_fwd(qkv, a.B, a.N, a.heads, hd)
     if not a.fwd_only:
-        ops.attn_bwd(qkv, out, dout, lse, a.B, a.N, a.heads, hd)
+        ops.attn_bwd(qkv, out, dout, lse, a.B, a.N, a.heads, hd, two_pass=a.two_pass)
 torch.cuda.synchronize()
-for name, mult in (("attn_fwd", 1.0), ("attn_bwd_dkv", 2.0), ("attn_bwd_dq", 1.5), ("attn_bwd_delta", 0.0)):
+for name, mult in (("attn_fwd", 1.0), ("attn_bwd_dkv", 2.0), ("attn_bwd_dq", 1.5), ("attn_bwd_fused", 2.5), ("attn_bwd_delta", 0.0),
+                   ("attn_bwd_dq_finish", 0.0)):
     if name in ops.TIMERS:
         ms = sum(e0.elapsed_time(e1) for e0, e1 in ops.TIMERS[name]) / len(ops.TIMERS[name])
         print(f"{name:16s} {ms:8.3f} ms  {fl * mult / ms / 1e9:8.1f} TFLOP/s")
