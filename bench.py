@@ -88,6 +88,32 @@ def flops_per_sample(cfg):
     return 3.0 * lin + 3.5 * att, att / depth, L
 
 
+def kernel_source_hash():
+    """sha256 (16 hex digits) of the attention kernel sources: a committed ncu DRAM-traffic figure is only reported while
+    the kernels it was captured from are unchanged."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("attn_tc.cu", "attn_bwd_fused.cuh", "common.cuh"):
+        try:
+            h.update(open(os.path.join(ROOT, "orbit2_b200", "csrc", f), "rb").read())
+        except OSError:
+            return None
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(kernel, B, L, heads):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, tools/ncu_traffic.py)
+    from profiles/traffic.json -- None unless the capture is of this shape AND of the current kernel sources."""
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = tr["kernels"].get(kernel)
+        if e and tr.get("src_sha") == kernel_source_hash() and (e["B"], e["N"], e["heads"]) == (B, L, heads):
+            return e["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_reference_step_time(case_name, B, steps, warmup, threads, budget_s=None):
     """Seconds per step of the CPU restatement (fp32, SDPA attention) of forward+clip+loss+backward.  With ``budget_s`` the
@@ -314,30 +340,24 @@ def run_ours(args):
     step_tflops = fl_sample * B / (ms_step * 1e-3) / 1e12
 
     # dominant kernel = the attention launch group with the largest share of the step
-    att_names = [n for n in ("attn_fwd", "attn_bwd_dkv", "attn_bwd_dq") if n in kern]
+    ATT_MULT = {"attn_fwd": 1.0, "attn_bwd_dkv": 2.0, "attn_bwd_dq": 1.5, "attn_bwd_fused": 2.5}   # 2 / 4 / 3 / 5 GEMMs of 2*L*L*D
+    att_names = [n for n in ATT_MULT if n in kern]
     roof = None
     if att_names:
         dom = max(att_names, key=lambda n: kern[n])
         nlaunch = len(timers[dom]) / args.steps
-        mult = {"attn_fwd": 1.0, "attn_bwd_dkv": 2.0, "attn_bwd_dq": 1.5}[dom]    # 2 / 4 / 3 GEMMs of 2*L*L*D each
-        fl = attn_fwd_flops_blk * mult * B                                       # per launch
+        fl = attn_fwd_flops_blk * ATT_MULT[dom] * B                              # ALGORITHMIC FLOPs per launch
         avg_ms = kern[dom] / nlaunch
         ach = fl / (avg_ms * 1e-3) / 1e12
-        traffic = None                       # DRAM bytes per launch from the committed ncu --set full capture (same shape only)
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom)
-            if tr and tr["B"] == B and tr["N"] == L and tr["heads"] == cfg["num_heads"]:
-                traffic = tr["dram_bytes_per_launch"]
-        except Exception:
-            pass
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tf_sust"], "traffic": traffic, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
+                "frac": ach / peaks["tf_sust"], "traffic": committed_traffic(dom, B, L, cfg["num_heads"]),
+                "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
                 "avg_launch_ms": avg_ms, "flops_per_launch": fl,
                 "share_of_step": kern[dom] / ms_step}
     kernels_ms = {k: round(v, 3) for k, v in sorted(kern.items(), key=lambda kv: -kv[1])}
     if "gemm" in kern and kern["gemm"] > 0:
         kernels_ms["gemm_tflops"] = round(gemm_flops / (kern["gemm"] * 1e-3) / 1e12, 1)
-    for n, mult in (("attn_fwd", 1.0), ("attn_bwd_dkv", 2.0), ("attn_bwd_dq", 1.5)):
+    for n, mult in ATT_MULT.items():
         if n in kern:
             kernels_ms[n + "_tflops"] = round(attn_fwd_flops_blk * mult * B * cfg["depth"] / (kern[n] * 1e-3) / 1e12, 1)
 

@@ -220,7 +220,7 @@ def test_model_117m_whole_model_vs_oracle(golden_dir):
     x, y = O.synthetic_batch(cfg, 1, cfg["in_vars"], cfg["out_vars"], seed=0)
     chk = sum(v.double().abs().sum().item() for v in sd.values())
     assert abs(chk - float(z["sd_checksum"])) < 1e-9 * chk, "the seeded init differs from the one the fixture was made with"
-    names = [k[8:] for k in z.files if k.startswith("g_absmax/")]
+    names = [k[len("g_absmax/"):] for k in z.files if k.startswith("g_absmax/")]
     assert len(names) >= 150                                 # 23 patch embeds, 8 blocks x 12, head, convs, embeddings
     # live fp32 CPU oracle (all elements)
     torch.set_num_threads(os.cpu_count() or 1)
