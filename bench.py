@@ -370,6 +370,15 @@ def run_ours(args):
                "sample": f"CPU restatement of the reference (oracle/, fp32, SDPA attention), {nt} fwd+clip+bayesian_tv+bwd "
                          f"step after {nw} warm-up, " + sample_note(ccfg, cb)}
 
+    extra = None
+    if world > 1 and not args.no_extra and args.workload == "117m" and not (args.full_shard or args.shard):
+        # secondary, UNTIMED-by-the-headline measurements of the other two ways the path shards
+        del eng, model, loss_fn, loss_pub, x_d, y_d
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        extra = extra_measurements(args, cfg, dev, rank, world, B, x_h, y_h, value)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -389,10 +398,120 @@ def run_ours(args):
             "kernels_ms_per_step": kernels_ms, "loss": loss_val,
             "hbm_peak_gib": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
         }
+        if extra is not None:
+            line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def extra_measurements(args, cfg, dev, rank, world, B, x_h, y_h, dp_value):
+    """N > 1 only, after the headline region: (1) the same interm_117m step under FSDP FULL_SHARD (the mode interm_1b /
+    interm_10b train in: per-Block all-gather in forward and backward, gradient reduce-scatter, sharded master + Adam;
+    reference intermediate_downscaling.py:583-637) and (2) TILES inference of one synthetic CONUS-like field that is SHARDED
+    over the ranks (div_v x div_h = world tiles, NCCL halo exchange of the raw input margins, per-tile network, all-gather of
+    the inner output blocks; reference utils/visualize.py:125-311 runs the tiles one after the other on one rank), checked
+    on rank 0 against the sequential tile loop.  Both are timed with CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from oracle import reslim_oracle as O
+    from orbit2_b200 import engine, losses, tiles
+    from orbit2_b200.reslim import Res_Slim_ViT
+
+    def make_model(tile_size=None):
+        torch.manual_seed(0)
+        m = Res_Slim_ViT(cfg["default_vars"], cfg["img_size"], len(cfg["default_vars"]), cfg["out_channels"], 1,
+                         superres_mag=cfg["superres_mag"], cnn_ratio=cfg["cnn_ratio"], patch_size=cfg["patch_size"],
+                         drop_path=0.0, drop_rate=0.0, learn_pos_emb=True, embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                         decoder_depth=cfg["decoder_depth"], num_heads=cfg["num_heads"], mlp_ratio=cfg["mlp_ratio"],
+                         compute_dtype=torch.bfloat16)
+        with torch.no_grad():
+            m.var_embed.normal_(0, 0.02)
+            m.var_query.normal_(0, 0.02)
+        m.spatial_resolution = cfg["spatial_resolution"]
+        if tile_size is not None:                # like the reference's data_config: pos_embed keeps its 2:1 grid and is
+            m.img_size = tuple(tile_size)        # resampled (bicubic, pos_embed.py:103-138) to the tile grid on the fly
+        return m.to(dev)
+
+    def max_ms(ms):
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    out = {}
+    # ---- (1) FULL_SHARD
+    model = make_model()
+    meta = losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None)
+    eng = engine.TrainEngine(model, losses.METRICS_REGISTRY["bayesian_tv"](aggregate_only=True, metainfo=meta), cfg["in_vars"],
+                             cfg["out_vars"], cfg["var_weights"], lr=2e-4, betas=(0.9, 0.99), weight_decay=1e-5,
+                             shard_params=True)
+    x_d, y_d = x_h.to(dev), y_h.to(dev)
+    for _ in range(2):
+        eng.step(x_d, y_d)
+    dist.barrier()
+    torch.cuda.synchronize()
+    g0, s0 = eng.fs.gathered_elems, eng.fs.scattered_elems
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_fs = 3
+    e0.record()
+    for _ in range(n_fs):
+        vec = eng.step(x_d, y_d)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = max_ms(e0.elapsed_time(e1) / n_fs)
+    fs_val = world * B / (ms * 1e-3)
+    out["full_shard_117m"] = {
+        "value": fs_val, "unit": "samples/s", "ms_per_step": ms, "steps": n_fs, "vs_dp": fs_val / dp_value,
+        "parallelism": f"fsdp{world} FULL_SHARD, one unit per Block",
+        "gathered_bytes_per_step_per_rank": (eng.fs.gathered_elems - g0) // n_fs * 2,
+        "reduce_scattered_bytes_per_step_per_rank": (eng.fs.scattered_elems - s0) // n_fs * 4,
+        "loss": float(vec[-1].item())}
+    del eng, model, x_d, y_d
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    # ---- (2) TILES over a sharded field: 360 x 720 low-resolution field -> 1440 x 2880 output, one tile per rank
+    div_v, div_h = {2: (1, 2), 4: (2, 2), 8: (2, 4)}.get(world, (1, world))
+    Hf, Wf, overlap = 360, 720, 4
+    th, tw = tiles.check_tiling(Hf, Wf, div_v, div_h, overlap, cfg["patch_size"])
+    model = make_model([th, tw]).eval()
+    fcfg = dict(cfg, img_size=[Hf, Wf])
+    xf, _ = O.synthetic_batch(fcfg, 1, cfg["in_vars"], cfg["out_vars"], seed=0)       # the same global field on every rank
+    geo = tiles.ShardedField(Hf, Wf, div_v, div_h, overlap)
+    oy1, oy2, ox1, ox2 = geo.own(rank)
+    x_own = xf[:, :, oy1:oy2, ox1:ox2].contiguous().to(dev)
+    n_it = 3
+    with torch.no_grad():
+        for it in range(n_it + 1):
+            if it == 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+                e0.record()
+            blk = tiles.sharded_tiled_forward(model, x_own, cfg["in_vars"], cfg["out_vars"], geo, rank)
+            full = tiles.gather_output(blk, geo)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = max_ms(e0.elapsed_time(e1) / n_it)
+        err, seq_ms = None, None
+        if rank == 0:
+            xg = xf.to(dev)
+            seq = tiles.tiled_forward(model, xg, cfg["in_vars"], cfg["out_vars"], div_v, overlap, div_h=div_h)
+            torch.cuda.synchronize()
+            e0.record()
+            seq = tiles.tiled_forward(model, xg, cfg["in_vars"], cfg["out_vars"], div_v, overlap, div_h=div_h)
+            e1.record()
+            torch.cuda.synchronize()
+            seq_ms = e0.elapsed_time(e1)
+            err = (full.float() - seq.float()).abs().max().item() / seq.float().abs().max().item()
+    out["tiles_sharded_field"] = {
+        "field": f"{Hf}x{Wf} -> {Hf * cfg['superres_mag']}x{Wf * cfg['superres_mag']}, V={len(cfg['in_vars'])}",
+        "tiles": f"{div_v}x{div_h}", "tile": f"{th}x{tw}", "overlap": overlap,
+        "halo_bytes_rank0": geo.halo_bytes(0, len(cfg["in_vars"]), 1), "ms_per_field": ms, "fields_per_s": 1e3 / ms,
+        "sequential_one_gpu_ms": seq_ms, "stitched_vs_sequential_rel_err": err}
+    return out
 
 
 def main():
@@ -415,6 +534,8 @@ def main():
     ap.add_argument("--full-shard", action="store_true",
                     help="FSDP FULL_SHARD: GEMM weights, fp32 masters, gradients and Adam state sharded per Block "
                          "(all-gather in forward and backward, reduce-scatter of gradients)")
+    ap.add_argument("--no-extra", action="store_true", help="N > 1: skip the secondary FULL_SHARD / sharded-field TILES "
+                    "measurements appended under `extra`")
     ap.add_argument("--ref-budget", type=float, default=1500.0, help="--impl reference: seconds the CPU arm may take; the "
                     "number of steps is cut to fit, the grid is always the GPU arm's")
     args = ap.parse_args()

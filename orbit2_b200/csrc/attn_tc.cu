@@ -1485,9 +1485,18 @@ int launch_bwd_fused(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const 
 
 }  // namespace
 
+// head dim 256 (interm_10b): attn_tc256.cu
+int o2_attn_fwd_tc256(const void* qkv, void* out, float* lse, int B, int N, int heads, float scale, cudaStream_t st);
+int o2_attn_bwd_tc256(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B,
+                      int N, int heads, float scale, int parts, cudaStream_t st);
+
 int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int hd, float scale, float p_drop,
                    uint64_t seed, uint32_t site, cudaStream_t st) {
-  O2_REQUIRE(hd == 64 || hd == 128, "attn_fwd_tc: head dim %d not supported (64 or 128)", hd);
+  if (hd == 256) {
+    if (p_drop > 0.f) O2_FAIL(O2_ERR_UNSUPPORTED, "attn_fwd_tc: head dim 256 has no dropout variant (use the fp32 arm)");
+    return o2_attn_fwd_tc256(qkv, out, lse, B, N, heads, scale, st);
+  }
+  O2_REQUIRE(hd == 64 || hd == 128, "attn_fwd_tc: head dim %d not supported (64, 128 or 256)", hd);
   O2_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0, "attn_fwd_tc: pointers must be 16-byte aligned");
   O2_REQUIRE((long long)B * heads <= 65535, "attn_fwd_tc: B*heads too large");
   CUtensorMap tm;
@@ -1508,7 +1517,11 @@ int o2_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int hea
 int o2_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta, int B,
                    int N, int heads, int hd, float scale, int parts, float p_drop, uint64_t seed, uint32_t site,
                    cudaStream_t st) {
-  O2_REQUIRE(hd == 64 || hd == 128, "attn_bwd_tc: head dim %d not supported (64 or 128)", hd);
+  if (hd == 256) {
+    if (p_drop > 0.f) O2_FAIL(O2_ERR_UNSUPPORTED, "attn_bwd_tc: head dim 256 has no dropout variant (use the fp32 arm)");
+    return o2_attn_bwd_tc256(qkv, out, dout, lse, dqkv, delta, B, N, heads, scale, parts, st);
+  }
+  O2_REQUIRE(hd == 64 || hd == 128, "attn_bwd_tc: head dim %d not supported (64, 128 or 256)", hd);
   O2_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dout % 16) == 0 &&
                  ((uintptr_t)dqkv % 16) == 0,
              "attn_bwd_tc: pointers must be 16-byte aligned");

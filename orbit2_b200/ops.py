@@ -123,16 +123,21 @@ def cast_f32(src: torch.Tensor):
     return dst
 
 
-# head dims of the tcgen05 attention kernels; a bf16 call with another head dim (256: interm_10b) runs the fp32 SIMT arm
-# on up-cast operands and rounds the result back (attention is < 1 % of that model's FLOPs at its 512-token grids)
-TC_HEAD_DIMS = (64, 128)
+# head dims of the tcgen05 attention kernels (256 = interm_10b: csrc/attn_tc256.cu, no attention-dropout variant); a bf16
+# call outside this set runs the fp32 SIMT arm on up-cast operands and rounds the result back
+TC_HEAD_DIMS = (64, 128, 256)
+TC_NO_DROPOUT_HEAD_DIMS = (256,)
+
+
+def _tc_ok(hd, drop):
+    return hd in TC_HEAD_DIMS and not (hd in TC_NO_DROPOUT_HEAD_DIMS and drop is not None and drop[0] > 0.0)
 
 
 def attn_fwd(qkv, B, N, heads, hd, drop=None):
     """qkv [B*N, 3*heads*hd] -> (out [B*N, heads*hd], lse [B,heads,N]).  drop = (p, seed, site): attention-probability
     dropout (training mode)."""
     lib = L.load()
-    if qkv.dtype == torch.bfloat16 and hd not in TC_HEAD_DIMS:
+    if qkv.dtype == torch.bfloat16 and not _tc_ok(hd, drop):
         out32, lse = attn_fwd(cast_f32(qkv), B, N, heads, hd, drop)
         return cast_bf16(out32), lse
     out = torch.empty(B * N, heads * hd, device=qkv.device, dtype=qkv.dtype)
@@ -149,20 +154,23 @@ def attn_fwd(qkv, B, N, heads, hd, drop=None):
 # head dims of the one-pass backward (5 GEMMs, dQ partials reduced through the L2 by TMA); O2_ATTN_BWD_TWO_PASS=1 keeps the
 # deterministic two-kernel backward (7 GEMMs, no atomics)
 FUSED_BWD_HEAD_DIMS = (64,)
-ATTN_BWD_TWO_PASS = bool(int(os.environ.get("O2_ATTN_BWD_TWO_PASS", "0")))
+
+
+def attn_bwd_two_pass_default() -> bool:
+    return bool(int(os.environ.get("O2_ATTN_BWD_TWO_PASS", "0")))         # read per call: tests flip it around engine runs
 
 
 def attn_bwd(qkv, out, dout, lse, B, N, heads, hd, drop=None, two_pass=None):
     """-> dqkv.  bf16, head dim 64: the one-pass kernel unless ``two_pass`` (default: O2_ATTN_BWD_TWO_PASS)."""
     lib = L.load()
-    if qkv.dtype == torch.bfloat16 and hd not in TC_HEAD_DIMS:
+    if qkv.dtype == torch.bfloat16 and not _tc_ok(hd, drop):
         return cast_bf16(attn_bwd(cast_f32(qkv), cast_f32(out), cast_f32(dout), lse, B, N, heads, hd, drop))
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, heads, N, device=qkv.device, dtype=torch.float32)
     impl = impl_for(qkv.dtype)
     p, seed, site = drop if drop is not None else (0.0, 0, 0)
     if two_pass is None:
-        two_pass = ATTN_BWD_TWO_PASS
+        two_pass = attn_bwd_two_pass_default()
     if impl == GEMM_TC_BF16 and hd in FUSED_BWD_HEAD_DIMS and not two_pass:
         ws_bytes = int(lib.o2_attn_bwd_fused_workspace(B, N, heads, hd))
         ws = torch.empty(ws_bytes // 4, device=qkv.device, dtype=torch.float32)        # caller-owned scratch (dQ accumulator)

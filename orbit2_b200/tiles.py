@@ -67,21 +67,24 @@ def check_tiling(h: int, w: int, div_v: int, div_h: int, overlap: int, patch_siz
     return th, tw
 
 
-def tiled_forward(model, x: torch.Tensor, in_variables, out_variables, div: int, overlap: int, mag: int = None):
+def tiled_forward(model, x: torch.Tensor, in_variables, out_variables, div: int, overlap: int, mag: int = None,
+                  div_h: int = None):
     """Sequential tiled inference on one device (the reference's visualize_at_index loop): returns the stitched
-    [B, C, H*mag, W*mag] prediction.  `model.img_size` must already be the tile size (data_config)."""
+    [B, C, H*mag, W*mag] prediction.  `model.img_size` must already be the tile size (data_config).  The reference tiles
+    div x div; ``div_h`` (default: div) allows the div x div_h grids a sharded field uses (2 x 4 over 8 GPUs)."""
     mag = mag or model.superres_mag
+    div_v, div_h = div, (div if div_h is None else div_h)
     B, V, H, W = x.shape
     top, bottom, left, right = overlap_margins(overlap)
     out = None
-    for v in range(div):
-        yi1, yi2, yt1, yt2 = axis_bounds(H, div, v, top, bottom)
-        for h in range(div):
-            xi1, xi2, xt1, xt2 = axis_bounds(W, div, h, left, right)
+    for v in range(div_v):
+        yi1, yi2, yt1, yt2 = axis_bounds(H, div_v, v, top, bottom)
+        for h in range(div_h):
+            xi1, xi2, xt1, xt2 = axis_bounds(W, div_h, h, left, right)
             pred = model(x[:, :, yi1:yi2, xi1:xi2].contiguous(), in_variables, out_variables)
             if out is None:
                 out = torch.empty(B, pred.shape[1], H * mag, W * mag, device=pred.device, dtype=pred.dtype)
-            oy, ox = H // div * v * mag, W // div * h * mag
+            oy, ox = H // div_v * v * mag, W // div_h * h * mag
             out[:, :, oy:oy + (yt2 - yt1) * mag, ox:ox + (xt2 - xt1) * mag] = \
                 pred[:, :, yt1 * mag:yt2 * mag, xt1 * mag:xt2 * mag]
     return out

@@ -14,6 +14,20 @@ from tests.util import build_model
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _deterministic_attention_backward():
+    """Engine-vs-engine equality is asserted to ~1e-5 after Adam steps: that needs the deterministic two-kernel attention
+    backward (the default one-pass kernel reduces dQ with L2 atomics: reproducible to fp32 rounding, not bit for bit).
+    ops.attn_bwd reads the variable at call time; spawned ranks inherit it."""
+    old = os.environ.get("O2_ATTN_BWD_TWO_PASS")
+    os.environ["O2_ATTN_BWD_TWO_PASS"] = "1"
+    yield
+    if old is None:
+        os.environ.pop("O2_ATTN_BWD_TWO_PASS", None)
+    else:
+        os.environ["O2_ATTN_BWD_TWO_PASS"] = old
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
     return p

@@ -1,4 +1,5 @@
-"""fp32 head-dim-256 attention arm (interm_10b: 32 heads x 256, L = 512) forward / backward timing."""
+"""Head-dim-256 attention (interm_10b: 32 heads x 256, L = 512) forward / backward timing: the fp32 SIMT arm and the bf16
+tcgen05 kernels (csrc/attn_tc256.cu).   python tools/attn256_bench.py [B N heads hd]"""
 import os
 import sys
 
@@ -27,8 +28,10 @@ def timed(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 
-out, lse = ops.attn_fwd(qkv, B, N, heads, hd)
 fl = 4.0 * B * heads * N * N * hd
-tf = timed(lambda: ops.attn_fwd(qkv, B, N, heads, hd))
-tb = timed(lambda: ops.attn_bwd(qkv, out, dout, lse, B, N, heads, hd))
-print(f"hd={hd} B={B} N={N} heads={heads}: fwd {tf:.3f} ms {fl / tf / 1e9:.1f} TFLOP/s   bwd {tb:.3f} ms {2.5 * fl / tb / 1e9:.1f} TFLOP/s")
+for name, (x, dy) in (("fp32 SIMT", (qkv, dout)), ("bf16 tcgen05", (qkv.bfloat16(), dout.bfloat16()))):
+    out, lse = ops.attn_fwd(x, B, N, heads, hd)
+    tf = timed(lambda: ops.attn_fwd(x, B, N, heads, hd))
+    tb = timed(lambda: ops.attn_bwd(x, out, dy, lse, B, N, heads, hd))
+    print(f"{name:13s} hd={hd} B={B} N={N} heads={heads}: fwd {tf:.3f} ms {fl / tf / 1e9:.1f} TFLOP/s   "
+          f"bwd {tb:.3f} ms {2.5 * fl / tb / 1e9:.1f} TFLOP/s (algorithmic)")
