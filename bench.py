@@ -343,8 +343,16 @@ def run_ours(args):
     ATT_MULT = {"attn_fwd": 1.0, "attn_bwd_dkv": 2.0, "attn_bwd_dq": 1.5, "attn_bwd_fused": 2.5}   # 2 / 4 / 3 / 5 GEMMs of 2*L*L*D
     att_names = [n for n in ATT_MULT if n in kern]
     roof = None
-    if att_names:
-        dom = max(att_names, key=lambda n: kern[n])
+    dom = max(att_names, key=lambda n: kern[n]) if att_names else None
+    if "gemm" in kern and (dom is None or kern["gemm"] > kern[dom]) and gemm_flops > 0:
+        # GEMM-dominated workloads (interm_1b / 10b): the launch group is every o2_gemm call of the step
+        nlaunch = (len(timers["gemm"]) / args.steps) or 1
+        ach = gemm_flops / (kern["gemm"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tc (all launches of the step)", "achieved": ach, "peak": peaks["tf_sust"],
+                "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"], "traffic": None,
+                "peak_source": peaks["src"] + " (sustained cuBLAS bf16)", "avg_launch_ms": kern["gemm"] / nlaunch,
+                "flops_per_launch": gemm_flops / nlaunch, "share_of_step": kern["gemm"] / ms_step}
+    elif dom is not None:
         nlaunch = len(timers[dom]) / args.steps
         fl = attn_fwd_flops_blk * ATT_MULT[dom] * B                              # ALGORITHMIC FLOPs per launch
         avg_ms = kern[dom] / nlaunch
