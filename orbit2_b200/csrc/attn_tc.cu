@@ -1473,11 +1473,27 @@ int launch_bwd(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const BwdArg
 
 #include "attn_bwd_fused.cuh"
 
+// attn_bwd_v3.cuh (N = 128 score MMAs, statistics from shared memory) is an experiment that did NOT win: 942 vs 958 TFLOP/s
+// at B = 2, 854 vs 895 at B = 8 (profiles/r02_attn_experiments.md).  It is compiled only into A/B builds
+// (tools/build_variant.sh v3 -DO2_ATTN_BWD_V3) and selected there with O2_ATTN_BWD_FUSED_V3=1.
+#ifdef O2_ATTN_BWD_V3
+#include "attn_bwd_v3.cuh"
+#endif
+
 template <bool kDrop>
 int launch_bwd_fused(const CUtensorMap& tm_qkv, const CUtensorMap& tm_do, const CUtensorMap& tm_dq, const BwdArgs& a,
                      cudaStream_t st) {
-  O2_SET_SMEM_ONCE((attn_bwd_fused_kernel<kDrop>), kFusedSmem);
   dim3 grid((a.N + BKV - 1) / BKV, a.B * a.heads);
+#ifdef O2_ATTN_BWD_V3
+  static const bool use_v3 = getenv("O2_ATTN_BWD_FUSED_V3") != nullptr;
+  if (use_v3) {
+    O2_SET_SMEM_ONCE((attn_bwd_v3_kernel<kDrop>), kV3Smem);
+    attn_bwd_v3_kernel<kDrop><<<grid, kV3Threads, kV3Smem, st>>>(tm_qkv, tm_do, tm_dq, a);
+    O2_LAUNCH_CHECK();
+    return O2_OK;
+  }
+#endif
+  O2_SET_SMEM_ONCE((attn_bwd_fused_kernel<kDrop>), kFusedSmem);
   attn_bwd_fused_kernel<kDrop><<<grid, kFusedThreads, kFusedSmem, st>>>(tm_qkv, tm_do, tm_dq, a);
   O2_LAUNCH_CHECK();
   return O2_OK;
