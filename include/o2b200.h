@@ -41,7 +41,10 @@ enum {
   O2_EPI_BIAS_GELU = 2, /* aux_out = acc + bias[n] (pre-activation, kept for backward); C = gelu   */
   O2_EPI_BIAS_RES = 3,  /* C = acc + bias[n] + aux[m % aux_rows, n] (residual / broadcast pos-emb) */
   O2_EPI_DGELU = 4,     /* C = acc * gelu'(aux[m, n])                                             */
-  O2_EPI_ACCUM = 5      /* C(f32) += acc (split-K atomics; weight gradients)                      */
+  O2_EPI_ACCUM = 5      /* C(f32) += acc (split-K atomics; weight gradients).  With trans_a=1 a non-NULL
+                         * `bias` is an OUTPUT: bias[m] (fp32 [M]) += sum_k A^T[m, k] -- the bias gradient
+                         * db = colsum(dY) computed from the dY tiles the weight-gradient GEMM dW = dY^T X
+                         * streams anyway (tcgen05 arm: by its epilogue warps during the K loop)        */
 };
 
 enum { O2_LOSS_MSE = 0, O2_LOSS_MAE = 1, O2_LOSS_BAYESIAN_TV = 2 };
@@ -183,6 +186,23 @@ int o2_scale_channels(void* g, int dtype, const float* scale, int B, int C, int6
 int o2_dropout(const void* y, const void* res, void* out, int dtype, int64_t rows, int64_t cols,
                int64_t rows_per_sample, float p, const float* sample_scale, uint64_t seed, uint32_t site, void* stream);
 
+/* The same mask fused into the epilogue of the tcgen05 GEMM that produces the tensor (bf16 arm only; the fp32 arm keeps
+ * the separate o2_dropout pass): e = m * N + n, mask m(e) = keep(e) / (1 - p), identical to o2_dropout on a [M, N] tensor.
+ *   O2_EPI_BIAS_RES : C = (acc + bias) * m(e) * sample_scale[m / rows_per_sample] + aux     x + drop_path(proj_drop(proj(.)))
+ *   O2_EPI_BIAS_GELU: aux_out = acc + bias;  C = gelu(aux_out) * m(e)                        drop1(act(fc1(.)))  mlp.py:63-65
+ *   O2_EPI_DGELU    : C = acc * m(e) * gelu'(aux)                                            backward of the line above
+ * sample_scale may be NULL (no drop-path); p may be 0 (drop-path only). */
+typedef struct {
+  float p;
+  uint64_t seed;
+  uint32_t site;
+  const float* sample_scale; /* fp32 [M / rows_per_sample] or NULL */
+  int64_t rows_per_sample;
+} O2GemmDrop;
+int o2_gemm_drop(const void* A, int trans_a, int64_t lda, const void* B, int trans_b, int64_t ldb, void* C, int64_t ldc,
+                 int64_t M, int64_t N, int64_t K, int epilogue, const float* bias, const void* aux, int64_t ld_aux,
+                 int64_t aux_rows, void* aux_out, int64_t ld_aux_out, const O2GemmDrop* drop, void* stream);
+
 /* ---- either side of the hot path: input normalisation and evaluation statistics ---------------
  * o2_normalize_fields replaces the per-sample host transforms of the data pipeline (data/itermodule.py:202-211,
  * iterdataset.py:360-379): x [B,V,hw] fp32 RAW fields, in place; kind[v] = 0: (x - mean[v]) / std[v] (torchvision
@@ -199,6 +219,14 @@ int o2_eval_stats(const void* pred, int dtype, const float* target, const float*
 int o2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* bf16 -> fp32: operands of the fp32 attention arm for head dims the tcgen05 kernels do not cover (256, interm_10b). */
 int o2_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+/* ---- position-embedding resample ------------------------------------------------------------------
+ * replaces interpolate_pos_embed_on_the_fly (components/pos_embed.py:103-138, called every forward at
+ * res_slimvit.py:271-278 when the token grid differs from the stored one: TILES mode, other-resolution inference):
+ * torch's bicubic upsample (align_corners=False, A = -0.75, taps clamped to the border) on a channels-last
+ * [ih*iw, D] fp32 table -> [oh*ow, D], and its exact adjoint (d_src OVERWRITTEN; gather form, deterministic). */
+int o2_bicubic_fwd(const float* src, float* dst, int ih, int iw, int oh, int ow, int D, void* stream);
+int o2_bicubic_bwd(const float* d_dst, float* d_src, int ih, int iw, int oh, int ow, int D, void* stream);
+
 /* out[n] += sum_m X[m, n]  (bias gradients), X act dtype with row pitch ld. */
 int o2_colsum(const void* X, int dtype, float* out, int64_t M, int64_t N, int64_t ld, void* stream);
 /* fused AdamW (torch.optim.AdamW semantics, intermediate_downscaling.py:642-644) over a flat fp32

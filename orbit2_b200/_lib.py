@@ -23,6 +23,7 @@ SIGNATURES = {
     "o2_last_error": ([], C.c_char_p),
     "o2_device_ok": ([], C.c_int),
     "o2_gemm": ([_i, _p, _i, _l, _p, _i, _l, _p, _i, _l, _l, _l, _l, _i, _p, _p, _l, _l, _p, _l, _i, _p], _i),
+    "o2_gemm_drop": ([_p, _i, _l, _p, _i, _l, _p, _l, _l, _l, _l, _i, _p, _p, _l, _l, _p, _l, _p, _p], _i),
     "o2_layernorm_fwd": ([_p, _p, _p, _p, _p, _p, _l, _i, _f, _i, _p], _i),
     "o2_layernorm_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p], _i),
     "o2_attn_fwd": ([_i, _p, _p, _p, _i, _i, _i, _i, _f, _p], _i),
@@ -46,11 +47,21 @@ SIGNATURES = {
     "o2_eval_stats": ([_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p], _i),
     "o2_cast_f32_to_bf16": ([_p, _p, _l, _p], _i),
     "o2_cast_bf16_to_f32": ([_p, _p, _l, _p], _i),
+    "o2_bicubic_fwd": ([_p, _p, _i, _i, _i, _i, _i, _p], _i),
+    "o2_bicubic_bwd": ([_p, _p, _i, _i, _i, _i, _i, _p], _i),
     "o2_colsum": ([_p, _i, _p, _l, _l, _l, _p], _i),
     "o2_adamw": ([_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _f, _p], _i),
     "o2_adamw_dev": ([_p, _p, _p, _p, _p, _l, _p, _p], _i),
     "o2_nonfinite": ([_p, _l, _p, _p], _i),
 }
+
+
+
+class GemmDrop(C.Structure):
+    """O2GemmDrop of include/o2b200.h"""
+    _fields_ = [("p", C.c_float), ("seed", C.c_uint64), ("site", C.c_uint32), ("sample_scale", C.c_void_p),
+                ("rows_per_sample", C.c_int64)]
+
 
 _lib = None
 

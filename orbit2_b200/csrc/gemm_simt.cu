@@ -106,18 +106,33 @@ int o2_gemm_simt(const void* A, int trans_a, int64_t lda, const void* B, int tra
 
 int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans_b, int64_t ldb, void* C, int c_dtype,
                int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue, const float* bias, const void* aux,
-               int64_t ld_aux, int64_t aux_rows, void* aux_out, int64_t ld_aux_out, int split_k, cudaStream_t st);
+               int64_t ld_aux, int64_t aux_rows, void* aux_out, int64_t ld_aux_out, int split_k, const O2GemmDrop* drop,
+               cudaStream_t st);
+
+extern "C" int o2_gemm_drop(const void* A, int trans_a, int64_t lda, const void* B, int trans_b, int64_t ldb, void* C,
+                            int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue, const float* bias, const void* aux,
+                            int64_t ld_aux, int64_t aux_rows, void* aux_out, int64_t ld_aux_out, const O2GemmDrop* drop,
+                            void* stream) {
+  O2_REQUIRE(drop != nullptr, "o2_gemm_drop: null dropout descriptor");
+  return o2_gemm_tc(A, trans_a, lda, B, trans_b, ldb, C, O2_BF16, ldc, M, N, K, epilogue, bias, aux, ld_aux, aux_rows, aux_out,
+                    ld_aux_out, 1, drop, (cudaStream_t)stream);
+}
 
 extern "C" int o2_gemm(int impl, const void* A, int trans_a, int64_t lda, const void* B, int trans_b, int64_t ldb,
                        void* C, int c_dtype, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,
                        const float* bias, const void* aux, int64_t ld_aux, int64_t aux_rows, void* aux_out,
                        int64_t ld_aux_out, int split_k, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == O2_GEMM_SIMT_F32)
-    return o2_gemm_simt(A, trans_a, lda, B, trans_b, ldb, C, c_dtype, ldc, M, N, K, epilogue, bias, aux, ld_aux, aux_rows,
-                        aux_out, ld_aux_out, split_k, st);
+  if (impl == O2_GEMM_SIMT_F32) {
+    const bool side = (epilogue == O2_EPI_ACCUM && bias != nullptr);   // bias gradient next to the weight gradient
+    if (side) O2_REQUIRE(trans_a, "o2_gemm: the column-sum side product of O2_EPI_ACCUM needs trans_a=1");
+    int rc = o2_gemm_simt(A, trans_a, lda, B, trans_b, ldb, C, c_dtype, ldc, M, N, K, epilogue, side ? nullptr : bias, aux,
+                          ld_aux, aux_rows, aux_out, ld_aux_out, split_k, st);
+    if (rc || !side) return rc;
+    return o2_colsum(A, O2_F32, const_cast<float*>(bias), K, M, lda, stream);   // the fp32 arm keeps the separate pass
+  }
   if (impl == O2_GEMM_TC_BF16)
     return o2_gemm_tc(A, trans_a, lda, B, trans_b, ldb, C, c_dtype, ldc, M, N, K, epilogue, bias, aux, ld_aux, aux_rows,
-                      aux_out, ld_aux_out, split_k, st);
+                      aux_out, ld_aux_out, split_k, nullptr, st);
   O2_FAIL(O2_ERR_ARG, "o2_gemm: unknown impl %d", impl);
 }

@@ -26,6 +26,15 @@ struct GemmArgs {
   int epi, c_f32, wide_st, wide_ld;   // C (and aux_out) / aux rows are 32-byte aligned -> 256-bit stores / loads
   long long ldc, ld_aux, aux_rows, ld_aux_out;
   const float* bias;
+  // token-stream dropout / stochastic depth fused into the epilogue (mask function of csrc/dropout.cu, e = row * N + col):
+  // BIAS_RES: C = (acc + bias) * m(e) * sample_scale[row / rows_per_sample] + aux;  BIAS_GELU: C = gelu(pre) * m(e);
+  // DGELU: C = acc * m(e) * gelu'(aux);  m = keep / (1 - p)
+  int drop;                  // 0: none
+  uint32_t drop_key, drop_thr16;
+  float drop_inv_keep;
+  const float* sample_scale;
+  long long rows_per_sample;
+  float* colsum;             // O2_EPI_ACCUM with MN-major A: colsum[m] += sum_k A^T[m, k] (bias gradient riding on the wgrad)
   const __nv_bfloat16* aux;
   __nv_bfloat16* aux_out;
   void* C;
@@ -70,10 +79,27 @@ __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float* v
   }
 }
 
-template <int BN, int EPI, bool C_F32>
+// keep / (1 - p) factors of the 16 elements (row, n .. n + 15) folded into v: one 32-bit hash per element pair
+__device__ __forceinline__ void drop_apply16(const GemmArgs& g, float (&v)[16], long long row, int n, float s) {
+  const unsigned long long pair0 = (unsigned long long)(row * (long long)g.N + n) >> 1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const unsigned long long pair = pair0 + j;
+    const uint32_t h = ptx::lowbias32((uint32_t)pair ^ g.drop_key ^ ((uint32_t)(pair >> 32) * 0x9E3779B1u));
+    v[2 * j] = ((h & 0xFFFFu) >= g.drop_thr16) ? v[2 * j] * s : 0.f;
+    v[2 * j + 1] = ((h >> 16) >= g.drop_thr16) ? v[2 * j + 1] * s : 0.f;
+  }
+}
+
+template <int BN, int EPI, bool C_F32, bool DROP = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&r)[32], long long row, int n0,
                                                const float* sbias, const uint4 (&ax)[4]) {
   if (row >= g.M) return;
+  float dscale = 1.f;
+  if (DROP) {
+    dscale = g.drop_inv_keep;
+    if (g.sample_scale) dscale *= __ldg(g.sample_scale + row / g.rows_per_sample);
+  }
 #pragma unroll
   for (int j0 = 0; j0 < 32; j0 += 16) {
     const int n = n0 + j0;
@@ -93,6 +119,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
     }
+    if (DROP) drop_apply16(g, v, row, n, dscale);        // before the residual / GELU' factor
     if (EPI == O2_EPI_BIAS_RES || EPI == O2_EPI_DGELU) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -135,9 +162,18 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, const uint3
       if (g.c_f32) epilogue_chunk<BN, O2_EPI_BIAS, true>(g, r, row, n0, sbias, ax);
       else epilogue_chunk<BN, O2_EPI_BIAS, false>(g, r, row, n0, sbias, ax);
       break;
-    case O2_EPI_BIAS_GELU: epilogue_chunk<BN, O2_EPI_BIAS_GELU, false>(g, r, row, n0, sbias, ax); break;
-    case O2_EPI_BIAS_RES: epilogue_chunk<BN, O2_EPI_BIAS_RES, false>(g, r, row, n0, sbias, ax); break;
-    case O2_EPI_DGELU: epilogue_chunk<BN, O2_EPI_DGELU, false>(g, r, row, n0, sbias, ax); break;
+    case O2_EPI_BIAS_GELU:
+      if (g.drop) epilogue_chunk<BN, O2_EPI_BIAS_GELU, false, true>(g, r, row, n0, sbias, ax);
+      else epilogue_chunk<BN, O2_EPI_BIAS_GELU, false>(g, r, row, n0, sbias, ax);
+      break;
+    case O2_EPI_BIAS_RES:
+      if (g.drop) epilogue_chunk<BN, O2_EPI_BIAS_RES, false, true>(g, r, row, n0, sbias, ax);
+      else epilogue_chunk<BN, O2_EPI_BIAS_RES, false>(g, r, row, n0, sbias, ax);
+      break;
+    case O2_EPI_DGELU:
+      if (g.drop) epilogue_chunk<BN, O2_EPI_DGELU, false, true>(g, r, row, n0, sbias, ax);
+      else epilogue_chunk<BN, O2_EPI_DGELU, false>(g, r, row, n0, sbias, ax);
+      break;
     default: epilogue_chunk<BN, O2_EPI_ACCUM, true>(g, r, row, n0, sbias, ax); break;
   }
 }
@@ -171,7 +207,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     ptx::prefetch_tmap(&tmap_b);
     for (int s = 0; s < C::kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], MC);
+      // + one arrival per epilogue warp when the bias-gradient side product reads the A tiles of a stage (below)
+      ptx::mbar_init(&empty_bar[s], MC + (g.colsum ? kEpiWarps : 0));
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
@@ -240,9 +277,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    // ------------------------------------------------ MMA issuer
+    // The WHOLE warp runs this loop (warp-uniform control flow: the shared-memory descriptors live in uniform registers and
+    // an MMA costs a couple of issue slots); one elected lane executes the tcgen05 instructions.  The first version ran the
+    // loop under `if (lane == 0)`: divergent code, descriptors rebuilt in vector registers and moved to uniform ones per MMA --
+    // measured in the attention kernels at ~150 cycles per MMA, longer than the 128 cycles a 128 x 256 x 16 MMA takes
+    // (ncu, qkv shape: tensor pipe 64 % busy with no memory unit above 48 %).
+    {
       const uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
+      const uint32_t sbase = ptx::smem_u32(smem);
+      const uint64_t da0 = g.a_mn ? ptx::umma_smem_desc(sbase, g.mn_lbo, g.mn_sbo) : ptx::umma_smem_desc(sbase, 16, 1024);
+      const uint64_t db0 = g.b_mn ? ptx::umma_smem_desc(sbase + kStageA, g.mn_lbo, g.mn_sbo)
+                                  : ptx::umma_smem_desc(sbase + kStageA, 16, 1024);
+      // descriptor start-address field counts 16-byte units: advance by (bytes >> 4); k slice of 16: 2048 B (MN-major) / 32 B
+      const uint32_t a_step = (g.a_mn ? 2048u : 32u) >> 4, b_step = (g.b_mn ? 2048u : 32u) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -252,27 +300,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int split = rest / num_m_items;
         const int kb0 = split * g.kb_per_split;
         const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+        const bool unsummed = g.colsum && (w % g.num_n_blk) != 0;   // the epilogue warps skip this item's main loop
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t sb = sa + kStageA;
+          if (ptx::elect_one()) {
+            const uint64_t da = da0 + (uint64_t)((uint32_t)stage * (C::kStageBytes >> 4));
+            const uint64_t db = db0 + (uint64_t)((uint32_t)stage * (C::kStageBytes >> 4));
+            if (kb == kb0) ptx::umma_ss_first(tmem_d, da, db, idesc);
+            else ptx::umma_ss_acc(tmem_d, da, db, idesc);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = g.a_mn ? ptx::umma_smem_desc(sa + k * 2048, g.mn_lbo, g.mn_sbo)
-                                       : ptx::umma_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = g.b_mn ? ptx::umma_smem_desc(sb + k * 2048, g.mn_lbo, g.mn_sbo)
-                                       : ptx::umma_smem_desc(sb + k * 32, 16, 1024);
-            ptx::umma_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 1; k < BK / 16; ++k) ptx::umma_ss_acc(tmem_d, da + (uint64_t)(k * a_step), db + (uint64_t)(k * b_step), idesc);
+            if (MC == 1) ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+            else ptx::umma_commit_mc(&empty_bar[stage], (1u << MC) - 1);   // ... in both CTAs of the pair
+            if (unsummed) ptx::mbar_arrive_cnt(&empty_bar[stage], kEpiWarps);
           }
-          if (MC == 1) ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          else ptx::umma_commit_mc(&empty_bar[stage], (1u << MC) - 1);   // ... in both CTAs of the pair
+          __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -283,9 +333,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     constexpr int kChunks = (BN / 32) / (kEpiWarps / 4);   // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
+    int cs_stage = 0;                 // the smem ring position of this item's first k block (bias-gradient side product)
+    uint32_t cs_phase = 0;
     for (int w = first_work; w < num_work; w += work_stride) {
       const int n_blk = w % g.num_n_blk;
       const int m_blk = ((w / g.num_n_blk) % num_m_items) * MC + (int)rank;
+      if (g.colsum) {
+        // Bias gradient on the weight-gradient GEMM: dW = dY^T X streams dY through shared memory as the MN-major A
+        // operand ([64 k rows][64 m] bf16 boxes, 128B-swizzled); the epilogue warps -- idle during a K loop of
+        // T / 64 ~ 2000 blocks -- add up the rows of every A tile of the items with n_blk == 0 (each A tile is loaded once
+        // per n block).  A warp reads 4 rows x 128 B per LDS.128 (conflict-free); lane (r4, pc) = (lane >> 3, lane & 7)
+        // sees physical 16-byte chunk pc of rows 4 q + r4, i.e. logical chunk pc ^ (row & 7): two accumulator sets by the
+        // parity of q.  Warp e of 8: box e >> 2 (m columns 64 box ..), rows 16 (e & 3) .. + 15 of the box.
+        const int rest = w / g.num_n_blk;
+        const int split = rest / num_m_items;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+        if (n_blk == 0) {
+          const int e = warp - 2;
+          const int r4 = lane >> 3, pc = lane & 7;
+          float cs[2][8];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cs[i][j] = 0.f;
+          float* sacc = sbias_all;                      // [128] fp32: this item's column sums (no bias with O2_EPI_ACCUM)
+          if (e * 32 + lane < BM) sacc[e * 32 + lane] = 0.f;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            ptx::mbar_wait(&full_bar[cs_stage], cs_phase);
+            const uint8_t* box = smem + cs_stage * C::kStageBytes + (e >> 2) * (BK * 128) + (e & 3) * 16 * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 v = *reinterpret_cast<const uint4*>(box + (4 * q + r4) * 128 + pc * 16);
+              const float2 a0 = unpack_bf16x2(v.x), a1 = unpack_bf16x2(v.y), a2 = unpack_bf16x2(v.z), a3 = unpack_bf16x2(v.w);
+              float* c = cs[q & 1];
+              c[0] += a0.x; c[1] += a0.y; c[2] += a1.x; c[3] += a1.y; c[4] += a2.x; c[5] += a2.y; c[6] += a3.x; c[7] += a3.y;
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty_bar[cs_stage]);
+            if (++cs_stage == C::kStages) { cs_stage = 0; cs_phase ^= 1; }
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");     // sacc is zeroed
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int chunk = pc ^ (4 * i + r4);          // rows 16 (e & 3) + 4 q + r4: (row & 7) = 4 (q & 1) + r4
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&sacc[(e >> 2) * 64 + chunk * 8 + j], cs[i][j]);
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+          const int mloc = e * 32 + lane;
+          if (mloc < BM && (long long)m_blk * BM + mloc < g.M) atomicAdd(g.colsum + (long long)m_blk * BM + mloc, sacc[mloc]);
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");     // sacc may be re-zeroed by the next item
+        } else {
+          const int nk = cs_stage + (kb1 - kb0);
+          cs_phase ^= (uint32_t)((nk / C::kStages) & 1);
+          cs_stage = nk % C::kStages;
+        }
+      }
       // stage this warp's bias slice (kChunks * 32 columns) in shared memory while the accumulator is still in flight
       const bool has_bias = (g.epi == O2_EPI_BIAS || g.epi == O2_EPI_BIAS_GELU || g.epi == O2_EPI_BIAS_RES);
       const bool has_aux = (g.epi == O2_EPI_BIAS_RES || g.epi == O2_EPI_DGELU);
@@ -377,7 +481,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& g, cudaStream
 
 int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans_b, int64_t ldb, void* Cp, int c_dtype,
                int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue, const float* bias, const void* aux,
-               int64_t ld_aux, int64_t aux_rows, void* aux_out, int64_t ld_aux_out, int split_k, cudaStream_t st) {
+               int64_t ld_aux, int64_t aux_rows, void* aux_out, int64_t ld_aux_out, int split_k, const O2GemmDrop* drop,
+               cudaStream_t st) {
   O2_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_tc: empty problem %lld x %lld x %lld", (long long)M, (long long)N, (long long)K);
   O2_REQUIRE(N % 8 == 0, "gemm_tc: N=%lld must be a multiple of 8", (long long)N);
   O2_REQUIRE((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0, "gemm_tc: operand row pitch must be 16-byte aligned");
@@ -392,6 +497,7 @@ int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans
   if (epilogue == O2_EPI_BIAS_GELU)
     O2_REQUIRE(aux_out != nullptr && ld_aux_out % 8 == 0, "gemm_tc: BIAS_GELU needs aux_out");
   if (epilogue == O2_EPI_ACCUM) O2_REQUIRE(c_dtype == O2_F32, "gemm_tc: ACCUM needs fp32 C");
+  if (epilogue == O2_EPI_ACCUM && bias) O2_REQUIRE(trans_a, "gemm_tc: the column-sum side product of ACCUM needs trans_a=1");
   if (epilogue == O2_EPI_BIAS_GELU || epilogue == O2_EPI_BIAS_RES || epilogue == O2_EPI_DGELU)
     O2_REQUIRE(c_dtype == O2_BF16, "gemm_tc: epilogue %d writes bf16", epilogue);
   if (split_k < 1) split_k = 1;
@@ -402,7 +508,21 @@ int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.epi = epilogue; g.c_f32 = (c_dtype == O2_F32);
   g.ldc = ldc; g.ld_aux = ld_aux; g.aux_rows = aux_rows > 0 ? aux_rows : M; g.ld_aux_out = ld_aux_out;
-  g.bias = bias; g.aux = (const __nv_bfloat16*)aux; g.aux_out = (__nv_bfloat16*)aux_out; g.C = Cp;
+  g.bias = (epilogue == O2_EPI_ACCUM) ? nullptr : bias;
+  g.colsum = (epilogue == O2_EPI_ACCUM) ? const_cast<float*>(bias) : nullptr;
+  g.aux = (const __nv_bfloat16*)aux; g.aux_out = (__nv_bfloat16*)aux_out; g.C = Cp;
+  if (drop) {
+    O2_REQUIRE(epilogue == O2_EPI_BIAS_RES || epilogue == O2_EPI_BIAS_GELU || epilogue == O2_EPI_DGELU,
+               "gemm_tc: dropout is fused into the BIAS_RES / BIAS_GELU / DGELU epilogues only (got %d)", epilogue);
+    O2_REQUIRE(drop->p >= 0.f && drop->p < 1.f, "gemm_tc: dropout p=%f outside [0, 1)", (double)drop->p);
+    O2_REQUIRE(!drop->sample_scale || drop->rows_per_sample > 0, "gemm_tc: rows_per_sample must be > 0 with sample_scale");
+    g.drop = 1;
+    g.drop_key = ptx::lowbias32((uint32_t)drop->seed ^ ptx::lowbias32(drop->site ^ (uint32_t)(drop->seed >> 32)));
+    g.drop_thr16 = (uint32_t)floor((double)drop->p * 65536.0);
+    g.drop_inv_keep = 1.f / (1.f - drop->p);
+    g.sample_scale = drop->sample_scale;
+    g.rows_per_sample = drop->sample_scale ? drop->rows_per_sample : 1;
+  }
   g.wide_st = (ldc % 16 == 0) && ((uintptr_t)Cp % 32 == 0) && (!aux_out || (ld_aux_out % 16 == 0 && (uintptr_t)aux_out % 32 == 0)) &&
               !getenv("O2_GEMM_NARROW_ST");
   g.wide_ld = aux && (ld_aux % 16 == 0) && ((uintptr_t)aux % 32 == 0) && !getenv("O2_GEMM_NARROW_ST");

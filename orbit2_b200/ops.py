@@ -45,8 +45,10 @@ def _count(n=1):
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, trans_b=False, epi=EPI_NONE,
-         bias=None, aux=None, aux_rows=0, aux_out=None, split_k=1, M=None, N=None, K=None):
-    """out[M,N] = op(a) @ op(b) with fused epilogue; a/b/out are 2-D row-major (last stride 1)."""
+         bias=None, aux=None, aux_rows=0, aux_out=None, split_k=1, M=None, N=None, K=None, drop=None):
+    """out[M,N] = op(a) @ op(b) with fused epilogue; a/b/out are 2-D row-major (last stride 1).
+    ``drop`` = (p, seed, site, sample_scale or None, rows_per_sample): the token-stream dropout / drop-path mask of
+    o2_dropout fused into the BIAS_RES / BIAS_GELU / DGELU epilogue (bf16 arm only, o2_gemm_drop)."""
     lib = L.load()
     assert a.dim() == 2 and b.dim() == 2 and out.dim() == 2
     assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
@@ -60,6 +62,21 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, 
     assert out.shape[0] == M and out.shape[1] == N
     impl = impl_for(a.dtype)
     assert b.dtype == a.dtype
+    if drop is not None:
+        assert impl == GEMM_TC_BF16 and split_k == 1 and out.dtype == torch.bfloat16, "fused dropout: bf16 arm only"
+        p, seed, site, ss, rps = drop
+        spec = L.GemmDrop(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF, ss.data_ptr() if ss is not None else None,
+                          int(rps) if ss is not None else 0)
+        with _timed("gemm"):
+            rc = lib.o2_gemm_drop(_ptr(a), int(trans_a), a.stride(0), _ptr(b), int(trans_b), b.stride(0), _ptr(out),
+                                  out.stride(0), M, N, K, epi, _ptr(bias), _ptr(aux), aux.stride(0) if aux is not None else 0,
+                                  aux_rows, _ptr(aux_out), aux_out.stride(0) if aux_out is not None else 0, C.byref(spec),
+                                  _stream())
+        if TIMERS is not None:
+            TIMERS.setdefault("gemm_flops", []).append(2.0 * M * N * K)
+        L.check(rc, "o2_gemm_drop")
+        _count()
+        return out
     with _timed("gemm"):
         rc = lib.o2_gemm(impl, _ptr(a), int(trans_a), a.stride(0), _ptr(b), int(trans_b), b.stride(0), _ptr(out), dt(out),
                          out.stride(0), M, N, K, epi, _ptr(bias), _ptr(aux), aux.stride(0) if aux is not None else 0,
@@ -203,6 +220,26 @@ def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None):
     L.check(lib.o2_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "o2_cast_f32_to_bf16")
     _count()
     return dst
+
+
+def bicubic_fwd(src: torch.Tensor, ih: int, iw: int, oh: int, ow: int) -> torch.Tensor:
+    """[ih*iw, D] fp32 -> [oh*ow, D]: torch's bicubic (align_corners=False) on a channels-last table (pos_embed.py:103-138)."""
+    lib = L.load()
+    assert src.dtype == torch.float32 and src.is_contiguous() and src.shape[0] == ih * iw
+    dst = torch.empty(oh * ow, src.shape[1], device=src.device, dtype=torch.float32)
+    L.check(lib.o2_bicubic_fwd(_ptr(src), _ptr(dst), ih, iw, oh, ow, src.shape[1], _stream()), "o2_bicubic_fwd")
+    _count()
+    return dst
+
+
+def bicubic_bwd(d_dst: torch.Tensor, ih: int, iw: int, oh: int, ow: int) -> torch.Tensor:
+    """adjoint of bicubic_fwd: [oh*ow, D] -> [ih*iw, D] (deterministic gather)."""
+    lib = L.load()
+    assert d_dst.dtype == torch.float32 and d_dst.is_contiguous() and d_dst.shape[0] == oh * ow
+    d_src = torch.empty(ih * iw, d_dst.shape[1], device=d_dst.device, dtype=torch.float32)
+    L.check(lib.o2_bicubic_bwd(_ptr(d_dst), _ptr(d_src), ih, iw, oh, ow, d_dst.shape[1], _stream()), "o2_bicubic_bwd")
+    _count()
+    return d_src
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor):

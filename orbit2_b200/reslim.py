@@ -169,8 +169,12 @@ def _block_forward(g: Geometry, P, Wc, i: int, tok):
     qkv = gemm(y1, Wc[b + "attn.qkv.weight"], 3 * D, epi=EPI_BIAS, bias=P[b + "attn.qkv.bias"])
     adrop = (dp.rate, dp.seed, drop_site(i, SITE_ATTN)) if (dp is not None and dp.rate > 0) else None
     ao, s["lse"] = ops.attn_fwd(qkv, g.B, g.L, g.heads, g.hd, adrop)                 # attention.py:75 attn_drop
-    if dp is not None and dp.branch_active(i):
+    fused = act == torch.bfloat16          # the tcgen05 GEMM applies the masks in its epilogue; the fp32 arm in a separate pass
+    if dp is not None and dp.branch_active(i) and fused:
         # x + drop_path1(proj_drop(proj(.))): attention.py:81, vit_blocks.py:78
+        xm = gemm(ao, Wc[b + "attn.proj.weight"], D, epi=EPI_BIAS_RES, bias=P[b + "attn.proj.bias"], aux=tok,
+                  drop=(dp.rate, dp.seed, drop_site(i, SITE_PROJ), dp.path[i][0], g.L))
+    elif dp is not None and dp.branch_active(i):
         br = gemm(ao, Wc[b + "attn.proj.weight"], D, epi=EPI_BIAS, bias=P[b + "attn.proj.bias"])
         xm = ops.dropout(br, dp.rate, dp.seed, drop_site(i, SITE_PROJ), res=tok, sample_scale=dp.path[i][0],
                          rows_per_sample=g.L, out=br)
@@ -178,10 +182,15 @@ def _block_forward(g: Geometry, P, Wc, i: int, tok):
         xm = gemm(ao, Wc[b + "attn.proj.weight"], D, epi=EPI_BIAS_RES, bias=P[b + "attn.proj.bias"], aux=tok)
     y2, s["mean2"], s["rstd2"] = ops.layernorm_fwd(xm, P[b + "norm2.weight"], P[b + "norm2.bias"])
     pre = torch.empty(T, g.hidden, device=dev, dtype=act)
-    h = gemm(y2, Wc[b + "mlp.fc1.weight"], g.hidden, epi=EPI_BIAS_GELU, bias=P[b + "mlp.fc1.bias"], aux_out=pre)
-    if dp is not None and dp.rate > 0:
-        ops.dropout(h, dp.rate, dp.seed, drop_site(i, SITE_DROP1), out=h)       # mlp.py:65 drop1
-    if dp is not None and dp.branch_active(i):
+    drop1 = (dp.rate, dp.seed, drop_site(i, SITE_DROP1), None, 0) if (dp is not None and dp.rate > 0) else None
+    h = gemm(y2, Wc[b + "mlp.fc1.weight"], g.hidden, epi=EPI_BIAS_GELU, bias=P[b + "mlp.fc1.bias"], aux_out=pre,
+             drop=drop1 if fused else None)                                     # mlp.py:65 drop1
+    if drop1 is not None and not fused:
+        ops.dropout(h, dp.rate, dp.seed, drop_site(i, SITE_DROP1), out=h)
+    if dp is not None and dp.branch_active(i) and fused:
+        out = gemm(h, Wc[b + "mlp.fc2.weight"], D, epi=EPI_BIAS_RES, bias=P[b + "mlp.fc2.bias"], aux=xm,
+                   drop=(dp.rate, dp.seed, drop_site(i, SITE_DROP2), dp.path[i][1], g.L))   # mlp.py:68 drop2, vit_blocks.py:79
+    elif dp is not None and dp.branch_active(i):
         br = gemm(h, Wc[b + "mlp.fc2.weight"], D, epi=EPI_BIAS, bias=P[b + "mlp.fc2.bias"])
         out = ops.dropout(br, dp.rate, dp.seed, drop_site(i, SITE_DROP2), res=xm, sample_scale=dp.path[i][1],
                           rows_per_sample=g.L, out=br)                          # mlp.py:68 drop2, vit_blocks.py:79
@@ -247,10 +256,11 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
 
     def wgrad(dy, a, name):
         """dW[n_out, n_in] += dY^T A  (fp32, split-K over the token dimension so that small weight matrices still
-        fill the machine; partial tiles are accumulated with atomics); db += colsum(dY)"""
+        fill the machine; partial tiles are accumulated with atomics); db += colsum(dY) rides on the same GEMM: its
+        epilogue warps add up the dY tiles that stream through shared memory (no separate pass over dY)"""
         w = G[name + ".weight"]
-        ops.gemm(dy, a, w, trans_a=True, trans_b=True, epi=EPI_ACCUM, split_k=_wgrad_split(w.shape[0], w.shape[1]))
-        ops.colsum(dy, G[name + ".bias"])
+        ops.gemm(dy, a, w, trans_a=True, trans_b=True, epi=EPI_ACCUM, split_k=_wgrad_split(w.shape[0], w.shape[1]),
+                 bias=G[name + ".bias"])
 
     def ready(names):
         if on_ready is not None:
@@ -289,8 +299,10 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
         dbr = ops.dropout(dx, dp.rate, dp.seed, drop_site(i, SITE_DROP2), sample_scale=dp.path[i][1],
                           rows_per_sample=g.L) if branch_drop else dx
         wgrad(dbr, s["h"], b + "mlp.fc2")
-        dpre = dgrad(dbr, Wc[b + "mlp.fc2.weight"], g.hidden, epi=EPI_DGELU, aux=s["pre"])
-        if dp is not None and dp.rate > 0:
+        drop1 = (dp.rate, dp.seed, drop_site(i, SITE_DROP1), None, 0) if (dp is not None and dp.rate > 0) else None
+        fused = act == torch.bfloat16
+        dpre = dgrad(dbr, Wc[b + "mlp.fc2.weight"], g.hidden, epi=EPI_DGELU, aux=s["pre"], drop=drop1 if fused else None)
+        if drop1 is not None and not fused:
             ops.dropout(dpre, dp.rate, dp.seed, drop_site(i, SITE_DROP1), out=dpre)
         del dbr
         wgrad(dpre, s["y2"], b + "mlp.fc1")
@@ -338,6 +350,19 @@ def _wgrad_split(m: int, n: int, sms: int = 148, max_split: int = 8) -> int:
         if eff > best_eff:
             best, best_eff = sp, eff
     return best
+
+
+class _BicubicResample(torch.autograd.Function):
+    """pos_embed [ih*iw, D] -> [oh*ow, D] on the o2_bicubic kernels (channels-last: none of the reference's permutes)."""
+
+    @staticmethod
+    def forward(ctx, table, ih, iw, oh, ow):
+        ctx.dims = (ih, iw, oh, ow)
+        return ops.bicubic_fwd(table.detach(), ih, iw, oh, ow)
+
+    @staticmethod
+    def backward(ctx, d):
+        return ops.bicubic_bwd(d.contiguous().float(), *ctx.dims), None, None, None, None
 
 
 class ReslimFunction(torch.autograd.Function):
@@ -517,9 +542,9 @@ class Res_Slim_ViT(nn.Module):
         n = pe.shape[1]
         oh = int((n // 2) ** 0.5)
         if oh != gh:                                           # the reference assumes W/H == 2 for the stored grid
-            t = pe.reshape(-1, oh, 2 * oh, self.embed_dim).permute(0, 3, 1, 2)
-            t = F.interpolate(t, size=(gh, gw), mode="bicubic", align_corners=False)
-            pe = t.permute(0, 2, 3, 1).flatten(1, 2)
+            if pe.shape[0] != 1 or n != 2 * oh * oh:
+                raise RuntimeError(f"pos_embed with {n} rows is not an h x 2h grid (pos_embed.py:108-113 assumes W/H == 2)")
+            pe = _BicubicResample.apply(pe[0].contiguous(), oh, 2 * oh, gh, gw).unsqueeze(0)
         res = self._dev_const(("res", float(self.spatial_resolution)), [float(self.spatial_resolution)], torch.float32)
         se = F.linear(res, self.spatial_embed.weight.to(torch.float32), self.spatial_embed.bias.to(torch.float32))
         return (pe[0] + se[None]).contiguous()           # fp32; the kernel schedule casts it to the activation dtype

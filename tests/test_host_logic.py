@@ -39,20 +39,6 @@ def test_frontend_collapse_matches_oracle(fixture):
     assert rel(tok0, taps["tokens0"]) < 1e-6          # pos_res_embed is computed in fp32
 
 
-def test_pos_embed_resample_matches_oracle():
-    from oracle import cases, reslim_oracle as O
-    cfg = cases.get_case("tiny")
-    m = build_model(cfg)
-    m.img_size = (12, 24)                              # grid differs from the 8x16 init grid -> bicubic resample
-    with torch.no_grad():
-        m.pos_embed.normal_()
-    m.spatial_resolution = 0.0
-    with torch.no_grad():
-        m.spatial_embed.bias.zero_()
-    ref = O.interp_pos_embed(m.pos_embed.detach(), 2, (12, 24))[0]
-    assert rel(m.pos_res_embed(6, 12, torch.float32), ref) < 1e-6
-
-
 def test_state_dict_abi():
     from oracle import cases, reslim_oracle as O
     for name in ("tiny", "8m"):

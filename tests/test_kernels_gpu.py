@@ -419,3 +419,53 @@ def test_attn_dropout_mask_bits(dtype, p):
     assert torch.equal(got > 0.5, M > 0)
     kept = got[got > 0.5]
     assert (kept - 65536.0 / (65536 - int(p * 65536))).abs().max().item() < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("ih,iw,oh,ow,D", [(4, 8, 6, 12, 64), (8, 16, 5, 11, 128), (45, 90, 49, 94, 256), (3, 6, 24, 48, 32),
+                                           (16, 32, 16, 30, 1024), (2, 4, 1, 2, 8)])
+def test_bicubic_resample(ih, iw, oh, ow, D):
+    """o2_bicubic_fwd / _bwd (channels-last pos_embed resample) vs torch's upsample_bicubic2d and its autograd adjoint on
+    the same fp32 table: up- and down-sampling, non-integer ratios, magnification 8 (many outputs per clamped border tap)."""
+    from orbit2_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(ih * 131 + ow)
+    src = torch.randn(ih * iw, D, generator=g, device="cuda")
+    d = torch.randn(oh * ow, D, generator=g, device="cuda")
+    t = src.double().reshape(1, ih, iw, D).permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.interpolate(t, size=(oh, ow), mode="bicubic", align_corners=False)
+    ref.backward(d.double().reshape(1, oh, ow, D).permute(0, 3, 1, 2))
+    # float64 torch: the tap weights differ by the fp32 rounding of the source coordinate (both torch's fp32 kernel and
+    # ours compute scale * (dst + 0.5) - 0.5 in fp32, as the reference does); fp32 torch on the same device: rounding order only
+    out = ops.bicubic_fwd(src, ih, iw, oh, ow)
+    assert rel(out, ref.permute(0, 2, 3, 1).reshape(oh * ow, D)) < 3e-5
+    t32 = src.reshape(1, ih, iw, D).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    ref32 = F.interpolate(t32, size=(oh, ow), mode="bicubic", align_corners=False)
+    ref32.backward(d.reshape(1, oh, ow, D).permute(0, 3, 1, 2))
+    assert rel(out, ref32.permute(0, 2, 3, 1).reshape(oh * ow, D)) < 3e-6
+    dsrc = ops.bicubic_bwd(d, ih, iw, oh, ow)
+    assert rel(dsrc, t.grad.permute(0, 2, 3, 1).reshape(ih * iw, D)) < 3e-5
+    assert rel(dsrc, t32.grad.permute(0, 2, 3, 1).reshape(ih * iw, D)) < 1e-5      # torch's backward scatters with atomics
+    assert torch.equal(dsrc, ops.bicubic_bwd(d, ih, iw, oh, ow))          # gather form: bit-reproducible
+
+
+def test_pos_embed_resample_matches_oracle():
+    """Res_Slim_ViT.pos_res_embed on a grid that differs from the stored one (pos_embed.py:103-138) vs the oracle's
+    F.interpolate restatement, value and pos_embed gradient."""
+    from oracle import cases, reslim_oracle as O
+    from tests.util import build_model
+    cfg = cases.get_case("tiny")
+    m = build_model(cfg).cuda()
+    m.img_size = (12, 24)                              # grid differs from the 8x16 init grid -> bicubic resample
+    with torch.no_grad():
+        m.pos_embed.normal_()
+        m.spatial_embed.bias.zero_()
+    m.spatial_resolution = 0.0
+    pe = m.pos_embed.detach().cpu().double().requires_grad_(True)
+    ref = O.interp_pos_embed(pe, 2, (12, 24))[0]
+    out = m.pos_res_embed(6, 12, torch.float32)
+    assert rel(out.cpu(), ref) < 3e-5                  # float64 oracle vs fp32 source coordinates
+    ref32 = O.interp_pos_embed(m.pos_embed.detach().cpu(), 2, (12, 24))[0]
+    assert rel(out.cpu(), ref32) < 3e-6
+    w = torch.randn(ref.shape, dtype=torch.float64)
+    (ref * w).sum().backward()
+    (out * w.float().cuda()).sum().backward()
+    assert rel(m.pos_embed.grad.cpu(), pe.grad) < 3e-5

@@ -46,6 +46,30 @@ for name, fn, fl in cases:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     print(f"{name:36s} {ms:7.3f} ms {fl / ms / 1e9:8.1f} TFLOP/s")
+if not only or only == "cublas":
+    # the library on the SAME shapes (torch -> cuBLASLt, bf16 bias epilogue where it has one): the calibration point
+    import torch.nn.functional as F
+    lib = [
+        ("cuBLASLt qkv fwd +bias", lambda: F.linear(x, wqkv, b3.to(bf)), 2.0 * T * D * 3 * D),
+        ("cuBLASLt proj fwd +bias", lambda: F.linear(x, wp, b1.to(bf)), 2.0 * T * D * D),
+        ("cuBLASLt fc1 fwd +bias (no gelu)", lambda: F.linear(x, wfc1, bh.to(bf)), 2.0 * T * D * H),
+        ("cuBLASLt fc2 fwd +bias", lambda: F.linear(xh, wfc2, b1.to(bf)), 2.0 * T * D * H),
+        ("cuBLASLt fc1 dgrad", lambda: xh @ wfc1, 2.0 * T * D * H),
+        ("cuBLASLt fc1 wgrad (bf16 out)", lambda: xh.t() @ x, 2.0 * T * D * H),
+        ("cuBLASLt qkv wgrad (bf16 out)", lambda: dy3.t() @ x, 2.0 * T * D * 3 * D),
+    ]
+    for name, fn, fl in lib:
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"{name:36s} {ms:7.3f} ms {fl / ms / 1e9:8.1f} TFLOP/s")
 if not only:
     a = torch.randn(8192, 8192, device=dev).to(bf)
     for _ in range(2):
