@@ -228,8 +228,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int num_work = num_m_items * g.num_n_blk * g.split_k;
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = first_work; w < num_work; w += work_stride) {
@@ -241,37 +241,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * C::kStageBytes;
-          uint8_t* sb = sa + kStageA;
-          ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-          if (!g.a_mn) {
-            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-          } else {
-#pragma unroll
-            for (int i = 0; i < BM / 64; ++i)
-              ptx::tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
-          }
-          if (MC == 1) {
-            if (!g.b_mn) {
-              ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (ptx::elect_one()) {
+            uint8_t* sa = smem + stage * C::kStageBytes;
+            uint8_t* sb = sa + kStageA;
+            ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+            if (!g.a_mn) {
+              ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
             } else {
 #pragma unroll
-              for (int i = 0; i < BN / 64; ++i)
-                ptx::tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
+              for (int i = 0; i < BM / 64; ++i)
+                ptx::tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
             }
-          } else {
-            constexpr uint16_t kMask = (1u << MC) - 1;
-            if (!g.b_mn) {           // rows [rank * BN/MC, +BN/MC) of the B tile, to both CTAs
-              ptx::tma_load_2d_mc(sb + rank * (BN / MC) * 128, &tmap_b, &full_bar[stage], kb * BK,
-                                  n_blk * BN + (int)rank * (BN / MC), kMask);
-            } else {                 // this CTA's share of the 64-column chunks
+            if (MC == 1) {
+              if (!g.b_mn) {
+                ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+              } else {
 #pragma unroll
-              for (int i = 0; i < BN / 64 / MC; ++i) {
-                const int ci = (int)rank * (BN / 64 / MC) + i;
-                ptx::tma_load_2d_mc(sb + ci * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + ci * 64, kb * BK, kMask);
+                for (int i = 0; i < BN / 64; ++i)
+                  ptx::tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
+              }
+            } else {
+              constexpr uint16_t kMask = (1u << MC) - 1;
+              if (!g.b_mn) {           // rows [rank * BN/MC, +BN/MC) of the B tile, to both CTAs
+                ptx::tma_load_2d_mc(sb + rank * (BN / MC) * 128, &tmap_b, &full_bar[stage], kb * BK,
+                                    n_blk * BN + (int)rank * (BN / MC), kMask);
+              } else {                 // this CTA's share of the 64-column chunks
+#pragma unroll
+                for (int i = 0; i < BN / 64 / MC; ++i) {
+                  const int ci = (int)rank * (BN / 64 / MC) + i;
+                  ptx::tma_load_2d_mc(sb + ci * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + ci * 64, kb * BK, kMask);
+                }
               }
             }
           }
+          __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
