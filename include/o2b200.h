@@ -186,6 +186,14 @@ int o2_scale_channels(void* g, int dtype, const float* scale, int B, int C, int6
 int o2_dropout(const void* y, const void* res, void* out, int dtype, int64_t rows, int64_t cols,
                int64_t rows_per_sample, float p, const float* sample_scale, uint64_t seed, uint32_t site, void* stream);
 
+/* CUDA-graph replay with dropout: after o2_dropout_seed_source(dev_word) every dropout-capable entry point called from this
+ * host thread (o2_dropout, o2_gemm_drop, o2_attn_fwd_drop, o2_attn_bwd_parts_drop, o2_attn_bwd_fused) XORs a hash of the
+ * 64-bit word at dev_word -- read ON THE DEVICE when the kernel runs -- into its seed, so a captured training step draws new
+ * masks on every replay once the host rewrites the word in between (the by-value `seed` arguments are frozen into the
+ * graph).  NULL restores by-value seeds.  Forward and backward kernels of one step must see the same word.  Restated in
+ * oracle/dropout_mask.py (step_word argument). */
+int o2_dropout_seed_source(const uint64_t* dev_word);
+
 /* The same mask fused into the epilogue of the tcgen05 GEMM that produces the tensor (bf16 arm only; the fp32 arm keeps
  * the separate o2_dropout pass): e = m * N + n, mask m(e) = keep(e) / (1 - p), identical to o2_dropout on a [M, N] tensor.
  *   O2_EPI_BIAS_RES : C = (acc + bias) * m(e) * sample_scale[m / rows_per_sample] + aux     x + drop_path(proj_drop(proj(.)))

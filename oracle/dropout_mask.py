@@ -25,15 +25,24 @@ def _lb(x: int) -> int:
     return int(lowbias32(torch.tensor([x], dtype=torch.int64))[0])
 
 
-def site_key(seed: int, site: int) -> int:
-    return _lb((seed & M32) ^ _lb((site & M32) ^ ((seed >> 32) & M32)))
+def step_word_mix(word) -> int:
+    """Contribution of the device-resident step word (o2_dropout_seed_source, CUDA-graph replay) to every key:
+    common.cuh step_word_mix; 0 when no word is installed.  ``word`` is the 64-bit pattern (negative int64 values wrap)."""
+    if word is None:
+        return 0
+    w = int(word) & 0xFFFFFFFFFFFFFFFF
+    return _lb((w & M32) ^ _lb(((w >> 32) & M32) ^ 0x5BD1E995))
 
 
-def keep_mask(seed: int, site: int, n: int, p: float) -> torch.Tensor:
+def site_key(seed: int, site: int, step_word=None) -> int:
+    return _lb((seed & M32) ^ _lb((site & M32) ^ ((seed >> 32) & M32))) ^ step_word_mix(step_word)
+
+
+def keep_mask(seed: int, site: int, n: int, p: float, step_word=None) -> torch.Tensor:
     """bool [n]: keep decision of elements 0..n-1 of a dropout site (n < 2^33 in tests: hi32 of the pair index is 0)."""
     e = torch.arange(n, dtype=torch.int64)
     pair = e >> 1
-    h = lowbias32((pair & M32) ^ site_key(seed, site) ^ (((pair >> 32) * 0x9E3779B1) & M32))
+    h = lowbias32((pair & M32) ^ site_key(seed, site, step_word) ^ (((pair >> 32) * 0x9E3779B1) & M32))
     half = torch.where((e & 1) == 1, h >> 16, h & 0xFFFF)
     return half >= math.floor(p * 65536.0)
 
@@ -54,7 +63,8 @@ def attn_keep_bit(k: torch.Tensor) -> torch.Tensor:
     return 7 - (kk >> 2) + 8 * (kk & 1) + 16 * ((kk >> 1) & 1)
 
 
-def attn_scaled_mask(seed: int, site: int, B: int, heads: int, N: int, p: float, dtype=torch.float64) -> torch.Tensor:
+def attn_scaled_mask(seed: int, site: int, B: int, heads: int, N: int, p: float, dtype=torch.float64,
+                     step_word=None) -> torch.Tensor:
     """[B, heads, N, N] pre-scaled keep mask of the attention-probability dropout (orbit2_b200/csrc/common.cuh, bit-sliced):
     one 32-bit keep word per (query q, 32-key block kb): base = lowbias32((q * ceil(N / 32) + kb) ^ key_bh), eight planes
     w_i = lo32(base * K_i) ^ hi32(base * K_i) of a uniform byte U per key, keep iff U >= thr (LSB plane first:
@@ -69,7 +79,7 @@ def attn_scaled_mask(seed: int, site: int, B: int, heads: int, N: int, p: float,
     kb = torch.arange(nkb, dtype=torch.int64).view(1, nkb)
     k = torch.arange(N, dtype=torch.int64)
     bit = attn_keep_bit(k).view(1, N)
-    sk = site_key(seed, site)
+    sk = site_key(seed, site, step_word)
     out = torch.empty(B, heads, N, N, dtype=dtype)
     lo16 = 0xFFFF
     for bh in range(B * heads):

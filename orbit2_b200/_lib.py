@@ -43,6 +43,7 @@ SIGNATURES = {
     "o2_clip_replace": ([_p, _i, _p, _i, _u, _i, _i, _i, _i, _i, _i, _p], _i),
     "o2_scale_channels": ([_p, _i, _p, _i, _i, _l, _p], _i),
     "o2_dropout": ([_p, _p, _p, _i, _l, _l, _l, _f, _p, C.c_uint64, _u, _p], _i),
+    "o2_dropout_seed_source": ([_p], _i),
     "o2_normalize_fields": ([_p, _p, _p, _p, _i, _i, _l, _p], _i),
     "o2_eval_stats": ([_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p], _i),
     "o2_cast_f32_to_bf16": ([_p, _p, _l, _p], _i),

@@ -12,6 +12,13 @@ void o2_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local const uint64_t* g_step_word = nullptr;
+const uint64_t* o2_step_word() { return g_step_word; }
+extern "C" int o2_dropout_seed_source(const uint64_t* dev_word) {
+  g_step_word = dev_word;
+  return O2_OK;
+}
+
 extern "C" int o2_version(void) { return 100; }
 extern "C" const char* o2_last_error(void) { return g_err; }
 
@@ -63,7 +70,7 @@ int o2_make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, c
   }
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     O2_FAIL(O2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu box %u,%u stride0 %llu base %p",

@@ -13,6 +13,7 @@
 
 // ---------------------------------------------------------------- error plumbing
 void o2_set_error(const char* fmt, ...);
+const uint64_t* o2_step_word();     // abi.cu: the calling thread's current o2_dropout_seed_source pointer (or NULL)
 #define O2_FAIL(code, ...)            \
   do {                                \
     o2_set_error(__VA_ARGS__);        \
@@ -333,6 +334,7 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 // let lane l build the word of query q0 + l and read the others' by shuffle.
 struct AttnDrop {
   uint32_t site_key, thr16, nkb, frac8;
+  const uint64_t* step_word;  // o2_dropout_seed_source: device word XORed into the seed at run time (CUDA-graph replay), or NULL
   float inv_keep;
   uint32_t tm[8], tn[8];      // plane masks of the byte thresholds hi8 and hi8 + 1
 };
@@ -342,8 +344,15 @@ __host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
   x ^= x >> 15;
   return x;
 }
+// contribution of the device-resident step word to every dropout key (0 when none is installed): the masks of a captured
+// step change between graph replays because the host rewrites the word, not the kernel arguments
+__device__ __forceinline__ uint32_t step_word_mix(const uint64_t* step_word) {
+  if (!step_word) return 0u;
+  const uint64_t w = *step_word;
+  return lowbias32((uint32_t)w ^ lowbias32((uint32_t)(w >> 32) ^ 0x5BD1E995u));
+}
 __device__ __forceinline__ uint32_t attn_drop_key(const AttnDrop& d, int bh) {
-  return lowbias32(d.site_key ^ ((uint32_t)bh * 0x9E3779B1u));
+  return lowbias32((d.site_key ^ step_word_mix(d.step_word)) ^ ((uint32_t)bh * 0x9E3779B1u));
 }
 __device__ __forceinline__ uint32_t attn_keep_word(const AttnDrop& d, uint32_t key_bh, uint32_t q, uint32_t kb) {
   constexpr uint32_t kMul[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu,
@@ -377,6 +386,7 @@ template <int T2, int E> __device__ __forceinline__ uint32_t keep_mask_f32(uint3
 }
 inline AttnDrop make_attn_drop(float p, uint64_t seed, uint32_t site, int N) {
   AttnDrop d;
+  d.step_word = ::o2_step_word();
   d.site_key = lowbias32((uint32_t)seed ^ lowbias32(site ^ (uint32_t)(seed >> 32)));
   double pc = (double)p;
   if (pc > 0.99) pc = 0.99;                                   // hi8 + 1 must stay a byte
@@ -491,4 +501,5 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
 // cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint so the library has no link-time
 // dependency on libcuda (it must dlopen on the GPU-less build box for the symbol-export test).
 int o2_make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
-                 const uint64_t* strides_bytes /*rank-1 entries, dims[1..]*/, const uint32_t* box, int swizzle128);
+                 const uint64_t* strides_bytes /*rank-1 entries, dims[1..]*/, const uint32_t* box,
+                 int swizzle128 /*0 none, 1 SWIZZLE_128B, 2 SWIZZLE_64B*/);

@@ -29,6 +29,7 @@ struct DropArgs {
   const void* y; const void* res; void* out; const float* sample_scale;
   long long n_vec, elems_per_sample;
   uint32_t key, thr16;
+  const uint64_t* step_word;
   float inv_keep;
 };
 
@@ -39,6 +40,7 @@ template <> struct V<__nv_bfloat16> { static constexpr int N = 8; };
 template <typename T>
 __global__ void __launch_bounds__(256) dropout_kernel(const DropArgs a) {
   constexpr int VN = V<T>::N;
+  const uint32_t key = a.key ^ ptx::step_word_mix(a.step_word);
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < a.n_vec; v += (long long)gridDim.x * blockDim.x) {
     const long long e0 = v * VN;
     float s = a.inv_keep;
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(256) dropout_kernel(const DropArgs a) {
 #pragma unroll
     for (int j = 0; j < VN; j += 2) {
       const unsigned long long pair = (unsigned long long)(e0 + j) >> 1;
-      const uint32_t h = lowbias32((uint32_t)pair ^ a.key ^ ((uint32_t)(pair >> 32) * 0x9E3779B1u));
+      const uint32_t h = lowbias32((uint32_t)pair ^ key ^ ((uint32_t)(pair >> 32) * 0x9E3779B1u));
       o[j] = rv[j] + (((h & 0xFFFFu) >= a.thr16) ? yv[j] * s : 0.f);
       o[j + 1] = rv[j + 1] + (((h >> 16) >= a.thr16) ? yv[j + 1] * s : 0.f);
     }
@@ -102,6 +104,7 @@ extern "C" int o2_dropout(const void* y, const void* res, void* out, int dtype, 
   a.n_vec = rows * cols / vn;
   a.elems_per_sample = sample_scale ? rows_per_sample * cols : 1;
   a.key = lowbias32((uint32_t)seed ^ lowbias32(site ^ (uint32_t)(seed >> 32)));
+  a.step_word = o2_step_word();
   a.thr16 = (uint32_t)floor((double)p * 65536.0);
   a.inv_keep = 1.f / (1.f - p);
   long long blocks = (a.n_vec + 255) / 256;

@@ -23,7 +23,8 @@ constexpr uint32_t kStageA = BM * BK * 2;  // 16 KiB
 
 struct GemmArgs {
   int M, N, K;
-  int epi, c_f32, wide_st, wide_ld;   // C (and aux_out) / aux rows are 32-byte aligned -> 256-bit stores / loads
+  int dbg;   // O2_GEMM_DBG (timing experiments only, results invalid): 1 = skip the pre-activation store, 2 = skip the GELU math
+  int epi, c_f32, wide_st, wide_ld, tma_st;   // tma_st: bf16 outputs leave through shared memory + TMA stores   // C (and aux_out) / aux rows are 32-byte aligned -> 256-bit stores / loads
   long long ldc, ld_aux, aux_rows, ld_aux_out;
   const float* bias;
   // token-stream dropout / stochastic depth fused into the epilogue (mask function of csrc/dropout.cu, e = row * N + col):
@@ -31,6 +32,7 @@ struct GemmArgs {
   // DGELU: C = acc * m(e) * gelu'(aux);  m = keep / (1 - p)
   int drop;                  // 0: none
   uint32_t drop_key, drop_thr16;
+  const uint64_t* step_word;
   float drop_inv_keep;
   const float* sample_scale;
   long long rows_per_sample;
@@ -48,7 +50,9 @@ template <int BN> struct Cfg {
   static constexpr uint32_t kStageB = BN * BK * 2;
   static constexpr uint32_t kStageBytes = kStageA + kStageB;
   static constexpr int kTmemCols = 2 * BN;  // 512 or 256
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 128 * 4 /*bias*/;
+  static constexpr uint32_t kStagingBytes = kEpiWarps * 2048;   // per epilogue warp: 32 rows x 32 bf16 columns for the TMA store
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                         8 * 128 * 4 /*bias*/;
 };
 
 // One 32-column chunk of one output row.  `sbias` = this warp's bias slice staged in shared memory (broadcast reads), `ax` =
@@ -79,26 +83,164 @@ __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float* v
   }
 }
 
+// erf-GELU and its derivative for a PAIR of values in packed fp32x2 arithmetic (FFMA2 / FMUL2: two lanes per issue slot).
+// Same Abramowitz & Stegun 7.1.26 erf as gelu_fast / dgelu_fast of common.cuh (|error| <= 1.5e-7), rearranged so that no
+// sign handling or 1 + erf term is left:   t = 1 / (1 + 0.2316419 |x|),  q = 0.5 P(t) e^(-x^2 / 2)  (the 0.5 folded into the
+// polynomial coefficients),   gelu(x) = max(x, 0) - |x| q,   Phi(x) = 0.5 + copysign(0.5 - q, x),
+// gelu'(x) = Phi(x) + x e^(-x^2 / 2) / sqrt(2 pi).  Per pair: 6 FFMA2 + 4 FMUL2 + 2 LOP3 + 2 FMNMX + 4 MUFU for gelu (the
+// scalar form: 30 FMA-pipe instructions + 4 MUFU; ncu of the fc1 shape: FMUL + FFMA = 41 % of all issued instructions,
+// epilogue warps at 27 instructions per element and the tensor pipe waiting for them at 57 %).
+#define O2_C2(x) ptx::pack2((x), (x))
+struct GeluPair {
+  uint64_t X, NAX, Q, E;   // x, -|x|, q, e^(-x^2 / 2)
+};
+__device__ __forceinline__ GeluPair gelu_pair(float x0, float x1) {
+  GeluPair r;
+  r.X = ptx::pack2(x0, x1);
+  r.NAX = ptx::pack2u(__float_as_uint(x0) | 0x80000000u, __float_as_uint(x1) | 0x80000000u);
+  const uint64_t D = ptx::fma2(r.NAX, O2_C2(-0.23164190f), O2_C2(1.0f));
+  float d0, d1, t0, t1;
+  ptx::unpack2(D, d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t T = ptx::pack2(t0, t1);
+  uint64_t P = ptx::fma2(T, O2_C2(0.5f * 1.061405429f), O2_C2(0.5f * -1.453152027f));
+  P = ptx::fma2(P, T, O2_C2(0.5f * 1.421413741f));
+  P = ptx::fma2(P, T, O2_C2(0.5f * -0.284496736f));
+  P = ptx::fma2(P, T, O2_C2(0.5f * 0.254829592f));
+  P = ptx::mul2(P, T);
+  const uint64_t U = ptx::mul2(ptx::mul2(r.X, r.X), O2_C2(-0.72134752044448170f));     // -x^2 / 2 * log2(e)
+  float u0, u1;
+  ptx::unpack2(U, u0, u1);
+  r.E = ptx::pack2(ptx::ex2(u0), ptx::ex2(u1));
+  r.Q = ptx::mul2(P, r.E);
+  return r;
+}
+// the same for kP pairs with every step applied to all pairs before the next one: the dependent chain of one pair (fma2 ->
+// rcp -> 4 Horner steps -> ...) is ~12 instructions of 4-30 cycles latency each, and with two epilogue warps per scheduler
+// the pairs have to overlap INSIDE a warp (ncu: "wait" + scoreboard stalls 58 % of the samples, 0.2 IPC per warp)
+template <int kP>
+__device__ __forceinline__ void gelu_pairs(float* v) {          // v[2 kP] in place
+  uint64_t X[kP], NAX[kP], T[kP], P[kP], E[kP];
+#pragma unroll
+  for (int k = 0; k < kP; ++k) {
+    X[k] = ptx::pack2(v[2 * k], v[2 * k + 1]);
+    NAX[k] = ptx::pack2u(__float_as_uint(v[2 * k]) | 0x80000000u, __float_as_uint(v[2 * k + 1]) | 0x80000000u);
+  }
+#pragma unroll
+  for (int k = 0; k < kP; ++k) T[k] = ptx::fma2(NAX[k], O2_C2(-0.23164190f), O2_C2(1.0f));
+#pragma unroll
+  for (int k = 0; k < kP; ++k) {
+    float d0, d1, t0, t1;
+    ptx::unpack2(T[k], d0, d1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+    T[k] = ptx::pack2(t0, t1);
+  }
+#pragma unroll
+  for (int k = 0; k < kP; ++k) E[k] = ptx::mul2(ptx::mul2(X[k], X[k]), O2_C2(-0.72134752044448170f));
+#pragma unroll
+  for (int k = 0; k < kP; ++k) {
+    float u0, u1;
+    ptx::unpack2(E[k], u0, u1);
+    E[k] = ptx::pack2(ptx::ex2(u0), ptx::ex2(u1));
+  }
+#pragma unroll
+  for (int k = 0; k < kP; ++k) P[k] = ptx::fma2(T[k], O2_C2(0.5f * 1.061405429f), O2_C2(0.5f * -1.453152027f));
+#pragma unroll
+  for (int k = 0; k < kP; ++k) P[k] = ptx::fma2(P[k], T[k], O2_C2(0.5f * 1.421413741f));
+#pragma unroll
+  for (int k = 0; k < kP; ++k) P[k] = ptx::fma2(P[k], T[k], O2_C2(0.5f * -0.284496736f));
+#pragma unroll
+  for (int k = 0; k < kP; ++k) P[k] = ptx::fma2(P[k], T[k], O2_C2(0.5f * 0.254829592f));
+#pragma unroll
+  for (int k = 0; k < kP; ++k) P[k] = ptx::mul2(ptx::mul2(P[k], T[k]), E[k]);      // q
+#pragma unroll
+  for (int k = 0; k < kP; ++k)
+    ptx::unpack2(ptx::fma2(NAX[k], P[k], ptx::pack2(fmaxf(v[2 * k], 0.f), fmaxf(v[2 * k + 1], 0.f))), v[2 * k], v[2 * k + 1]);
+}
+__device__ __forceinline__ void gelu2(float& v0, float& v1) {
+  const GeluPair p = gelu_pair(v0, v1);
+  ptx::unpack2(ptx::fma2(p.NAX, p.Q, ptx::pack2(fmaxf(v0, 0.f), fmaxf(v1, 0.f))), v0, v1);
+}
+// (v0, v1) *= gelu'(a0, a1)
+__device__ __forceinline__ void dgelu_mul2(float& v0, float& v1, float a0, float a1) {
+  const GeluPair p = gelu_pair(a0, a1);
+  float h0, h1;
+  ptx::unpack2(ptx::fma2(p.Q, O2_C2(-1.0f), O2_C2(0.5f)), h0, h1);              // 0.5 - q >= 0
+  const uint64_t S = ptx::pack2u(__float_as_uint(h0) | (__float_as_uint(a0) & 0x80000000u),
+                                 __float_as_uint(h1) | (__float_as_uint(a1) & 0x80000000u));
+  const uint64_t Dg = ptx::fma2(ptx::mul2(p.X, O2_C2(0.39894228040143268f)), p.E, ptx::add2(S, O2_C2(0.5f)));
+  ptx::unpack2(ptx::mul2(ptx::pack2(v0, v1), Dg), v0, v1);
+}
+
 // keep / (1 - p) factors of the 16 elements (row, n .. n + 15) folded into v: one 32-bit hash per element pair
 __device__ __forceinline__ void drop_apply16(const GemmArgs& g, float (&v)[16], long long row, int n, float s) {
+  const uint32_t key = g.drop_key ^ ptx::step_word_mix(g.step_word);
   const unsigned long long pair0 = (unsigned long long)(row * (long long)g.N + n) >> 1;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const unsigned long long pair = pair0 + j;
-    const uint32_t h = ptx::lowbias32((uint32_t)pair ^ g.drop_key ^ ((uint32_t)(pair >> 32) * 0x9E3779B1u));
+    const uint32_t h = ptx::lowbias32((uint32_t)pair ^ key ^ ((uint32_t)(pair >> 32) * 0x9E3779B1u));
     v[2 * j] = ((h & 0xFFFFu) >= g.drop_thr16) ? v[2 * j] * s : 0.f;
     v[2 * j + 1] = ((h >> 16) >= g.drop_thr16) ? v[2 * j + 1] * s : 0.f;
   }
 }
 
+// bf16 outputs through shared memory and TMA.  A row-per-lane `st.global.v8` touches 32 different 128-byte lines per warp
+// instruction and costs the L1 data pipe ~64 wavefronts (ncu, fc1 + GELU shape: l1tex LSU wavefronts 65 % busy, two output
+// streams = 8 k wavefront cycles per tile against 8 k cycles of MMA -- the epilogue-"bound" shapes were store-path bound;
+// packed GELU math and prefetched TMEM loads changed nothing).  Each epilogue warp stages its 32 rows x 32 columns (64 B per
+// row, SWIZZLE_64B: 16-byte chunk c of row r at c ^ ((r >> 1) & 3), conflict-free for one row per lane) and one lane hands
+// the 2 KiB block to the TMA, which also clips rows >= M / columns >= N.
+struct StoreCtx {
+  uint8_t* stage;              // this warp's 2 KiB staging block (1 KiB aligned), or nullptr: direct stores
+  const CUtensorMap* tm_c;
+  const CUtensorMap* tm_aux;
+  int row0;                    // global row of lane 0
+  int lane;
+};
+__device__ __forceinline__ void stage_row16p(const StoreCtx& sc, int j0, const uint4& lo, const uint4& hi);
+__device__ __forceinline__ void stage_row16(const StoreCtx& sc, int j0, const float* v) {   // columns j0 .. j0 + 15 of the chunk
+  stage_row16p(sc, j0, pack8(v), pack8(v + 8));
+}
+__device__ __forceinline__ void stage_row16p(const StoreCtx& sc, int j0, const uint4& lo, const uint4& hi) {
+  const uint32_t swz = (uint32_t)(sc.lane >> 1) & 3u;
+  uint8_t* rowp = sc.stage + sc.lane * 64;
+  *reinterpret_cast<uint4*>(rowp + ((((uint32_t)j0 >> 3)) ^ swz) * 16) = lo;
+  *reinterpret_cast<uint4*>(rowp + ((((uint32_t)j0 >> 3) + 1) ^ swz) * 16) = hi;
+}
+__device__ __forceinline__ void stage_wait(const StoreCtx& sc) {     // the previous TMA store has read the block
+  if (sc.lane == 0) ptx::bulk_wait_read0();
+  __syncwarp();
+}
+__device__ __forceinline__ void stage_store(const StoreCtx& sc, const CUtensorMap* tm, int n0) {
+  ptx::fence_proxy_async_smem();
+  __syncwarp();
+  if (sc.lane == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(tm), "r"(ptx::smem_u32(sc.stage)), "r"(n0), "r"(sc.row0) : "memory");
+    ptx::bulk_commit_group();
+  }
+}
+
 template <int BN, int EPI, bool C_F32, bool DROP = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&r)[32], long long row, int n0,
-                                               const float* sbias, const uint4 (&ax)[4]) {
-  if (row >= g.M) return;
+                                               const float* sbias, const uint4 (&ax)[4], const StoreCtx& sc) {
+  constexpr bool kBf16Out = (EPI != O2_EPI_ACCUM) && !C_F32;
+  const bool tma = kBf16Out && sc.stage != nullptr;
+  uint4 keep[4];                                       // packed GELU outputs wait here while the pre-activation block is stored
+  if (tma) {
+    if (n0 >= g.N) return;                             // warp-uniform
+    stage_wait(sc);
+  }
+  // rows past M (zero accumulators: the TMA zero-fills them) run through the same arithmetic and only skip their stores,
+  // so the warp never diverges here (the early return cost a BSSY / BSYNC pair per chunk: 19 % of the stall samples)
+  const bool row_ok = row < g.M;
   float dscale = 1.f;
   if (DROP) {
     dscale = g.drop_inv_keep;
-    if (g.sample_scale) dscale *= __ldg(g.sample_scale + row / g.rows_per_sample);
+    if (g.sample_scale && row_ok) dscale *= __ldg(g.sample_scale + row / g.rows_per_sample);
   }
 #pragma unroll
   for (int j0 = 0; j0 < 32; j0 += 16) {
@@ -115,9 +257,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
       }
     }
     if (EPI == O2_EPI_BIAS_GELU) {
-      store_bf16x16(g.aux_out + row * g.ld_aux_out + n, v, n, g.N, g.wide_st);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+      if (tma) stage_row16(sc, j0, v);
+      else if (row_ok) store_bf16x16(g.aux_out + row * g.ld_aux_out + n, v, n, g.N, g.wide_st);
+      if (!(g.dbg & 2)) {
+        gelu_pairs<4>(v);
+        gelu_pairs<4>(v + 8);
+      }
     }
     if (DROP) drop_apply16(g, v, row, n, dscale);        // before the residual / GELU' factor
     if (EPI == O2_EPI_BIAS_RES || EPI == O2_EPI_DGELU) {
@@ -127,10 +272,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
         const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
         const float a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          v[8 * h + j] = (EPI == O2_EPI_BIAS_RES) ? (v[8 * h + j] + a[j]) : (v[8 * h + j] * dgelu_fast(a[j]));
+        for (int j = 0; j < 8; j += 2) {
+          if (EPI == O2_EPI_BIAS_RES) { v[8 * h + j] += a[j]; v[8 * h + j + 1] += a[j + 1]; }
+          else dgelu_mul2(v[8 * h + j], v[8 * h + j + 1], a[j], a[j + 1]);
+        }
       }
     }
+    if (kBf16Out && tma) {
+      if (EPI == O2_EPI_BIAS_GELU) {
+        keep[j0 >> 3] = pack8(v);
+        keep[(j0 >> 3) + 1] = pack8(v + 8);
+      } else {
+        stage_row16(sc, j0, v);
+      }
+      continue;
+    }
+    if (!row_ok) continue;
     if (EPI == O2_EPI_ACCUM) {
       float* c = reinterpret_cast<float*>(g.C) + row * g.ldc + n;
 #pragma unroll
@@ -148,33 +305,44 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
       store_bf16x16(reinterpret_cast<__nv_bfloat16*>(g.C) + row * g.ldc + n, v, n, g.N, g.wide_st);
     }
   }
+  if (tma) {
+    if (EPI == O2_EPI_BIAS_GELU) {
+      if (!(g.dbg & 1)) {
+        stage_store(sc, sc.tm_aux, n0);                // the pre-activation block
+        stage_wait(sc);
+      }
+      stage_row16p(sc, 0, keep[0], keep[1]);
+      stage_row16p(sc, 16, keep[2], keep[3]);
+    }
+    stage_store(sc, sc.tm_c, n0);
+  }
 }
 
 template <int BN>
 __device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, const uint32_t (&r)[32], long long row, int n0,
-                                                  const float* sbias, const uint4 (&ax)[4]) {
+                                                  const float* sbias, const uint4 (&ax)[4], const StoreCtx& sc) {
   switch (g.epi) {
     case O2_EPI_NONE:
-      if (g.c_f32) epilogue_chunk<BN, O2_EPI_NONE, true>(g, r, row, n0, sbias, ax);
-      else epilogue_chunk<BN, O2_EPI_NONE, false>(g, r, row, n0, sbias, ax);
+      if (g.c_f32) epilogue_chunk<BN, O2_EPI_NONE, true>(g, r, row, n0, sbias, ax, sc);
+      else epilogue_chunk<BN, O2_EPI_NONE, false>(g, r, row, n0, sbias, ax, sc);
       break;
     case O2_EPI_BIAS:
-      if (g.c_f32) epilogue_chunk<BN, O2_EPI_BIAS, true>(g, r, row, n0, sbias, ax);
-      else epilogue_chunk<BN, O2_EPI_BIAS, false>(g, r, row, n0, sbias, ax);
+      if (g.c_f32) epilogue_chunk<BN, O2_EPI_BIAS, true>(g, r, row, n0, sbias, ax, sc);
+      else epilogue_chunk<BN, O2_EPI_BIAS, false>(g, r, row, n0, sbias, ax, sc);
       break;
     case O2_EPI_BIAS_GELU:
-      if (g.drop) epilogue_chunk<BN, O2_EPI_BIAS_GELU, false, true>(g, r, row, n0, sbias, ax);
-      else epilogue_chunk<BN, O2_EPI_BIAS_GELU, false>(g, r, row, n0, sbias, ax);
+      if (g.drop) epilogue_chunk<BN, O2_EPI_BIAS_GELU, false, true>(g, r, row, n0, sbias, ax, sc);
+      else epilogue_chunk<BN, O2_EPI_BIAS_GELU, false>(g, r, row, n0, sbias, ax, sc);
       break;
     case O2_EPI_BIAS_RES:
-      if (g.drop) epilogue_chunk<BN, O2_EPI_BIAS_RES, false, true>(g, r, row, n0, sbias, ax);
-      else epilogue_chunk<BN, O2_EPI_BIAS_RES, false>(g, r, row, n0, sbias, ax);
+      if (g.drop) epilogue_chunk<BN, O2_EPI_BIAS_RES, false, true>(g, r, row, n0, sbias, ax, sc);
+      else epilogue_chunk<BN, O2_EPI_BIAS_RES, false>(g, r, row, n0, sbias, ax, sc);
       break;
     case O2_EPI_DGELU:
-      if (g.drop) epilogue_chunk<BN, O2_EPI_DGELU, false, true>(g, r, row, n0, sbias, ax);
-      else epilogue_chunk<BN, O2_EPI_DGELU, false>(g, r, row, n0, sbias, ax);
+      if (g.drop) epilogue_chunk<BN, O2_EPI_DGELU, false, true>(g, r, row, n0, sbias, ax, sc);
+      else epilogue_chunk<BN, O2_EPI_DGELU, false>(g, r, row, n0, sbias, ax, sc);
       break;
-    default: epilogue_chunk<BN, O2_EPI_ACCUM, true>(g, r, row, n0, sbias, ax); break;
+    default: epilogue_chunk<BN, O2_EPI_ACCUM, true>(g, r, row, n0, sbias, ax, sc); break;
   }
 }
 
@@ -183,18 +351,19 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, const uint3
 // kernel is bound by that traffic: 87 -> 131 FLOP per operand byte at BN = 256).  A stage is refilled only after BOTH
 // CTAs' MMAs have drained it (multicast tcgen05.commit onto both "empty" barriers).
 template <int BN, int MC>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)   // (a 320-thread block is allocated as 384: 168 registers per thread at most)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmArgs g) {
+               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux, const GemmArgs g) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* sstaging = smem + C::kStages * C::kStageBytes;          // [kEpiWarps][2 KiB], 1 KiB aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sstaging + C::kStagingBytes);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tfull_bar = empty_bar + C::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* sbias_all = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 256);   // [kEpiWarps][BN / 2] fp32
+  float* sbias_all = reinterpret_cast<float*>(sstaging + C::kStagingBytes + 256);   // [kEpiWarps][BN / 2] fp32
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -205,6 +374,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    if (g.tma_st) {
+      ptx::prefetch_tmap(&tmap_c);
+      if (g.epi == O2_EPI_BIAS_GELU) ptx::prefetch_tmap(&tmap_aux);
+    }
     for (int s = 0; s < C::kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       // + one arrival per epilogue warp when the bias-gradient side product reads the A tiles of a stage (below)
@@ -434,23 +607,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      // (Prefetching the next chunk's tcgen05.ld under this chunk's math -- two register buffers -- changed nothing: the
+      // epilogue was bound by its store path, see StoreCtx.)  The accumulator stage is handed back to the MMA warp as soon as
+      // its last chunk is in registers.
+      StoreCtx sc;
+      sc.stage = g.tma_st ? sstaging + (warp - 2) * 2048 : nullptr;
+      sc.tm_c = &tmap_c;
+      sc.tm_aux = &tmap_aux;
+      sc.row0 = m_blk * BM + q * 32;
+      sc.lane = lane;
+      const int cbase = cpart * kChunks;
 #pragma unroll 1
-      for (int c = cpart * kChunks; c < (cpart + 1) * kChunks; ++c) {
+      for (int i = 0; i < kChunks; ++i) {
+        const int c = cbase + i;
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr + c * 32, r);
         uint4 axn[4];
-        if (c + 1 < (cpart + 1) * kChunks) load_aux(c + 1, axn);      // next chunk's aux rides under this chunk's math
+        if (i + 1 < kChunks) load_aux(c + 1, axn);      // next chunk's aux rides under this chunk's math
         ptx::tmem_ld_wait();
-        epilogue_dispatch<BN>(g, r, row, n_blk * BN + c * 32, sb + (c - cpart * kChunks) * 32, ax);
+        if (i + 1 == kChunks) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tempty_bar[acc]);
+        }
+        epilogue_dispatch<BN>(g, r, row, n_blk * BN + c * 32, sb + i * 32, ax, sc);
 #pragma unroll
         for (int j = 0; j < 4; ++j) ax[j] = axn[j];
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
+  if (warp >= 2 && g.tma_st && lane == 0) ptx::bulk_wait0();   // this lane's TMA stores have left shared memory and landed
   ptx::tc_fence_before();
   __syncthreads();
   if (MC > 1) ptx::cluster_sync();       // no multicast / remote arrive may still target a CTA that has exited
@@ -458,7 +645,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 template <int BN, int MC>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& g, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, GemmArgs& g,
+           cudaStream_t st) {
   using C = Cfg<BN>;
   O2_SET_SMEM_ONCE((gemm_tc_kernel<BN, MC>), C::kSmemBytes);
   const int num_work = ((g.num_m_blk + MC - 1) / MC) * g.num_n_blk * g.split_k;
@@ -476,7 +664,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& g, cudaStream
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  O2_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MC>, ta, tb, g));
+  O2_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MC>, ta, tb, tc, tx, g));
   return O2_OK;
 }
 
@@ -521,6 +709,7 @@ int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans
     O2_REQUIRE(!drop->sample_scale || drop->rows_per_sample > 0, "gemm_tc: rows_per_sample must be > 0 with sample_scale");
     g.drop = 1;
     g.drop_key = ptx::lowbias32((uint32_t)drop->seed ^ ptx::lowbias32(drop->site ^ (uint32_t)(drop->seed >> 32)));
+    g.step_word = o2_step_word();
     g.drop_thr16 = (uint32_t)floor((double)drop->p * 65536.0);
     g.drop_inv_keep = 1.f / (1.f - drop->p);
     g.sample_scale = drop->sample_scale;
@@ -557,6 +746,22 @@ int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans
     rc = o2_make_tmap(&tb, B, 2, 2, dims, str, box, 1);
     if (rc) return rc;
   }
-  if (MC == 2) return BN == 256 ? launch<256, 2>(ta, tb, g, st) : launch<128, 2>(ta, tb, g, st);
-  return BN == 256 ? launch<256, 1>(ta, tb, g, st) : launch<128, 1>(ta, tb, g, st);
+  // bf16 outputs leave through TMA stores (32 x 32 boxes, SWIZZLE_64B); fp32 outputs / split-K atomics keep direct stores
+  CUtensorMap tc = ta, tx = ta;
+  if (const char* e = getenv("O2_GEMM_DBG")) g.dbg = atoi(e);
+  g.tma_st = (epilogue != O2_EPI_ACCUM && c_dtype == O2_BF16 && !getenv("O2_GEMM_DIRECT_ST")) ? 1 : 0;
+  if (g.tma_st) {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)ldc * 2};
+    uint32_t box[2] = {32, 32};
+    int rc = o2_make_tmap(&tc, Cp, 2, 2, dims, str, box, 2);
+    if (rc) return rc;
+    if (epilogue == O2_EPI_BIAS_GELU) {
+      str[0] = (uint64_t)ld_aux_out * 2;
+      O2_REQUIRE(((uintptr_t)aux_out % 16) == 0, "gemm_tc: aux_out must be 16-byte aligned");
+      rc = o2_make_tmap(&tx, aux_out, 2, 2, dims, str, box, 2);
+      if (rc) return rc;
+    }
+  }
+  if (MC == 2) return BN == 256 ? launch<256, 2>(ta, tb, tc, tx, g, st) : launch<128, 2>(ta, tb, tc, tx, g, st);
+  return BN == 256 ? launch<256, 1>(ta, tb, tc, tx, g, st) : launch<128, 1>(ta, tb, tc, tx, g, st);
 }

@@ -151,6 +151,7 @@ class TrainEngine:
             model.external_wc = self.Wc
         # CUDA-graph mode (enable_graph): the whole step is captured once and replayed; see graph_step
         self._graph = None
+        self._drop_word = None
         self._graph_warm = 0
         self._sc_dev = None
 
@@ -280,16 +281,17 @@ class TrainEngine:
     def enable_graph(self, warm_steps: int = 3):
         """Replay the whole step (forward, loss, backward, AdamW) as ONE captured CUDA graph from step ``warm_steps`` + 1
         on.  For launch-bound configurations (interm_8m: ~180 kernels of a few microseconds each, paced by the host's
-        issue rate when launched one by one).  Restrictions: one GPU (world size 1), replicated parameters, dropout 0
-        (the dropout counters are kernel arguments and would be frozen into the graph), fixed batch shape.  ``lr`` may
-        change between steps: AdamW reads its scalars from device memory (o2_adamw_dev).  The loss vector returned by
-        ``step`` is then ONE static tensor that every replay overwrites (read or clone it before the next step)."""
+        issue rate when launched one by one).  Restrictions: one GPU (world size 1), replicated parameters, fixed batch
+        shape, no dynamic grad scaler.  ``lr`` may change between steps: AdamW reads its scalars from device memory
+        (o2_adamw_dev).  Dropout / drop-path work under replay: the seeds the kernels were captured with stay fixed, but
+        every mask hash also mixes in a 64-bit step word read from device memory at run time (o2_dropout_seed_source) and
+        the per-sample drop-path factors live in fixed device buffers; both are rewritten before each replay.  The loss
+        vector returned by ``step`` is then ONE static tensor that every replay overwrites (read or clone it before the
+        next step)."""
         if self.world > 1 or self.fs is not None or self.sharded:
             raise RuntimeError("enable_graph: single-GPU, replicated-parameter engines only")
         if self.scaler is not None:
             raise RuntimeError("enable_graph: the dynamic grad scaler decides on the host whether to step")
-        if self.model.training and (self.model.drop_rate > 0 or self.model.drop_path > 0):
-            raise RuntimeError("enable_graph: dropout / drop-path must be 0 (their counters are frozen into a graph)")
         self._graph_warm = max(1, int(warm_steps))
 
     def graph_step(self, x, y):
@@ -300,11 +302,23 @@ class TrainEngine:
         if self._graph is None:
             self._gx, self._gy = x.clone(), y.clone()
             self._sc_dev = torch.zeros(8, device=self.device, dtype=torch.float32)
+            m = self.model
+            self._drop_word = None
+            if m.training and (m.drop_rate > 0 or m.drop_path > 0):
+                from .reslim import DropPlan
+                dpr = [float(v) for v in torch.linspace(0, m.drop_path, m.depth)] if m.depth else []
+                m.static_drop_plan = DropPlan(m.drop_rate, dpr, x.shape[0], int(torch.randint(0, 2 ** 62, (1,)).item()),
+                                              self.device)
+                self._drop_word = torch.zeros(1, device=self.device, dtype=torch.int64)
             g = torch.cuda.CUDAGraph()
             count = self.step_count
-            with torch.cuda.graph(g):
-                self._gvec = self.forward_backward(self._gx, self._gy)
-                self.optimizer_step()
+            ops.dropout_seed_source(self._drop_word)    # baked into the arguments of every captured dropout kernel
+            try:
+                with torch.cuda.graph(g):
+                    self._gvec = self.forward_backward(self._gx, self._gy)
+                    self.optimizer_step()
+            finally:
+                ops.dropout_seed_source(None)
             self.step_count = count                     # capture executes nothing
             self._graph = g
         if x.shape != self._gx.shape or y.shape != self._gy.shape:
@@ -314,5 +328,9 @@ class TrainEngine:
         self.step_count += 1
         # pageable source: the driver stages it before the call returns, so the next step cannot overwrite it in flight
         self._sc_dev.copy_(torch.tensor(self._adam_scalars(), dtype=torch.float32), non_blocking=True)
+        if self._drop_word is not None:                 # new masks for this replay (seeds come from torch's CPU generator)
+            word = torch.randint(-2 ** 62, 2 ** 62, (1,), dtype=torch.int64)
+            self._drop_word.copy_(word, non_blocking=True)
+            self.model.static_drop_plan.redraw_paths(int(word.item()) & 0x3FFFFFFFFFFFFFFF)
         self._graph.replay()
         return self._gvec

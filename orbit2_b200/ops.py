@@ -436,6 +436,15 @@ def dropout(y, p, seed, site, *, res=None, sample_scale=None, rows_per_sample=0,
     return out
 
 
+def dropout_seed_source(word: Optional[torch.Tensor]):
+    """Install (or with None remove) the device-resident 64-bit step word that every dropout-capable call of this thread XORs
+    into its seed at kernel run time (include/o2b200.h o2_dropout_seed_source): masks that change between CUDA-graph replays."""
+    lib = L.load()
+    if word is not None:
+        assert word.is_cuda and word.dtype == torch.int64 and word.numel() == 1
+    L.check(lib.o2_dropout_seed_source(_ptr(word)), "o2_dropout_seed_source")
+
+
 def normalize_fields_(x, mean, std, kind):
     """x [B,V,H,W] fp32 raw fields, normalised in place; mean/std fp32 [V], kind int32 [V] (0 Normalize, 1 LogTransform)."""
     lib = L.load()

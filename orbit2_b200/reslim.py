@@ -119,15 +119,30 @@ class DropPlan:
 
     def __init__(self, rate: float, dpr: Sequence[float], B: int, seed: int, device):
         self.rate, self.seed = float(rate), int(seed)
+        self.dpr, self.B = [float(d) for d in dpr], int(B)
         self.path = []
-        for i, dp in enumerate(dpr):
+        for i, sc in enumerate(self._draw(self.seed)):
+            self.path.append((None, None) if sc is None else (sc[0].to(device), sc[1].to(device)))
+
+    def _draw(self, seed: int):
+        out = []
+        for i, dp in enumerate(self.dpr):
             if dp > 0.0:
-                gen = torch.Generator().manual_seed((self.seed + 7919 * (i + 1)) & 0x7FFFFFFFFFFFFFFF)
-                keep = 1.0 - float(dp)
-                sc = (torch.rand(2, B, generator=gen) < keep).to(torch.float32) / keep
-                self.path.append((sc[0].to(device), sc[1].to(device)))
+                gen = torch.Generator().manual_seed((seed + 7919 * (i + 1)) & 0x7FFFFFFFFFFFFFFF)
+                keep = 1.0 - dp
+                out.append((torch.rand(2, self.B, generator=gen) < keep).to(torch.float32) / keep)
             else:
-                self.path.append((None, None))
+                out.append(None)
+        return out
+
+    def redraw_paths(self, seed: int):
+        """CUDA-graph mode: new per-sample drop-path factors written INTO the existing device tensors (the captured
+        kernels keep reading the same addresses); the element masks change through the device step word instead
+        (o2_dropout_seed_source), ``self.seed`` stays what the graph captured."""
+        for (a, b), sc in zip(self.path, self._draw(int(seed))):
+            if sc is not None:
+                a.copy_(sc[0], non_blocking=True)
+                b.copy_(sc[1], non_blocking=True)
 
     def branch_active(self, i: int) -> bool:
         return self.rate > 0.0 or self.path[i][0] is not None
@@ -600,7 +615,12 @@ class Res_Slim_ViT(nn.Module):
         g.act = act
         g.ckpt = bool(getattr(self, "activation_checkpointing", False))
         g.drop = None
-        if self.training and (self.drop_rate > 0 or self.drop_path > 0):
+        static_plan = getattr(self, "static_drop_plan", None)     # CUDA-graph engines: one plan with fixed device buffers
+        if self.training and static_plan is not None:
+            if static_plan.B != B:
+                raise RuntimeError("static_drop_plan was built for another batch size")
+            g.drop = static_plan
+        elif self.training and (self.drop_rate > 0 or self.drop_path > 0):
             # seeds come from torch's CPU generator: reproducible under torch.manual_seed, no device sync
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             dpr = [float(v) for v in torch.linspace(0, self.drop_path, self.depth)] if self.depth else []

@@ -469,3 +469,43 @@ def test_pos_embed_resample_matches_oracle():
     (ref * w).sum().backward()
     (out * w.float().cuda()).sum().backward()
     assert rel(m.pos_embed.grad.cpu(), pe.grad) < 3e-5
+
+
+def test_dropout_step_word_masks():
+    """o2_dropout_seed_source: with a device-resident step word installed, the token-stream and attention masks are the
+    restatement's masks for (seed, site, word) -- the word is read by the KERNEL, so rewriting it changes the next launch
+    with identical host arguments (what a CUDA-graph replay does) -- and removing it restores the by-value masks."""
+    from oracle import dropout_mask as DM
+    from orbit2_b200 import ops
+    seed, site, p = 0x0FED_CBA9_8765_4321, 21, 0.3
+    y = torch.ones(40, 64, device="cuda")
+    word = torch.zeros(1, device="cuda", dtype=torch.int64)
+    B, N, heads, hd = 1, 64, 2, 64
+    qkv = torch.zeros(B, N, 3, heads, hd, device="cuda")
+    qkv[:, torch.arange(N), 2, :, torch.arange(N)] = 1.0
+    qkv = qkv.reshape(B * N, 3 * heads * hd).to(torch.bfloat16)
+    plain = ops.dropout(y, p, seed, site)
+    try:
+        ops.dropout_seed_source(word)
+        seen = []
+        for w in (0, 0x1111_2222_3333_4444, -5):
+            word.fill_(w)
+            got = ops.dropout(y, p, seed, site)
+            ref = DM.keep_mask(seed, site, y.numel(), p, step_word=w).view_as(y).cuda()
+            assert torch.equal(got > 0, ref), hex(w & 0xFFFFFFFFFFFFFFFF)
+            out, _ = ops.attn_fwd(qkv, B, N, heads, hd, (p, seed, site))
+            am = out.float().reshape(B, N, heads, hd).permute(0, 2, 1, 3)[..., :N] * N > 0.5
+            assert torch.equal(am, DM.attn_scaled_mask(seed, site, B, heads, N, p, step_word=w).cuda() > 0)
+            # the GEMM epilogue reads the same word
+            a = torch.ones(40, 64, device="cuda", dtype=torch.bfloat16)
+            wgt = torch.eye(64, device="cuda", dtype=torch.bfloat16)
+            c = ops.gemm(a, wgt, torch.empty(40, 64, device="cuda", dtype=torch.bfloat16), epi=ops.EPI_BIAS_RES,
+                         bias=torch.zeros(64, device="cuda"), aux=torch.zeros(40, 64, device="cuda", dtype=torch.bfloat16),
+                         drop=(p, seed, site, None, 0))
+            assert torch.equal(c > 0, ref)
+            seen.append(got > 0)
+        assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
+    finally:
+        ops.dropout_seed_source(None)
+    assert torch.equal(ops.dropout(y, p, seed, site), plain)
+    assert torch.equal(plain > 0, DM.keep_mask(seed, site, y.numel(), p).view_as(y).cuda())

@@ -228,9 +228,12 @@ def test_activation_checkpointing(dtype, drop):
         m.activation_checkpointing = ckpt
         m.train()
         torch.manual_seed(7)
+        import gc
+        gc.collect()                                   # autograd contexts of earlier tests die only in a collection
         torch.cuda.synchronize(); torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
         pred = m(x, cfg["in_vars"], cfg["out_vars"])
-        held = torch.cuda.memory_allocated()
+        held = torch.cuda.memory_allocated() - base    # what this forward keeps alive for its backward
         loss = loss_fn(pred, y, var_names=cfg["out_vars"], var_weights=cfg["var_weights"], clip_out_variables=cfg["out_vars"])
         loss.backward()
         res.append((pred.detach().clone(), {k: p.grad.detach().double().clone() for k, p in m.named_parameters()

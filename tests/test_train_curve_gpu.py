@@ -87,6 +87,36 @@ def test_cuda_graph_step_equals_eager(dtype):
         eng.step(batches[0][0][:1], batches[0][1][:1])       # batch shape is frozen into the graph
 
 
+def test_cuda_graph_step_with_dropout():
+    """Graph mode at the YAMLs' dropout 0.1 / drop-path 0.1 (interm_8m trains like that): the captured step draws NEW masks
+    on every replay (device step word + refreshed drop-path factors) -- the same batch gives different losses step to step
+    and with another torch seed, the same ones with the same seed -- and it trains."""
+    from oracle import cases, reslim_oracle as O
+    from orbit2_b200 import engine, losses
+    cfg = cases.get_case("tiny")
+    sd0 = O.init_state_dict(cfg, seed=7)
+    x, y = (t.cuda() for t in O.synthetic_batch(cfg, 4, cfg["in_vars"], cfg["out_vars"], seed=0))
+
+    def run(seed, lr):
+        torch.manual_seed(seed)
+        m = build_model(cfg, sd0, "cuda", torch.bfloat16, drop_rate=0.1, drop_path=0.1).train()
+        loss_fn = losses.METRICS_REGISTRY["bayesian_tv"](
+            aggregate_only=True, metainfo=losses.MetricsMetaInfo(cfg["in_vars"], cfg["out_vars"], None, None))
+        eng = engine.TrainEngine(m, loss_fn, cfg["in_vars"], cfg["out_vars"], cfg["var_weights"], lr=lr, betas=(0.9, 0.99),
+                                 weight_decay=1e-5)
+        eng.enable_graph(warm_steps=2)
+        out = [eng.step(x, y)[-1].item() for _ in range(40)]
+        assert eng._graph is not None and eng._drop_word is not None
+        return out
+    frozen = run(1, 0.0)                                       # lr = 0: the weights never move, only the masks do
+    replays = frozen[3:]
+    assert len(set(replays)) > len(replays) // 2, "the replayed step keeps drawing the same masks"
+    assert run(1, 0.0) == frozen                               # reproducible under torch.manual_seed
+    assert run(2, 0.0)[3:] != replays
+    trained = run(1, 2e-3)
+    assert sum(trained[-5:]) < 0.95 * sum(trained[:5])
+
+
 def test_grad_scaler_semantics():
     """bf16 branch of the reference driver (intermediate_downscaling.py:733-742): gradients are produced pre-scaled, the
     update un-scales them (same trajectory as the unscaled engine up to bf16 rounding of the scaled dL/dpred), and a step

@@ -31,6 +31,18 @@ cases = [
     ("qkv  wgrad [3D,T]x[T,D] f32", lambda: ops.gemm(dy3, x, torch.zeros(3 * D, D, device=dev), trans_a=True, trans_b=True, epi=EPI_ACCUM, split_k=_wgrad_split(3 * D, D)), 2.0 * T * D * 3 * D),
     ("proj wgrad [D,T]x[T,D] f32", lambda: ops.gemm(x, x, torch.zeros(D, D, device=dev), trans_a=True, trans_b=True, epi=EPI_ACCUM, split_k=_wgrad_split(D, D)), 2.0 * T * D * D),
 ]
+if len(sys.argv) > 1 and sys.argv[1] == "probe":
+    # shape vs epilogue: the fc1 shape (N = 4096, K = 1024) with the plain epilogues, the qkv shape (N = 3072) with GELU
+    cases = [
+        ("fc1 shape, no epilogue", lambda: ops.gemm(x, wfc1, torch.empty(T, H, device=dev, dtype=bf)), 2.0 * T * D * H),
+        ("fc1 shape, +bias", lambda: ops.gemm(x, wfc1, torch.empty(T, H, device=dev, dtype=bf), epi=EPI_BIAS, bias=bh), 2.0 * T * D * H),
+        ("fc1 shape, +bias+gelu", lambda: ops.gemm(x, wfc1, torch.empty(T, H, device=dev, dtype=bf), epi=EPI_BIAS_GELU, bias=bh, aux_out=torch.empty(T, H, device=dev, dtype=bf)), 2.0 * T * D * H),
+        ("qkv shape, +bias", lambda: ops.gemm(x, wqkv, torch.empty(T, 3 * D, device=dev, dtype=bf), epi=EPI_BIAS, bias=b3), 2.0 * T * D * 3 * D),
+        ("qkv shape, +bias+gelu", lambda: ops.gemm(x, wqkv, torch.empty(T, 3 * D, device=dev, dtype=bf), epi=EPI_BIAS_GELU, bias=b3, aux_out=torch.empty(T, 3 * D, device=dev, dtype=bf)), 2.0 * T * D * 3 * D),
+        ("N=2048 shape, +bias", lambda: ops.gemm(x, wfc1[:2048], torch.empty(T, 2048, device=dev, dtype=bf), epi=EPI_BIAS, bias=bh[:2048]), 2.0 * T * D * 2048),
+        ("N=8192 (2x fc1 rows), +bias", lambda: ops.gemm(x, torch.cat([wfc1, wfc1]), torch.empty(T, 8192, device=dev, dtype=bf), epi=EPI_BIAS, bias=torch.cat([bh, bh])), 2.0 * T * D * 8192),
+    ]
+    sys.argv[1:] = []
 only = sys.argv[1] if len(sys.argv) > 1 else None
 for name, fn, fl in cases:
     if only and only not in name:
@@ -46,7 +58,7 @@ for name, fn, fl in cases:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     print(f"{name:36s} {ms:7.3f} ms {fl / ms / 1e9:8.1f} TFLOP/s")
-if not only or only == "cublas":
+if (not only and len(cases) > 8) or only == "cublas":
     # the library on the SAME shapes (torch -> cuBLASLt, bf16 bias epilogue where it has one): the calibration point
     import torch.nn.functional as F
     lib = [
@@ -70,7 +82,7 @@ if not only or only == "cublas":
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         print(f"{name:36s} {ms:7.3f} ms {fl / ms / 1e9:8.1f} TFLOP/s")
-if not only:
+if not only and len(cases) > 8:
     a = torch.randn(8192, 8192, device=dev).to(bf)
     for _ in range(2):
         a @ a
