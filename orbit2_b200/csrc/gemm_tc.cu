@@ -533,8 +533,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) cs[i][j] = 0.f;
-          float* sacc = sbias_all;                      // [128] fp32: this item's column sums (no bias with O2_EPI_ACCUM)
-          if (e * 32 + lane < BM) sacc[e * 32 + lane] = 0.f;
+          // per-item reduction in a FIXED order (no shared-memory atomics): 32 partial rows (4 warps x 4 row lanes x 2
+          // parity sets) x 128 columns of fp32 in the TMA-store staging block, which O2_EPI_ACCUM does not use
+          float* spart = reinterpret_cast<float*>(sstaging);
           for (int kb = kb0; kb < kb1; ++kb) {
             ptx::mbar_wait(&full_bar[cs_stage], cs_phase);
             const uint8_t* box = smem + cs_stage * C::kStageBytes + (e >> 2) * (BK * 128) + (e & 3) * 16 * 128;
@@ -549,17 +550,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (lane == 0) ptx::mbar_arrive(&empty_bar[cs_stage]);
             if (++cs_stage == C::kStages) { cs_stage = 0; cs_phase ^= 1; }
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");     // sacc is zeroed
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             const int chunk = pc ^ (4 * i + r4);          // rows 16 (e & 3) + 4 q + r4: (row & 7) = 4 (q & 1) + r4
-#pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(&sacc[(e >> 2) * 64 + chunk * 8 + j], cs[i][j]);
+            const int slot = ((e & 3) * 4 + r4) * 2 + i;
+            float* dst = spart + slot * BM + (e >> 2) * 64 + chunk * 8;
+            *reinterpret_cast<float4*>(dst) = make_float4(cs[i][0], cs[i][1], cs[i][2], cs[i][3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(cs[i][4], cs[i][5], cs[i][6], cs[i][7]);
           }
           asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
           const int mloc = e * 32 + lane;
-          if (mloc < BM && (long long)m_blk * BM + mloc < g.M) atomicAdd(g.colsum + (long long)m_blk * BM + mloc, sacc[mloc]);
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");     // sacc may be re-zeroed by the next item
+          if (mloc < BM && (long long)m_blk * BM + mloc < g.M) {
+            float t = 0.f;
+#pragma unroll 8
+            for (int sl = 0; sl < 32; ++sl) t += spart[sl * BM + mloc];
+            atomicAdd(g.colsum + (long long)m_blk * BM + mloc, t);     // one addend per (m block, K split)
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");     // spart may be rewritten by the next item
         } else {
           const int nk = cs_stage + (kb1 - kb0);
           cs_phase ^= (uint32_t)((nk / C::kStages) & 1);
