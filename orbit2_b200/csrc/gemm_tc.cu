@@ -17,13 +17,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-// epilogue warps: kEpiWarps / 4 per TMEM lane quarter, each draining a column slice.  12 = three per quarter (2 / 3 / 3 of the
-// eight 32-column chunks of a 128 x 256 tile): the epilogue is a latency-bound serial path per tile (ncu: 0.2 IPC per warp on
-// scoreboard / fixed-latency stalls), so a warp's share of the tile sets the pace of the GELU / residual shapes.  448 threads
-// are allocated as 512: 128 registers per thread; 16 warps (2 chunks each) would leave 96 and no room for their staging
-// blocks in shared memory.
-constexpr int kEpiWarps = 12;
-constexpr int kSumWarps = 8;    // of them, the ones that add up the A tiles for the bias-gradient side product
+constexpr int kEpiWarps = 8;    // epilogue warps: kEpiWarps / 4 per TMEM lane quarter, each draining a column slice
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // + TMA warp + MMA warp
 constexpr uint32_t kStageA = BM * BK * 2;  // 16 KiB
 
@@ -57,10 +51,8 @@ template <int BN> struct Cfg {
   static constexpr uint32_t kStageBytes = kStageA + kStageB;
   static constexpr int kTmemCols = 2 * BN;  // 512 or 256
   static constexpr uint32_t kStagingBytes = kEpiWarps * 2048;   // per epilogue warp: 32 rows x 32 bf16 columns for the TMA store
-  static constexpr uint32_t kBiasFloats = 128;                  // per epilogue warp: up to 3 chunks x 32 columns
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                         kEpiWarps * kBiasFloats * 4;
-  static_assert(kSmemBytes <= 232448, "shared memory budget");
+                                         8 * 128 * 4 /*bias*/;
 };
 
 // One 32-column chunk of one output row.  `sbias` = this warp's bias slice staged in shared memory (broadcast reads), `ax` =
@@ -389,7 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int s = 0; s < C::kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       // + one arrival per epilogue warp when the bias-gradient side product reads the A tiles of a stage (below)
-      ptx::mbar_init(&empty_bar[s], MC + (g.colsum ? kSumWarps : 0));
+      ptx::mbar_init(&empty_bar[s], MC + (g.colsum ? kEpiWarps : 0));
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
@@ -500,7 +492,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int k = 1; k < BK / 16; ++k) ptx::umma_ss_acc(tmem_d, da + (uint64_t)(k * a_step), db + (uint64_t)(k * b_step), idesc);
             if (MC == 1) ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
             else ptx::umma_commit_mc(&empty_bar[stage], (1u << MC) - 1);   // ... in both CTAs of the pair
-            if (unsummed) ptx::mbar_arrive_cnt(&empty_bar[stage], kSumWarps);
+            if (unsummed) ptx::mbar_arrive_cnt(&empty_bar[stage], kEpiWarps);
           }
           __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -514,9 +506,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ------------------------------------------------ epilogue: TMEM -> registers -> global
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int cpart = (warp - 2) >> 2;  // which slice of the tile's columns this warp drains
-    constexpr int kParts = kEpiWarps / 4, kNC = BN / 32;
-    const int cbeg = (cpart * kNC) / kParts, cend = ((cpart + 1) * kNC) / kParts;   // this warp's 32-column chunks
-    const int nchunks = cend - cbeg;
+    constexpr int kChunks = (BN / 32) / (kEpiWarps / 4);   // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
     int cs_stage = 0;                 // the smem ring position of this item's first k block (bias-gradient side product)
@@ -535,7 +525,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int split = rest / num_m_items;
         const int kb0 = split * g.kb_per_split;
         const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
-        if (n_blk == 0 && warp - 2 < kSumWarps) {
+        if (n_blk == 0) {
           const int e = warp - 2;
           const int r4 = lane >> 3, pc = lane & 7;
           float cs[2][8];
@@ -568,7 +558,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             *reinterpret_cast<float4*>(dst) = make_float4(cs[i][0], cs[i][1], cs[i][2], cs[i][3]);
             *reinterpret_cast<float4*>(dst + 4) = make_float4(cs[i][4], cs[i][5], cs[i][6], cs[i][7]);
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * kSumWarps) : "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
           const int mloc = e * 32 + lane;
           if (mloc < BM && (long long)m_blk * BM + mloc < g.M) {
             float t = 0.f;
@@ -576,21 +566,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int sl = 0; sl < 32; ++sl) t += spart[sl * BM + mloc];
             atomicAdd(g.colsum + (long long)m_blk * BM + mloc, t);     // one addend per (m block, K split)
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * kSumWarps) : "memory");     // spart may be rewritten by the next item
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");     // spart may be rewritten by the next item
         } else {
           const int nk = cs_stage + (kb1 - kb0);
           cs_phase ^= (uint32_t)((nk / C::kStages) & 1);
           cs_stage = nk % C::kStages;
         }
       }
-      // stage this warp's bias slice (nchunks * 32 columns) in shared memory while the accumulator is still in flight
+      // stage this warp's bias slice (kChunks * 32 columns) in shared memory while the accumulator is still in flight
       const bool has_bias = (g.epi == O2_EPI_BIAS || g.epi == O2_EPI_BIAS_GELU || g.epi == O2_EPI_BIAS_RES);
       const bool has_aux = (g.epi == O2_EPI_BIAS_RES || g.epi == O2_EPI_DGELU);
-      const int ncol0 = n_blk * BN + cbeg * 32;
-      float* sb = sbias_all + (warp - 2) * C::kBiasFloats;
+      const int ncol0 = n_blk * BN + cpart * kChunks * 32;
+      float* sb = sbias_all + (warp - 2) * (kChunks * 32);
       __syncwarp();
       if (has_bias) {
-        for (int i = lane * 4; i < nchunks * 32; i += 128) {
+        for (int i = lane * 4; i < kChunks * 32; i += 128) {
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ncol0 + i < g.N) bv = *reinterpret_cast<const float4*>(g.bias + ncol0 + i);
           *reinterpret_cast<float4*>(sb + i) = bv;
@@ -620,7 +610,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       };
       uint4 ax[4];
-      load_aux(cbeg, ax);                            // first chunk's aux before waiting for the accumulator
+      load_aux(cpart * kChunks, ax);                 // first chunk's aux before waiting for the accumulator
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -633,16 +623,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       sc.tm_aux = &tmap_aux;
       sc.row0 = m_blk * BM + q * 32;
       sc.lane = lane;
-      const int cbase = cbeg;
+      const int cbase = cpart * kChunks;
 #pragma unroll 1
-      for (int i = 0; i < nchunks; ++i) {
+      for (int i = 0; i < kChunks; ++i) {
         const int c = cbase + i;
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr + c * 32, r);
         uint4 axn[4];
-        if (i + 1 < nchunks) load_aux(c + 1, axn);      // next chunk's aux rides under this chunk's math
+        if (i + 1 < kChunks) load_aux(c + 1, axn);      // next chunk's aux rides under this chunk's math
         ptx::tmem_ld_wait();
-        if (i + 1 == nchunks) {
+        if (i + 1 == kChunks) {
           ptx::tc_fence_before();
           ptx::mbar_arrive(&tempty_bar[acc]);
         }
