@@ -45,14 +45,18 @@ struct GemmArgs {
   uint32_t mn_lbo, mn_sbo;  // descriptor strides for MN-major operands (bytes)
 };
 
-template <int BN> struct Cfg {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
-  static constexpr uint32_t kStageB = BN * BK * 2;
+// PAIR: the CTA pair runs ONE tcgen05.mma.cta_group::2 per k slice (256 x BN tile): a CTA holds its 128 rows of A and only
+// HALF of the B tile (32 instead of 48 KiB per stage at BN = 256 -> 6 stages instead of 4, and 64 instead of 96 bytes per
+// clock of shared-memory operand reads per SM).
+template <int BN, bool PAIR> struct Cfg {
+  static constexpr uint32_t kStageB = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr uint32_t kStageBytes = kStageA + kStageB;
+  static constexpr int kStages = PAIR ? (BN == 256 ? 6 : 8) : (BN == 256 ? 4 : 6);
   static constexpr int kTmemCols = 2 * BN;  // 512 or 256
   static constexpr uint32_t kStagingBytes = kEpiWarps * 2048;   // per epilogue warp: 32 rows x 32 bf16 columns for the TMA store
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
                                          8 * 128 * 4 /*bias*/;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 // One 32-column chunk of one output row.  `sbias` = this warp's bias slice staged in shared memory (broadcast reads), `ax` =
@@ -350,11 +354,12 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmArgs& g, const uint3
 // shared memories, so the L2 -> SM operand traffic per 128 x BN x 64 block drops from 16 + 32 KiB to 16 + 16 KiB (the
 // kernel is bound by that traffic: 87 -> 131 FLOP per operand byte at BN = 256).  A stage is refilled only after BOTH
 // CTAs' MMAs have drained it (multicast tcgen05.commit onto both "empty" barriers).
-template <int BN, int MC>
+template <int BN, int MC, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)   // (a 320-thread block is allocated as 384: 168 registers per thread at most)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux, const GemmArgs g) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
+  static_assert(!PAIR || MC == 2, "a CTA pair is a cluster of two");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* sstaging = smem + C::kStages * C::kStageBytes;          // [kEpiWarps][2 KiB], 1 KiB aligned
@@ -381,15 +386,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int s = 0; s < C::kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       // + one arrival per epilogue warp when the bias-gradient side product reads the A tiles of a stage (below)
-      ptx::mbar_init(&empty_bar[s], MC + (g.colsum ? kEpiWarps : 0));
+      ptx::mbar_init(&empty_bar[s], PAIR ? 1 : MC + (g.colsum ? kEpiWarps : 0));   // PAIR: the leader's multicast commit
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 32 * kEpiWarps);
+      ptx::mbar_init(&tempty_bar[a], PAIR ? 2 * kEpiWarps : 32 * kEpiWarps);       // PAIR: one arrival per epilogue warp of both CTAs
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) ptx::tmem_alloc_pair<C::kTmemCols>(tmem_slot);
+    else ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (MC > 1) ptx::cluster_sync();       // the peer's barriers are initialised before any multicast can reach them
@@ -414,6 +422,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (PAIR) {
+            // both CTAs' bytes are counted on the LEADER's barrier (the one its MMA warp waits on); each CTA fills its own
+            // shared memory: A rows of its m block, B rows [rank * BN / 2, + BN / 2) of the n block.  No multicast.
+            if (ptx::elect_one()) {
+              uint8_t* sa = smem + stage * C::kStageBytes;
+              uint8_t* sb = sa + kStageA;
+              if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+              const uint32_t lbar = ptx::mapa_u32(&full_bar[stage], 0);
+              if (!g.a_mn) {
+                ptx::tma_load_2d_pair(sa, &tmap_a, lbar, kb * BK, m_blk * BM);
+              } else {
+#pragma unroll
+                for (int i = 0; i < BM / 64; ++i)
+                  ptx::tma_load_2d_pair(sa + i * (BK * 128), &tmap_a, lbar, m_blk * BM + i * 64, kb * BK);
+              }
+              if (!g.b_mn) {
+                ptx::tma_load_2d_pair(sb, &tmap_b, lbar, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+              } else {
+#pragma unroll
+                for (int i = 0; i < BN / 128; ++i)
+                  ptx::tma_load_2d_pair(sb + i * (BK * 128), &tmap_b, lbar, n_blk * BN + (int)rank * (BN / 2) + i * 64, kb * BK);
+              }
+            }
+            __syncwarp();
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (ptx::elect_one()) {
             uint8_t* sa = smem + stage * C::kStageBytes;
             uint8_t* sb = sa + kStageA;
@@ -459,8 +494,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // loop under `if (lane == 0)`: divergent code, descriptors rebuilt in vector registers and moved to uniform ones per MMA --
     // measured in the attention kernels at ~150 cycles per MMA, longer than the 128 cycles a 128 x 256 x 16 MMA takes
     // (ncu, qkv shape: tensor pipe 64 % busy with no memory unit above 48 %).
-    {
-      const uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
+    if (!PAIR || rank == 0) {             // PAIR: only the leader CTA issues; its MMAs read both CTAs' shared memory
+      const uint32_t idesc = ptx::umma_idesc_bf16(PAIR ? 2 * BM : BM, BN, g.a_mn, g.b_mn);
       const uint32_t sbase = ptx::smem_u32(smem);
       const uint64_t da0 = g.a_mn ? ptx::umma_smem_desc(sbase, g.mn_lbo, g.mn_sbo) : ptx::umma_smem_desc(sbase, 16, 1024);
       const uint64_t db0 = g.b_mn ? ptx::umma_smem_desc(sbase + kStageA, g.mn_lbo, g.mn_sbo)
@@ -483,6 +518,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
+          if (PAIR) {
+            if (ptx::elect_one()) {
+              const uint64_t da = da0 + (uint64_t)((uint32_t)stage * (C::kStageBytes >> 4));
+              const uint64_t db = db0 + (uint64_t)((uint32_t)stage * (C::kStageBytes >> 4));
+              if (kb == kb0) ptx::umma_pair_first(tmem_d, da, db, idesc);
+              else ptx::umma_pair_acc(tmem_d, da, db, idesc);
+#pragma unroll
+              for (int k = 1; k < BK / 16; ++k) ptx::umma_pair_acc(tmem_d, da + (uint64_t)(k * a_step), db + (uint64_t)(k * b_step), idesc);
+              ptx::umma_commit_pair(&empty_bar[stage]);        // frees the stage in BOTH CTAs once these MMAs retire
+            }
+            __syncwarp();
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (ptx::elect_one()) {
             const uint64_t da = da0 + (uint64_t)((uint32_t)stage * (C::kStageBytes >> 4));
             const uint64_t db = db0 + (uint64_t)((uint32_t)stage * (C::kStageBytes >> 4));
@@ -497,7 +546,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (ptx::elect_one()) {                                   // accumulator complete -> epilogue (PAIR: of both CTAs)
+          if (PAIR) ptx::umma_commit_pair(&tfull_bar[acc]);
+          else ptx::umma_commit(&tfull_bar[acc]);
+        }
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -632,14 +684,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint4 axn[4];
         if (i + 1 < kChunks) load_aux(c + 1, axn);      // next chunk's aux rides under this chunk's math
         ptx::tmem_ld_wait();
+#ifndef O2_GEMM_LATE_RELEASE
         if (i + 1 == kChunks) {
           ptx::tc_fence_before();
-          ptx::mbar_arrive(&tempty_bar[acc]);
+          if (PAIR) {                                   // one arrival per warp on the LEADER's barrier (its MMA warp waits there)
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(&tempty_bar[acc], 0));
+          } else {
+            ptx::mbar_arrive(&tempty_bar[acc]);
+          }
         }
+#endif
         epilogue_dispatch<BN>(g, r, row, n_blk * BN + c * 32, sb + i * 32, ax, sc);
 #pragma unroll
         for (int j = 0; j < 4; ++j) ax[j] = axn[j];
       }
+#ifdef O2_GEMM_LATE_RELEASE
+      ptx::tc_fence_before();
+      if (PAIR) {
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(&tempty_bar[acc], 0));
+      } else {
+        ptx::mbar_arrive(&tempty_bar[acc]);
+      }
+#endif
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -648,14 +716,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   ptx::tc_fence_before();
   __syncthreads();
   if (MC > 1) ptx::cluster_sync();       // no multicast / remote arrive may still target a CTA that has exited
-  if (warp == 1) ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+  if (warp == 1) {
+    if (PAIR) ptx::tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+    else ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
 }
 
-template <int BN, int MC>
+template <int BN, int MC, bool PAIR = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, GemmArgs& g,
            cudaStream_t st) {
-  using C = Cfg<BN>;
-  O2_SET_SMEM_ONCE((gemm_tc_kernel<BN, MC>), C::kSmemBytes);
+  using C = Cfg<BN, PAIR>;
+  O2_SET_SMEM_ONCE((gemm_tc_kernel<BN, MC, PAIR>), C::kSmemBytes);
   const int num_work = ((g.num_m_blk + MC - 1) / MC) * g.num_n_blk * g.split_k;
   int ctas = num_work * MC < o2_num_sms() ? num_work * MC : o2_num_sms() / MC * MC;
   cudaLaunchConfig_t cfg;
@@ -671,7 +742,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  O2_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MC>, ta, tb, tc, tx, g));
+  O2_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MC, PAIR>, ta, tb, tc, tx, g));
   return O2_OK;
 }
 
@@ -769,6 +840,12 @@ int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans
       if (rc) return rc;
     }
   }
+  // cta_group::2 pairs for the forward and data-gradient GEMMs (A K-major): qkv fwd 1325 -> 1427, qkv dgrad 1375 -> 1480,
+  // fc2 fwd 1330 -> 1407 TFLOP/s (cuBLASLt: 1400 / 1590 / 1570).  Weight gradients (both operands MN-major) keep the
+  // multicast kernel: it is faster for them (fc2 wgrad 1314 vs 1175, D x D wgrad 1250 vs 994 in pair mode) and the epilogue
+  // warps of the bias-gradient side product wait on the CTA-local "full" barrier, which in pair mode only the leader has.
+  if (MC == 2 && !g.colsum && !g.a_mn && !getenv("O2_GEMM_NO_PAIR"))
+    return BN == 256 ? launch<256, 2, true>(ta, tb, tc, tx, g, st) : launch<128, 2, true>(ta, tb, tc, tx, g, st);
   if (MC == 2) return BN == 256 ? launch<256, 2>(ta, tb, tc, tx, g, st) : launch<128, 2>(ta, tb, tc, tx, g, st);
   return BN == 256 ? launch<256, 1>(ta, tb, tc, tx, g, st) : launch<128, 1>(ta, tb, tc, tx, g, st);
 }
