@@ -145,7 +145,7 @@ def test_head_tail_and_loss_full_grid(dtype):
     G = {k: torch.zeros_like(v) for k, v in dict(w1=w1, b1=b1, w2=w2, b2=b2, wo=wo, bo=bo).items()}
     dho, dh1 = ops.headtail_bwd(dpred, ho, h1, wo, w2, G["wo"], G["bo"], G["w2"], G["b2"], B, C, gh, gw, p, mag, g1=g1)
     ops.path2_conv1_bwd(x, idx, dh1, G["w1"], G["b1"])
-    gt = 2e-5 if dtype == torch.float32 else 2.5e-2
+    gt = 2e-5 if dtype == torch.float32 else 2e-2
     assert rel(dho, hod.grad) < gt
     for k, r in dict(wo=wod, bo=bod, w2=w2d, b2=b2d, w1=w1d, b1=b1d).items():
         assert rel(G[k], r.grad) < gt, k

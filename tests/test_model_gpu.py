@@ -49,10 +49,19 @@ def test_golden(fixture, dtype):
             continue
         assert k in grads, f"no gradient for {k}"
         worst[k] = rel(grads[k], gr)
-    # bf16 gradients: 2e-2 on the loss/prediction; parameter gradients are sums of bf16-rounded terms -> 5e-2, and the
-    # MAE gradient is sign(pred - target), discontinuous in the (bf16-perturbed) prediction -> 1e-1
-    gtol = tol if dtype == torch.float32 else (1e-1 if meta[2] == "mae" else 5e-2)
-    bad = {k: v for k, v in worst.items() if v > gtol}
+    # bf16 parameter gradients: 2e-2 like prediction and loss (measured: <= 9e-3 for mse / bayesian_tv, BELOW the reference
+    # schedule's own bf16-autocast error of 1.3-1.5e-2, profiles/r02_bf16_grad_error.md).  The MAE gradient is
+    # sign(pred - target), discontinuous in the bf16-perturbed prediction: there the bound is derived, per run, from what the
+    # reference schedule itself loses in bf16 on the same inputs (its worst parameter: ~5e-2) -- ours <= 2 x that.
+    if dtype == torch.float32 or meta[2] != "mae":
+        bad = {k: v for k, v in worst.items() if v > tol}
+    else:
+        from oracle import reslim_oracle as O
+        from tests.util import reference_schedule_bf16_grads
+        ref = reference_schedule_bf16_grads(cfg, sd, x, y, meta[2], O.lat_weights(z["lat"]) if meta[4] == "1" else None)
+        floor = max(rel(ref[k], gr) for k, gr in gref.items() if gr.abs().max() > 0 and k in ref)
+        assert floor < 1e-1, floor
+        bad = {k: v for k, v in worst.items() if v > max(tol, 2.0 * floor)}
     assert not bad, bad
 
 
@@ -72,7 +81,13 @@ def test_8m_vs_oracle(dtype):
     tol = TOL[dtype]
     assert rel(vec[-1], loss) < tol
     worst = {k: rel(grads[k], v.grad) for k, v in sd64.items() if v.grad is not None and v.grad.abs().max() > 0}
-    bad = {k: v for k, v in worst.items() if v > tol * (1 if dtype == torch.float32 else 2.5)}
+    # bf16: 2e-2 for every parameter but the LayerNorm scales, which get 3e-2: d(gamma) = sum_t dy * xhat is the one gradient
+    # whose two operands are BOTH bf16-stored activations -- this implementation keeps the residual stream x in bf16 (half the
+    # HBM traffic of every LayerNorm / residual pass), the reference keeps it in fp32 under autocast.  Measured here:
+    # blocks.0.norm2.weight 2.5e-2 (reference schedule under bf16 autocast: 0.9e-2), every other parameter < 2e-2.
+    def bound(k):
+        return 3e-2 if (dtype == torch.bfloat16 and k.split(".")[-2].startswith("norm") and k.endswith(".weight")) else tol
+    bad = {k: v for k, v in worst.items() if v > bound(k)}
     assert not bad, bad
 
 
@@ -92,7 +107,7 @@ def test_1b_widths_vs_oracle(dtype):
     tol = TOL[dtype]
     assert rel(vec[-1], loss) < tol
     worst = {k: rel(grads[k], v.grad) for k, v in sd64.items() if v.grad is not None and v.grad.abs().max() > 0}
-    bad = {k: v for k, v in worst.items() if v > tol * (1 if dtype == torch.float32 else 2.5)}
+    bad = {k: v for k, v in worst.items() if v > tol}
     assert not bad, bad
 
 
@@ -114,7 +129,7 @@ def test_10b_head_dim_vs_oracle(dtype):
     tol = TOL[dtype]
     assert rel(vec[-1], loss) < tol
     worst = {k: rel(grads[k], v.grad) for k, v in sd64.items() if v.grad is not None and v.grad.abs().max() > 0}
-    bad = {k: v for k, v in worst.items() if v > tol * (1 if dtype == torch.float32 else 2.5)}
+    bad = {k: v for k, v in worst.items() if v > tol}
     assert not bad, bad
 
 
@@ -182,7 +197,7 @@ def test_dropout_training_mode_vs_oracle(dtype, rate, path):
     assert rel(vec[-1], loss) < tol
     grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
     worst = {k: rel(grads[k], v.grad) for k, v in sd64.items() if v.grad is not None and v.grad.abs().max() > 0}
-    bad = {k: v for k, v in worst.items() if v > tol * (1 if dtype == torch.float32 else 2.5)}
+    bad = {k: v for k, v in worst.items() if v > tol}
     assert not bad, bad
     # eval mode ignores dropout
     m.eval()
@@ -264,7 +279,7 @@ def test_8m_vs_reference_fixture(dtype):
     clipped = O.clip_replace_constant(torch.from_numpy(z["y"]).double(), pred.double().cpu(), cfg["out_vars"])
     assert rel(clipped, torch.from_numpy(z["pred"]).double()) < tol
     assert rel(vec, torch.from_numpy(z["loss_vec"])) < tol
-    gtol = tol if dtype == torch.float32 else 5e-2
+    gtol = tol if dtype == torch.float32 else 2e-2
     bad = {}
     for k in z.files:
         if not k.startswith("g"):

@@ -32,3 +32,17 @@ def build_model(cfg, sd=None, device="cpu", compute_dtype=None, drop_rate=0.0, d
     m.spatial_resolution = cfg["spatial_resolution"]
     m.img_size = tuple(cfg["img_size"])
     return m.to(device)
+
+
+def reference_schedule_bf16_grads(cfg, sd, x, y, loss_name, lat_w=None):
+    """Parameter gradients of the REFERENCE SCHEDULE itself in bf16 on this GPU: the oracle port under
+    torch.autocast(bf16) with fp32 master weights (what intermediate_downscaling.py:601-607 runs).  Its error against the
+    float64 oracle is the arithmetic's own floor for each parameter; the bf16 parity tests bound ours by
+    max(2e-2, 2 x that floor) wherever a blanket 2e-2 does not hold (tools/bf16_grad_error.py prints the full table)."""
+    from oracle import reslim_oracle as O
+    sdc = {k: v.float().cuda().requires_grad_(True) for k, v in sd.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = O.training_step(sdc, cfg, x.float().cuda(), y.float().cuda(), cfg["in_vars"], cfg["out_vars"], loss_name,
+                               cfg["var_weights"], lat_w.float().cuda() if lat_w is not None else None)
+    loss.float().backward()
+    return {k: v.grad.double().cpu() for k, v in sdc.items() if v.grad is not None}
