@@ -23,7 +23,7 @@ constexpr uint32_t kStageA = BM * BK * 2;  // 16 KiB
 
 struct GemmArgs {
   int M, N, K;
-  int dbg;   // O2_GEMM_DBG (timing experiments only, results invalid): 1 = skip the pre-activation store, 2 = skip the GELU math
+  int dbg;   // -DO2_GEMM_ABLATE builds only (timing experiments, results invalid): O2_GEMM_DBG=1 skips the pre-activation store, 2 the GELU math
   int epi, c_f32, wide_st, wide_ld, tma_st;   // tma_st: bf16 outputs leave through shared memory + TMA stores   // C (and aux_out) / aux rows are 32-byte aligned -> 256-bit stores / loads
   long long ldc, ld_aux, aux_rows, ld_aux_out;
   const float* bias;
@@ -826,7 +826,9 @@ int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans
   }
   // bf16 outputs leave through TMA stores (32 x 32 boxes, SWIZZLE_64B); fp32 outputs / split-K atomics keep direct stores
   CUtensorMap tc = ta, tx = ta;
+#ifdef O2_GEMM_ABLATE
   if (const char* e = getenv("O2_GEMM_DBG")) g.dbg = atoi(e);
+#endif
   g.tma_st = (epilogue != O2_EPI_ACCUM && c_dtype == O2_BF16 && !getenv("O2_GEMM_DIRECT_ST")) ? 1 : 0;
   if (g.tma_st) {
     uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)ldc * 2};
