@@ -197,6 +197,7 @@ int o2_dropout_seed_source(const uint64_t* dev_word);
 /* The same mask fused into the epilogue of the tcgen05 GEMM that produces the tensor (bf16 arm only; the fp32 arm keeps
  * the separate o2_dropout pass): e = m * N + n, mask m(e) = keep(e) / (1 - p), identical to o2_dropout on a [M, N] tensor.
  *   O2_EPI_BIAS_RES : C = (acc + bias) * m(e) * sample_scale[m / rows_per_sample] + aux     x + drop_path(proj_drop(proj(.)))
+ *                     (after_residual: the mask multiplies the sum instead)
  *   O2_EPI_BIAS_GELU: aux_out = acc + bias;  C = gelu(aux_out) * m(e)                        drop1(act(fc1(.)))  mlp.py:63-65
  *   O2_EPI_DGELU    : C = acc * m(e) * gelu'(aux)                                            backward of the line above
  * sample_scale may be NULL (no drop-path); p may be 0 (drop-path only). */
@@ -206,7 +207,15 @@ typedef struct {
   uint32_t site;
   const float* sample_scale; /* fp32 [M / rows_per_sample] or NULL */
   int64_t rows_per_sample;
+  int32_t after_residual;    /* O2_EPI_BIAS_RES only: C = (acc + bias + aux) * m(e) -- pos_drop(tokens + pos_embed),
+                              * res_slimvit.py:281-284 -- instead of (acc + bias) * m(e) + aux */
 } O2GemmDrop;
+/* LayerNorm backward with a second, masked output (bf16, D <= 1024): dx as o2_layernorm_bwd, and dx_masked = dx * m(e) *
+ * sample_scale[row / rows_per_sample], e = row * D + col -- the gradient entering a residual branch whose forward was
+ * x + drop_path(drop(branch(.))), without a separate pass over dx. */
+int o2_layernorm_bwd_drop(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                          const void* dres, void* dx, void* dx_masked, float* dgamma, float* dbeta, int64_t T, int D,
+                          const O2GemmDrop* drop, void* stream);
 int o2_gemm_drop(const void* A, int trans_a, int64_t lda, const void* B, int trans_b, int64_t ldb, void* C, int64_t ldc,
                  int64_t M, int64_t N, int64_t K, int epilogue, const float* bias, const void* aux, int64_t ld_aux,
                  int64_t aux_rows, void* aux_out, int64_t ld_aux_out, const O2GemmDrop* drop, void* stream);

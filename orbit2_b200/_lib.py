@@ -26,6 +26,7 @@ SIGNATURES = {
     "o2_gemm_drop": ([_p, _i, _l, _p, _i, _l, _p, _l, _l, _l, _l, _i, _p, _p, _l, _l, _p, _l, _p, _p], _i),
     "o2_layernorm_fwd": ([_p, _p, _p, _p, _p, _p, _l, _i, _f, _i, _p], _i),
     "o2_layernorm_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p], _i),
+    "o2_layernorm_bwd_drop": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _p, _p], _i),
     "o2_attn_fwd": ([_i, _p, _p, _p, _i, _i, _i, _i, _f, _p], _i),
     "o2_attn_bwd": ([_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p], _i),
     "o2_attn_bwd_parts": ([_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p], _i),
@@ -61,7 +62,7 @@ SIGNATURES = {
 class GemmDrop(C.Structure):
     """O2GemmDrop of include/o2b200.h"""
     _fields_ = [("p", C.c_float), ("seed", C.c_uint64), ("site", C.c_uint32), ("sample_scale", C.c_void_p),
-                ("rows_per_sample", C.c_int64)]
+                ("rows_per_sample", C.c_int64), ("after_residual", C.c_int32)]
 
 
 _lib = None

@@ -30,7 +30,7 @@ struct GemmArgs {
   // token-stream dropout / stochastic depth fused into the epilogue (mask function of csrc/dropout.cu, e = row * N + col):
   // BIAS_RES: C = (acc + bias) * m(e) * sample_scale[row / rows_per_sample] + aux;  BIAS_GELU: C = gelu(pre) * m(e);
   // DGELU: C = acc * m(e) * gelu'(aux);  m = keep / (1 - p)
-  int drop;                  // 0: none
+  int drop;                  // 0: none, 1: mask before the residual add, 2: after it (pos_drop)
   uint32_t drop_key, drop_thr16;
   const uint64_t* step_word;
   float drop_inv_keep;
@@ -163,10 +163,6 @@ __device__ __forceinline__ void gelu_pairs(float* v) {          // v[2 kP] in pl
   for (int k = 0; k < kP; ++k)
     ptx::unpack2(ptx::fma2(NAX[k], P[k], ptx::pack2(fmaxf(v[2 * k], 0.f), fmaxf(v[2 * k + 1], 0.f))), v[2 * k], v[2 * k + 1]);
 }
-__device__ __forceinline__ void gelu2(float& v0, float& v1) {
-  const GeluPair p = gelu_pair(v0, v1);
-  ptx::unpack2(ptx::fma2(p.NAX, p.Q, ptx::pack2(fmaxf(v0, 0.f), fmaxf(v1, 0.f))), v0, v1);
-}
 // (v0, v1) *= gelu'(a0, a1)
 __device__ __forceinline__ void dgelu_mul2(float& v0, float& v1, float a0, float a1) {
   const GeluPair p = gelu_pair(a0, a1);
@@ -268,7 +264,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
         gelu_pairs<4>(v + 8);
       }
     }
-    if (DROP) drop_apply16(g, v, row, n, dscale);        // before the residual / GELU' factor
+    if (DROP && g.drop == 1) drop_apply16(g, v, row, n, dscale);        // before the residual / GELU' factor
     if (EPI == O2_EPI_BIAS_RES || EPI == O2_EPI_DGELU) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -282,6 +278,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
         }
       }
     }
+    if (DROP && EPI == O2_EPI_BIAS_RES && g.drop == 2) drop_apply16(g, v, row, n, dscale);   // pos_drop(x + pos)
     if (kBf16Out && tma) {
       if (EPI == O2_EPI_BIAS_GELU) {
         keep[j0 >> 3] = pack8(v);
@@ -785,7 +782,8 @@ int o2_gemm_tc(const void* A, int trans_a, int64_t lda, const void* B, int trans
                "gemm_tc: dropout is fused into the BIAS_RES / BIAS_GELU / DGELU epilogues only (got %d)", epilogue);
     O2_REQUIRE(drop->p >= 0.f && drop->p < 1.f, "gemm_tc: dropout p=%f outside [0, 1)", (double)drop->p);
     O2_REQUIRE(!drop->sample_scale || drop->rows_per_sample > 0, "gemm_tc: rows_per_sample must be > 0 with sample_scale");
-    g.drop = 1;
+    O2_REQUIRE(!drop->after_residual || epilogue == O2_EPI_BIAS_RES, "gemm_tc: after_residual is a BIAS_RES option");
+    g.drop = drop->after_residual ? 2 : 1;
     g.drop_key = ptx::lowbias32((uint32_t)drop->seed ^ ptx::lowbias32(drop->site ^ (uint32_t)(drop->seed >> 32)));
     g.step_word = o2_step_word();
     g.drop_thr16 = (uint32_t)floor((double)drop->p * 65536.0);

@@ -278,12 +278,23 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                :: "r"(ptx::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(ptx::smem_u32(bar)) : "memory");
 }
 
+// optional second output of the backward: the same dx through a token-stream dropout / drop-path mask (the gradient that
+// enters the residual branch whose forward was x + drop_path(drop(branch)): mask function of dropout.cu, e = row * D + col)
+struct LnDrop {
+  __nv_bfloat16* out;           // nullptr: no second output
+  uint32_t key, thr16;
+  float inv_keep;
+  const float* sample_scale;
+  long long rows_per_sample;
+  const uint64_t* step_word;
+};
+
 template <int NV>
 __global__ void __launch_bounds__(kLnWarps * 32, 2) ln_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                                                        const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dres,
                                                                        __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
-                                                                       float* __restrict__ dbeta, long long rows, int D) {
+                                                                       float* __restrict__ dbeta, long long rows, int D, const LnDrop dm) {
   constexpr int W = NV * 256;                       // padded row width (elements)
   extern __shared__ __align__(128) uint8_t ln_smem[];
   __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(ln_smem);                 // [warp][stage][x | dy | dres][W]
@@ -369,6 +380,22 @@ __global__ void __launch_bounds__(kLnWarps * 32, 2) ln_bwd_ring_kernel(const __n
           o[j] += rs * (gy - s1 - xh * s2);
         }
         Vec<__nv_bfloat16>::store(dx + row * D + vi * 8, o);
+        if (dm.out) {
+          float sc = dm.inv_keep;
+          if (dm.sample_scale) sc *= __ldg(dm.sample_scale + row / dm.rows_per_sample);
+          const uint32_t key = dm.key ^ ptx::step_word_mix(dm.step_word);
+          const unsigned long long pair0 = (unsigned long long)(row * D + vi * 8) >> 1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const unsigned long long pair = pair0 + j;
+            const uint32_t h = ptx::lowbias32((uint32_t)pair ^ key ^ ((uint32_t)(pair >> 32) * 0x9E3779B1u));
+            // the mask multiplies the ROUNDED dx, so the result is bit for bit what o2_dropout makes of the stored dx
+            const float a = __bfloat162float(__float2bfloat16_rn(o[2 * j])), b = __bfloat162float(__float2bfloat16_rn(o[2 * j + 1]));
+            o[2 * j] = ((h & 0xFFFFu) >= dm.thr16) ? a * sc : 0.f;
+            o[2 * j + 1] = ((h >> 16) >= dm.thr16) ? b * sc : 0.f;
+          }
+          Vec<__nv_bfloat16>::store(dm.out + row * D + vi * 8, o);
+        }
       }
     }
     __syncwarp();                                   // every lane is done reading this stage
@@ -447,10 +474,12 @@ int ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float*
 
 template <typename T>
 int ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
-           void* dx, float* dgamma, float* dbeta, long long T_, int D, cudaStream_t st) {
+           void* dx, float* dgamma, float* dbeta, long long T_, int D, cudaStream_t st, const LnDrop& dm) {
   constexpr int VN = Vec<T>::N;
   const int nv = (D / VN + 31) / 32;
-  if (std::is_same<T, __nv_bfloat16>::value && nv <= 4 && !getenv("O2_LN_BWD_SPLIT")) {
+  const bool ring = std::is_same<T, __nv_bfloat16>::value && nv <= 4 && !getenv("O2_LN_BWD_SPLIT");
+  O2_REQUIRE(!dm.out || ring, "layernorm_bwd: the masked second output needs the bf16 row kernel (D <= 1024); apply o2_dropout to dx instead");
+  if (ring) {
     auto launch = [&](auto kern, int nvt) -> int {
       const size_t smem = (size_t)kLnWarps * kLnStages * 3 * nvt * 256 * 2 + (size_t)3 * nvt * 256 * 4 + kLnWarps * kLnStages * 8;
       O2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -458,7 +487,7 @@ int ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLnWarps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
       const long long grid = std::min((long long)o2_num_sms() * per_sm, (T_ + kLnWarps - 1) / kLnWarps);
       kern<<<(unsigned)grid, kLnWarps * 32, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, gamma, mean, rstd,
-                                                       (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, dgamma, dbeta, T_, D);
+                                                       (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, dgamma, dbeta, T_, D, dm);
       O2_LAUNCH_CHECK();
       return O2_OK;
     };
@@ -531,6 +560,27 @@ extern "C" int o2_layernorm_bwd(const void* dy, const void* x, const float* gamm
   if (rc) return rc;
   O2_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  return dtype == O2_F32 ? ln_bwd<float>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, T_, D, st)
-                         : ln_bwd<__nv_bfloat16>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, T_, D, st);
+  LnDrop dm;
+  memset(&dm, 0, sizeof(dm));
+  return dtype == O2_F32 ? ln_bwd<float>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, T_, D, st, dm)
+                         : ln_bwd<__nv_bfloat16>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, T_, D, st, dm);
+}
+
+extern "C" int o2_layernorm_bwd_drop(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                     const void* dres, void* dx, void* dx_masked, float* dgamma, float* dbeta, int64_t T_, int D,
+                                     const O2GemmDrop* drop, void* stream) {
+  int rc = check_dims(T_, D, O2_BF16);
+  if (rc) return rc;
+  O2_REQUIRE(dy && x && gamma && mean && rstd && dx && dx_masked && dgamma && dbeta && drop, "layernorm_bwd_drop: null pointer");
+  O2_REQUIRE(drop->p >= 0.f && drop->p < 1.f, "layernorm_bwd_drop: p=%f outside [0, 1)", (double)drop->p);
+  O2_REQUIRE(!drop->sample_scale || drop->rows_per_sample > 0, "layernorm_bwd_drop: rows_per_sample must be > 0 with sample_scale");
+  LnDrop dm;
+  dm.out = (__nv_bfloat16*)dx_masked;
+  dm.key = ptx::lowbias32((uint32_t)drop->seed ^ ptx::lowbias32(drop->site ^ (uint32_t)(drop->seed >> 32)));
+  dm.thr16 = (uint32_t)floor((double)drop->p * 65536.0);
+  dm.inv_keep = 1.f / (1.f - drop->p);
+  dm.sample_scale = drop->sample_scale;
+  dm.rows_per_sample = drop->sample_scale ? drop->rows_per_sample : 1;
+  dm.step_word = o2_step_word();
+  return ln_bwd<__nv_bfloat16>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, T_, D, (cudaStream_t)stream, dm);
 }

@@ -47,8 +47,8 @@ def _count(n=1):
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, trans_b=False, epi=EPI_NONE,
          bias=None, aux=None, aux_rows=0, aux_out=None, split_k=1, M=None, N=None, K=None, drop=None):
     """out[M,N] = op(a) @ op(b) with fused epilogue; a/b/out are 2-D row-major (last stride 1).
-    ``drop`` = (p, seed, site, sample_scale or None, rows_per_sample): the token-stream dropout / drop-path mask of
-    o2_dropout fused into the BIAS_RES / BIAS_GELU / DGELU epilogue (bf16 arm only, o2_gemm_drop)."""
+    ``drop`` = (p, seed, site, sample_scale or None, rows_per_sample[, after_residual]): the token-stream dropout / drop-path
+    mask of o2_dropout fused into the BIAS_RES / BIAS_GELU / DGELU epilogue (bf16 arm only, o2_gemm_drop)."""
     lib = L.load()
     assert a.dim() == 2 and b.dim() == 2 and out.dim() == 2
     assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
@@ -64,9 +64,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, 
     assert b.dtype == a.dtype
     if drop is not None:
         assert impl == GEMM_TC_BF16 and split_k == 1 and out.dtype == torch.bfloat16, "fused dropout: bf16 arm only"
-        p, seed, site, ss, rps = drop
+        p, seed, site, ss, rps = drop[:5]
         spec = L.GemmDrop(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF, ss.data_ptr() if ss is not None else None,
-                          int(rps) if ss is not None else 0)
+                          int(rps) if ss is not None else 0, 1 if (len(drop) > 5 and drop[5]) else 0)
         with _timed("gemm"):
             rc = lib.o2_gemm_drop(_ptr(a), int(trans_a), a.stride(0), _ptr(b), int(trans_b), b.stride(0), _ptr(out),
                                   out.stride(0), M, N, K, epi, _ptr(bias), _ptr(aux), aux.stride(0) if aux is not None else 0,
@@ -101,14 +101,31 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None):
-    """returns dx (= LN'(dy) + dres); dgamma/dbeta fp32 are accumulated into."""
+LN_DROP_MAX_D = 1024      # widest row of the bf16 LayerNorm-backward kernel that can emit the masked second output
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None, drop=None):
+    """returns dx (= LN'(dy) + dres); dgamma/dbeta fp32 are accumulated into.  With ``drop`` = (p, seed, site, sample_scale or
+    None, rows_per_sample) returns (dx, dx * mask): the second tensor is what o2_dropout would make of dx (bf16, D <= 1024:
+    written by the same kernel; otherwise by a separate o2_dropout pass)."""
     lib = L.load()
     T, D = x.shape
     dx = torch.empty_like(x)
+    if drop is not None and x.dtype == torch.bfloat16 and D <= LN_DROP_MAX_D and not os.environ.get("O2_LN_BWD_SPLIT"):
+        p, seed, site, ss, rps = drop
+        spec = L.GemmDrop(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF, ss.data_ptr() if ss is not None else None,
+                          int(rps) if ss is not None else 0, 0)
+        dxm = torch.empty_like(x)
+        L.check(lib.o2_layernorm_bwd_drop(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx), _ptr(dxm),
+                                          _ptr(dgamma), _ptr(dbeta), T, D, C.byref(spec), _stream()), "o2_layernorm_bwd_drop")
+        _count()
+        return dx, dxm
     L.check(lib.o2_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx),
                                  _ptr(dgamma), _ptr(dbeta), T, D, dt(x), _stream()), "o2_layernorm_bwd")
     _count()
+    if drop is not None:
+        p, seed, site, ss, rps = drop
+        return dx, dropout(dx, p, seed, site, sample_scale=ss, rows_per_sample=rps if ss is not None else 0)
     return dx
 
 

@@ -228,10 +228,13 @@ def reslim_forward(g: Geometry, P: Dict[str, torch.Tensor], Wc: Dict[str, torch.
 
     S["h1"], S["g1"] = h1, g1 = ops.path2_conv1_fwd(x, g.idx7, P["path2.0.weight"], P["path2.0.bias"], act, mag=g.mag)
     S["o"] = o = ops.frontend_fwd(x, tab_s, tab_v, g.p, g.gh, g.gw, g.hd, act)
-    tok = gemm(o, Wc["var_agg.proj.weight"], D, epi=EPI_BIAS_RES, bias=P["var_agg.proj.bias"], aux=posres, aux_rows=g.L)
     dp = getattr(g, "drop", None)
-    if dp is not None and dp.rate > 0:
-        ops.dropout(tok, dp.rate, dp.seed, SITE_POS, out=tok)                       # pos_drop, res_slimvit.py:284
+    pos_drop = dp is not None and dp.rate > 0                                       # pos_drop, res_slimvit.py:284
+    fused = act == torch.bfloat16
+    tok = gemm(o, Wc["var_agg.proj.weight"], D, epi=EPI_BIAS_RES, bias=P["var_agg.proj.bias"], aux=posres, aux_rows=g.L,
+               drop=(dp.rate, dp.seed, SITE_POS, None, 0, True) if (pos_drop and fused) else None)
+    if pos_drop and not fused:
+        ops.dropout(tok, dp.rate, dp.seed, SITE_POS, out=tok)
     blocks = []
     ckpt = bool(getattr(g, "ckpt", False))
     for i in range(g.depth):
@@ -301,9 +304,19 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
         else:
             d = dgrad(d, Wc[f"head.{2 * j}.weight"], D)
     ready([f"head.{2 * j}.{s}" for j in range(g.dec + 1) for s in ("weight", "bias")])
-    dx = ops.layernorm_bwd(d, S["xf"], P["norm.weight"], S["meanf"], S["rstdf"], G["norm.weight"], G["norm.bias"])
-    ready(["norm.weight", "norm.bias"])
     dp = getattr(g, "drop", None)
+
+    def branch_mask(i, which, path_ix):
+        """(p, seed, site, sample_scale, rows) of the gradient mask of Block i's residual branch, or None: the LayerNorm
+        backward that produces the stream gradient also writes its masked copy (same mask, same scale as the forward)"""
+        if i < 0 or dp is None or not dp.branch_active(i):
+            return None
+        return (dp.rate, dp.seed, drop_site(i, which), dp.path[i][path_ix], g.L)
+
+    mk = branch_mask(g.depth - 1, SITE_DROP2, 1)
+    dx = ops.layernorm_bwd(d, S["xf"], P["norm.weight"], S["meanf"], S["rstdf"], G["norm.weight"], G["norm.bias"], drop=mk)
+    dx, dx_masked = dx if mk is not None else (dx, None)
+    ready(["norm.weight", "norm.bias"])
     for i in range(g.depth - 1, -1, -1):
         b = f"blocks.{i}."
         s = S["blocks"][i]
@@ -311,8 +324,7 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
             _, s = _block_forward(g, P, Wc, i, s["x"])
         branch_drop = dp is not None and dp.branch_active(i)
         # gradient entering the MLP branch = the stream gradient through drop_path2 / drop2 (same mask, same scale)
-        dbr = ops.dropout(dx, dp.rate, dp.seed, drop_site(i, SITE_DROP2), sample_scale=dp.path[i][1],
-                          rows_per_sample=g.L) if branch_drop else dx
+        dbr = dx_masked if branch_drop else dx
         wgrad(dbr, s["h"], b + "mlp.fc2")
         drop1 = (dp.rate, dp.seed, drop_site(i, SITE_DROP1), None, 0) if (dp is not None and dp.rate > 0) else None
         fused = act == torch.bfloat16
@@ -323,10 +335,11 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
         wgrad(dpre, s["y2"], b + "mlp.fc1")
         dy2 = dgrad(dpre, Wc[b + "mlp.fc1.weight"], D)
         del dpre
+        mk = branch_mask(i, SITE_PROJ, 0)
         dxm = ops.layernorm_bwd(dy2, s["xm"], P[b + "norm2.weight"], s["mean2"], s["rstd2"], G[b + "norm2.weight"],
-                                G[b + "norm2.bias"], dres=dx)
-        dbr = ops.dropout(dxm, dp.rate, dp.seed, drop_site(i, SITE_PROJ), sample_scale=dp.path[i][0],
-                          rows_per_sample=g.L) if branch_drop else dxm
+                                G[b + "norm2.bias"], dres=dx, drop=mk)
+        dxm, dbr = dxm if mk is not None else (dxm, dxm)
+        del dx_masked
         wgrad(dbr, s["ao"], b + "attn.proj")
         dao = dgrad(dbr, Wc[b + "attn.proj.weight"], D)
         del dbr
@@ -335,15 +348,19 @@ def reslim_backward(g: Geometry, P, Wc, x, tab_s, tab_v, S, dpreds, G: Dict[str,
         wgrad(dqkv, s["y1"], b + "attn.qkv")
         dy1 = dgrad(dqkv, Wc[b + "attn.qkv.weight"], D)
         del dqkv
+        mk = branch_mask(i - 1, SITE_DROP2, 1)
+        if i == 0 and dp is not None and dp.rate > 0:       # the gradient leaving Block 0 goes through pos_drop: only the
+            mk = (dp.rate, dp.seed, SITE_POS, None, 0)      # masked copy is needed below
         dx = ops.layernorm_bwd(dy1, s["x"], P[b + "norm1.weight"], s["mean1"], s["rstd1"], G[b + "norm1.weight"],
-                               G[b + "norm1.bias"], dres=dxm)
+                               G[b + "norm1.bias"], dres=dxm, drop=mk)
+        dx, dx_masked = dx if mk is not None else (dx, None)
         s.clear()
         ready([b + n for n in ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight",
                                "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias",
                                "mlp.fc2.weight", "mlp.fc2.bias")])
     # tok = pos_drop(proj(o) + bias + posres)
     if dp is not None and dp.rate > 0:
-        dx = ops.dropout(dx, dp.rate, dp.seed, SITE_POS, out=dx)
+        dx = dx_masked if g.depth > 0 else ops.dropout(dx, dp.rate, dp.seed, SITE_POS, out=dx)
     dposres = torch.zeros(g.L * D, device=dev, dtype=torch.float32)
     ops.colsum(dx.view(g.B, g.L * D), dposres)
     wgrad(dx, S["o"], "var_agg.proj")

@@ -509,3 +509,27 @@ def test_dropout_step_word_masks():
         ops.dropout_seed_source(None)
     assert torch.equal(ops.dropout(y, p, seed, site), plain)
     assert torch.equal(plain > 0, DM.keep_mask(seed, site, y.numel(), p).view_as(y).cuda())
+
+
+@pytest.mark.parametrize("T,D,rps", [(1000, 1024, 250), (129, 128, 129), (67, 512, 10), (300, 3072, 100)])
+def test_layernorm_bwd_masked_second_output(T, D, rps):
+    """o2_layernorm_bwd_drop: the second output is bit for bit what o2_dropout makes of dx (same hash mask, drop-path factor
+    per sample); dx, dgamma, dbeta are those of the plain call.  D = 3072 takes the separate-pass fallback of ops.layernorm_bwd."""
+    from orbit2_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(T + D)
+    bf = torch.bfloat16
+    x = (torch.randn(T, D, generator=g, device="cuda") * 2 + 0.5).to(bf)
+    gamma = torch.randn(D, generator=g, device="cuda")
+    beta = torch.randn(D, generator=g, device="cuda")
+    dy = torch.randn(T, D, generator=g, device="cuda").to(bf)
+    dres = torch.randn(T, D, generator=g, device="cuda").to(bf)
+    ss = (torch.rand((T + rps - 1) // rps, generator=g, device="cuda") < 0.8).float() / 0.8
+    _, mean, rstd = ops.layernorm_fwd(x, gamma, beta)
+    dg0, db0 = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dx0 = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dg0, db0, dres=dres)
+    for p, scale in ((0.2, ss), (0.0, ss), (0.3, None)):
+        dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+        dx, dxm = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dg, db, dres=dres, drop=(p, 0xABCDEF0123, 9, scale, rps))
+        assert torch.equal(dx, dx0)
+        assert torch.equal(dxm, ops.dropout(dx0, p, 0xABCDEF0123, 9, sample_scale=scale, rows_per_sample=rps if scale is not None else 0))
+        assert rel(dg, dg0) < 1e-5 and rel(db, db0) < 1e-5            # column sums: atomics order only
