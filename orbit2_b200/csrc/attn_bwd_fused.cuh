@@ -159,7 +159,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
         uint4* dst = reinterpret_cast<uint4*>(sStat + idx * 128);
         dst[(2 * stage) ^ (idx & 7)] = neg_split3(xs[e]);
         dst[(2 * stage + 1) ^ (idx & 7)] = neg_split3(ys[e]);
-        if (kDrop) reinterpret_cast<float*>(dst + (6 ^ (idx & 7)))[stage] = ys[e];
+        if (kDrop) reinterpret_cast<float*>(dst + (6 ^ (idx & 7)))[stage] = -ys[e];     // raw -delta for the softmax threads
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
@@ -380,26 +380,31 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
       ptx::tmem_ld_wait();
       uint32_t pk[16], dk[16];
       if (kDrop) {
+        // Keep decisions of this thread's key for its 32 queries as ONE word in the bit order the PRMT mask expansion wants
+        // (pi = attn_keep_bit): lane l builds the keep word of query qb + pi^-1(l) (32 keys of this warp's key block), the
+        // 32 x 32 bit matrix is transposed across the warp with five butterfly shuffles, and the row of key `key` (bit
+        // position pi(key)) is fetched from the lane that holds it: 6 shuffles per 32 elements (the first version
+        // shuffled every word to every lane: 32), masks applied as AND-masks on packed values, math back in fp32x2.
         const int qb = pp * BQ + buf * BS + chalf * 32;
-        const uint32_t kbit = 1u << ptx::attn_keep_bit((uint32_t)key);
-        const uint32_t my_word = ptx::attn_keep_word(a.drop, drop_key, (uint32_t)(qb + lane), (uint32_t)(key >> 5));
-        const float* dl = reinterpret_cast<const float*>(sStat) + dstage;
+        const uint32_t my_word = ptx::attn_keep_word(a.drop, drop_key, (uint32_t)(qb + (int)ptx::attn_keep_bit_inv((uint32_t)lane)),
+                                                     (uint32_t)(key >> 5));
+        uint32_t T = ptx::warp_transpose32(my_word, lane);
+        T = __shfl_sync(0xffffffffu, T, (int)ptx::attn_keep_bit((uint32_t)key));
+        drop_apply_f32(dv_, T);                                     // dP^T through the mask (dropped -> +0)
+        const float* dl = reinterpret_cast<const float*>(sStat) + dstage;      // -delta of the tile's 128 queries
+        const uint64_t ik2 = ptx::pack2(a.drop.inv_keep, a.drop.inv_keep);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const uint64_t X = ptx::mul2(ptx::pack2u(sv_[i], sv_[i + 1]), sc2);
           const uint64_t Pq = ptx::exp2_pair<false>(X);
-          const bool k0_ = (__shfl_sync(0xffffffffu, my_word, i) & kbit) != 0u;
-          const bool k1_ = (__shfl_sync(0xffffffffu, my_word, i + 1) & kbit) != 0u;
-          float p0_, p1_;
-          ptx::unpack2(Pq, p0_, p1_);
           const int qi = buf * BS + chalf * 32 + i;                // row of the 128-query statistics tile
-          const float de0 = dl[(qi * 128 + ((6 ^ (qi & 7)) * 16)) >> 2];
-          const float de1 = dl[((qi + 1) * 128 + ((6 ^ ((qi + 1) & 7)) * 16)) >> 2];
-          const float g0 = k0_ ? __uint_as_float(dv_[i]) * a.drop.inv_keep : 0.f;
-          const float g1 = k1_ ? __uint_as_float(dv_[i + 1]) * a.drop.inv_keep : 0.f;
-          pk[i >> 1] = pack_bf16x2(k0_ ? p0_ : 0.f, k1_ ? p1_ : 0.f);
-          dk[i >> 1] = pack_bf16x2(p0_ * (g0 - de0), p1_ * (g1 - de1));
+          const uint64_t nd = ptx::pack2(dl[(qi * 128 + ((6 ^ (qi & 7)) * 16)) >> 2],
+                                         dl[((qi + 1) * 128 + ((6 ^ ((qi + 1) & 7)) * 16)) >> 2]);
+          const uint64_t G = ptx::fma2(ptx::pack2u(dv_[i], dv_[i + 1]), ik2, nd);    // M dP / keep - delta
+          pk[i >> 1] = ptx::pack_bf16x2_pair(Pq);
+          dk[i >> 1] = ptx::pack_bf16x2_pair(ptx::mul2(Pq, G));
         }
+        drop_apply_bf16x2(pk, T);                                   // dV uses the masked probabilities
       } else {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {

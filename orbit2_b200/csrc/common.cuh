@@ -419,6 +419,21 @@ __host__ __device__ __forceinline__ uint32_t attn_keep_bit(uint32_t k) {
   const uint32_t kk = k & 31u;
   return 7u - (kk >> 2) + 8u * (kk & 1u) + 16u * ((kk >> 1) & 1u);
 }
+// inverse of attn_keep_bit: the key (0..31) whose decision sits at bit b
+__host__ __device__ __forceinline__ uint32_t attn_keep_bit_inv(uint32_t b) {
+  return 4u * (7u - (b & 7u)) + 2u * (b >> 4) + ((b >> 3) & 1u);
+}
+// 32 x 32 bit-matrix transpose across the lanes of a warp: lane l passes row l, lane j gets column j (bit c of the result =
+// bit j of lane c's word).  Five butterfly exchanges (Hacker's Delight 7-3 with the row dimension spread over the lanes).
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const uint32_t m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+    x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y << s) & ~m));
+  }
+  return x;
+}
 // AND-masks of keys (4 s + 2 t, 4 s + 2 t + 1) of a keep word, given ws = word << s: a bf16x2 mask, or two fp32 masks
 template <int T2> __device__ __forceinline__ uint32_t keep_mask_bf16x2(uint32_t ws) {
   uint32_t m;
