@@ -63,7 +63,7 @@ def whole_step(case, B, dtype, tf32, steps):
             "samples_per_s": B / (ms * 1e-3), "hbm_peak_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
 
 
-def attention_only(B, N, heads, hd, iters):
+def attention_only(B, N, heads, hd, iters, p_drop=0.0):
     """Library SDPA (the back ends torch picks for bf16: flash / cuDNN / mem-efficient) vs this repo's tcgen05 kernels."""
     from torch.nn.attention import SDPBackend, sdpa_kernel
     from orbit2_b200 import ops
@@ -78,22 +78,23 @@ def attention_only(B, N, heads, hd, iters):
                      ("efficient", SDPBackend.EFFICIENT_ATTENTION)):
         try:
             with sdpa_kernel([be]):
-                f_ms = event_ms(lambda: F.scaled_dot_product_attention(q, k, v), iters)
-                o = F.scaled_dot_product_attention(q, k, v)
+                f_ms = event_ms(lambda: F.scaled_dot_product_attention(q, k, v, dropout_p=p_drop), iters)
+                o = F.scaled_dot_product_attention(q, k, v, dropout_p=p_drop)
 
                 def bwd():
                     for t in (q, k, v):
                         t.grad = None
                     o.backward(do4, retain_graph=True)
                 b_ms = event_ms(bwd, iters)
-            out.append({"what": f"torch SDPA backend {name}", "B": B, "N": N, "heads": heads, "hd": hd, "fwd_ms": f_ms,
+            out.append({"what": f"torch SDPA backend {name}", "dropout_p": p_drop, "B": B, "N": N, "heads": heads, "hd": hd, "fwd_ms": f_ms,
                         "bwd_ms": b_ms, "fwd_tflops": fl_fwd / f_ms / 1e9, "bwd_tflops_algorithmic": 2.5 * fl_fwd / b_ms / 1e9})
         except Exception as e:                                    # a back end that is not built / not eligible here
             out.append({"what": f"torch SDPA backend {name}", "unavailable": repr(e)[:200]})
-    o2, lse = ops.attn_fwd(qkv, B, N, heads, hd)
-    f_ms = event_ms(lambda: ops.attn_fwd(qkv, B, N, heads, hd), iters)
-    b_ms = event_ms(lambda: ops.attn_bwd(qkv, o2, dout, lse, B, N, heads, hd), iters)
-    out.append({"what": "orbit2_b200 tcgen05 attention (this repo)", "B": B, "N": N, "heads": heads, "hd": hd, "fwd_ms": f_ms,
+    dr = (p_drop, 1234567, 3) if p_drop > 0 else None
+    o2, lse = ops.attn_fwd(qkv, B, N, heads, hd, dr)
+    f_ms = event_ms(lambda: ops.attn_fwd(qkv, B, N, heads, hd, dr), iters)
+    b_ms = event_ms(lambda: ops.attn_bwd(qkv, o2, dout, lse, B, N, heads, hd, dr), iters)
+    out.append({"what": "orbit2_b200 tcgen05 attention (this repo)", "dropout_p": p_drop, "B": B, "N": N, "heads": heads, "hd": hd, "fwd_ms": f_ms,
                 "bwd_ms": b_ms, "fwd_tflops": fl_fwd / f_ms / 1e9, "bwd_tflops_algorithmic": 2.5 * fl_fwd / b_ms / 1e9})
     return out
 
@@ -104,8 +105,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--workload", default="117m")
     ap.add_argument("--skip-step", action="store_true")
+    ap.add_argument("--drop", type=float, default=0.0, help="attention-probability dropout for the attention-only comparison")
     a = ap.parse_args()
-    for row in attention_only(a.batch, 16200, 16, 64, 3):
+    for row in attention_only(a.batch, 16200, 16, 64, 3, a.drop):
         print(json.dumps(row), flush=True)
     if a.skip_step:
         return
