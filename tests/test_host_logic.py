@@ -181,3 +181,25 @@ def test_keep_masks_known_answer(golden_dir):
     assert sorted(z.files) == sorted(got)
     for k in z.files:
         assert np.array_equal(z[k], got[k]), k
+
+
+def test_drop_plan_redraw_keeps_buffers():
+    """CUDA-graph mode keeps ONE DropPlan whose per-sample drop-path factors live in fixed tensors: redraw_paths must write
+    new bernoulli(keep) / keep factors into the SAME storage (captured kernels keep reading those addresses), reproducibly
+    for a given seed, and leave the blocks without drop-path (rate 0) alone."""
+    from orbit2_b200.reslim import DropPlan
+    dpr = [0.0, 0.1, 0.2, 0.3]
+    plan = DropPlan(0.1, dpr, 64, seed=5, device="cpu")
+    assert plan.path[0] == (None, None) and plan.branch_active(0)           # element dropout alone keeps the branch active
+    ptrs = [(a.data_ptr(), b.data_ptr()) for a, b in plan.path[1:]]
+    before = [a.clone() for a, _ in plan.path[1:]]
+    plan.redraw_paths(1234)
+    assert [(a.data_ptr(), b.data_ptr()) for a, b in plan.path[1:]] == ptrs
+    assert any(not torch.equal(x, a) for x, (a, _) in zip(before, plan.path[1:]))
+    again = DropPlan(0.1, dpr, 64, seed=5, device="cpu")
+    again.redraw_paths(1234)
+    for (a, b), (c, d), dp in zip(plan.path[1:], again.path[1:], dpr[1:]):
+        assert torch.equal(a, c) and torch.equal(b, d)
+        for v in set(a.tolist()) | set(b.tolist()):
+            assert v == 0.0 or abs(v - 1.0 / (1.0 - dp)) < 1e-6
+    assert not DropPlan(0.0, [0.0, 0.0], 4, 1, "cpu").branch_active(1)
