@@ -3,6 +3,9 @@
 //
 // reference semantics: components/attention.py:54-78 (autograd backward of softmax(q k^T hd^-0.5) v, attn_drop included).
 //
+// NOTE (measured after this was written, tools/mma_rate.cu): an M = 128, K = 16 MMA takes 45.5 cycles at N = 64 (TS; 48.1 SS)
+// and 64.1 at N = 128 -- not the 58 / 64 vs 32 assumed below -- so the N = 64 score MMAs of the shipped kernel already ran at
+// 70 % of the math rate and the tensor pipe was never the limiter; this version measured 942 vs 958 TFLOP/s and is not shipped.
 // Why a third version.  ncu of attn_bwd_fused_kernel (profiles/r02_attn_fused_ncu.md): tensor pipe 52 % busy although the
 // issue queue never runs dry.  A tcgen05.mma of 128 x 64 x 16 does 32 cycles of math but takes ~64 (TS: the 4 KiB A slice
 // is read from tensor memory at 64 B/clk) or ~58 (SS: 6 KiB from shared memory at 128 B/clk); only N = 128 instructions
