@@ -86,7 +86,8 @@ def build(conf: dict, data_key: str, img_size: Tuple[int, int], device, pos_grid
                       grad_scaler=GradScaler() if (dtype == torch.bfloat16 and not int(os.environ.get("O2_GRAPH", "0")))
                       else None)
     # launch-bound configurations (interm_8m): replay the step as one CUDA graph (trainer --graph / O2_GRAPH=1); only
-    # where the engine allows it: one GPU, replicated parameters, dropout / drop-path 0
+    # where the engine allows it: one GPU, replicated parameters; dropout / drop-path stay on (device-resident step word),
+    # the dynamic grad scaler is left out (its skip decision is taken on the host; bf16 has fp32's exponent range)
     if int(os.environ.get("O2_GRAPH", "0")):
         eng.enable_graph()
     return model, loss, eng
@@ -354,7 +355,7 @@ def main():
     ap.add_argument("--full-shard", action="store_true", help="FSDP FULL_SHARD: per-Block weight / gradient / Adam shards "
                     "(interm_1b / interm_10b); default is the YAML's parallelism.fsdp -> sharded optimizer")
     ap.add_argument("--graph", action="store_true", help="replay the training step as one captured CUDA graph (one GPU, "
-                    "dropout 0; for launch-bound configurations such as interm_8m)")
+                    "no dynamic grad scaler; for launch-bound configurations such as interm_8m, at the YAML's dropout)")
     a = ap.parse_args()
     if a.act_ckpt:
         os.environ["O2_ACT_CKPT"] = "1"
